@@ -1,0 +1,112 @@
+/*
+ * qocb200.h - C ABI of the B200-native GRAPE propagate-and-differentiate hot path.
+ *
+ * The reference (SchusterLab/qoc) is pure Python and has no FFI; the seam this library replaces is
+ *   (1) _evaluate_schroedinger_discrete(controls, pstate, reporter) -> error
+ *       (qoc/core/schroedingerdiscrete.py:356-438, also used by evolve_schroedinger_discrete, :101), and
+ *   (2) ans_jacobian(_evaluate_schroedinger_discrete, 0)(controls, pstate, reporter) -> (error, grads)
+ *       (qoc/core/schroedingerdiscrete.py:318, qoc/standard/utils/autogradutil.py:10-31),
+ * and the Lindblad twins (qoc/core/lindbladdiscrete.py:357-441, :322).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add at those two call sites.
+ *
+ * Conventions
+ *   - every pointer is a HOST pointer unless the name ends in `_dev`; the caller owns all host buffers;
+ *   - complex arrays are interleaved (re, im) doubles in NumPy C order (complex128);
+ *   - controls are REAL channels: real controls -> KR = K; complex controls -> KR = 2K with
+ *     x = [Re u_0..Re u_{K-1}, Im u_0..Im u_{K-1}] per control step, and the Hamiltonian is the real-linear form
+ *     H(x) = H0 + sum_r x_r A_r (the Python layer extracts H0, A_r from the user's callable);
+ *   - gradients are dE/dx_r (real).  For complex controls dE/dRe u + i dE/dIm u is what qoc's optimiser
+ *     receives after the wrapper's conjugate (qoc/core/schroedingerdiscrete.py:320-324);
+ *   - every function returns 0 on success; on failure a negative code, message via qocb_last_error();
+ *   - a plan is not re-entrant; distinct plans are independent; calls block until outputs are on the host
+ *     unless stated otherwise.  The plan owns all device memory and its stream.
+ */
+#ifndef QOCB200_H
+#define QOCB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qocb_plan qocb_plan;
+
+typedef struct {
+    int32_t hilbert_size;        /* n */
+    int32_t state_count;         /* S */
+    int32_t control_count;       /* KR: real control channels */
+    int32_t control_eval_count;  /* M  (qoc/models/programstate.py:40-41) */
+    int32_t system_eval_count;   /* N  (N-1 time slices, dt = T/(N-1), programstate.py:44) */
+    int32_t magnus_order;        /* 2, 4 or 6  (qoc/models/magnuspolicy.py:8-26) */
+    int32_t cost_eval_step;      /* >= 1 */
+    int32_t ensemble_count;      /* E >= 1: members differ in the drift H0 only; cost = mean over members */
+    int32_t device;              /* CUDA device ordinal */
+    int32_t store_tape;          /* 1: keep Pade intermediates of the forward pass in HBM for the reverse pass;
+                                    0: recompute them in the reverse pass (less memory, ~25% more flops) */
+    int32_t chunks_per_member;   /* 0 = automatic */
+    int32_t reserved;
+    double evolution_time;       /* T */
+} qocb_problem;
+
+/* cost kinds (qoc/standard/costs): vectors are `state_count x fmax` column vectors of length n */
+#define QOCB_COST_TARGET_COHERENT 0   /* w * (1 - |sum_s <t_s|psi_s>|^2 / S^2)   targetstateinfidelity.py:52-56 */
+#define QOCB_COST_TARGET_INCOHERENT 1 /* w * (1 - sum_s |<t_s|psi_s>|^2 / S)     targetstateinfidelity.py:57-61 */
+#define QOCB_COST_FORBID 2            /* w * sum_s (1/F_s) sum_f |<f_sf|psi_s>|^2  forbidstates.py:64-81         */
+
+int qocb_plan_create(const qocb_problem *problem, qocb_plan **plan_out);
+int qocb_plan_destroy(qocb_plan *plan);
+const char *qocb_last_error(const qocb_plan *plan);           /* plan may be NULL: last creation error */
+
+/* H0: [E][n][n] complex (E = ensemble_count), A: [KR][n][n] complex */
+int qocb_set_operators(qocb_plan *plan, const double *h0, const double *a_ops);
+/* psi0: [S][n] complex */
+int qocb_set_states(qocb_plan *plan, const double *psi0);
+/* vectors: [S][fmax][n] complex; counts: [S] number of valid vectors per state (NULL = fmax for all);
+   weight = cost_multiplier / normalisation; step_cost != 0: evaluated at every cost step, else final step only */
+int qocb_add_cost(qocb_plan *plan, int32_t kind, int32_t step_cost, double weight,
+                  const double *vectors, const int32_t *counts, int32_t fmax);
+int qocb_clear_costs(qocb_plan *plan);
+
+/* controls: [M][KR] real.  cost: 1 double.  final_states: [E][S][n] complex or NULL. */
+int qocb_cost(qocb_plan *plan, const double *controls, double *cost, double *final_states);
+/* grad: [M][KR] real */
+int qocb_cost_and_grad(qocb_plan *plan, const double *controls, double *cost, double *grad, double *final_states);
+/* all states of the last evaluation: [E][N][S][n] complex (the reference's save_intermediate_states payload,
+   qoc/core/schroedingerdiscrete.py:395-402) */
+int qocb_get_states(qocb_plan *plan, double *states);
+/* slice propagators U_j of the last evaluation: [E][N-1][n][n] complex */
+int qocb_get_propagators(qocb_plan *plan, double *props);
+
+/* device-resident pipeline for benchmarking: controls already in HBM, no host transfer, no sync.
+   qocb_upload_controls stages them; qocb_run_resident enqueues the whole evaluation on the plan stream;
+   qocb_sync waits; qocb_download_result copies cost/grad to the host. */
+int qocb_upload_controls(qocb_plan *plan, const double *controls);
+int qocb_run_resident(qocb_plan *plan, int32_t with_grad);
+int qocb_sync(qocb_plan *plan);
+int qocb_download_result(qocb_plan *plan, double *cost, double *grad);
+/* time `iters` resident evaluations with CUDA events on the plan stream after `warmup` untimed ones.
+   ms_total[0] = total ms; kernel_ms[8] = summed ms of each pipeline stage (expm forward, boundary fwd, sweep
+   fwd, sweep bwd (all three), expm reverse, gather, finalize, spare); flush_l2 != 0 writes a 256 MiB buffer
+   between evaluations (outside the stage timers, inside ms_total only if count_flush != 0). */
+int qocb_time_resident(qocb_plan *plan, int32_t with_grad, int32_t warmup, int32_t iters, int32_t flush_l2,
+                       double *ms_total, double *stage_ms);
+/* number of kernel launches of one evaluation */
+int qocb_launch_count(qocb_plan *plan, int32_t with_grad);
+void *qocb_stream(qocb_plan *plan);                           /* cudaStream_t of the plan */
+
+/* standalone batched matrix exponential (qoc/standard/functions/expm.py:210-252), bench / test hook.
+   a, out: [batch][n][n] complex on the host. */
+int qocb_expm_batched(int32_t n, int64_t batch, const double *a, double *out, int32_t device);
+/* same with adjoint: given ubar [batch][n][n] (cotangent of the output, autograd convention) returns
+   abar [batch][n][n] (cotangent of the input) - exercises the reverse pass in isolation */
+int qocb_expm_vjp_batched(int32_t n, int64_t batch, const double *a, const double *ubar, double *out, double *abar,
+                          int32_t device);
+/* device-resident timing of the batched expm: returns ms per launch (best of `iters`) */
+int qocb_expm_batched_time(int32_t n, int64_t batch, double norm_scale, int32_t iters, double *ms_best, int32_t device);
+
+const char *qocb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QOCB200_H */

@@ -1,0 +1,211 @@
+"""
+plan.py - host side of the drop-in boundary: turns the reference's program state (user `hamiltonian`
+callable, cost objects, states) into a device plan of the C ABI (include/qocb200.h) and evaluates
+cost / cost+gradient on the GPU.
+
+What happens here, once per `grape_*` / `evolve_*` call:
+  * Hamiltonian structure extraction.  The reference calls the opaque Python callable `hamiltonian(controls, t)`
+    at every Magnus node of every slice (qoc/core/schroedingerdiscrete.py:483-486) and differentiates through
+    it.  The CUDA path needs the operator structure, so the callable is probed: H0 = h(0), A_k = h(e_k) - H0,
+    B_k = h(i e_k) - H0 (complex controls), and real-linearity in (Re u, Im u) plus time-independence are
+    verified with random probes.  Every hamiltonian in the reference's examples/tests has this form
+    (examples/0_transmon_pi.py:24-26, examples/tutorial.py:101-106, tests/test_core.py:529-531,582); anything
+    else raises NotImplementedError - there is no CPU fallback.
+  * cost recognition: the qoc cost classes provide device descriptors (`device_terms`) or, for control-only
+    costs, an analytic host value+gradient (`control_value_and_grad`).
+"""
+import ctypes
+
+import numpy as np
+
+from qoc_b200 import _lib
+from qoc_b200.models.enums import InterpolationPolicy, MagnusPolicy
+
+_PROBE_RTOL = 1e-10
+
+
+def extract_hamiltonian_structure(hamiltonian, control_count, complex_controls, evolution_time, hilbert_size=None,
+                                  seed=1234):
+    """Returns (h0 [n x n], a_ops [KR x n x n]) with H(x) = H0 + sum_r x_r A_r, x = [Re u, Im u]."""
+    rng = np.random.default_rng(seed)
+    t0, t1 = 0.0, 0.37 * evolution_time
+    if control_count == 0:
+        h0 = np.asarray(hamiltonian(None, t0), dtype=np.complex128)
+        h1 = np.asarray(hamiltonian(None, t1), dtype=np.complex128)
+        if not np.allclose(h0, h1, rtol=_PROBE_RTOL, atol=_PROBE_RTOL * max(1.0, np.abs(h0).max())):
+            raise NotImplementedError("time-dependent hamiltonian callables are not supported by the CUDA path yet")
+        return h0, np.zeros((0,) + h0.shape, dtype=np.complex128)
+    dtype = np.complex128 if complex_controls else np.float64
+    zero = np.zeros(control_count, dtype=dtype)
+    h0 = np.array(hamiltonian(zero, t0), dtype=np.complex128)
+    if h0.ndim != 2 or h0.shape[0] != h0.shape[1]:
+        raise ValueError("hamiltonian(controls, time) must return a square matrix")
+    ops = []
+    parts = (1.0, 1j) if complex_controls else (1.0,)
+    for part in parts:
+        for k in range(control_count):
+            e = zero.copy()
+            e[k] = part
+            ops.append(np.array(hamiltonian(e, t0), dtype=np.complex128) - h0)
+    a_ops = np.stack(ops)
+    scale = max(1.0, np.abs(h0).max(), np.abs(a_ops).max())
+    for trial in range(3):
+        u = rng.standard_normal(control_count) * (1.0 + trial)
+        if complex_controls:
+            u = u + 1j * rng.standard_normal(control_count) * (1.0 + trial)
+        x = np.concatenate([u.real, u.imag]) if complex_controls else u
+        model = h0 + np.tensordot(x, a_ops, axes=(0, 0))
+        for t in (t0, t1):
+            got = np.asarray(hamiltonian(u.astype(dtype), t), dtype=np.complex128)
+            if not np.allclose(got, model, rtol=0, atol=_PROBE_RTOL * scale * (1 + np.abs(x).sum())):
+                raise NotImplementedError(
+                    "hamiltonian(controls, time) is not of the form H0 + sum_k Re(u_k) A_k + Im(u_k) B_k with "
+                    "time-independent operators; general (non-linear or time-dependent) callables are not "
+                    "supported by the CUDA path yet (no CPU fallback)")
+    return h0, a_ops
+
+
+class SchroedingerPlan(object):
+    """Device plan for `_evaluate_schroedinger_discrete` and its jacobian (schroedingerdiscrete.py:356-438,
+    :318).  `cost(controls)` and `cost_and_grad(controls)` take controls in cost-function format
+    ((M x K) float64 or complex128) and return what the reference seam returns."""
+
+    def __init__(self, hamiltonian, initial_states, costs, evolution_time, system_eval_count,
+                 control_eval_count=0, control_count=0, complex_controls=False,
+                 magnus_policy=MagnusPolicy.M2, cost_eval_step=1,
+                 interpolation_policy=InterpolationPolicy.LINEAR, device=0, store_tape=True,
+                 chunks_per_member=0, ensemble_drifts=None, structure=None):
+        if interpolation_policy != InterpolationPolicy.LINEAR:
+            raise NotImplementedError("The interpolation policy {} is not yet supported for this method."
+                                      "".format(interpolation_policy))
+        if not isinstance(magnus_policy, MagnusPolicy):
+            raise ValueError("Unrecognized magnus policy {}.".format(magnus_policy))
+        self.lib = _lib.load()
+        initial_states = np.asarray(initial_states)
+        self.S, self.n = initial_states.shape[0], initial_states.shape[1]
+        self.K = int(control_count)
+        self.M = int(control_eval_count)
+        self.N = int(system_eval_count)
+        self.complex_controls = bool(complex_controls)
+        self.KR = self.K * (2 if self.complex_controls else 1)
+        self.costs = list(costs)
+        if structure is None:
+            structure = extract_hamiltonian_structure(hamiltonian, self.K, self.complex_controls, evolution_time)
+        h0, a_ops = structure
+        if h0.shape[0] != self.n:
+            raise ValueError("hamiltonian size {} does not match the states' hilbert size {}".format(h0.shape[0], self.n))
+        if ensemble_drifts is not None:          # build-side extension: members differ in the drift only
+            h0s = np.ascontiguousarray(ensemble_drifts, dtype=np.complex128)
+        else:
+            h0s = np.ascontiguousarray(h0[None], dtype=np.complex128)
+        self.E = h0s.shape[0]
+        pb = _lib.Problem(hilbert_size=self.n, state_count=self.S, control_count=self.KR,
+                          control_eval_count=self.M, system_eval_count=self.N,
+                          magnus_order=magnus_policy.order, cost_eval_step=int(cost_eval_step),
+                          ensemble_count=self.E, device=int(device), store_tape=int(bool(store_tape)),
+                          chunks_per_member=int(chunks_per_member), reserved=0,
+                          evolution_time=float(evolution_time))
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.qocb_plan_create(ctypes.byref(pb), ctypes.byref(handle)))
+        self.handle = handle
+        a_ops = np.ascontiguousarray(a_ops, dtype=np.complex128)
+        _lib.check(self.lib.qocb_set_operators(handle, _lib.ptr(h0s), _lib.ptr(a_ops) if self.KR else None), handle)
+        psi0 = np.ascontiguousarray(initial_states.reshape(self.S, self.n), dtype=np.complex128)
+        _lib.check(self.lib.qocb_set_states(handle, _lib.ptr(psi0)), handle)
+        self.control_costs = []
+        for c in self.costs:
+            terms = c.device_terms(self.S, self.n)
+            if not terms:
+                self.control_costs.append(c)
+            for kind, step, weight, vecs, counts in terms:
+                vecs = np.ascontiguousarray(vecs, dtype=np.complex128)
+                cnt = None if counts is None else np.ascontiguousarray(counts, dtype=np.int32)
+                _lib.check(self.lib.qocb_add_cost(handle, kind, step, float(weight), _lib.ptr(vecs),
+                                                  None if cnt is None else cnt.ctypes.data_as(ctypes.c_void_p),
+                                                  vecs.shape[1]), handle)
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _real_channels(self, controls):
+        if self.KR == 0:
+            return None
+        controls = np.asarray(controls)
+        if controls.shape != (self.M, self.K):
+            raise ValueError("controls must have shape {}".format((self.M, self.K)))
+        if self.complex_controls:
+            return np.ascontiguousarray(np.concatenate([controls.real, controls.imag], axis=1), dtype=np.float64)
+        return np.ascontiguousarray(controls, dtype=np.float64)
+
+    def _control_costs(self, controls, want_grad):
+        value, grad = 0.0, None
+        for c in self.control_costs:
+            v, g = c.control_value_and_grad(controls)
+            value += v
+            if want_grad and g is not None:
+                grad = g if grad is None else grad + g
+        return value, grad
+
+    def _final_states(self, buf):
+        fs = buf.reshape(self.E, self.S, self.n, 1)
+        return fs[0] if self.E == 1 else fs
+
+    # -- the seam ---------------------------------------------------------------------------------------
+    def cost(self, controls):
+        x = self._real_channels(controls)
+        out = np.zeros(1)
+        fs = np.empty((self.E, self.S, self.n), dtype=np.complex128)
+        _lib.check(self.lib.qocb_cost(self.handle, _lib.ptr(x), _lib.ptr(out), _lib.ptr(fs)), self.handle)
+        extra, _ = self._control_costs(controls, False) if controls is not None else (0.0, None)
+        return float(out[0]) + extra, self._final_states(fs)
+
+    def cost_and_grad(self, controls):
+        """returns (error, grads, final_states); grads has controls' shape and dtype and is
+        dE/dRe(u) + i dE/dIm(u) for complex controls (the value after the wrapper's conjugate,
+        schroedingerdiscrete.py:323-324)."""
+        x = self._real_channels(controls)
+        out = np.zeros(1)
+        g = np.zeros((self.M, self.KR))
+        fs = np.empty((self.E, self.S, self.n), dtype=np.complex128)
+        _lib.check(self.lib.qocb_cost_and_grad(self.handle, _lib.ptr(x), _lib.ptr(out), _lib.ptr(g), _lib.ptr(fs)),
+                   self.handle)
+        grads = g[:, :self.K] + 1j * g[:, self.K:] if self.complex_controls else g
+        extra, extra_grad = self._control_costs(np.asarray(controls), True)
+        if extra_grad is not None:
+            grads = grads + extra_grad
+        return float(out[0]) + extra, grads, self._final_states(fs)
+
+    def intermediate_states(self):
+        """[N][S][n][1] states of the last evaluation (member 0 unless E > 1: then [E][N][S][n][1])."""
+        buf = np.empty((self.E, self.N, self.S, self.n), dtype=np.complex128)
+        _lib.check(self.lib.qocb_get_states(self.handle, _lib.ptr(buf)), self.handle)
+        buf = buf[..., None]
+        return buf[0] if self.E == 1 else buf
+
+    def propagators(self):
+        buf = np.empty((self.E, self.N - 1, self.n, self.n), dtype=np.complex128)
+        _lib.check(self.lib.qocb_get_propagators(self.handle, _lib.ptr(buf)), self.handle)
+        return buf[0] if self.E == 1 else buf
+
+    # -- device-resident benchmarking hooks --------------------------------------------------------------
+    def upload(self, controls):
+        _lib.check(self.lib.qocb_upload_controls(self.handle, _lib.ptr(self._real_channels(controls))), self.handle)
+
+    def time_resident(self, with_grad=True, warmup=3, iters=10, flush_l2=True):
+        total = np.zeros(1)
+        stages = np.zeros(8)
+        _lib.check(self.lib.qocb_time_resident(self.handle, int(with_grad), warmup, iters, int(flush_l2),
+                                               _lib.ptr(total), _lib.ptr(stages)), self.handle)
+        return float(total[0]), stages
+
+    def launch_count(self, with_grad=True):
+        return int(self.lib.qocb_launch_count(self.handle, int(with_grad)))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.qocb_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,864 @@
+// capi.cu - kernels' global entry points, the plan object and the C ABI declared in include/qocb200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qocb200.h"
+#include "expm_slice.cuh"
+#include "sweep.cuh"
+
+using namespace qocb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define CU_TRY(plan, expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            char buf__[512];                                                                            \
+            snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            set_error(plan, buf__);                                                                     \
+            return -2;                                                                                  \
+        }                                                                                               \
+    } while (0)
+
+constexpr int kCtaTapeR = 16;            // squaring slots of the per-CTA (recompute) tape
+constexpr int kStoredTapeR = 2;          // squaring slots of the stored per-slice tape
+
+struct KArgs {
+    GenArgs ga;                 // ga.G0 points at member 0
+    int N, E, s_cap, tape_mats;
+    const int *chunk_begin;
+    double *U;                  // [E*(N-1)][GMAT]
+    double *tape;               // stored tape or nullptr
+    int *tape_piv;              // [E*(N-1)][NP]
+    int *meta;                  // [E*(N-1)] squaring count of each slice
+    double *scratch;            // [nchunks][S_COUNT][GMAT]
+    double *cta_tape;           // [nchunks][8 + kCtaTapeR][GMAT]
+    int *cta_piv;               // [nchunks][NP]
+    double *chunkP;             // [nchunks][GMAT]
+    const double *psi, *lam;    // [E][N][S][2][NP]
+    double *node_grad;          // [E*(N-1)][q][KR]
+    int S;
+    int *err_flag;
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_forward(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<C> sm(smem_raw);
+    const int c = blockIdx.x;
+    const int wb = a.chunk_begin[c], we = a.chunk_begin[c + 1];
+    double *scratch = a.scratch + (size_t)c * S_COUNT * C::GMAT;
+    double *gP = a.chunkP + (size_t)c * C::GMAT;
+    for (int w = wb; w < we; ++w) {
+        const int e = w / (a.N - 1), j = w - e * (a.N - 1);
+        GenArgs ga = a.ga;
+        ga.G0 += (size_t)e * C::GMAT;
+        load_coefs<C>(sm, ga, j);
+        magnus_forward<C>(sm, ga, scratch);
+        double *tape = a.tape ? a.tape + (size_t)w * a.tape_mats * C::GMAT : nullptr;
+        int *piv = a.tape ? a.tape_piv + (size_t)w * C::NP : nullptr;
+        const int s = pade_forward<C>(sm, tape, piv, scratch + (size_t)S_T0 * C::GMAT, scratch + (size_t)S_T1 * C::GMAT, a.s_cap);
+        if (threadIdx.x == 0) a.meta[w] = s;
+        double *gU = a.U + (size_t)w * C::GMAT;
+        if (w == wb) {
+            for_owned<C>([&](int, int, int row, int col) {
+                const c2 u = lds2<C>(sm.X1, row, col);
+                stg2<C>(gU, row, col, u);
+                stg2<C>(gP, row, col, u);
+            });
+        } else {
+            for_owned<C>([&](int, int, int row, int col) { stg2<C>(gU, row, col, lds2<C>(sm.X1, row, col)); });
+            g2s<C>(sm.X0, gP);
+            __syncthreads();
+            Acc<C> acc; acc.zero();
+            mma_smem<C, false, false, false>(acc, sm.X1, sm.X0);      // P <- U_j P
+            for_owned<C>([&](int i, int jj, int row, int col) { stg2<C>(gP, row, col, accv<C>(acc, i, jj)); });
+        }
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_backward(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<C> sm(smem_raw);
+    const int c = blockIdx.x;
+    const int wb = a.chunk_begin[c], we = a.chunk_begin[c + 1];
+    double *scratch = a.scratch + (size_t)c * S_COUNT * C::GMAT;
+    double *ctape = a.cta_tape + (size_t)c * (8 + kCtaTapeR) * C::GMAT;
+    int *cpiv = a.cta_piv + (size_t)c * C::NP;
+    const int VS = a.S * 2 * C::NP;
+    for (int w = wb; w < we; ++w) {
+        const int e = w / (a.N - 1), j = w - e * (a.N - 1);
+        GenArgs ga = a.ga;
+        ga.G0 += (size_t)e * C::GMAT;
+        load_coefs<C>(sm, ga, j);
+        const double *tape; const int *piv; int s;
+        if (a.tape && a.meta[w] <= a.s_cap) {
+            tape = a.tape + (size_t)w * a.tape_mats * C::GMAT;
+            piv = a.tape_piv + (size_t)w * C::NP;
+            s = a.meta[w];
+        } else {
+            magnus_forward<C>(sm, ga, scratch);
+            s = pade_forward<C>(sm, ctape, cpiv, scratch + (size_t)S_T0 * C::GMAT, scratch + (size_t)S_T1 * C::GMAT, kCtaTapeR);
+            if (s > kCtaTapeR && threadIdx.x == 0) *a.err_flag = 1;
+            tape = ctape; piv = cpiv;
+            __syncthreads();
+        }
+        // ubar = sum_s lam_{j+1,s} psi_{j,s}^T   (cotangent of U_j from states = U_j psi)
+        const double *psi = a.psi + ((size_t)e * a.N + j) * VS;
+        const double *lam = a.lam + ((size_t)e * a.N + j + 1) * VS;
+        for_owned<C>([&](int, int, int row, int col) {
+            c2 u = czero();
+            for (int s_ = 0; s_ < a.S; ++s_) {
+                const double lr = lam[s_ * 2 * C::NP + row], li = lam[s_ * 2 * C::NP + C::NP + row];
+                const double2 pr = *reinterpret_cast<const double2 *>(psi + s_ * 2 * C::NP + col);
+                const double2 pi = *reinterpret_cast<const double2 *>(psi + s_ * 2 * C::NP + C::NP + col);
+                u.r0 += lr * pr.x - li * pi.x; u.i0 += lr * pi.x + li * pr.x;
+                u.r1 += lr * pr.y - li * pi.y; u.i1 += lr * pi.y + li * pr.y;
+            }
+            sts2<C>(sm.X0, row, col, u);
+        });
+        __syncthreads();
+        pade_backward<C>(sm, tape, piv, s, a.U + (size_t)w * C::GMAT, scratch);
+        magnus_backward<C>(sm, ga, scratch, a.node_grad + (size_t)w * ga.q * ga.KR);
+    }
+}
+
+// grad[m][r] = (1/E) sum_e sum_{(j,i) using control point m} weight * node_grad[e][j][i][r]
+__global__ void k_gather_grad(const int *csr_ptr, const int *csr_idx, const double *csr_w, const double *node_grad,
+                              double *grad, int M, int KR, int q, int Nm1, int E) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M * KR) return;
+    const int m = t / KR, r = t % KR;
+    double sum = 0.;
+    for (int p = csr_ptr[m]; p < csr_ptr[m + 1]; ++p) {
+        const int ji = csr_idx[p];
+        const double w = csr_w[p];
+        double sub = 0.;
+        for (int e = 0; e < E; ++e) sub += node_grad[((size_t)e * Nm1 * q + ji) * KR + r];
+        sum += w * sub;
+    }
+    grad[t] = sum / E;
+}
+
+__global__ void k_finalize_cost(const double *cost_part, int nchunks, int E, double *cost) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.;
+        for (int c = 0; c < nchunks; ++c) s += cost_part[c];
+        *cost = s / E;
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_expm(const double *in, double *out, double *scratch, long long batch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<C> sm(smem_raw);
+    double *sc = scratch + (size_t)blockIdx.x * 3 * C::GMAT;
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        __syncthreads();
+        g2s<C>(sm.X2, in + (size_t)b * C::GMAT);
+        __syncthreads();
+        pade_forward<C>(sm, nullptr, nullptr, sc, sc + C::GMAT, 0);
+        for_owned<C>([&](int, int, int row, int col) { stg2<C>(out + (size_t)b * C::GMAT, row, col, lds2<C>(sm.X1, row, col)); });
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_expm_vjp(const double *in, const double *ubar, double *out, double *abar,
+                                                    double *scratch, double *cta_tape, int *cta_piv, long long batch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<C> sm(smem_raw);
+    double *sc = scratch + (size_t)blockIdx.x * S_COUNT * C::GMAT;
+    double *tape = cta_tape + (size_t)blockIdx.x * (8 + kCtaTapeR) * C::GMAT;
+    int *piv = cta_piv + (size_t)blockIdx.x * C::NP;
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        __syncthreads();
+        g2s<C>(sm.X2, in + (size_t)b * C::GMAT);
+        __syncthreads();
+        const int s = pade_forward<C>(sm, tape, piv, sc + (size_t)S_T0 * C::GMAT, sc + (size_t)S_T1 * C::GMAT, kCtaTapeR);
+        double *gU = out + (size_t)b * C::GMAT;
+        for_owned<C>([&](int, int, int row, int col) { stg2<C>(gU, row, col, lds2<C>(sm.X1, row, col)); });
+        g2s<C>(sm.X0, ubar + (size_t)b * C::GMAT);
+        __syncthreads();
+        pade_backward<C>(sm, tape, piv, s, gU, sc);
+        for_owned<C>([&](int, int, int row, int col) { stg2<C>(abar + (size_t)b * C::GMAT, row, col, lds2<C>(sm.X0, row, col)); });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int pad_dim(int n) {
+    if (n <= 8) return 8;
+    if (n <= 16) return 16;
+    if (n <= 32) return 32;
+    if (n <= 64) return 64;
+    return -1;
+}
+
+// interleaved complex n x n (host) -> planar padded NP x NP; generator: G = -1j * H
+void to_planar(const double *src, double *dst, int n, int NP, bool generator) {
+    std::fill(dst, dst + 2 * (size_t)NP * NP, 0.0);
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) {
+            const double re = src[2 * ((size_t)r * n + c)], im = src[2 * ((size_t)r * n + c) + 1];
+            dst[(size_t)r * NP + c] = generator ? im : re;
+            dst[(size_t)NP * NP + (size_t)r * NP + c] = generator ? -re : im;
+        }
+}
+void from_planar(const double *src, double *dst, int n, int NP) {
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) {
+            dst[2 * ((size_t)r * n + c)] = src[(size_t)r * NP + c];
+            dst[2 * ((size_t)r * n + c) + 1] = src[(size_t)NP * NP + (size_t)r * NP + c];
+        }
+}
+
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; n = 0; }
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct qocb_plan {
+    qocb_problem pb;
+    int NP = 0, q = 0, nchunks = 0, tape_mats = 0, num_sms = 0;
+    bool ops_set = false, states_set = false, have_step_costs = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[16] = {};
+    DevBuf<double> G0, G, controls, itab_w, U, tape, scratch, cta_tape, chunkP, psi, lam, part, cost_part, psi0,
+        node_grad, grad, cost, csr_w, vecs, flush;
+    DevBuf<int> itab_idx, tape_piv, meta, cta_piv, chunk_begin, member_chunk0, csr_ptr, csr_idx, counts, err_flag;
+    DevBuf<CostTerm> terms;
+    std::vector<CostTerm> h_terms;
+    std::vector<double> h_vecs;
+    std::vector<int> h_counts;
+    int ip_total = 0;
+    double *h_pinned = nullptr;         // [M*KR controls | M*KR grad | 1 cost]
+    std::string err;
+};
+
+namespace {
+
+void set_error(qocb_plan *plan, const char *msg) {
+    if (plan) plan->err = msg;
+    g_last_error = msg;
+}
+void set_error(const qocb_plan *plan, const char *msg) { set_error(const_cast<qocb_plan *>(plan), msg); }
+
+template <class C> int launch_forward(qocb_plan *p, const KArgs &a) {
+    CU_TRY(p, cudaFuncSetAttribute(k_forward<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
+    k_forward<C><<<p->nchunks, C::NT, Smem<C>::bytes(), p->stream>>>(a);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+template <class C> int launch_backward(qocb_plan *p, const KArgs &a) {
+    CU_TRY(p, cudaFuncSetAttribute(k_backward<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
+    k_backward<C><<<p->nchunks, C::NT, Smem<C>::bytes(), p->stream>>>(a);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+using C8 = Cfg<8, 1, 1>;
+using C16 = Cfg<16, 2, 2>;
+using C32 = Cfg<32, 2, 2>;
+using C64 = Cfg<64, 2, 4>;
+
+template <class F8, class F16, class F32, class F64>
+int dispatch(int NP, F8 f8, F16 f16, F32 f32, F64 f64) {
+    switch (NP) {
+        case 8: return f8();
+        case 16: return f16();
+        case 32: return f32();
+        case 64: return f64();
+    }
+    return -3;
+}
+
+template <class C> int occupancy_fwd() {
+    int occ = 0;
+    cudaFuncSetAttribute(k_backward<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_backward<C>, C::NT, Smem<C>::bytes());
+    return occ < 1 ? 1 : occ;
+}
+
+KArgs make_kargs(qocb_plan *p) {
+    KArgs a;
+    a.ga.G0 = p->G0.p; a.ga.G = p->G.p; a.ga.controls = p->controls.p;
+    a.ga.itab_idx = p->itab_idx.p; a.ga.itab_w = p->itab_w.p;
+    a.ga.KR = p->pb.control_count; a.ga.q = p->q; a.ga.order = p->pb.magnus_order;
+    a.ga.dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
+    a.N = p->pb.system_eval_count; a.E = p->pb.ensemble_count;
+    a.s_cap = kStoredTapeR; a.tape_mats = p->tape_mats;
+    a.chunk_begin = p->chunk_begin.p;
+    a.U = p->U.p; a.tape = p->tape.p; a.tape_piv = p->tape_piv.p; a.meta = p->meta.p;
+    a.scratch = p->scratch.p; a.cta_tape = p->cta_tape.p; a.cta_piv = p->cta_piv.p; a.chunkP = p->chunkP.p;
+    a.psi = p->psi.p; a.lam = p->lam.p; a.node_grad = p->node_grad.p; a.S = p->pb.state_count;
+    a.err_flag = p->err_flag.p;
+    return a;
+}
+
+SweepArgs make_sargs(qocb_plan *p) {
+    SweepArgs s;
+    s.NP = p->NP; s.S = p->pb.state_count; s.N = p->pb.system_eval_count; s.E = p->pb.ensemble_count;
+    s.ces = p->pb.cost_eval_step; s.nterms = (int)p->h_terms.size(); s.ip_total = p->ip_total;
+    s.terms = p->terms.p; s.vecs = p->vecs.p; s.counts = p->counts.p;
+    s.U = p->U.p; s.chunkP = p->chunkP.p; s.chunk_begin = p->chunk_begin.p; s.member_chunk0 = p->member_chunk0.p;
+    s.psi = p->psi.p; s.lam = p->lam.p; s.part = p->part.p; s.cost_part = p->cost_part.p; s.psi0 = p->psi0.p;
+    return s;
+}
+
+int upload_costs(qocb_plan *p) {
+    if (p->terms.n == p->h_terms.size() && p->terms.n > 0) return 0;
+    CU_TRY(p, p->terms.alloc(std::max<size_t>(1, p->h_terms.size())));
+    CU_TRY(p, p->vecs.alloc(std::max<size_t>(1, p->h_vecs.size())));
+    CU_TRY(p, p->counts.alloc(std::max<size_t>(1, p->h_counts.size())));
+    if (!p->h_terms.empty()) {
+        CU_TRY(p, cudaMemcpy(p->terms.p, p->h_terms.data(), sizeof(CostTerm) * p->h_terms.size(), cudaMemcpyHostToDevice));
+        CU_TRY(p, cudaMemcpy(p->vecs.p, p->h_vecs.data(), sizeof(double) * p->h_vecs.size(), cudaMemcpyHostToDevice));
+        CU_TRY(p, cudaMemcpy(p->counts.p, p->h_counts.data(), sizeof(int) * p->h_counts.size(), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// enqueue one evaluation on the plan stream; ev != nullptr records stage boundaries (9 events)
+int enqueue_eval(qocb_plan *p, bool with_grad, cudaEvent_t *ev) {
+    if (!p->ops_set || !p->states_set) { set_error(p, "operators and states must be set before evaluation"); return -1; }
+    if (upload_costs(p)) return -2;
+    KArgs ka = make_kargs(p);
+    if (!with_grad) { ka.tape = nullptr; }
+    SweepArgs sa = make_sargs(p);
+    const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
+    const int NP = p->NP;
+    auto rec = [&](int i) { if (ev) cudaEventRecord(ev[i], p->stream); };
+    rec(0);
+    int rc = dispatch(NP, [&] { return launch_forward<C8>(p, ka); }, [&] { return launch_forward<C16>(p, ka); },
+                      [&] { return launch_forward<C32>(p, ka); }, [&] { return launch_forward<C64>(p, ka); });
+    if (rc) return rc;
+    rec(1);
+    k_boundary_fwd<<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa);
+    rec(2);
+    k_sweep_fwd<<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
+    rec(3);
+    if (with_grad) {
+        if (p->have_step_costs) k_sweep_bwd<true><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
+        k_boundary_bwd<<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa, p->have_step_costs ? 1 : 0);
+        k_sweep_bwd<false><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
+        rec(4);
+        rc = dispatch(NP, [&] { return launch_backward<C8>(p, ka); }, [&] { return launch_backward<C16>(p, ka); },
+                      [&] { return launch_backward<C32>(p, ka); }, [&] { return launch_backward<C64>(p, ka); });
+        if (rc) return rc;
+        rec(5);
+        const int tot = p->pb.control_eval_count * p->pb.control_count;
+        k_gather_grad<<<(tot + 127) / 128, 128, 0, p->stream>>>(p->csr_ptr.p, p->csr_idx.p, p->csr_w.p, p->node_grad.p,
+                                                              p->grad.p, p->pb.control_eval_count, p->pb.control_count,
+                                                              p->q, p->pb.system_eval_count - 1, p->pb.ensemble_count);
+        rec(6);
+    } else {
+        rec(4); rec(5); rec(6);
+    }
+    k_finalize_cost<<<1, 32, 0, p->stream>>>(p->cost_part.p, p->nchunks, p->pb.ensemble_count, p->cost.p);
+    rec(7);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+int check_device_flag(qocb_plan *p) {
+    int flag = 0;
+    CU_TRY(p, cudaMemcpy(&flag, p->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) { set_error(p, "device error flag set: scaling count exceeded the recompute tape capacity"); return -4; }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *qocb_version(void) { return "qocb200 0.1 (sm_100a, complex128)"; }
+
+const char *qocb_last_error(const qocb_plan *plan) { return plan ? plan->err.c_str() : g_last_error.c_str(); }
+
+void *qocb_stream(qocb_plan *plan) { return plan ? (void *)plan->stream : nullptr; }
+
+int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
+    if (!pb || !out) { set_error((qocb_plan *)nullptr, "null argument"); return -1; }
+    *out = nullptr;
+    const int NP = pad_dim(pb->hilbert_size);
+    if (pb->hilbert_size < 1 || NP < 0) { set_error((qocb_plan *)nullptr, "hilbert_size must be in [1, 64] in this build (larger dims: not implemented yet)"); return -1; }
+    if (pb->magnus_order != 2 && pb->magnus_order != 4 && pb->magnus_order != 6) { set_error((qocb_plan *)nullptr, "magnus_order must be 2, 4 or 6"); return -1; }
+    if (pb->system_eval_count < 2) { set_error((qocb_plan *)nullptr, "system_eval_count must be >= 2"); return -1; }
+    if (pb->control_count < 0 || pb->control_count > kMaxKR) { set_error((qocb_plan *)nullptr, "control_count (real channels) must be in [0, 16]"); return -1; }
+    if (pb->control_count > 0 && pb->control_eval_count < 2) { set_error((qocb_plan *)nullptr, "control_eval_count must be >= 2"); return -1; }
+    if (pb->state_count < 1 || pb->cost_eval_step < 1 || pb->ensemble_count < 1) { set_error((qocb_plan *)nullptr, "state_count, cost_eval_step, ensemble_count must be >= 1"); return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error((qocb_plan *)nullptr, "no CUDA device available (this library has no CPU path)"); return -2; }
+    qocb_plan *p = new qocb_plan();
+    p->pb = *pb;
+    p->NP = NP;
+    p->q = pb->magnus_order / 2;
+    auto fail = [&](int rc) { std::string m = p->err; delete p; g_last_error = m; return rc; };
+#define PTRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { char b__[512]; snprintf(b__, sizeof(b__), "%s failed: %s", #expr, cudaGetErrorString(e__)); p->err = b__; return fail(-2); } } while (0)
+    PTRY(cudaSetDevice(pb->device));
+    cudaDeviceProp prop;
+    PTRY(cudaGetDeviceProperties(&prop, pb->device));
+    p->num_sms = prop.multiProcessorCount;
+    PTRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (auto &e : p->ev) PTRY(cudaEventCreate(&e));
+    const int N = pb->system_eval_count, Nm1 = N - 1, E = pb->ensemble_count, M = pb->control_eval_count;
+    const int KR = pb->control_count, S = pb->state_count, q = p->q;
+    const size_t GM = 2 * (size_t)NP * NP;
+    // ---- chunks -------------------------------------------------------------------------------------
+    int occ = dispatch(NP, [] { return occupancy_fwd<C8>(); }, [] { return occupancy_fwd<C16>(); },
+                       [] { return occupancy_fwd<C32>(); }, [] { return occupancy_fwd<C64>(); });
+    int cpm = pb->chunks_per_member;
+    if (cpm <= 0) cpm = (p->num_sms * occ + E - 1) / E;
+    cpm = std::max(1, std::min(cpm, Nm1));
+    p->nchunks = cpm * E;
+    std::vector<int> cb(p->nchunks + 1), mc0(E + 1);
+    for (int e = 0; e < E; ++e) {
+        mc0[e] = e * cpm;
+        for (int c = 0; c < cpm; ++c) cb[e * cpm + c] = e * Nm1 + (int)(((long long)c * Nm1) / cpm);
+    }
+    mc0[E] = E * cpm; cb[p->nchunks] = E * Nm1;
+    PTRY(p->chunk_begin.alloc(cb.size())); PTRY(p->member_chunk0.alloc(mc0.size()));
+    PTRY(cudaMemcpy(p->chunk_begin.p, cb.data(), sizeof(int) * cb.size(), cudaMemcpyHostToDevice));
+    PTRY(cudaMemcpy(p->member_chunk0.p, mc0.data(), sizeof(int) * mc0.size(), cudaMemcpyHostToDevice));
+    // ---- interpolation table (qoc/core/mathmethods.py:36-67 on linspace(0, T, M), programstate.py:41) ----
+    {
+        const double T = pb->evolution_time, dt = T / Nm1;
+        const double s3 = std::sqrt(3.0), s15 = std::sqrt(15.0);
+        double nodes[3];
+        if (q == 1) nodes[0] = 0.5;
+        else if (q == 2) { nodes[0] = 0.5 - s3 / 6; nodes[1] = 0.5 + s3 / 6; }
+        else { nodes[0] = 0.5 - s15 / 10; nodes[1] = 0.5; nodes[2] = 0.5 + s15 / 10; }
+        std::vector<int> idx((size_t)Nm1 * q * 2, 0);
+        std::vector<double> w((size_t)Nm1 * q * 2, 0.0);
+        std::vector<std::vector<std::pair<int, double>>> inv(std::max(M, 1));
+        if (KR > 0) {
+            std::vector<double> xs(M);
+            for (int m = 0; m < M; ++m) xs[m] = (M == 1) ? 0.0 : (m == M - 1 ? T : m * (T / (M - 1)));   // numpy.linspace
+            for (int j = 0; j < Nm1; ++j)
+                for (int i = 0; i < q; ++i) {
+                    const double x = j * dt + dt * nodes[i];
+                    int i0, i1;
+                    if (x <= xs[0]) { i0 = 0; i1 = 1; }
+                    else if (x >= xs[M - 1]) { i0 = M - 2; i1 = M - 1; }
+                    else { i1 = 0; while (!(x <= xs[i1])) ++i1; i0 = i1 - 1; }
+                    const double w1 = (x - xs[i0]) / (xs[i1] - xs[i0]);
+                    const size_t o = ((size_t)j * q + i) * 2;
+                    idx[o] = i0; idx[o + 1] = i1; w[o] = 1.0 - w1; w[o + 1] = w1;
+                    inv[i0].push_back({j * q + i, 1.0 - w1});
+                    inv[i1].push_back({j * q + i, w1});
+                }
+        }
+        PTRY(p->itab_idx.alloc(idx.size())); PTRY(p->itab_w.alloc(w.size()));
+        PTRY(cudaMemcpy(p->itab_idx.p, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+        PTRY(cudaMemcpy(p->itab_w.p, w.data(), sizeof(double) * w.size(), cudaMemcpyHostToDevice));
+        std::vector<int> ptr(std::max(M, 1) + 1, 0), ci; std::vector<double> cw;
+        for (int m = 0; m < std::max(M, 1); ++m) {
+            for (auto &pr : inv[m]) { ci.push_back(pr.first); cw.push_back(pr.second); }
+            ptr[m + 1] = (int)ci.size();
+        }
+        PTRY(p->csr_ptr.alloc(ptr.size())); PTRY(p->csr_idx.alloc(std::max<size_t>(1, ci.size()))); PTRY(p->csr_w.alloc(std::max<size_t>(1, cw.size())));
+        PTRY(cudaMemcpy(p->csr_ptr.p, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
+        if (!ci.empty()) {
+            PTRY(cudaMemcpy(p->csr_idx.p, ci.data(), sizeof(int) * ci.size(), cudaMemcpyHostToDevice));
+            PTRY(cudaMemcpy(p->csr_w.p, cw.data(), sizeof(double) * cw.size(), cudaMemcpyHostToDevice));
+        }
+    }
+    // ---- buffers -------------------------------------------------------------------------------------
+    const size_t W = (size_t)E * Nm1;
+    p->tape_mats = 8 + kStoredTapeR;
+    PTRY(p->G0.alloc((size_t)E * GM)); PTRY(p->G.alloc(std::max<size_t>(1, (size_t)KR) * GM));
+    PTRY(p->controls.alloc(std::max<size_t>(1, (size_t)M * KR)));
+    PTRY(p->U.alloc(W * GM));
+    if (pb->store_tape) {
+        cudaError_t e = p->tape.alloc(W * p->tape_mats * GM);
+        if (e != cudaSuccess) { cudaGetLastError(); p->tape.release(); }       // fall back to recompute mode on the GPU
+        else PTRY(p->tape_piv.alloc(W * NP));
+    }
+    PTRY(p->meta.alloc(W));
+    PTRY(p->scratch.alloc((size_t)p->nchunks * S_COUNT * GM));
+    PTRY(p->cta_tape.alloc((size_t)p->nchunks * (8 + kCtaTapeR) * GM));
+    PTRY(p->cta_piv.alloc((size_t)p->nchunks * NP));
+    PTRY(p->chunkP.alloc((size_t)p->nchunks * GM));
+    const size_t VS = (size_t)S * 2 * NP;
+    PTRY(p->psi.alloc((size_t)E * N * VS)); PTRY(p->lam.alloc((size_t)E * N * VS));
+    PTRY(p->part.alloc((size_t)p->nchunks * VS)); PTRY(p->cost_part.alloc(p->nchunks)); PTRY(p->psi0.alloc(VS));
+    PTRY(p->node_grad.alloc(std::max<size_t>(1, W * q * KR))); PTRY(p->grad.alloc(std::max<size_t>(1, (size_t)M * KR)));
+    PTRY(p->cost.alloc(1)); PTRY(p->err_flag.alloc(1));
+    PTRY(cudaMemset(p->err_flag.p, 0, sizeof(int)));
+    PTRY(cudaMemset(p->controls.p, 0, sizeof(double) * p->controls.n));
+    PTRY(cudaMemset(p->grad.p, 0, sizeof(double) * p->grad.n));
+    PTRY(cudaMemset(p->psi.p, 0, sizeof(double) * p->psi.n)); PTRY(cudaMemset(p->lam.p, 0, sizeof(double) * p->lam.n));
+    PTRY(cudaMallocHost(&p->h_pinned, sizeof(double) * (2 * std::max<size_t>(1, (size_t)M * KR) + 8)));
+    // sweep kernels may need > 48 KB of dynamic shared memory
+    {
+        const int big = 200 * 1024;
+        PTRY(cudaFuncSetAttribute(k_boundary_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        PTRY(cudaFuncSetAttribute(k_sweep_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        PTRY(cudaFuncSetAttribute(k_sweep_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        PTRY(cudaFuncSetAttribute(k_sweep_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        PTRY(cudaFuncSetAttribute(k_boundary_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    }
+#undef PTRY
+    *out = p;
+    return 0;
+}
+
+int qocb_plan_destroy(qocb_plan *p) {
+    if (!p) return 0;
+    cudaSetDevice(p->pb.device);
+    if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
+    for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->h_pinned) cudaFreeHost(p->h_pinned);
+    delete p;
+    return 0;
+}
+
+int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
+    if (!p || !h0) { set_error(p, "null argument"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const int n = p->pb.hilbert_size, NP = p->NP, E = p->pb.ensemble_count, KR = p->pb.control_count;
+    const size_t GM = 2 * (size_t)NP * NP;
+    std::vector<double> buf((size_t)std::max(E, KR) * GM);
+    for (int e = 0; e < E; ++e) to_planar(h0 + (size_t)e * 2 * n * n, buf.data() + (size_t)e * GM, n, NP, true);
+    CU_TRY(p, cudaMemcpy(p->G0.p, buf.data(), sizeof(double) * E * GM, cudaMemcpyHostToDevice));
+    if (KR > 0) {
+        if (!a_ops) { set_error(p, "a_ops is null but control_count > 0"); return -1; }
+        for (int r = 0; r < KR; ++r) to_planar(a_ops + (size_t)r * 2 * n * n, buf.data() + (size_t)r * GM, n, NP, true);
+        CU_TRY(p, cudaMemcpy(p->G.p, buf.data(), sizeof(double) * KR * GM, cudaMemcpyHostToDevice));
+    }
+    p->ops_set = true;
+    return 0;
+}
+
+int qocb_set_states(qocb_plan *p, const double *psi0) {
+    if (!p || !psi0) { set_error(p, "null argument"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const int n = p->pb.hilbert_size, NP = p->NP, S = p->pb.state_count;
+    std::vector<double> buf((size_t)S * 2 * NP, 0.0);
+    for (int s = 0; s < S; ++s)
+        for (int a = 0; a < n; ++a) {
+            buf[(size_t)s * 2 * NP + a] = psi0[2 * ((size_t)s * n + a)];
+            buf[(size_t)s * 2 * NP + NP + a] = psi0[2 * ((size_t)s * n + a) + 1];
+        }
+    CU_TRY(p, cudaMemcpy(p->psi0.p, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
+    p->states_set = true;
+    return 0;
+}
+
+int qocb_clear_costs(qocb_plan *p) {
+    if (!p) return -1;
+    p->h_terms.clear(); p->h_vecs.clear(); p->h_counts.clear(); p->ip_total = 0; p->have_step_costs = false;
+    p->terms.release();
+    return 0;
+}
+
+int qocb_add_cost(qocb_plan *p, int32_t kind, int32_t step_cost, double weight, const double *vectors,
+                  const int32_t *counts, int32_t fmax) {
+    if (!p || !vectors) { set_error(p, "null argument"); return -1; }
+    if (kind < 0 || kind > 2 || fmax < 1) { set_error(p, "bad cost kind or fmax"); return -1; }
+    if (kind != QOCB_COST_FORBID && fmax != 1) { set_error(p, "target costs take one vector per state"); return -1; }
+    const int n = p->pb.hilbert_size, NP = p->NP, S = p->pb.state_count;
+    CostTerm t;
+    t.kind = kind; t.step = step_cost ? 1 : 0; t.fmax = fmax; t.w = weight;
+    t.vec_off = (int)(p->h_vecs.size() / (2 * (size_t)NP));
+    t.cnt_off = (int)p->h_counts.size();
+    t.ip_off = p->ip_total;
+    p->ip_total += S * fmax;
+    const size_t base = p->h_vecs.size();
+    p->h_vecs.resize(base + (size_t)S * fmax * 2 * NP, 0.0);
+    for (int s = 0; s < S; ++s) {
+        const int F = counts ? counts[s] : fmax;
+        if (F < 1 || F > fmax) { set_error(p, "counts[s] must be in [1, fmax]"); return -1; }
+        p->h_counts.push_back(F);
+        for (int f = 0; f < fmax; ++f)
+            for (int a = 0; a < n; ++a) {
+                const size_t src = 2 * (((size_t)s * fmax + f) * n + a);
+                const size_t dst = base + ((size_t)s * fmax + f) * 2 * NP;
+                p->h_vecs[dst + a] = vectors[src];
+                p->h_vecs[dst + NP + a] = vectors[src + 1];
+            }
+    }
+    p->h_terms.push_back(t);
+    if (t.step) p->have_step_costs = true;
+    p->terms.release();          // force re-upload
+    return 0;
+}
+
+int qocb_upload_controls(qocb_plan *p, const double *controls) {
+    if (!p) return -1;
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const size_t cnt = (size_t)p->pb.control_eval_count * p->pb.control_count;
+    if (cnt == 0) return 0;
+    if (!controls) { set_error(p, "controls is null"); return -1; }
+    std::memcpy(p->h_pinned, controls, sizeof(double) * cnt);
+    CU_TRY(p, cudaMemcpyAsync(p->controls.p, p->h_pinned, sizeof(double) * cnt, cudaMemcpyHostToDevice, p->stream));
+    return 0;
+}
+
+int qocb_run_resident(qocb_plan *p, int32_t with_grad) {
+    if (!p) return -1;
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    return enqueue_eval(p, with_grad != 0, nullptr);
+}
+
+int qocb_sync(qocb_plan *p) {
+    if (!p) return -1;
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int qocb_download_result(qocb_plan *p, double *cost, double *grad) {
+    if (!p) return -1;
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const size_t cnt = (size_t)p->pb.control_eval_count * p->pb.control_count;
+    double *hg = p->h_pinned + std::max<size_t>(1, cnt), *hc = hg + std::max<size_t>(1, cnt);
+    if (grad && cnt) CU_TRY(p, cudaMemcpyAsync(hg, p->grad.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaMemcpyAsync(hc, p->cost.p, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    if (grad && cnt) std::memcpy(grad, hg, sizeof(double) * cnt);
+    if (cost) *cost = *hc;
+    return check_device_flag(p);
+}
+
+static int fetch_final_states(qocb_plan *p, double *final_states) {
+    if (!final_states) return 0;
+    const int n = p->pb.hilbert_size, NP = p->NP, S = p->pb.state_count, N = p->pb.system_eval_count, E = p->pb.ensemble_count;
+    const size_t VS = (size_t)S * 2 * NP;
+    std::vector<double> buf(VS);
+    for (int e = 0; e < E; ++e) {
+        CU_TRY(p, cudaMemcpy(buf.data(), p->psi.p + ((size_t)e * N + (N - 1)) * VS, sizeof(double) * VS, cudaMemcpyDeviceToHost));
+        for (int s = 0; s < S; ++s)
+            for (int a = 0; a < n; ++a) {
+                final_states[2 * (((size_t)e * S + s) * n + a)] = buf[(size_t)s * 2 * NP + a];
+                final_states[2 * (((size_t)e * S + s) * n + a) + 1] = buf[(size_t)s * 2 * NP + NP + a];
+            }
+    }
+    return 0;
+}
+
+int qocb_cost(qocb_plan *p, const double *controls, double *cost, double *final_states) {
+    if (!p) return -1;
+    int rc = qocb_upload_controls(p, controls); if (rc) return rc;
+    rc = enqueue_eval(p, false, nullptr); if (rc) return rc;
+    rc = qocb_download_result(p, cost, nullptr); if (rc) return rc;
+    return fetch_final_states(p, final_states);
+}
+
+int qocb_cost_and_grad(qocb_plan *p, const double *controls, double *cost, double *grad, double *final_states) {
+    if (!p) return -1;
+    int rc = qocb_upload_controls(p, controls); if (rc) return rc;
+    rc = enqueue_eval(p, true, nullptr); if (rc) return rc;
+    rc = qocb_download_result(p, cost, grad); if (rc) return rc;
+    return fetch_final_states(p, final_states);
+}
+
+int qocb_get_states(qocb_plan *p, double *states) {
+    if (!p || !states) return -1;
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const int n = p->pb.hilbert_size, NP = p->NP, S = p->pb.state_count, N = p->pb.system_eval_count, E = p->pb.ensemble_count;
+    const size_t VS = (size_t)S * 2 * NP, tot = (size_t)E * N * VS;
+    std::vector<double> buf(tot);
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    CU_TRY(p, cudaMemcpy(buf.data(), p->psi.p, sizeof(double) * tot, cudaMemcpyDeviceToHost));
+    for (size_t en = 0; en < (size_t)E * N; ++en)
+        for (int s = 0; s < S; ++s)
+            for (int a = 0; a < n; ++a) {
+                states[2 * ((en * S + s) * n + a)] = buf[en * VS + (size_t)s * 2 * NP + a];
+                states[2 * ((en * S + s) * n + a) + 1] = buf[en * VS + (size_t)s * 2 * NP + NP + a];
+            }
+    return 0;
+}
+
+int qocb_get_propagators(qocb_plan *p, double *props) {
+    if (!p || !props) return -1;
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const int n = p->pb.hilbert_size, NP = p->NP;
+    const size_t W = (size_t)p->pb.ensemble_count * (p->pb.system_eval_count - 1), GM = 2 * (size_t)NP * NP;
+    std::vector<double> buf(GM);
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    for (size_t w = 0; w < W; ++w) {
+        CU_TRY(p, cudaMemcpy(buf.data(), p->U.p + w * GM, sizeof(double) * GM, cudaMemcpyDeviceToHost));
+        from_planar(buf.data(), props + w * 2 * n * n, n, NP);
+    }
+    return 0;
+}
+
+int qocb_launch_count(qocb_plan *p, int32_t with_grad) {
+    if (!p) return -1;
+    return with_grad ? (p->have_step_costs ? 9 : 8) : 4;
+}
+
+int qocb_time_resident(qocb_plan *p, int32_t with_grad, int32_t warmup, int32_t iters, int32_t flush_l2,
+                       double *ms_total, double *stage_ms) {
+    if (!p) return -1;
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const size_t flush_bytes = 256ull << 20;
+    if (flush_l2 && p->flush.n == 0) CU_TRY(p, p->flush.alloc(flush_bytes / sizeof(double)));
+    for (int i = 0; i < warmup; ++i) { int rc = enqueue_eval(p, with_grad != 0, nullptr); if (rc) return rc; }
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    double tot = 0.;
+    double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < iters; ++i) {
+        if (flush_l2) CU_TRY(p, cudaMemsetAsync(p->flush.p, i & 0xff, flush_bytes, p->stream));
+        int rc = enqueue_eval(p, with_grad != 0, p->ev);
+        if (rc) return rc;
+        CU_TRY(p, cudaStreamSynchronize(p->stream));
+        float ms = 0.f;
+        CU_TRY(p, cudaEventElapsedTime(&ms, p->ev[0], p->ev[7]));
+        tot += ms;
+        for (int s = 0; s < 7; ++s) { CU_TRY(p, cudaEventElapsedTime(&ms, p->ev[s], p->ev[s + 1])); st[s] += ms; }
+    }
+    if (ms_total) *ms_total = tot;
+    if (stage_ms) for (int s = 0; s < 8; ++s) stage_ms[s] = st[s];
+    return check_device_flag(p);
+}
+
+// ---- standalone batched expm --------------------------------------------------------------------------
+}  // extern "C"
+
+template <class C>
+static int expm_batched_impl(int n, long long batch, const double *a, const double *ubar, double *out, double *abar) {
+    const size_t GM = C::GMAT;
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    DevBuf<double> din, dout, dub, dab, scratch, tape; DevBuf<int> piv;
+    std::vector<double> h((size_t)batch * GM);
+    qocb_plan *np = nullptr;
+    CU_TRY(np, din.alloc((size_t)batch * GM)); CU_TRY(np, dout.alloc((size_t)batch * GM));
+    for (long long b = 0; b < batch; ++b) to_planar(a + (size_t)b * 2 * n * n, h.data() + (size_t)b * GM, n, C::NP, false);
+    CU_TRY(np, cudaMemcpy(din.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+    const int grid = (int)std::min<long long>(batch, (long long)sms * 8);
+    CU_TRY(np, scratch.alloc((size_t)grid * S_COUNT * GM));
+    if (ubar) {
+        CU_TRY(np, dub.alloc((size_t)batch * GM)); CU_TRY(np, dab.alloc((size_t)batch * GM));
+        CU_TRY(np, tape.alloc((size_t)grid * (8 + kCtaTapeR) * GM)); CU_TRY(np, piv.alloc((size_t)grid * C::NP));
+        for (long long b = 0; b < batch; ++b) to_planar(ubar + (size_t)b * 2 * n * n, h.data() + (size_t)b * GM, n, C::NP, false);
+        CU_TRY(np, cudaMemcpy(dub.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+        CU_TRY(np, cudaFuncSetAttribute(k_expm_vjp<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
+        k_expm_vjp<C><<<grid, C::NT, Smem<C>::bytes()>>>(din.p, dub.p, dout.p, dab.p, scratch.p, tape.p, piv.p, batch);
+    } else {
+        CU_TRY(np, cudaFuncSetAttribute(k_expm<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
+        k_expm<C><<<grid, C::NT, Smem<C>::bytes()>>>(din.p, dout.p, scratch.p, batch);
+    }
+    CU_TRY(np, cudaGetLastError());
+    CU_TRY(np, cudaDeviceSynchronize());
+    CU_TRY(np, cudaMemcpy(h.data(), dout.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+    for (long long b = 0; b < batch; ++b) from_planar(h.data() + (size_t)b * GM, out + (size_t)b * 2 * n * n, n, C::NP);
+    if (ubar) {
+        CU_TRY(np, cudaMemcpy(h.data(), dab.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        for (long long b = 0; b < batch; ++b) from_planar(h.data() + (size_t)b * GM, abar + (size_t)b * 2 * n * n, n, C::NP);
+    }
+    return 0;
+}
+
+extern "C" {
+
+int qocb_expm_batched(int32_t n, int64_t batch, const double *a, double *out, int32_t device) {
+    if (!a || !out || batch < 1) { set_error((qocb_plan *)nullptr, "bad argument"); return -1; }
+    const int NP = pad_dim(n);
+    if (NP < 0) { set_error((qocb_plan *)nullptr, "n must be in [1, 64] in this build"); return -1; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error((qocb_plan *)nullptr, "cudaSetDevice failed (no CPU path)"); return -2; }
+    return dispatch(NP, [&] { return expm_batched_impl<C8>(n, batch, a, nullptr, out, nullptr); },
+                    [&] { return expm_batched_impl<C16>(n, batch, a, nullptr, out, nullptr); },
+                    [&] { return expm_batched_impl<C32>(n, batch, a, nullptr, out, nullptr); },
+                    [&] { return expm_batched_impl<C64>(n, batch, a, nullptr, out, nullptr); });
+}
+
+int qocb_expm_vjp_batched(int32_t n, int64_t batch, const double *a, const double *ubar, double *out, double *abar,
+                          int32_t device) {
+    if (!a || !out || !ubar || !abar || batch < 1) { set_error((qocb_plan *)nullptr, "bad argument"); return -1; }
+    const int NP = pad_dim(n);
+    if (NP < 0) { set_error((qocb_plan *)nullptr, "n must be in [1, 64] in this build"); return -1; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error((qocb_plan *)nullptr, "cudaSetDevice failed (no CPU path)"); return -2; }
+    return dispatch(NP, [&] { return expm_batched_impl<C8>(n, batch, a, ubar, out, abar); },
+                    [&] { return expm_batched_impl<C16>(n, batch, a, ubar, out, abar); },
+                    [&] { return expm_batched_impl<C32>(n, batch, a, ubar, out, abar); },
+                    [&] { return expm_batched_impl<C64>(n, batch, a, ubar, out, abar); });
+}
+
+}  // extern "C"
+
+template <class C>
+static int expm_time_impl(int n, long long batch, double norm_scale, int iters, double *ms_best) {
+    const size_t GM = C::GMAT;
+    qocb_plan *np = nullptr;
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    DevBuf<double> din, dout, scratch;
+    CU_TRY(np, din.alloc((size_t)batch * GM)); CU_TRY(np, dout.alloc((size_t)batch * GM));
+    // a few distinct anti-hermitian matrices -i*H scaled to one-norm `norm_scale`, tiled over the batch
+    const int distinct = 16;
+    std::vector<double> h((size_t)distinct * GM, 0.0);
+    unsigned long long st = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return ((st >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0; };
+    for (int d = 0; d < distinct; ++d) {
+        std::vector<double> hr((size_t)n * n), hi((size_t)n * n);
+        for (int r = 0; r < n; ++r)
+            for (int c = r; c < n; ++c) {
+                const double x = rnd(), y = (r == c) ? 0.0 : rnd();
+                hr[(size_t)r * n + c] = x; hi[(size_t)r * n + c] = y; hr[(size_t)c * n + r] = x; hi[(size_t)c * n + r] = -y;
+            }
+        double nrm = 0;
+        for (int c = 0; c < n; ++c) { double s = 0; for (int r = 0; r < n; ++r) s += std::hypot(hr[(size_t)r * n + c], hi[(size_t)r * n + c]); nrm = std::max(nrm, s); }
+        const double f = norm_scale / nrm;
+        double *dst = h.data() + (size_t)d * GM;
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c < n; ++c) {          // -i * H
+                dst[(size_t)r * C::NP + c] = f * hi[(size_t)r * n + c];
+                dst[(size_t)C::NP * C::NP + (size_t)r * C::NP + c] = -f * hr[(size_t)r * n + c];
+            }
+    }
+    for (long long b = 0; b < batch; b += distinct) {
+        const long long cnt = std::min<long long>(distinct, batch - b);
+        CU_TRY(np, cudaMemcpy(din.p + (size_t)b * GM, h.data(), sizeof(double) * cnt * GM, cudaMemcpyHostToDevice));
+    }
+    const int grid = (int)std::min<long long>(batch, (long long)sms * 8);
+    CU_TRY(np, scratch.alloc((size_t)grid * 3 * GM));
+    CU_TRY(np, cudaFuncSetAttribute(k_expm<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 1e30;
+    for (int i = 0; i < iters + 2; ++i) {
+        cudaEventRecord(e0);
+        k_expm<C><<<grid, C::NT, Smem<C>::bytes()>>>(din.p, dout.p, scratch.p, batch);
+        cudaEventRecord(e1);
+        CU_TRY(np, cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CU_TRY(np, cudaGetLastError());
+    *ms_best = best;
+    return 0;
+}
+
+extern "C" {
+
+int qocb_expm_batched_time(int32_t n, int64_t batch, double norm_scale, int32_t iters, double *ms_best, int32_t device) {
+    if (!ms_best || batch < 1) return -1;
+    const int NP = pad_dim(n);
+    if (NP < 0) { set_error((qocb_plan *)nullptr, "n must be in [1, 64] in this build"); return -1; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error((qocb_plan *)nullptr, "cudaSetDevice failed (no CPU path)"); return -2; }
+    return dispatch(NP, [&] { return expm_time_impl<C8>(n, batch, norm_scale, iters, ms_best); },
+                    [&] { return expm_time_impl<C16>(n, batch, norm_scale, iters, ms_best); },
+                    [&] { return expm_time_impl<C32>(n, batch, norm_scale, iters, ms_best); },
+                    [&] { return expm_time_impl<C64>(n, batch, norm_scale, iters, ms_best); });
+}
+
+}  // extern "C"

@@ -1,0 +1,527 @@
+// expm_slice.cuh - per-slice forward and reverse passes of the GRAPE hot path, one CTA per time slice.
+//
+// forward  : interpolated controls -> generator(s) a_i = G0 + sum_r c_r G_r (G = -1j H pieces)
+//            -> Magnus M2/M4/M6 (qoc/core/mathmethods.py:72-164)
+//            -> Pade-13 scaling and squaring with a pivoted LU solve (qoc/standard/functions/expm.py:210-252)
+// backward : reverse mode over exactly that graph in HIPS-autograd's cotangent convention
+//            (what ans_jacobian, qoc/standard/utils/autogradutil.py:10-31, produces on the reference tape),
+//            then the Magnus adjoint and the contraction with the control operators.
+// The NumPy statement of the same algebra is oracle/adjoint_model.py (tests only).
+//
+// Shared memory: three padded matrix buffers X0, X1, X2.  Named intermediates that the reverse pass needs
+// live on a "tape" in global memory (per slice when stored, per CTA when recomputed).
+#pragma once
+#include "tile.cuh"
+
+namespace qocb {
+
+__device__ __constant__ double kB[14] = {
+    64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
+    129060195264000., 10559470521600., 670442572800., 33522128640., 1323241920.,
+    40840800., 960960., 16380., 182., 1.};
+#define QOCB_THETA13 5.371920351148152
+#define QOCB_S3 1.7320508075688772
+#define QOCB_S15 3.872983346207417
+
+// tape slots (each GMAT doubles)
+enum { T_A = 0, T_A2, T_A4, T_A6, T_W1, T_X1, T_Y, T_LU, T_R = 8 };
+// CTA scratch slots
+enum { S_A = 0, S_A2, S_A4, S_A6, S_B3, S_C12, S_E, S_P, S_QM, S_T0, S_T1, S_T2, S_T3, S_COUNT };
+
+constexpr int kMaxKR = 16;      // real control channels
+constexpr int kMaxQ = 3;        // Magnus nodes
+
+template <class C>
+struct Smem {
+    double *X0, *X1, *X2;
+    double *red;                // 64 + kMaxQ*kMaxKR*NWARP doubles of reduction scratch
+    double *coef;               // [kMaxQ][kMaxKR]
+    int *piv;                   // [NP]
+    __device__ __forceinline__ Smem(unsigned char *base) {
+        double *d = reinterpret_cast<double *>(base);
+        X0 = d; X1 = d + C::SMAT; X2 = d + 2 * C::SMAT;
+        red = d + 3 * C::SMAT;
+        coef = red + 64 + kMaxQ * kMaxKR * C::NWARP;
+        piv = reinterpret_cast<int *>(coef + kMaxQ * kMaxKR);
+    }
+    static constexpr size_t bytes() {
+        return sizeof(double) * (3 * C::SMAT + 64 + kMaxQ * kMaxKR * C::NWARP + kMaxQ * kMaxKR) + sizeof(int) * C::NP;
+    }
+};
+
+struct GenArgs {
+    const double *G0;           // this member's drift generator, planar padded
+    const double *G;            // [KR][GMAT] control generators
+    const double *controls;     // [M][KR]
+    const int *itab_idx;        // [N-1][q][2]
+    const double *itab_w;       // [N-1][q][2]
+    int KR, q, order;
+    double dt;
+};
+
+// interpolated control coefficients of slice j at the Magnus nodes -> sm.coef[i*kMaxKR + r]
+template <class C>
+__device__ __forceinline__ void load_coefs(const Smem<C> &sm, const GenArgs &ga, int j) {
+    for (int e = threadIdx.x; e < ga.q * ga.KR; e += C::NT) {
+        const int i = e / ga.KR, r = e % ga.KR;
+        const int *id = ga.itab_idx + (j * ga.q + i) * 2;
+        const double *w = ga.itab_w + (j * ga.q + i) * 2;
+        sm.coef[i * kMaxKR + r] = ga.controls[id[0] * ga.KR + r] * w[0] + ga.controls[id[1] * ga.KR + r] * w[1];
+    }
+    __syncthreads();
+}
+
+// owned pair of  alpha0 * G0 + sum_r cf[r] * G_r
+template <class C>
+__device__ __forceinline__ c2 gen_pair(const GenArgs &ga, int row, int col, double alpha0, const double *cf) {
+    c2 v = alpha0 * ldg2<C>(ga.G0, row, col);
+    for (int r = 0; r < ga.KR; ++r) v = v + cf[r] * ldg2<C>(ga.G + (size_t)r * C::GMAT, row, col);
+    return v;
+}
+
+// acc = op(A) op(B) - op(B') op(A') style helpers: load two global matrices into X0/X1 and multiply.
+template <class C, bool TA, bool TB, bool NEG>
+__device__ __forceinline__ void gmm(const Smem<C> &sm, Acc<C> &acc, const double *gA, const double *gB) {
+    __syncthreads();
+    g2s<C>(sm.X0, gA);
+    if (gB != gA) g2s<C>(sm.X1, gB);
+    __syncthreads();
+    mma_smem<C, TA, TB, NEG>(acc, sm.X0, gB != gA ? sm.X1 : sm.X0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Magnus forward: leaves M (unscaled) in X2.  M6 uses CTA scratch slots S_B3, S_C12.
+template <class C>
+__device__ void magnus_forward(const Smem<C> &sm, const GenArgs &ga, double *scratch) {
+    const double dt = ga.dt;
+    if (ga.order == 2) {
+        for_owned<C>([&](int, int, int row, int col) {
+            sts2<C>(sm.X2, row, col, dt * gen_pair<C>(ga, row, col, 1.0, sm.coef));
+        });
+        __syncthreads();
+        return;
+    }
+    if (ga.order == 4) {
+        for_owned<C>([&](int, int, int row, int col) {
+            sts2<C>(sm.X0, row, col, gen_pair<C>(ga, row, col, 1.0, sm.coef));
+            sts2<C>(sm.X1, row, col, gen_pair<C>(ga, row, col, 1.0, sm.coef + kMaxKR));
+        });
+        __syncthreads();
+        Acc<C> acc; acc.zero();
+        mma_smem<C, false, false, false>(acc, sm.X1, sm.X0);        // a2 a1
+        mma_smem<C, false, false, true>(acc, sm.X0, sm.X1);         // - a1 a2
+        const double f = (QOCB_S3 / 12.0) * dt * dt;
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 m = (0.5 * dt) * (lds2<C>(sm.X0, row, col) + lds2<C>(sm.X1, row, col)) + f * accv<C>(acc, i, j);
+            sts2<C>(sm.X2, row, col, m);
+        });
+        __syncthreads();
+        return;
+    }
+    // order 6: b1 = dt a2, b2 = (sqrt15/3) dt (a3 - a1), b3 = (10/3) dt (a3 - 2 a2 + a1); the drift cancels in b2, b3
+    double *gB3 = scratch + (size_t)S_B3 * C::GMAT, *gC12 = scratch + (size_t)S_C12 * C::GMAT;
+    {
+        double c2f[kMaxKR], c3f[kMaxKR];
+        for (int r = 0; r < ga.KR; ++r) {
+            const double c1 = sm.coef[r], cc2 = sm.coef[kMaxKR + r], c3 = sm.coef[2 * kMaxKR + r];
+            c2f[r] = (QOCB_S15 / 3.0) * dt * (c3 - c1);
+            c3f[r] = (10.0 / 3.0) * dt * (c3 - 2.0 * cc2 + c1);
+        }
+        for_owned<C>([&](int, int, int row, int col) {
+            sts2<C>(sm.X0, row, col, dt * gen_pair<C>(ga, row, col, 1.0, sm.coef + kMaxKR));    // b1
+            sts2<C>(sm.X1, row, col, gen_pair<C>(ga, row, col, 0.0, c2f));                      // b2
+            stg2<C>(gB3, row, col, gen_pair<C>(ga, row, col, 0.0, c3f));                        // b3
+        });
+    }
+    __syncthreads();
+    Acc<C> acc; acc.zero();
+    mma_smem<C, false, false, false>(acc, sm.X0, sm.X1);
+    mma_smem<C, false, false, true>(acc, sm.X1, sm.X0);             // c12 = [b1, b2]
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 c12 = accv<C>(acc, i, j);
+        stg2<C>(gC12, row, col, c12);
+        sts2<C>(sm.X2, row, col, 2.0 * ldg2<C>(gB3, row, col) + c12);                           // e
+    });
+    __syncthreads();
+    acc.zero();
+    mma_smem<C, false, false, false>(acc, sm.X0, sm.X2);
+    mma_smem<C, false, false, true>(acc, sm.X2, sm.X0);             // d = [b1, e]
+    __syncthreads();
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 b1 = lds2<C>(sm.X0, row, col), b2 = lds2<C>(sm.X1, row, col);
+        const c2 b3 = ldg2<C>(gB3, row, col), c12 = ldg2<C>(gC12, row, col);
+        sts2<C>(sm.X1, row, col, b2 - (1.0 / 60.0) * accv<C>(acc, i, j));                       // qm
+        sts2<C>(sm.X2, row, col, (-20.0) * b1 - b3 + c12);                                      // p
+    });
+    __syncthreads();
+    acc.zero();
+    mma_smem<C, false, false, false>(acc, sm.X2, sm.X1);
+    mma_smem<C, false, false, true>(acc, sm.X1, sm.X2);             // [p, qm]
+    __syncthreads();
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 m = lds2<C>(sm.X0, row, col) + 0.5 * ldg2<C>(gB3, row, col) + (1.0 / 240.0) * accv<C>(acc, i, j);
+        sts2<C>(sm.X2, row, col, m);
+    });
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pade-13 forward.  In: M in X2.  Out: U = expm(M) in X1 (all threads past a barrier); returns s.
+// tape: 8 + s matrices are written when tape != nullptr (T_R + i holds R_i for i < s); piv_out: int[NP].
+template <class C>
+__device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, double *tmpY, double *tmpV, int s_cap) {
+    // one-norm: max column sum of |m_ij|   (expm.py:103-116)
+    for (int c = threadIdx.x; c < C::NP; c += C::NT) {
+        double s = 0.;
+        for (int r = 0; r < C::NP; ++r) {
+            const double xr = sm.X2[r * C::LD + c], xi = sm.X2[C::PLANE + r * C::LD + c];
+            s += sqrt(xr * xr + xi * xi);
+        }
+        sm.red[c] = s;
+    }
+    __syncthreads();
+    double norm = 0.;
+    for (int c = 0; c < C::NP; ++c) norm = fmax(norm, sm.red[c]);
+    int s = 0;
+    if (!(norm < QOCB_THETA13)) {                                   // expm.py:238-241
+        s = (int)ceil(log2(norm / QOCB_THETA13));
+        if (s < 0) s = 0;
+    }
+    const double scale = ldexp(1.0, -s);
+    const bool keep = tape != nullptr;
+    double *tA = keep ? tape + (size_t)T_A * C::GMAT : tmpV;        // A is always needed once more (for Uo)
+    // A = M * 2^-s   -> X2 and tape
+    for_owned<C>([&](int, int, int row, int col) {
+        const c2 a = scale * lds2<C>(sm.X2, row, col);
+        sts2<C>(sm.X2, row, col, a);
+        stg2<C>(tA, row, col, a);
+    });
+    __syncthreads();
+    Acc<C> acc;
+    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X2);     // A2
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 v = accv<C>(acc, i, j);
+        sts2<C>(sm.X0, row, col, v);
+        if (keep) stg2<C>(tape + (size_t)T_A2 * C::GMAT, row, col, v);
+    });
+    __syncthreads();
+    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X0, sm.X0);     // A4
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 v = accv<C>(acc, i, j);
+        sts2<C>(sm.X1, row, col, v);
+        if (keep) stg2<C>(tape + (size_t)T_A4 * C::GMAT, row, col, v);
+    });
+    __syncthreads();
+    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X0, sm.X1);     // A6 -> X2 (A is on the tape)
+    __syncthreads();                                                    // X0, X1 (operands) are overwritten below
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 a6 = accv<C>(acc, i, j);
+        const c2 a2 = lds2<C>(sm.X0, row, col), a4 = lds2<C>(sm.X1, row, col);
+        const c2 w1 = kB[13] * a6 + kB[11] * a4 + kB[9] * a2;
+        const c2 x1 = kB[12] * a6 + kB[10] * a4 + kB[8] * a2;
+        const c2 yu = add_diag(kB[7] * a6 + kB[5] * a4 + kB[3] * a2, row, col, kB[1]);
+        const c2 yv = add_diag(kB[6] * a6 + kB[4] * a4 + kB[2] * a2, row, col, kB[0]);
+        sts2<C>(sm.X2, row, col, a6);
+        sts2<C>(sm.X0, row, col, w1);          // over A2 (own elements only)
+        sts2<C>(sm.X1, row, col, x1);          // over A4
+        stg2<C>(tmpY, row, col, yu);
+        stg2<C>(keep ? tape + (size_t)T_LU * C::GMAT : tmpV + C::GMAT, row, col, yv);   // parked until Ve is formed
+        if (keep) {
+            stg2<C>(tape + (size_t)T_A6 * C::GMAT, row, col, a6);
+            stg2<C>(tape + (size_t)T_W1 * C::GMAT, row, col, w1);
+            stg2<C>(tape + (size_t)T_X1 * C::GMAT, row, col, x1);
+        }
+    });
+    __syncthreads();
+    double *gYV = keep ? tape + (size_t)T_LU * C::GMAT : tmpV + C::GMAT;
+    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X0);     // A6 W1
+    __syncthreads();
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 y = accv<C>(acc, i, j) + ldg2<C>(tmpY, row, col);
+        sts2<C>(sm.X0, row, col, y);                                    // Y over W1
+        if (keep) stg2<C>(tape + (size_t)T_Y * C::GMAT, row, col, y);
+    });
+    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X1);     // A6 X1   (X0 not an operand)
+    __syncthreads();
+    for_owned<C>([&](int i, int j, int row, int col) {
+        sts2<C>(sm.X1, row, col, accv<C>(acc, i, j) + ldg2<C>(gYV, row, col));   // Ve over X1
+    });
+    g2s<C>(sm.X2, tA);                                                  // A back into X2 (A6 is dead)
+    __syncthreads();
+    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X0);     // Uo = A Y
+    __syncthreads();
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 ve = lds2<C>(sm.X1, row, col), uo = accv<C>(acc, i, j);
+        sts2<C>(sm.X1, row, col, ve + uo);                              // P
+        sts2<C>(sm.X2, row, col, ve - uo);                              // Q
+    });
+    __syncthreads();
+    lu_factor_smem<C>(sm.X2, sm.piv, sm.red);
+    lu_solve_smem<C, false>(sm.X2, sm.piv, sm.X1);                      // R0 = Q^-1 P in X1
+    if (keep) {
+        s2g<C>(tape + (size_t)T_LU * C::GMAT, sm.X2);
+        for (int c = threadIdx.x; c < C::NP; c += C::NT) piv_out[c] = sm.piv[c];
+    }
+    for (int i = 0; i < s; ++i) {                                        // expm.py:249-250
+        if (keep && i < s_cap) s2g<C>(tape + (size_t)(T_R + i) * C::GMAT, sm.X1);
+        acc.zero(); mma_smem<C, false, false, false>(acc, sm.X1, sm.X1);
+        __syncthreads();
+        for_owned<C>([&](int ii, int jj, int row, int col) { sts2<C>(sm.X1, row, col, accv<C>(acc, ii, jj)); });
+        __syncthreads();
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Reverse pass of the Pade graph.  In: ubar (cotangent of U, unconjugated convention) in X0; tape of the
+// slice; gU = U_j (== R_s).  Out: mbar (cotangent of the unscaled Magnus matrix) in X0, past a barrier.
+template <class C>
+__device__ void pade_backward(const Smem<C> &sm, const double *tape, const int *tpiv, int s,
+                              const double *gU, double *scratch) {
+    Acc<C> acc;
+    double *sA = scratch + (size_t)S_A * C::GMAT, *sA2 = scratch + (size_t)S_A2 * C::GMAT;
+    double *sA4 = scratch + (size_t)S_A4 * C::GMAT, *sA6 = scratch + (size_t)S_A6 * C::GMAT;
+    // squarings: R_i = R_{i-1}^2  =>  rbar_{i-1} = rbar_i R_{i-1}^T + R_{i-1}^T rbar_i
+    for (int i = s; i >= 1; --i) {
+        g2s<C>(sm.X1, tape + (size_t)(T_R + i - 1) * C::GMAT);
+        __syncthreads();
+        acc.zero();
+        mma_smem<C, false, true, false>(acc, sm.X0, sm.X1);
+        mma_smem<C, true, false, false>(acc, sm.X1, sm.X0);
+        __syncthreads();
+        for_owned<C>([&](int ii, int jj, int row, int col) { sts2<C>(sm.X0, row, col, accv<C>(acc, ii, jj)); });
+        __syncthreads();
+    }
+    // R0 = Q^-1 P:  pbar = Q^-T rbar ; qbar = -pbar R0^T
+    g2s<C>(sm.X2, tape + (size_t)T_LU * C::GMAT);
+    for (int c = threadIdx.x; c < C::NP; c += C::NT) sm.piv[c] = tpiv[c];
+    g2s<C>(sm.X1, s > 0 ? tape + (size_t)T_R * C::GMAT : gU);
+    __syncthreads();
+    lu_solve_smem<C, true>(sm.X2, sm.piv, sm.X0);                        // X0 = pbar
+    acc.zero(); mma_smem<C, false, true, false>(acc, sm.X0, sm.X1);      // pbar R0^T = -qbar
+    __syncthreads();
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 pb = lds2<C>(sm.X0, row, col), t = accv<C>(acc, i, j);
+        sts2<C>(sm.X0, row, col, pb + t);                               // uobar = pbar - qbar
+        sts2<C>(sm.X2, row, col, pb - t);                               // vebar = pbar + qbar
+    });
+    g2s<C>(sm.X1, tape + (size_t)T_Y * C::GMAT);
+    __syncthreads();
+    acc.zero(); mma_smem<C, false, true, false>(acc, sm.X0, sm.X1);      // abar  = uobar Y^T
+    for_owned<C>([&](int i, int j, int row, int col) { stg2<C>(sA, row, col, accv<C>(acc, i, j)); });
+    __syncthreads();
+    g2s<C>(sm.X1, tape + (size_t)T_A * C::GMAT);
+    __syncthreads();
+    acc.zero(); mma_smem<C, true, false, false>(acc, sm.X1, sm.X0);      // ybar = A^T uobar
+    __syncthreads();
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 yb = accv<C>(acc, i, j), vb = lds2<C>(sm.X2, row, col);
+        sts2<C>(sm.X0, row, col, yb);                                   // X0 = ybar, X2 = vebar
+        stg2<C>(sA6, row, col, kB[7] * yb + kB[6] * vb);
+        stg2<C>(sA4, row, col, kB[5] * yb + kB[4] * vb);
+        stg2<C>(sA2, row, col, kB[3] * yb + kB[2] * vb);
+    });
+    g2s<C>(sm.X1, tape + (size_t)T_W1 * C::GMAT);
+    __syncthreads();
+    acc.zero(); mma_smem<C, false, true, false>(acc, sm.X0, sm.X1);      // ybar W1^T
+    __syncthreads();
+    g2s<C>(sm.X1, tape + (size_t)T_X1 * C::GMAT);
+    __syncthreads();
+    mma_smem<C, false, true, false>(acc, sm.X2, sm.X1);                 // + vebar X1^T
+    for_owned<C>([&](int i, int j, int row, int col) {
+        stg2<C>(sA6, row, col, ldg2<C>(sA6, row, col) + accv<C>(acc, i, j));
+    });
+    __syncthreads();
+    g2s<C>(sm.X1, tape + (size_t)T_A6 * C::GMAT);
+    __syncthreads();
+    acc.zero(); mma_smem<C, true, false, false>(acc, sm.X1, sm.X0);      // w1bar = A6^T ybar
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 w = accv<C>(acc, i, j);
+        stg2<C>(sA6, row, col, ldg2<C>(sA6, row, col) + kB[13] * w);
+        stg2<C>(sA4, row, col, ldg2<C>(sA4, row, col) + kB[11] * w);
+        stg2<C>(sA2, row, col, ldg2<C>(sA2, row, col) + kB[9] * w);
+    });
+    acc.zero(); mma_smem<C, true, false, false>(acc, sm.X1, sm.X2);      // x1bar = A6^T vebar
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 w = accv<C>(acc, i, j);
+        stg2<C>(sA6, row, col, ldg2<C>(sA6, row, col) + kB[12] * w);
+        stg2<C>(sA4, row, col, ldg2<C>(sA4, row, col) + kB[10] * w);
+        stg2<C>(sA2, row, col, ldg2<C>(sA2, row, col) + kB[8] * w);
+    });
+    __syncthreads();
+    // A6 = A2 A4
+    g2s<C>(sm.X0, sA6);
+    g2s<C>(sm.X1, tape + (size_t)T_A4 * C::GMAT);
+    g2s<C>(sm.X2, tape + (size_t)T_A2 * C::GMAT);
+    __syncthreads();
+    acc.zero(); mma_smem<C, false, true, false>(acc, sm.X0, sm.X1);      // a6bar A4^T
+    for_owned<C>([&](int i, int j, int row, int col) { stg2<C>(sA2, row, col, ldg2<C>(sA2, row, col) + accv<C>(acc, i, j)); });
+    acc.zero(); mma_smem<C, true, false, false>(acc, sm.X2, sm.X0);      // A2^T a6bar
+    for_owned<C>([&](int i, int j, int row, int col) { stg2<C>(sA4, row, col, ldg2<C>(sA4, row, col) + accv<C>(acc, i, j)); });
+    __syncthreads();
+    // A4 = A2 A2
+    g2s<C>(sm.X0, sA4);
+    __syncthreads();
+    acc.zero();
+    mma_smem<C, false, true, false>(acc, sm.X0, sm.X2);
+    mma_smem<C, true, false, false>(acc, sm.X2, sm.X0);
+    for_owned<C>([&](int i, int j, int row, int col) { stg2<C>(sA2, row, col, ldg2<C>(sA2, row, col) + accv<C>(acc, i, j)); });
+    __syncthreads();
+    // A2 = A A ; mbar = abar * 2^-s
+    g2s<C>(sm.X0, sA2);
+    g2s<C>(sm.X1, tape + (size_t)T_A * C::GMAT);
+    __syncthreads();
+    acc.zero();
+    mma_smem<C, false, true, false>(acc, sm.X0, sm.X1);
+    mma_smem<C, true, false, false>(acc, sm.X1, sm.X0);
+    __syncthreads();
+    const double scale = ldexp(1.0, -s);
+    for_owned<C>([&](int i, int j, int row, int col) {
+        sts2<C>(sm.X0, row, col, scale * (ldg2<C>(sA, row, col) + accv<C>(acc, i, j)));   // X0 = mbar
+    });
+    __syncthreads();
+}
+
+// Magnus adjoint + contraction  cbar_{i,r} = Re sum_ab abar_i[ab] G_r[ab].  In: mbar in X0, coefficients of
+// the slice in sm.coef.  Out: gout[i*KR + r] = dE/dc_{i,r}.
+template <class C>
+__device__ void magnus_backward(const Smem<C> &sm, const GenArgs &ga, double *scratch, double *gout) {
+    Acc<C> acc;
+    const double dt = ga.dt;
+    double part[kMaxQ * kMaxKR];
+#pragma unroll
+    for (int e = 0; e < kMaxQ * kMaxKR; ++e) part[e] = 0.;
+    auto contract = [&](int node, int row, int col, const c2 &ab) {
+        for (int r = 0; r < ga.KR; ++r) {
+            const c2 g = ldg2<C>(ga.G + (size_t)r * C::GMAT, row, col);
+            part[node * kMaxKR + r] += ab.r0 * g.r0 - ab.i0 * g.i0 + ab.r1 * g.r1 - ab.i1 * g.i1;
+        }
+    };
+    if (ga.order == 2) {
+        for_owned<C>([&](int, int, int row, int col) { contract(0, row, col, dt * lds2<C>(sm.X0, row, col)); });
+    } else if (ga.order == 4) {
+        for_owned<C>([&](int, int, int row, int col) {
+            sts2<C>(sm.X1, row, col, gen_pair<C>(ga, row, col, 1.0, sm.coef));                  // a1
+            sts2<C>(sm.X2, row, col, gen_pair<C>(ga, row, col, 1.0, sm.coef + kMaxKR));         // a2
+        });
+        __syncthreads();
+        const double f = (QOCB_S3 / 12.0) * dt * dt;
+        acc.zero();
+        mma_smem<C, true, false, false>(acc, sm.X2, sm.X0);             // a2^T mbar
+        mma_smem<C, false, true, true>(acc, sm.X0, sm.X2);              // - mbar a2^T
+        for_owned<C>([&](int i, int j, int row, int col) {
+            contract(0, row, col, (0.5 * dt) * lds2<C>(sm.X0, row, col) + f * accv<C>(acc, i, j));
+        });
+        acc.zero();
+        mma_smem<C, false, true, false>(acc, sm.X0, sm.X1);             // mbar a1^T
+        mma_smem<C, true, false, true>(acc, sm.X1, sm.X0);              // - a1^T mbar
+        for_owned<C>([&](int i, int j, int row, int col) {
+            contract(1, row, col, (0.5 * dt) * lds2<C>(sm.X0, row, col) + f * accv<C>(acc, i, j));
+        });
+    } else {
+        // order 6 (oracle/adjoint_model.py:magnus_bwd), everything staged through CTA scratch
+        double *gMB = scratch + (size_t)S_T0 * C::GMAT;      // mbar
+        double *gB1 = scratch + (size_t)S_T1 * C::GMAT, *gB2 = scratch + (size_t)S_T2 * C::GMAT;
+        double *gB3 = scratch + (size_t)S_B3 * C::GMAT, *gC12 = scratch + (size_t)S_C12 * C::GMAT;
+        double *gE = scratch + (size_t)S_E * C::GMAT, *gP = scratch + (size_t)S_P * C::GMAT;
+        double *gQM = scratch + (size_t)S_QM * C::GMAT;
+        double *gB1b = scratch + (size_t)S_A * C::GMAT, *gB2b = scratch + (size_t)S_A2 * C::GMAT;   // reuse
+        double *gB3b = scratch + (size_t)S_A4 * C::GMAT, *gT = scratch + (size_t)S_A6 * C::GMAT;
+        double *gX = scratch + (size_t)S_T3 * C::GMAT;
+        double c2f[kMaxKR], c3f[kMaxKR];
+        for (int r = 0; r < ga.KR; ++r) {
+            const double c1 = sm.coef[r], cc2 = sm.coef[kMaxKR + r], c3 = sm.coef[2 * kMaxKR + r];
+            c2f[r] = (QOCB_S15 / 3.0) * dt * (c3 - c1);
+            c3f[r] = (10.0 / 3.0) * dt * (c3 - 2.0 * cc2 + c1);
+        }
+        for_owned<C>([&](int, int, int row, int col) {
+            stg2<C>(gMB, row, col, lds2<C>(sm.X0, row, col));
+            stg2<C>(gB1, row, col, dt * gen_pair<C>(ga, row, col, 1.0, sm.coef + kMaxKR));
+            stg2<C>(gB2, row, col, gen_pair<C>(ga, row, col, 0.0, c2f));
+            stg2<C>(gB3, row, col, gen_pair<C>(ga, row, col, 0.0, c3f));
+        });
+        // forward pieces again: c12 = [b1,b2], e = 2 b3 + c12, d = [b1,e], qm = b2 - d/60, p = -20 b1 - b3 + c12
+        acc.zero();
+        gmm<C, false, false, false>(sm, acc, gB1, gB2);
+        mma_smem<C, false, false, true>(acc, sm.X1, sm.X0);
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 c12 = accv<C>(acc, i, j);
+            stg2<C>(gC12, row, col, c12);
+            stg2<C>(gE, row, col, 2.0 * ldg2<C>(gB3, row, col) + c12);
+            stg2<C>(gP, row, col, (-20.0) * ldg2<C>(gB1, row, col) - ldg2<C>(gB3, row, col) + c12);
+        });
+        acc.zero();
+        gmm<C, false, false, false>(sm, acc, gB1, gE);
+        mma_smem<C, false, false, true>(acc, sm.X1, sm.X0);
+        for_owned<C>([&](int i, int j, int row, int col) {
+            stg2<C>(gQM, row, col, ldg2<C>(gB2, row, col) - (1.0 / 60.0) * accv<C>(acc, i, j));
+        });
+        // cb = mbar/240: pbar = cb qm^T - qm^T cb ; qbar = p^T cb - cb p^T
+        acc.zero();
+        gmm<C, false, true, false>(sm, acc, gMB, gQM);                  // X0 = mbar, X1 = qm
+        mma_smem<C, true, false, true>(acc, sm.X1, sm.X0);
+        for_owned<C>([&](int i, int j, int row, int col) { stg2<C>(gT, row, col, (1.0 / 240.0) * accv<C>(acc, i, j)); });   // pbar
+        acc.zero();
+        gmm<C, true, false, false>(sm, acc, gP, gMB);                   // X0 = p, X1 = mbar
+        mma_smem<C, false, true, true>(acc, sm.X1, sm.X0);
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 qb = (1.0 / 240.0) * accv<C>(acc, i, j);
+            stg2<C>(gB2b, row, col, qb);                                // b2bar = qbar
+            stg2<C>(gX, row, col, (-1.0 / 60.0) * qb);                  // dbar
+        });
+        // t1 = dbar e^T - e^T dbar ; ebar = b1^T dbar - dbar b1^T
+        acc.zero();
+        gmm<C, false, true, false>(sm, acc, gX, gE);                    // X0 = dbar, X1 = e
+        mma_smem<C, true, false, true>(acc, sm.X1, sm.X0);
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 pb = ldg2<C>(gT, row, col);
+            stg2<C>(gB1b, row, col, ldg2<C>(gMB, row, col) + accv<C>(acc, i, j) - 20.0 * pb);   // b1bar (so far)
+        });
+        acc.zero();
+        gmm<C, true, false, false>(sm, acc, gB1, gX);                   // X0 = b1, X1 = dbar
+        mma_smem<C, false, true, true>(acc, sm.X1, sm.X0);
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 eb = accv<C>(acc, i, j), pb = ldg2<C>(gT, row, col);
+            stg2<C>(gB3b, row, col, 0.5 * ldg2<C>(gMB, row, col) + 2.0 * eb - pb);              // b3bar
+            stg2<C>(gX, row, col, eb + pb);                                                     // c12bar (dbar dead)
+        });
+        // c12 = [b1, b2]: b1bar += c12bar b2^T - b2^T c12bar ; b2bar += b1^T c12bar - c12bar b1^T
+        acc.zero();
+        gmm<C, false, true, false>(sm, acc, gX, gB2);                   // X0 = c12bar, X1 = b2
+        mma_smem<C, true, false, true>(acc, sm.X1, sm.X0);
+        for_owned<C>([&](int i, int j, int row, int col) { stg2<C>(gB1b, row, col, ldg2<C>(gB1b, row, col) + accv<C>(acc, i, j)); });
+        acc.zero();
+        gmm<C, true, false, false>(sm, acc, gB1, gX);                   // X0 = b1, X1 = c12bar
+        mma_smem<C, false, true, true>(acc, sm.X1, sm.X0);
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 b2b = ldg2<C>(gB2b, row, col) + accv<C>(acc, i, j);
+            const c2 b1b = ldg2<C>(gB1b, row, col), b3b = ldg2<C>(gB3b, row, col);
+            contract(0, row, col, (-(QOCB_S15 / 3.0) * dt) * b2b + ((10.0 / 3.0) * dt) * b3b);
+            contract(1, row, col, dt * b1b - ((20.0 / 3.0) * dt) * b3b);
+            contract(2, row, col, ((QOCB_S15 / 3.0) * dt) * b2b + ((10.0 / 3.0) * dt) * b3b);
+        });
+    }
+    // block reduction of the q*KR partial sums
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        double *red = sm.red + 64;
+        __syncthreads();
+        for (int i = 0; i < ga.q; ++i)
+            for (int r = 0; r < ga.KR; ++r) {
+                double v = part[i * kMaxKR + r];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[(i * kMaxKR + r) * C::NWARP + warp] = v;
+            }
+        __syncthreads();
+        for (int e = threadIdx.x; e < ga.q * ga.KR; e += C::NT) {
+            const int i = e / ga.KR, r = e % ga.KR;
+            double v = 0.;
+            for (int w = 0; w < C::NWARP; ++w) v += red[(i * kMaxKR + r) * C::NWARP + w];
+            gout[i * ga.KR + r] = v;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace qocb
