@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py - GRAPE cost+gradient evaluations per second on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+A "step" is one cost+gradient evaluation of the hot path (Magnus assembly -> batched Pade-13 expm -> state /
+costate sweeps -> cost reductions -> gradient) on one batch of synthetic random controls.  Default workload =
+the shape BASELINE.json's target is quoted on: dim 64 x 2000 slices, Magnus M4, K = 4 real controls, S = 4
+states, TargetStateInfidelity.  One JSON line is printed by rank 0.
+
+  value        evals/s with the controls already resident in HBM (device timed, CUDA events on the plan stream)
+  e2e          evals/s through the public API `SchroedingerPlan.cost_and_grad(controls)` = C-ABI
+               `qocb_cost_and_grad` with HOST buffers: H2D of the controls and D2H of cost, gradient and final
+               states are inside the timed region
+  roofline     dominant kernel against the FP64 tensor (DMMA) pipe: algorithmic FLOPs / measured duration
+  cpu_baseline the oracle (CPU restatement of the reference, torch complex128 + autograd) on the box's host
+               cores, on a bounded sample of the same workload
+
+N > 1 (torchrun): the time slices of ONE evaluation are sharded across the ranks (strong scaling) with an NCCL
+exchange of the shard boundary propagators and costates.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests.problems import Problem  # noqa: E402
+
+FP64_TENSOR_PEAK_TFLOPS = 37.1   # measured on this pool's B200: DMMA m8n8k4 issue-bound loop and cuBLAS ZGEMM 4096
+#                                  (profiles/r01_microbench_fp64.jsonl); MEASURED_PEAKS.json has no FP64 entry
+
+WORKLOADS = {
+    # name: (n, slices, K, S, order, complex_controls, F)
+    "n64_2000_M4": (64, 2000, 4, 4, 4, False, 0),
+    "cfg3_n60_2000_M4": (60, 2000, 2, 4, 4, True, 6),
+    "cfg1_n2_10_M2": (2, 10, 1, 1, 2, True, 0),
+    "n32_2000_M4": (32, 2000, 4, 4, 4, False, 0),
+    "n16_2000_M4": (16, 2000, 4, 4, 4, False, 0),
+    "n8_2000_M2": (8, 2000, 2, 2, 2, False, 0),
+}
+
+
+def flops_per_slice(n, S, order, s=0):
+    """F = W (21 2/3 + 3 s + 3 c) + 24 n^2 S, W = 8 n^3, c = 0/2/6 commutator matmuls."""
+    c = {2: 0, 4: 2, 6: 6}[order]
+    W = 8.0 * n ** 3
+    fwd = W * (c + 22.0 / 3 + s) + 8.0 * n * n * S
+    bwd = W * (2 * c + 12 + 2 * s + 7.0 / 3) + 16.0 * n * n * S
+    return fwd, bwd
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_problem(name):
+    n, slices, K, S, order, cc, F = WORKLOADS[name]
+    return Problem(n, slices, K, S, order, complex_controls=cc, F=F, seed=0)
+
+
+def oracle_time(p, sample_slices, reps, threads):
+    """seconds per cost+gradient evaluation of a `sample_slices`-slice truncation of the workload (same dt,
+    same operators, first sample_slices+1 control points), oracle = CPU restatement of the reference."""
+    import torch
+    from oracle import qoc_oracle as orc
+    torch.set_num_threads(threads)
+    N = sample_slices + 1
+    controls = np.ascontiguousarray(p.controls[:N])
+    ham = orc.make_hamiltonian(p.h0, p.drives, p.complex_controls)
+    q = Problem.__new__(Problem)
+    q.__dict__.update(p.__dict__)
+    q.N = N
+    times = []
+    for r in range(reps + 1):
+        t0 = time.perf_counter()
+        orc.schroedinger_cost_and_grad(controls, ham, p.initial_states, q.costs(orc), float(sample_slices), N,
+                                       order=p.order, cost_eval_step=p.cost_eval_step)
+        times.append(time.perf_counter() - t0)
+    return float(np.median(times[1:]))
+
+
+def pick_threads(p):
+    """the oracle's BLAS threading can hurt at small n: calibrate 1 thread vs all cores on a
+    few slices and use the faster."""
+    allc = os.cpu_count() or 1
+    t1 = oracle_time(p, 8, 1, 1)
+    ta = oracle_time(p, 8, 1, allc) if allc > 1 else float("inf")
+    return (1, t1, ta) if t1 <= ta else (allc, t1, ta)
+
+
+def run_reference(args, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    p = make_problem(name)
+    slices = p.N - 1
+    threads, t1, ta = pick_threads(p)
+    sample = max(4, min(slices, int(args.ref_slices)))
+    for _ in range(args.warmup):
+        oracle_time(p, min(sample, 8), 0 + 1, threads)
+    t0 = time.perf_counter()
+    per = []
+    for _ in range(args.steps):
+        per.append(oracle_time(p, sample, 1, threads) * slices / sample)
+    wall = time.perf_counter() - t0
+    sec = float(np.mean(per))
+    val = 1.0 / sec
+    out = {"impl": "reference", "metric": "grape_cost_grad_evals_per_sec", "value": val, "unit": "evals/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64)",
+           "data": "synthetic", "config": workload_config(name, p),
+           "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
+                            "sample": "%d of %d slices per step (fwd+bwd), scaled linearly; oracle = torch complex128 "
+                                      "restatement of the reference (autograd absent in this image); 1 thread %.3fs vs %d "
+                                      "threads %.3fs on an 8-slice calibration" % (sample, slices, t1, os.cpu_count() or 1, ta)},
+           "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": wall}
+    print(json.dumps(out))
+
+
+def workload_config(name, p):
+    return {"workload": name, "hilbert_dim": p.n, "slices": p.N - 1, "controls": p.K,
+            "complex_controls": p.complex_controls, "states": p.S, "magnus": "M%d" % p.order,
+            "costs": "TargetStateInfidelity" + ("+ForbidStates" if p.F else ""),
+            "l2": "working set (propagators + tape) > 126 MB L2 and a 256 MiB flush write between timed iterations"}
+
+
+def run_b200(args, name):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the GRAPE hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import qoc_b200.standard as std
+    from qoc_b200.core.plan import SchroedingerPlan
+    from qoc_b200.models import MagnusPolicy
+    pol = {2: MagnusPolicy.M2, 4: MagnusPolicy.M4, 6: MagnusPolicy.M6}
+    p = make_problem(name)
+    slices = p.N - 1
+    kw = {}
+    if world > 1:
+        from qoc_b200.core.sharded import ShardedSchroedingerPlan as PlanCls
+    else:
+        PlanCls = SchroedingerPlan
+    plan = PlanCls(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M,
+                   control_count=p.K, complex_controls=p.complex_controls, magnus_policy=pol[p.order],
+                   cost_eval_step=p.cost_eval_step, device=local, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ("value") -------------------------------------------------------------
+    plan.upload(p.controls)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    total_ms, stages = plan.time_resident(with_grad=True, warmup=args.warmup, iters=args.steps, flush_l2=True)
+    barrier()
+    # ---- end-to-end timing through the public API with host buffers ----------------------------------------
+    for _ in range(args.warmup):
+        plan.cost_and_grad(p.controls)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        err, grads, finals = plan.cost_and_grad(p.controls)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = 1e3 / ms_per_step
+    KR = plan.KR
+    h2d = p.M * KR * 8
+    d2h = p.M * KR * 8 + 8 + plan.E * p.S * p.n * 16
+    fwd_f, bwd_f = flops_per_slice(p.n, p.S, p.order)
+    names = ["expm_fwd", "boundary_fwd", "sweep_fwd", "sweep_bwd", "expm_bwd", "gather", "finalize", "spare"]
+    stage_ms = {k: float(v) / args.steps for k, v in zip(names, stages)}
+    dom = max(("expm_fwd", "expm_bwd"), key=lambda k: stage_ms[k])
+    dom_flops = (fwd_f if dom == "expm_fwd" else bwd_f) * slices / world
+    achieved = dom_flops / (stage_ms[dom] * 1e-3) / 1e12
+    total_flops = (fwd_f + bwd_f) * slices
+    out = {"metric": "grape_cost_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+           "config": workload_config(name, p),
+           "e2e": {"value": args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h},
+           "gpu_launches": plan.launch_count(True) * args.steps,
+           "roofline": {"bound": "tensor", "kernel": "k_backward" if dom == "expm_bwd" else "k_forward",
+                        "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                        "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": None,
+                        "peak_source": "FP64 DMMA pipe measured on this pool (profiles/r01_microbench_fp64.jsonl); "
+                                       "MEASURED_PEAKS.json has HBM and bf16 only",
+                        "algorithmic_flops_per_launch": dom_flops,
+                        "whole_eval_tflops": total_flops / (ms_per_step * 1e-3) / 1e12,
+                        "whole_eval_frac": total_flops / (ms_per_step * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS / world},
+           "stage_ms": stage_ms, "clocks": clocks, "cost": err}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            threads, t1, ta = pick_threads(p)
+            sample = min(slices, args.cpu_slices)
+            sec = oracle_time(p, sample, 3, threads) * slices / sample
+            out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "evals/s", "cores": threads, "kind": "port",
+                                   "sample": "%d of %d slices (fwd+bwd), median of 3 after 1 warm-up, scaled linearly; "
+                                             "1 thread %.3fs vs %d threads %.3fs on an 8-slice calibration; published "
+                                             "reference figure: 0.187 evals/s at n=64 x 1000 slices on 1 core i7-6700K "
+                                             "(report.tex:110)" % (sample, slices, t1, os.cpu_count() or 1, ta)}
+            # parity gate on the same controls (bounded: first `sample` slices)
+            out["parity"] = parity_gate(p, min(sample, 64), std, SchroedingerPlan, pol)
+        print(json.dumps(out))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def parity_gate(p, sample, std, Plan, pol):
+    from oracle import qoc_oracle as orc
+    q = Problem.__new__(Problem)
+    q.__dict__.update(p.__dict__)
+    q.N = sample + 1
+    controls = np.ascontiguousarray(p.controls[:q.N])
+    plan = Plan(p.hamiltonian_numpy(), p.initial_states, q.costs(std), float(sample), q.N, control_eval_count=q.N,
+                control_count=p.K, complex_controls=p.complex_controls, magnus_policy=pol[p.order],
+                cost_eval_step=p.cost_eval_step)
+    err, grads, _ = plan.cost_and_grad(controls)
+    plan.close()
+    o_err, o_grad, _ = orc.schroedinger_cost_and_grad(controls, orc.make_hamiltonian(p.h0, p.drives, p.complex_controls),
+                                                      p.initial_states, q.costs(orc), float(sample), q.N, order=p.order,
+                                                      cost_eval_step=p.cost_eval_step)
+    return {"slices": sample, "cost_rel_err": abs(err - o_err) / abs(o_err),
+            "grad_rel_err": float(np.linalg.norm(grads - o_grad) / np.linalg.norm(o_grad)), "tolerance": 1e-10}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="n64_2000_M4", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-slices", type=int, default=400, help="slices of the bounded CPU-baseline sample")
+    ap.add_argument("--ref-slices", type=int, default=100, help="slices per step of the --impl reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args, args.workload)
+    else:
+        run_b200(args, args.workload)
+
+
+if __name__ == "__main__":
+    main()
