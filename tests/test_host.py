@@ -1,0 +1,193 @@
+"""CPU: host-side mirror of the reference interface (control plumbing, optimisers, cost classes, Hamiltonian
+structure extraction, constants) against the golden vectors and the reference's own known answers."""
+import numpy as np
+import pytest
+
+import qoc_b200.standard as std
+from qoc_b200.core.common import (clip_control_norms, gen_controls_flat, initialize_controls, slap_controls,
+                                  strip_controls)
+from qoc_b200.core.plan import extract_hamiltonian_structure
+from qoc_b200.models import MagnusPolicy, InterpolationPolicy, ProgramType
+from tests.problems import Problem, load_golden
+
+
+def test_clip_control_norms_reference_values():
+    """tests/test_core.py:6-19 and the golden random case."""
+    controls = np.array(((1 + 2j, 7 + 8j), (3 + 4j, 5), (5 + 6j, 10,), (1 - 3j, -10),))
+    clip_control_norms(controls, np.array((7, 8,)))
+    expected = np.array(((1 + 2j, (7 + 8j) * np.divide(8, np.sqrt(113))), (3 + 4j, 5),
+                         ((5 + 6j) * np.divide(7, np.sqrt(61)), 8,), (1 - 3j, -8)))
+    assert np.allclose(controls, expected)
+    d = load_golden("unit_vectors.npz")
+    c = d["clip_in"].copy()
+    clip_control_norms(c, d["clip_max"])
+    assert np.allclose(c, d["clip_out"], rtol=1e-15, atol=0)
+
+
+def test_strip_slap_roundtrip():
+    """tests/test_core.py:22-60."""
+    big = 100
+    for complex_controls in (False, True):
+        shape = (5, 3)
+        c = np.random.default_rng(0).uniform(-big, big, shape)
+        if complex_controls:
+            c = c + 1j * np.random.default_rng(1).uniform(-big, big, shape)
+        flat = strip_controls(complex_controls, c)
+        assert flat.ndim == 1 and flat.dtype == np.float64
+        assert flat.shape[0] == (30 if complex_controls else 15)
+        assert np.array_equal(slap_controls(complex_controls, flat, shape), c)
+    # real controls: slap returns a VIEW, so the in-place clip reaches the optimiser's array (common.py:8-30)
+    flat = np.arange(6.0)
+    view = slap_controls(False, flat, (3, 2))
+    clip_control_norms(view, np.array([2.0, 2.0]))
+    assert flat.max() == 2.0
+
+
+def test_initialize_controls_defaults_and_validation():
+    c, m = initialize_controls(True, 2, 4, 1.0, None, None)
+    assert np.allclose(m, 1) and np.allclose(c, 0.1 * (1 - 1j) / np.sqrt(2))
+    assert np.allclose(gen_controls_flat(False, 1, 3, 1.0, np.array([5.0])), 0.5)
+    with pytest.raises(ValueError):
+        initialize_controls(False, 1, 3, 1.0, np.ones((3, 1)) * 2, np.ones(1))        # exceeds max norm
+    with pytest.raises(ValueError):
+        initialize_controls(False, 1, 3, 1.0, np.ones((3, 1), dtype=complex), np.ones(1))   # dtype mismatch
+
+
+def test_adam_golden_trajectories():
+    d = load_golden("unit_vectors.npz")
+    for kw, key in ((dict(learning_rate=1e-2), "adam_traj"),
+                    (dict(learning_rate=5e-2, clip_grads=0.5, scale_grads=2.0, learning_rate_decay=3.0), "adam2_traj")):
+        ad = std.Adam(**kw)
+        ad.gradient_moment = np.zeros(6)
+        ad.gradient_square_moment = np.zeros(6)
+        ad.iteration_count = 0
+        p = np.ones(6)
+        for g, want in zip(d["adam_grads"], d[key]):
+            p = ad.update(g, p)
+            assert np.allclose(p, want, rtol=1e-14, atol=0)
+
+
+def test_optimizer_protocol():
+    calls = []
+
+    def jac(params, tag):
+        calls.append(params.copy())
+        return 2 * params, bool(np.abs(params).max() < 0.5)
+
+    for opt in (std.Adam(learning_rate=0.2), std.SGD(learning_rate=0.2)):
+        calls.clear()
+        opt.run(None, 50, np.array([1.0, -1.0]), jac, args=("x",))
+        assert 1 < len(calls) < 50 and np.abs(calls[-1]).max() < 0.5
+    res = {}
+    std.LBFGSB().run(lambda p, tag: (float(np.sum(p ** 2)), False), 20, np.array([1.0, -2.0]),
+                     lambda p, tag: (2 * p, False), args=("x",))
+
+
+def test_state_cost_known_answers():
+    """tests/test_standard.py:70-90 (5/80), :166-191, :194-223."""
+    sec = 11
+    forbidden = np.stack([np.stack([np.array([[1], [0], [0], [0]]), np.array([[0], [1], [0], [0]])])] * 2)
+    states = np.array([[[1], [1], [0], [0]], [[1], [1], [1], [1]]]) / 2
+    fs = std.ForbidStates(forbidden, sec, cost_eval_step=2)
+    assert np.isclose(fs.cost(None, states, 2), (0.5 / 2 + 0.5 / 2) / (5 * 2))
+    s0 = np.array([[[1], [0]]])
+    s1 = np.array([[[0], [1]]])
+    tsi = std.TargetStateInfidelity(s1)
+    assert np.isclose(tsi.cost(None, s0, 0), 1) and np.isclose(tsi.cost(None, s1, 0), 0)
+    tsit = std.TargetStateInfidelityTime(11, s1)
+    assert np.isclose(tsit.cost(None, s0, 1), 0.1)
+    s00 = np.array([[[1], [0]], [[1], [0]]])
+    s11 = np.array([[[1], [1]], [[1], [1]]]) / np.sqrt(2)
+    assert np.isclose(std.TargetStateInfidelity(s00).cost(None, s11, 0), 0.5)
+    # density costs (tests/test_standard.py:93-126): identical pure states give 1 - 1/n
+    rho = np.array([[[1, 0], [0, 0]]], dtype=complex)
+    assert np.isclose(std.TargetDensityInfidelity(rho).cost(None, rho, 0), 0.5)
+    assert np.isclose(std.TargetDensityInfidelityTime(11, rho).cost(None, rho, 0), 0.05)
+    fd = std.ForbidDensities(np.array([[[[1, 0], [0, 0]]]], dtype=complex), 11)
+    assert np.isclose(fd.cost(None, rho, 1), 0.25 / 10)
+
+
+def test_control_costs_value_and_gradient():
+    """values against the oracle (which restates the reference formulas) and analytic gradients against central
+    differences, real and complex controls, in the optimiser's convention dE/dx + i dE/dy."""
+    import torch
+    from oracle import qoc_oracle as orc
+    rng = np.random.default_rng(4)
+    M, K = 16, 2
+    mx = np.array([1.5, 2.5])
+    d = load_golden("unit_vectors.npz")
+    cbm = std.ControlBandwidthMax(2, 32, 10.0, np.array([0.4, 0.9]), cost_multiplier=0.7)
+    assert np.isclose(cbm.cost(d["cbm_controls"], None, 0), float(d["cbm_value"]), rtol=1e-13)
+    for cplx in (False, True):
+        u = rng.standard_normal((M, K)) + (1j * rng.standard_normal((M, K)) if cplx else 0)
+        pairs = [
+            (std.ControlNorm(K, M, cost_multiplier=0.3, max_control_norms=mx), orc.ControlNorm(K, M, cost_multiplier=0.3, max_control_norms=mx)),
+            (std.ControlNorm(K, M, control_weights=np.array([0.5, 2.0])), orc.ControlNorm(K, M, control_weights=np.array([0.5, 2.0]))),
+            (std.ControlVariation(K, M, cost_multiplier=0.2, max_control_norms=mx, order=1), orc.ControlVariation(K, M, cost_multiplier=0.2, max_control_norms=mx, order=1)),
+            (std.ControlVariation(K, M, max_control_norms=mx, order=3), orc.ControlVariation(K, M, max_control_norms=mx, order=3)),
+            (std.ControlArea(K, M, cost_multiplier=0.4, max_control_norms=mx), orc.ControlArea(K, M, cost_multiplier=0.4, max_control_norms=mx)),
+            (std.ControlBandwidthMax(K, M, 3.0, np.array([0.5, 1.0]), cost_multiplier=0.6), orc.ControlBandwidthMax(K, M, 3.0, np.array([0.5, 1.0]), cost_multiplier=0.6)),
+        ]
+        for mine, ref in pairs:
+            v, g = mine.control_value_and_grad(u)
+            ut = torch.tensor(u, requires_grad=True)
+            rv = ref.cost(ut, None, 0)
+            rv.backward()
+            assert np.isclose(v, float(rv.detach()), rtol=1e-12), type(mine).__name__
+            assert np.allclose(g, ut.grad.numpy(), rtol=1e-9, atol=1e-12), type(mine).__name__
+            assert np.asarray(g).shape == u.shape
+
+
+def test_hamiltonian_structure_extraction():
+    p = Problem(5, 6, 2, 1, 2, complex_controls=True, seed=3)
+    h0, a_ops = extract_hamiltonian_structure(p.hamiltonian_numpy(), 2, True, p.T)
+    assert np.allclose(h0, p.h0)
+    dd = p.drives.conj().transpose(0, 2, 1)
+    assert np.allclose(a_ops[:2], p.drives + dd) and np.allclose(a_ops[2:], 1j * (p.drives - dd))
+    u = np.array([0.3 - 0.2j, -1.1 + 0.7j])
+    x = np.concatenate([u.real, u.imag])
+    assert np.allclose(h0 + np.tensordot(x, a_ops, axes=(0, 0)), p.hamiltonian_numpy()(u, 0.0))
+    pr = Problem(4, 6, 3, 1, 2, complex_controls=False, seed=3)
+    h0, a_ops = extract_hamiltonian_structure(pr.hamiltonian_numpy(), 3, False, pr.T)
+    assert np.allclose(a_ops, pr.drives)
+    with pytest.raises(NotImplementedError):
+        extract_hamiltonian_structure(lambda c, t: pr.h0 + np.sin(c[0]) * pr.drives[0], 3, False, pr.T)
+    with pytest.raises(NotImplementedError):
+        extract_hamiltonian_structure(lambda c, t: pr.h0 + t * c[0] * pr.drives[0], 3, False, pr.T)
+    with pytest.raises(NotImplementedError):
+        extract_hamiltonian_structure(lambda c, t: pr.h0 * np.cos(t), 0, False, pr.T)
+
+
+def test_constants_and_enums():
+    """tests/test_standard.py:7-20."""
+    n = 5
+    a, ad = std.get_annihilation_operator(n), std.get_creation_operator(n)
+    assert np.allclose(ad @ a, np.diag(np.arange(n)))
+    assert np.allclose(std.get_eij(1, 2, 3), np.array([[0, 0, 0], [0, 0, 1], [0, 0, 0]]))
+    assert np.allclose(std.SIGMA_X @ std.SIGMA_Y, 1j * std.SIGMA_Z)
+    assert MagnusPolicy.M2.order == 2 and MagnusPolicy.M4.order == 4 and MagnusPolicy.M6.order == 6
+    assert InterpolationPolicy.LINEAR is not None and ProgramType.GRAPE != ProgramType.EVOLVE
+    x = np.arange(6).reshape(2, 3)
+    assert np.array_equal(std.commutator(np.eye(2), np.ones((2, 2))), np.zeros((2, 2)))
+    assert np.array_equal(std.conjugate_transpose(x + 1j), (x - 1j).T)
+    assert np.isclose(std.rms_norm(np.array([3.0, 4.0])), np.sqrt(12.5))
+    cols = std.matrix_to_column_vector_list(np.eye(3))
+    assert np.array_equal(std.column_vector_list_to_matrix(cols), np.eye(3))
+    assert np.array_equal(std.krons(np.eye(2), np.eye(2)), np.eye(4))
+    assert np.array_equal(std.matmuls(np.eye(2), 2 * np.eye(2), 3 * np.eye(2)), 6 * np.eye(2))
+
+
+def test_program_state_fields():
+    """fields the seam reads (qoc/core/schroedingerdiscrete.py:371-388) and dt / control_eval_times
+    (qoc/models/programstate.py:41,44,52-60)."""
+    from qoc_b200.models import GrapeSchroedingerDiscreteState
+    init = np.array([[[1], [0]]], dtype=complex)
+    costs = [std.TargetStateInfidelity(init), std.ForbidStates(init[None], 11), std.ControlNorm(1, 6)]
+    ps = GrapeSchroedingerDiscreteState(True, 1, 6, 2, costs, 10.0, lambda c, t: None, None, np.zeros((6, 1), dtype=complex),
+                                        init, InterpolationPolicy.LINEAR, 5, 1, np.ones(1), MagnusPolicy.M4, 0.0,
+                                        std.Adam(), None, False, 0, 11)
+    assert ps.dt == 1.0 and np.allclose(ps.control_eval_times, np.linspace(0, 10, 6))
+    assert ps.final_system_eval_step == 10 and ps.cost_eval_step == 2
+    assert [c.name for c in ps.step_costs] == ["forbid_states"]
+    assert ps.controls_shape == (6, 1) and ps.program_type == ProgramType.GRAPE
+    assert ps.save_intermediate_states_ is False
