@@ -240,10 +240,17 @@ def run_b200(args, name):
     fwd_f, bwd_f = flops_per_slice(p.n, p.S, p.order)
     names = ["expm_fwd", "boundary_fwd", "sweep_fwd", "sweep_bwd", "expm_bwd", "gather", "finalize", "spare"]
     stage_ms = {k: float(v) / args.steps for k, v in zip(names, stages)}
-    dom = max(("expm_fwd", "expm_bwd"), key=lambda k: stage_ms[k])
-    dom_flops = (fwd_f if dom == "expm_fwd" else bwd_f) * slices / world
-    achieved = dom_flops / (stage_ms[dom] * 1e-3) / 1e12
     total_flops = (fwd_f + bwd_f) * slices
+    if world == 1:
+        dom = max(("expm_fwd", "expm_bwd"), key=lambda k: stage_ms[k])
+        dom_flops = (fwd_f if dom == "expm_fwd" else bwd_f) * slices
+        achieved = dom_flops / (stage_ms[dom] * 1e-3) / 1e12
+        dom_name = "k_backward" if dom == "expm_bwd" else "k_forward"
+    else:       # no per-kernel split across the collectives: whole evaluation, per GPU
+        dom_flops = total_flops / world
+        achieved = dom_flops / (ms_per_step * 1e-3) / 1e12
+        dom_name = "whole evaluation incl. NCCL exchange (per GPU)"
+        stage_ms = {"total": ms_per_step}
     out = {"metric": "grape_cost_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
@@ -251,7 +258,7 @@ def run_b200(args, name):
            "e2e": {"value": args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h},
            "gpu_launches": plan.launch_count(True) * args.steps,
-           "roofline": {"bound": "tensor", "kernel": "k_backward" if dom == "expm_bwd" else "k_forward",
+           "roofline": {"bound": "tensor", "kernel": dom_name,
                         "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
                         "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": None,
                         "peak_source": "FP64 DMMA pipe measured on this pool (profiles/r01_microbench_fp64.jsonl); "
@@ -260,6 +267,27 @@ def run_b200(args, name):
                         "whole_eval_tflops": total_flops / (ms_per_step * 1e-3) / 1e12,
                         "whole_eval_frac": total_flops / (ms_per_step * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS / world},
            "stage_ms": stage_ms, "clocks": clocks, "cost": err}
+    if args.check and world > 1:
+        ok = True
+        if rank == 0:
+            ref = SchroedingerPlan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M,
+                                   control_count=p.K, complex_controls=p.complex_controls, magnus_policy=pol[p.order],
+                                   cost_eval_step=p.cost_eval_step, device=local)
+            r_err, r_grad, r_fin = ref.cost_and_grad(p.controls)
+            ref.close()
+            out["sharded_vs_unsharded"] = {"cost_rel": abs(err - r_err) / abs(r_err),
+                                           "grad_rel": float(np.linalg.norm(grads - r_grad) / np.linalg.norm(r_grad)),
+                                           "finals_rel": float(np.linalg.norm(finals - r_fin) / np.linalg.norm(r_fin))}
+            ok = max(out["sharded_vs_unsharded"].values()) < 1e-10
+            if p.n <= 16:
+                from oracle import qoc_oracle as orc
+                o_err, o_grad, _ = orc.schroedinger_cost_and_grad(p.controls, orc.make_hamiltonian(p.h0, p.drives, p.complex_controls),
+                                                                  p.initial_states, p.costs(orc), p.T, p.N, order=p.order,
+                                                                  cost_eval_step=p.cost_eval_step)
+                out["sharded_vs_oracle"] = {"cost_rel": abs(err - o_err) / abs(o_err),
+                                            "grad_rel": float(np.linalg.norm(grads - o_grad) / np.linalg.norm(o_grad))}
+                ok = ok and max(out["sharded_vs_oracle"].values()) < 1e-10
+            out["sharded_vs_oracle_ok"] = bool(ok)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads, t1, ta = pick_threads(p)
@@ -306,6 +334,7 @@ def main():
     ap.add_argument("--cpu-slices", type=int, default=400, help="slices of the bounded CPU-baseline sample")
     ap.add_argument("--ref-slices", type=int, default=100, help="slices per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check", action="store_true", help="N > 1: compare the sharded result with the unsharded CUDA path (and the oracle for n <= 16)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

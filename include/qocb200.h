@@ -44,6 +44,8 @@ typedef struct {
     int32_t store_tape;          /* 1: keep Pade intermediates of the forward pass in HBM for the reverse pass;
                                     0: recompute them in the reverse pass (less memory, ~25% more flops) */
     int32_t chunks_per_member;   /* 0 = automatic */
+    int32_t slice_begin;         /* time-slice sharding: this plan owns slices [slice_begin, slice_end) of the N-1 */
+    int32_t slice_end;           /* (both 0 = the whole pulse, unsharded).  See the qocb_shard_* calls below */
     int32_t reserved;
     double evolution_time;       /* T */
 } qocb_problem;
@@ -90,9 +92,38 @@ int qocb_download_result(qocb_plan *plan, double *cost, double *grad);
    between evaluations (outside the stage timers, inside ms_total only if count_flush != 0). */
 int qocb_time_resident(qocb_plan *plan, int32_t with_grad, int32_t warmup, int32_t iters, int32_t flush_l2,
                        double *ms_total, double *stage_ms);
+/* enqueue a 256 MiB write on the plan stream (evicts the 126 MB L2 between timed iterations) */
+int qocb_flush_l2(qocb_plan *plan);
 /* number of kernel launches of one evaluation */
 int qocb_launch_count(qocb_plan *plan, int32_t with_grad);
 void *qocb_stream(qocb_plan *plan);                           /* cudaStream_t of the plan */
+
+/* ---- time-slice sharding (one plan per rank, created with a slice range) ---------------------
+   The four phase calls only ENQUEUE work on the plan stream.  `*_dev` pointers are DEVICE buffers owned by the
+   caller: the host language allocates them and runs the collectives between the phases on the same stream
+   (qoc_b200/core/sharded.py uses torch.distributed / NCCL over NVLink):
+     1. qocb_shard_forward_local(plan, with_grad, shardP_dev)   Magnus + expm of the local slices; product of the
+        local propagators -> shardP_dev[qocb_shard_matrix_doubles]
+        -- all-gather shardP_dev -> allP_dev[world][matrix_doubles]
+     2. qocb_shard_forward_finish(plan, allP_dev, rank)         incoming boundary state P_{rank-1}..P_0 psi0, local
+        state sweeps, cost partial
+     3. qocb_shard_backward_particular(plan, b_dev)             costate at the shard's first state for a zero incoming
+        costate -> b_dev[qocb_shard_vector_doubles]             (the affine recursion's particular part)
+        -- all-gather b_dev -> allb_dev[world][vector_doubles]
+     4. qocb_shard_backward_finish(plan, allP_dev, allb_dev, rank, world)
+        incoming costate by suffix combination, local costate sweeps, expm/Magnus adjoints, gradient scatter
+     5. qocb_shard_pack_result(plan, with_grad, result_dev)     result_dev[qocb_shard_result_doubles] =
+        [partial gradient M*KR | partial cost | final states S*2*NP planar, zeros unless this shard owns the last
+        slice] -- all-reduce(sum) it.  A forward-only evaluation runs phases 1, 2, 5 (with_grad = 0). */
+int qocb_shard_matrix_doubles(qocb_plan *plan);
+int qocb_shard_vector_doubles(qocb_plan *plan);
+int qocb_shard_forward_local(qocb_plan *plan, int32_t with_grad, double *shardP_dev);
+int qocb_shard_forward_finish(qocb_plan *plan, const double *allP_dev, int32_t rank);
+int qocb_shard_backward_particular(qocb_plan *plan, double *b_dev);
+int qocb_shard_backward_finish(qocb_plan *plan, const double *allP_dev, const double *allb_dev, int32_t rank,
+                               int32_t world);
+int qocb_shard_result_doubles(qocb_plan *plan);
+int qocb_shard_pack_result(qocb_plan *plan, int32_t with_grad, double *result_dev);
 
 /* standalone batched matrix exponential (qoc/standard/functions/expm.py:210-252), bench / test hook.
    a, out: [batch][n][n] complex on the host. */

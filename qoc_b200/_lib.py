@@ -22,7 +22,10 @@ EXPORTS = [
     "qocb_add_cost", "qocb_clear_costs", "qocb_cost", "qocb_cost_and_grad", "qocb_get_states",
     "qocb_get_propagators", "qocb_upload_controls", "qocb_run_resident", "qocb_sync", "qocb_download_result",
     "qocb_time_resident", "qocb_launch_count", "qocb_stream", "qocb_expm_batched", "qocb_expm_vjp_batched",
-    "qocb_expm_batched_time", "qocb_version",
+    "qocb_expm_batched_time", "qocb_version", "qocb_flush_l2", "qocb_shard_matrix_doubles",
+    "qocb_shard_vector_doubles", "qocb_shard_forward_local", "qocb_shard_forward_finish",
+    "qocb_shard_backward_particular", "qocb_shard_backward_finish", "qocb_shard_result_doubles",
+    "qocb_shard_pack_result",
 ]
 
 
@@ -31,7 +34,8 @@ class Problem(C.Structure):
     _fields_ = [("hilbert_size", C.c_int32), ("state_count", C.c_int32), ("control_count", C.c_int32),
                 ("control_eval_count", C.c_int32), ("system_eval_count", C.c_int32), ("magnus_order", C.c_int32),
                 ("cost_eval_step", C.c_int32), ("ensemble_count", C.c_int32), ("device", C.c_int32),
-                ("store_tape", C.c_int32), ("chunks_per_member", C.c_int32), ("reserved", C.c_int32),
+                ("store_tape", C.c_int32), ("chunks_per_member", C.c_int32), ("slice_begin", C.c_int32),
+                ("slice_end", C.c_int32), ("reserved", C.c_int32),
                 ("evolution_time", C.c_double)]
 
 
@@ -97,6 +101,15 @@ def load():
     lib.qocb_expm_vjp_batched.argtypes = [i32, i64, vp, vp, vp, vp, i32]
     lib.qocb_expm_batched_time.argtypes = [i32, i64, dbl, i32, vp, i32]
     lib.qocb_version.restype = C.c_char_p
+    lib.qocb_flush_l2.argtypes = [vp]
+    lib.qocb_shard_matrix_doubles.argtypes = [vp]
+    lib.qocb_shard_vector_doubles.argtypes = [vp]
+    lib.qocb_shard_forward_local.argtypes = [vp, i32, vp]
+    lib.qocb_shard_forward_finish.argtypes = [vp, vp, i32]
+    lib.qocb_shard_backward_particular.argtypes = [vp, vp]
+    lib.qocb_shard_backward_finish.argtypes = [vp, vp, vp, i32, i32]
+    lib.qocb_shard_result_doubles.argtypes = [vp]
+    lib.qocb_shard_pack_result.argtypes = [vp, i32, vp]
     _lib = lib
     return lib
 

@@ -74,7 +74,7 @@ class SchroedingerPlan(object):
                  control_eval_count=0, control_count=0, complex_controls=False,
                  magnus_policy=MagnusPolicy.M2, cost_eval_step=1,
                  interpolation_policy=InterpolationPolicy.LINEAR, device=0, store_tape=True,
-                 chunks_per_member=0, ensemble_drifts=None, structure=None):
+                 chunks_per_member=0, ensemble_drifts=None, structure=None, slice_range=None):
         if interpolation_policy != InterpolationPolicy.LINEAR:
             raise NotImplementedError("The interpolation policy {} is not yet supported for this method."
                                       "".format(interpolation_policy))
@@ -103,7 +103,9 @@ class SchroedingerPlan(object):
                           control_eval_count=self.M, system_eval_count=self.N,
                           magnus_order=magnus_policy.order, cost_eval_step=int(cost_eval_step),
                           ensemble_count=self.E, device=int(device), store_tape=int(bool(store_tape)),
-                          chunks_per_member=int(chunks_per_member), reserved=0,
+                          chunks_per_member=int(chunks_per_member),
+                          slice_begin=0 if slice_range is None else int(slice_range[0]),
+                          slice_end=0 if slice_range is None else int(slice_range[1]), reserved=0,
                           evolution_time=float(evolution_time))
         handle = ctypes.c_void_p()
         _lib.check(self.lib.qocb_plan_create(ctypes.byref(pb), ctypes.byref(handle)))

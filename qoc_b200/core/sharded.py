@@ -1,0 +1,216 @@
+"""
+sharded.py - time-slice sharding of ONE GRAPE evaluation across the GPUs of a box.
+
+Magnus + expm of a slice depend only on the controls, so every rank owns a contiguous range of slices; only the
+states (forward) and costates (backward) chain.  Protocol per cost+gradient evaluation (all stream-ordered, no
+host synchronisation until the result is read):
+
+    1. local   : expm of the local slices, product of the local propagators  -> P_g           (n x n)
+       ALLGATHER P_g
+    2. local   : incoming state P_{g-1} .. P_0 psi_0, local state sweeps, cost partial
+    3. local   : costate at the shard's first state for zero incoming costate  -> b_g          (S x n)
+       ALLGATHER b_g                                (affine recursion lam_in(g) = P_{g+1}^T lam_in(g+1) + b_{g+1})
+    4. local   : incoming costate, local costate sweeps, expm / Magnus adjoints, gradient scatter
+    5. ALLREDUCE [partial grad | partial cost | final states]
+
+The CUDA phases are the `qocb_shard_*` entry points of the C ABI (include/qocb200.h); the collectives are
+torch.distributed (NCCL over NVLink / NVSwitch on GPUs; gloo in the CPU protocol tests).  The driver below is
+engine-agnostic: `CudaShardEngine` runs the phases on a B200, tests plug a NumPy engine in to exercise the
+protocol at world_size 2 on CPU.
+"""
+import ctypes
+
+import numpy as np
+
+from qoc_b200 import _lib
+from qoc_b200.core.plan import SchroedingerPlan
+from qoc_b200.models.enums import InterpolationPolicy, MagnusPolicy
+
+
+def slice_bounds(slice_count, world):
+    """contiguous, balanced partition of `slice_count` time slices: rank g owns [b[g], b[g+1])."""
+    if world > slice_count:
+        raise ValueError("cannot shard {} time slices over {} ranks".format(slice_count, world))
+    return [(g * slice_count) // world for g in range(world + 1)]
+
+
+class CudaShardEngine(object):
+    """one rank's phases on its GPU.  Exchange buffers are torch CUDA tensors; their device pointers go through the
+    C ABI.  All work is enqueued on the plan's stream (exposed as `self.stream`, a torch ExternalStream)."""
+
+    def __init__(self, rank, world, hamiltonian, initial_states, costs, evolution_time, system_eval_count,
+                 control_eval_count=0, control_count=0, complex_controls=False, magnus_policy=MagnusPolicy.M2,
+                 cost_eval_step=1, interpolation_policy=InterpolationPolicy.LINEAR, device=0, store_tape=True,
+                 chunks_per_member=0, structure=None):
+        import torch
+        self.torch = torch
+        self.rank, self.world = rank, world
+        b = slice_bounds(system_eval_count - 1, world)
+        self.slice_range = (b[rank], b[rank + 1])
+        self.plan = SchroedingerPlan(hamiltonian, initial_states, costs, evolution_time, system_eval_count,
+                                     control_eval_count=control_eval_count, control_count=control_count,
+                                     complex_controls=complex_controls, magnus_policy=magnus_policy,
+                                     cost_eval_step=cost_eval_step, interpolation_policy=interpolation_policy,
+                                     device=device, store_tape=store_tape, chunks_per_member=chunks_per_member,
+                                     structure=structure, slice_range=self.slice_range)
+        p, lib = self.plan, self.plan.lib
+        self.lib, self.h = lib, p.handle
+        self.GM = lib.qocb_shard_matrix_doubles(self.h)
+        self.VS = lib.qocb_shard_vector_doubles(self.h)
+        self.RS = lib.qocb_shard_result_doubles(self.h)
+        self.NP = self.VS // (2 * p.S)
+        self.dev = torch.device("cuda", device)
+        self.stream = torch.cuda.ExternalStream(lib.qocb_stream(self.h), device=self.dev)
+        kw = dict(dtype=torch.float64, device=self.dev)
+        self.P, self.b, self.result = torch.zeros(self.GM, **kw), torch.zeros(self.VS, **kw), torch.zeros(self.RS, **kw)
+
+    def _ptr(self, t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def upload(self, controls):
+        self.plan.upload(controls)
+
+    def forward_local(self, with_grad):
+        _lib.check(self.lib.qocb_shard_forward_local(self.h, int(with_grad), self._ptr(self.P)), self.h)
+        return self.P
+
+    def forward_finish(self, all_p):
+        _lib.check(self.lib.qocb_shard_forward_finish(self.h, self._ptr(all_p), self.rank), self.h)
+
+    def backward_particular(self):
+        _lib.check(self.lib.qocb_shard_backward_particular(self.h, self._ptr(self.b)), self.h)
+        return self.b
+
+    def backward_finish(self, all_p, all_b):
+        _lib.check(self.lib.qocb_shard_backward_finish(self.h, self._ptr(all_p), self._ptr(all_b), self.rank,
+                                                       self.world), self.h)
+
+    def pack_result(self, with_grad):
+        _lib.check(self.lib.qocb_shard_pack_result(self.h, int(with_grad), self._ptr(self.result)), self.h)
+        return self.result
+
+    def flush_l2(self):
+        _lib.check(self.lib.qocb_flush_l2(self.h), self.h)
+
+    def unpack(self, host):
+        """host: 1-D float64 array [grad M*KR | cost | finals S*2*NP] -> (cost, grad (M x KR), finals (S x n x 1))."""
+        p = self.plan
+        cnt = p.M * p.KR
+        fin = host[cnt + 1:].reshape(p.S, 2, self.NP)
+        finals = (fin[:, 0, :p.n] + 1j * fin[:, 1, :p.n])[:, :, None]
+        return float(host[cnt]), host[:cnt].reshape(p.M, p.KR).copy(), finals
+
+    def launch_count(self, with_grad=True):
+        return self.plan.launch_count(with_grad)
+
+    def close(self):
+        self.plan.close()
+
+
+class TorchDistComm(object):
+    """collectives of the protocol on torch.distributed (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+
+    def all_gather(self, out, inp):
+        self.dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, group=self.group)
+
+
+def sharded_evaluate(engine, comm, all_p, all_b, with_grad):
+    """the protocol of the module docstring for one rank; returns the all-reduced result tensor (device)."""
+    p_loc = engine.forward_local(with_grad)
+    comm.all_gather(all_p, p_loc)
+    engine.forward_finish(all_p)
+    if with_grad:
+        b_loc = engine.backward_particular()
+        comm.all_gather(all_b, b_loc)
+        engine.backward_finish(all_p, all_b)
+    res = engine.pack_result(with_grad)
+    comm.all_reduce_sum(res)
+    return res
+
+
+class ShardedSchroedingerPlan(object):
+    """`SchroedingerPlan` interface (cost / cost_and_grad / upload / time_resident / launch_count / close) over
+    all ranks of the default torch.distributed group, one process per GPU."""
+
+    def __init__(self, hamiltonian, initial_states, costs, evolution_time, system_eval_count, device=0,
+                 group=None, **kw):
+        import torch
+        import torch.distributed as dist
+        self.torch = torch
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.comm = TorchDistComm(group)
+        self.engine = CudaShardEngine(self.rank, self.world, hamiltonian, initial_states, costs, evolution_time,
+                                      system_eval_count, device=device, **kw)
+        e = self.engine
+        self.plan = e.plan
+        self.KR, self.K, self.M, self.S, self.n, self.E = e.plan.KR, e.plan.K, e.plan.M, e.plan.S, e.plan.n, 1
+        self.complex_controls = e.plan.complex_controls
+        kwt = dict(dtype=torch.float64, device=e.dev)
+        self.all_p = torch.zeros(self.world * e.GM, **kwt)
+        self.all_b = torch.zeros(self.world * e.VS, **kwt)
+        self.host = torch.zeros(e.RS, dtype=torch.float64).pin_memory()
+
+    def _run(self, with_grad):
+        with self.torch.cuda.stream(self.engine.stream):
+            res = sharded_evaluate(self.engine, self.comm, self.all_p, self.all_b, with_grad)
+        return res
+
+    def _evaluate(self, controls, with_grad):
+        e = self.engine
+        e.upload(controls)
+        with self.torch.cuda.stream(e.stream):
+            res = sharded_evaluate(e, self.comm, self.all_p, self.all_b, with_grad)
+            self.host.copy_(res, non_blocking=True)
+        e.stream.synchronize()
+        return e.unpack(self.host.numpy())
+
+    def cost(self, controls):
+        cost, _, finals = self._evaluate(controls, False)
+        extra, _ = self.plan._control_costs(controls, False) if controls is not None else (0.0, None)
+        return cost + extra, finals
+
+    def cost_and_grad(self, controls):
+        cost, g, finals = self._evaluate(controls, True)
+        grads = g[:, :self.K] + 1j * g[:, self.K:] if self.complex_controls else g
+        extra, extra_grad = self.plan._control_costs(np.asarray(controls), True)
+        if extra_grad is not None:
+            grads = grads + extra_grad
+        return cost + extra, grads, finals
+
+    def upload(self, controls):
+        self.engine.upload(controls)
+
+    def time_resident(self, with_grad=True, warmup=3, iters=10, flush_l2=True):
+        """device time of `iters` resident evaluations (CUDA events on the plan stream; this rank's clock - the
+        caller takes the max over ranks).  Stage split is not available across the collectives: stages[0] = total."""
+        torch, e = self.torch, self.engine
+        for _ in range(warmup):
+            self._run(with_grad)
+        e.stream.synchronize()
+        total = 0.0
+        for _ in range(iters):
+            if flush_l2:
+                e.flush_l2()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(e.stream):
+                t0.record()
+                sharded_evaluate(e, self.comm, self.all_p, self.all_b, with_grad)
+                t1.record()
+            e.stream.synchronize()
+            total += t0.elapsed_time(t1)
+        stages = np.zeros(8)
+        stages[0] = total
+        return total, stages
+
+    def launch_count(self, with_grad=True):
+        return self.engine.launch_count(with_grad)
+
+    def close(self):
+        self.engine.close()

@@ -193,6 +193,35 @@ __global__ void __launch_bounds__(C::NT) k_expm_vjp(const double *in, const doub
     }
 }
 
+// [partial gradient | partial cost | final states (owner rank only, zeros elsewhere)] -> one all-reduce payload
+__global__ void k_pack_result(const double *grad, const double *cost, const double *fin, double *out, int count, int VS) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < count) out[t] = grad ? grad[t] : 0.0;
+    else if (t == count) out[t] = *cost;
+    else if (t < count + 1 + VS) out[t] = fin ? fin[t - count - 1] : 0.0;
+}
+
+// pairwise product tree over propagators: out[i] = in[2i+1] * in[2i] (later slices on the left); an odd tail is copied
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_reduce_props(const double *in, double *out, int count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<C> sm(smem_raw);
+    const int i = blockIdx.x;
+    const double *lo = in + (size_t)(2 * i) * C::GMAT;
+    double *dst = out + (size_t)i * C::GMAT;
+    if (2 * i + 1 >= count) {
+        for (int idx = threadIdx.x; idx < C::GMAT / 2; idx += C::NT)
+            reinterpret_cast<double2 *>(dst)[idx] = reinterpret_cast<const double2 *>(lo)[idx];
+        return;
+    }
+    g2s<C>(sm.X0, lo);
+    g2s<C>(sm.X1, lo + C::GMAT);
+    __syncthreads();
+    Acc<C> acc; acc.zero();
+    mma_smem<C, false, false, false>(acc, sm.X1, sm.X0);
+    for_owned<C>([&](int ii, int jj, int row, int col) { stg2<C>(dst, row, col, accv<C>(acc, ii, jj)); });
+}
+
 // ---------------------------------------------------------------------------------------------------------
 int pad_dim(int n) {
     if (n <= 8) return 8;
@@ -239,11 +268,13 @@ template <class T> struct DevBuf {
 struct qocb_plan {
     qocb_problem pb;
     int NP = 0, q = 0, nchunks = 0, tape_mats = 0, num_sms = 0;
+    int j0 = 0, Nloc = 0;               // time sharding: first local slice (global index), local state count
+    bool sharded = false, owns_final = true;
     bool ops_set = false, states_set = false, have_step_costs = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16] = {};
     DevBuf<double> G0, G, controls, itab_w, U, tape, scratch, cta_tape, chunkP, psi, lam, part, cost_part, psi0,
-        node_grad, grad, cost, csr_w, vecs, flush;
+        node_grad, grad, cost, csr_w, vecs, flush, redA, redB, psi_in, lam_in;
     DevBuf<int> itab_idx, tape_piv, meta, cta_piv, chunk_begin, member_chunk0, csr_ptr, csr_idx, counts, err_flag;
     DevBuf<CostTerm> terms;
     std::vector<CostTerm> h_terms;
@@ -304,7 +335,7 @@ KArgs make_kargs(qocb_plan *p) {
     a.ga.itab_idx = p->itab_idx.p; a.ga.itab_w = p->itab_w.p;
     a.ga.KR = p->pb.control_count; a.ga.q = p->q; a.ga.order = p->pb.magnus_order;
     a.ga.dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
-    a.N = p->pb.system_eval_count; a.E = p->pb.ensemble_count;
+    a.N = p->Nloc; a.E = p->pb.ensemble_count;
     a.s_cap = kStoredTapeR; a.tape_mats = p->tape_mats;
     a.chunk_begin = p->chunk_begin.p;
     a.U = p->U.p; a.tape = p->tape.p; a.tape_piv = p->tape_piv.p; a.meta = p->meta.p;
@@ -316,11 +347,13 @@ KArgs make_kargs(qocb_plan *p) {
 
 SweepArgs make_sargs(qocb_plan *p) {
     SweepArgs s;
-    s.NP = p->NP; s.S = p->pb.state_count; s.N = p->pb.system_eval_count; s.E = p->pb.ensemble_count;
+    s.NP = p->NP; s.S = p->pb.state_count; s.N = p->Nloc; s.E = p->pb.ensemble_count;
+    s.j_off = p->j0; s.Nglob = p->pb.system_eval_count; s.add_final_seed = p->owns_final ? 1 : 0;
+    s.lam_in = nullptr; s.b_out = nullptr;
     s.ces = p->pb.cost_eval_step; s.nterms = (int)p->h_terms.size(); s.ip_total = p->ip_total;
     s.terms = p->terms.p; s.vecs = p->vecs.p; s.counts = p->counts.p;
     s.U = p->U.p; s.chunkP = p->chunkP.p; s.chunk_begin = p->chunk_begin.p; s.member_chunk0 = p->member_chunk0.p;
-    s.psi = p->psi.p; s.lam = p->lam.p; s.part = p->part.p; s.cost_part = p->cost_part.p; s.psi0 = p->psi0.p;
+    s.psi = p->psi.p; s.lam = p->lam.p; s.part = p->part.p; s.cost_part = p->cost_part.p; s.psi_in = p->psi0.p;
     return s;
 }
 
@@ -337,45 +370,112 @@ int upload_costs(qocb_plan *p) {
     return 0;
 }
 
-// enqueue one evaluation on the plan stream; ev != nullptr records stage boundaries (9 events)
-int enqueue_eval(qocb_plan *p, bool with_grad, cudaEvent_t *ev) {
+template <class C> int launch_reduce(qocb_plan *p, const double *in, double *out, int count) {
+    CU_TRY(p, cudaFuncSetAttribute(k_reduce_props<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
+    k_reduce_props<C><<<(count + 1) / 2, C::NT, Smem<C>::bytes(), p->stream>>>(in, out, count);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+int ready(qocb_plan *p) {
     if (!p->ops_set || !p->states_set) { set_error(p, "operators and states must be set before evaluation"); return -1; }
-    if (upload_costs(p)) return -2;
+    return upload_costs(p);
+}
+
+// ---- pipeline phases (each only enqueues on the plan stream) -----------------------------------------------
+int enqueue_expm_forward(qocb_plan *p, bool with_grad) {
     KArgs ka = make_kargs(p);
-    if (!with_grad) { ka.tape = nullptr; }
-    SweepArgs sa = make_sargs(p);
-    const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
-    const int NP = p->NP;
-    auto rec = [&](int i) { if (ev) cudaEventRecord(ev[i], p->stream); };
-    rec(0);
-    int rc = dispatch(NP, [&] { return launch_forward<C8>(p, ka); }, [&] { return launch_forward<C16>(p, ka); },
-                      [&] { return launch_forward<C32>(p, ka); }, [&] { return launch_forward<C64>(p, ka); });
-    if (rc) return rc;
-    rec(1);
-    k_boundary_fwd<<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa);
-    rec(2);
-    k_sweep_fwd<<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
-    rec(3);
-    if (with_grad) {
-        if (p->have_step_costs) k_sweep_bwd<true><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
-        k_boundary_bwd<<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa, p->have_step_costs ? 1 : 0);
-        k_sweep_bwd<false><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
-        rec(4);
-        rc = dispatch(NP, [&] { return launch_backward<C8>(p, ka); }, [&] { return launch_backward<C16>(p, ka); },
-                      [&] { return launch_backward<C32>(p, ka); }, [&] { return launch_backward<C64>(p, ka); });
+    if (!with_grad) ka.tape = nullptr;
+    return dispatch(p->NP, [&] { return launch_forward<C8>(p, ka); }, [&] { return launch_forward<C16>(p, ka); },
+                    [&] { return launch_forward<C32>(p, ka); }, [&] { return launch_forward<C64>(p, ka); });
+}
+
+// product of all chunk propagators of this shard (member 0) -> out_dev[GMAT]
+int enqueue_shard_propagator(qocb_plan *p, double *out_dev) {
+    const size_t GM = 2 * (size_t)p->NP * p->NP;
+    const double *in = p->chunkP.p;
+    int count = p->nchunks;
+    double *bufs[2] = {p->redA.p, p->redB.p};
+    int which = 0;
+    if (count == 1) {
+        CU_TRY(p, cudaMemcpyAsync(out_dev, in, sizeof(double) * GM, cudaMemcpyDeviceToDevice, p->stream));
+        return 0;
+    }
+    while (count > 1) {
+        double *out = (count <= 2) ? out_dev : bufs[which];
+        int rc = dispatch(p->NP, [&] { return launch_reduce<C8>(p, in, out, count); }, [&] { return launch_reduce<C16>(p, in, out, count); },
+                          [&] { return launch_reduce<C32>(p, in, out, count); }, [&] { return launch_reduce<C64>(p, in, out, count); });
         if (rc) return rc;
-        rec(5);
-        const int tot = p->pb.control_eval_count * p->pb.control_count;
+        in = out; count = (count + 1) / 2; which ^= 1;
+    }
+    return 0;
+}
+
+int enqueue_state_forward(qocb_plan *p, const double *psi_in_dev, cudaEvent_t mid) {
+    SweepArgs sa = make_sargs(p);
+    sa.psi_in = psi_in_dev;
+    const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
+    k_boundary_fwd<<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa);
+    if (mid) cudaEventRecord(mid, p->stream);
+    k_sweep_fwd<<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+// costate pass.  particular_only: chunk particular parts (if step costs) + boundary pass with `lam_in_dev`
+// (nullptr = zero) writing the costate at the first local state to b_out_dev; otherwise also the local sweeps.
+int enqueue_costate(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, bool do_particular, bool do_sweeps) {
+    SweepArgs sa = make_sargs(p);
+    sa.lam_in = lam_in_dev; sa.b_out = b_out_dev;
+    const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
+    if (do_particular && p->have_step_costs) k_sweep_bwd<true><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
+    k_boundary_bwd<<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa, p->have_step_costs ? 1 : 0);
+    if (do_sweeps) k_sweep_bwd<false><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+int enqueue_expm_backward(qocb_plan *p, cudaEvent_t mid) {
+    KArgs ka = make_kargs(p);
+    int rc = dispatch(p->NP, [&] { return launch_backward<C8>(p, ka); }, [&] { return launch_backward<C16>(p, ka); },
+                      [&] { return launch_backward<C32>(p, ka); }, [&] { return launch_backward<C64>(p, ka); });
+    if (rc) return rc;
+    if (mid) cudaEventRecord(mid, p->stream);
+    const int tot = p->pb.control_eval_count * p->pb.control_count;
+    if (tot > 0)
         k_gather_grad<<<(tot + 127) / 128, 128, 0, p->stream>>>(p->csr_ptr.p, p->csr_idx.p, p->csr_w.p, p->node_grad.p,
                                                               p->grad.p, p->pb.control_eval_count, p->pb.control_count,
-                                                              p->q, p->pb.system_eval_count - 1, p->pb.ensemble_count);
+                                                              p->q, p->Nloc - 1, p->pb.ensemble_count);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+int enqueue_finalize(qocb_plan *p) {
+    k_finalize_cost<<<1, 32, 0, p->stream>>>(p->cost_part.p, p->nchunks, p->pb.ensemble_count, p->cost.p);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+// enqueue one (unsharded) evaluation on the plan stream; ev != nullptr records stage boundaries (8 events)
+int enqueue_eval(qocb_plan *p, bool with_grad, cudaEvent_t *ev) {
+    if (p->sharded) { set_error(p, "this plan covers a slice range: use the qocb_shard_* phase calls"); return -1; }
+    int rc = ready(p); if (rc) return rc;
+    auto rec = [&](int i) { if (ev) cudaEventRecord(ev[i], p->stream); };
+    rec(0);
+    rc = enqueue_expm_forward(p, with_grad); if (rc) return rc;
+    rec(1);
+    rc = enqueue_state_forward(p, p->psi0.p, ev ? ev[2] : nullptr); if (rc) return rc;
+    rec(3);
+    if (with_grad) {
+        rc = enqueue_costate(p, nullptr, nullptr, true, true); if (rc) return rc;
+        rec(4);
+        rc = enqueue_expm_backward(p, ev ? ev[5] : nullptr); if (rc) return rc;
         rec(6);
     } else {
         rec(4); rec(5); rec(6);
     }
-    k_finalize_cost<<<1, 32, 0, p->stream>>>(p->cost_part.p, p->nchunks, p->pb.ensemble_count, p->cost.p);
+    rc = enqueue_finalize(p); if (rc) return rc;
     rec(7);
-    CU_TRY(p, cudaGetLastError());
     return 0;
 }
 
@@ -406,12 +506,19 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     if (pb->control_count < 0 || pb->control_count > kMaxKR) { set_error((qocb_plan *)nullptr, "control_count (real channels) must be in [0, 16]"); return -1; }
     if (pb->control_count > 0 && pb->control_eval_count < 2) { set_error((qocb_plan *)nullptr, "control_eval_count must be >= 2"); return -1; }
     if (pb->state_count < 1 || pb->cost_eval_step < 1 || pb->ensemble_count < 1) { set_error((qocb_plan *)nullptr, "state_count, cost_eval_step, ensemble_count must be >= 1"); return -1; }
+    const bool sliced = !(pb->slice_begin == 0 && pb->slice_end == 0);
+    if (sliced && (pb->slice_begin < 0 || pb->slice_end <= pb->slice_begin || pb->slice_end > pb->system_eval_count - 1)) { set_error((qocb_plan *)nullptr, "bad slice range: need 0 <= slice_begin < slice_end <= system_eval_count - 1"); return -1; }
+    if (sliced && pb->ensemble_count != 1) { set_error((qocb_plan *)nullptr, "time-slice sharding and ensembles are mutually exclusive (shard the members instead)"); return -1; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error((qocb_plan *)nullptr, "no CUDA device available (this library has no CPU path)"); return -2; }
     qocb_plan *p = new qocb_plan();
     p->pb = *pb;
     p->NP = NP;
     p->q = pb->magnus_order / 2;
+    p->sharded = sliced;
+    p->j0 = sliced ? pb->slice_begin : 0;
+    p->Nloc = (sliced ? pb->slice_end - pb->slice_begin : pb->system_eval_count - 1) + 1;
+    p->owns_final = !sliced || pb->slice_end == pb->system_eval_count - 1;
     auto fail = [&](int rc) { std::string m = p->err; delete p; g_last_error = m; return rc; };
 #define PTRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { char b__[512]; snprintf(b__, sizeof(b__), "%s failed: %s", #expr, cudaGetErrorString(e__)); p->err = b__; return fail(-2); } } while (0)
     PTRY(cudaSetDevice(pb->device));
@@ -420,7 +527,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     p->num_sms = prop.multiProcessorCount;
     PTRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     for (auto &e : p->ev) PTRY(cudaEventCreate(&e));
-    const int N = pb->system_eval_count, Nm1 = N - 1, E = pb->ensemble_count, M = pb->control_eval_count;
+    const int N = p->Nloc, Nm1 = N - 1, E = pb->ensemble_count, M = pb->control_eval_count;   // LOCAL counts
     const int KR = pb->control_count, S = pb->state_count, q = p->q;
     const size_t GM = 2 * (size_t)NP * NP;
     // ---- chunks -------------------------------------------------------------------------------------
@@ -441,7 +548,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     PTRY(cudaMemcpy(p->member_chunk0.p, mc0.data(), sizeof(int) * mc0.size(), cudaMemcpyHostToDevice));
     // ---- interpolation table (qoc/core/mathmethods.py:36-67 on linspace(0, T, M), programstate.py:41) ----
     {
-        const double T = pb->evolution_time, dt = T / Nm1;
+        const double T = pb->evolution_time, dt = T / (pb->system_eval_count - 1);
         const double s3 = std::sqrt(3.0), s15 = std::sqrt(15.0);
         double nodes[3];
         if (q == 1) nodes[0] = 0.5;
@@ -455,7 +562,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
             for (int m = 0; m < M; ++m) xs[m] = (M == 1) ? 0.0 : (m == M - 1 ? T : m * (T / (M - 1)));   // numpy.linspace
             for (int j = 0; j < Nm1; ++j)
                 for (int i = 0; i < q; ++i) {
-                    const double x = j * dt + dt * nodes[i];
+                    const double x = (p->j0 + j) * dt + dt * nodes[i];
                     int i0, i1;
                     if (x <= xs[0]) { i0 = 0; i1 = 1; }
                     else if (x >= xs[M - 1]) { i0 = M - 2; i1 = M - 1; }
@@ -501,6 +608,10 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     const size_t VS = (size_t)S * 2 * NP;
     PTRY(p->psi.alloc((size_t)E * N * VS)); PTRY(p->lam.alloc((size_t)E * N * VS));
     PTRY(p->part.alloc((size_t)p->nchunks * VS)); PTRY(p->cost_part.alloc(p->nchunks)); PTRY(p->psi0.alloc(VS));
+    if (sliced) {
+        PTRY(p->redA.alloc((size_t)((p->nchunks + 1) / 2) * GM)); PTRY(p->redB.alloc((size_t)((p->nchunks + 3) / 4) * GM));
+        PTRY(p->psi_in.alloc(VS)); PTRY(p->lam_in.alloc(VS));
+    }
     PTRY(p->node_grad.alloc(std::max<size_t>(1, W * q * KR))); PTRY(p->grad.alloc(std::max<size_t>(1, (size_t)M * KR)));
     PTRY(p->cost.alloc(1)); PTRY(p->err_flag.alloc(1));
     PTRY(cudaMemset(p->err_flag.p, 0, sizeof(int)));
@@ -516,6 +627,8 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
         PTRY(cudaFuncSetAttribute(k_sweep_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         PTRY(cudaFuncSetAttribute(k_sweep_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         PTRY(cudaFuncSetAttribute(k_boundary_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        PTRY(cudaFuncSetAttribute(k_prefix_states, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        PTRY(cudaFuncSetAttribute(k_suffix_costates, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     }
 #undef PTRY
     *out = p;
@@ -641,7 +754,7 @@ int qocb_download_result(qocb_plan *p, double *cost, double *grad) {
 
 static int fetch_final_states(qocb_plan *p, double *final_states) {
     if (!final_states) return 0;
-    const int n = p->pb.hilbert_size, NP = p->NP, S = p->pb.state_count, N = p->pb.system_eval_count, E = p->pb.ensemble_count;
+    const int n = p->pb.hilbert_size, NP = p->NP, S = p->pb.state_count, N = p->Nloc, E = p->pb.ensemble_count;
     const size_t VS = (size_t)S * 2 * NP;
     std::vector<double> buf(VS);
     for (int e = 0; e < E; ++e) {
@@ -674,7 +787,7 @@ int qocb_cost_and_grad(qocb_plan *p, const double *controls, double *cost, doubl
 int qocb_get_states(qocb_plan *p, double *states) {
     if (!p || !states) return -1;
     CU_TRY(p, cudaSetDevice(p->pb.device));
-    const int n = p->pb.hilbert_size, NP = p->NP, S = p->pb.state_count, N = p->pb.system_eval_count, E = p->pb.ensemble_count;
+    const int n = p->pb.hilbert_size, NP = p->NP, S = p->pb.state_count, N = p->Nloc, E = p->pb.ensemble_count;
     const size_t VS = (size_t)S * 2 * NP, tot = (size_t)E * N * VS;
     std::vector<double> buf(tot);
     CU_TRY(p, cudaStreamSynchronize(p->stream));
@@ -692,7 +805,7 @@ int qocb_get_propagators(qocb_plan *p, double *props) {
     if (!p || !props) return -1;
     CU_TRY(p, cudaSetDevice(p->pb.device));
     const int n = p->pb.hilbert_size, NP = p->NP;
-    const size_t W = (size_t)p->pb.ensemble_count * (p->pb.system_eval_count - 1), GM = 2 * (size_t)NP * NP;
+    const size_t W = (size_t)p->pb.ensemble_count * (p->Nloc - 1), GM = 2 * (size_t)NP * NP;
     std::vector<double> buf(GM);
     CU_TRY(p, cudaStreamSynchronize(p->stream));
     for (size_t w = 0; w < W; ++w) {
@@ -704,7 +817,12 @@ int qocb_get_propagators(qocb_plan *p, double *props) {
 
 int qocb_launch_count(qocb_plan *p, int32_t with_grad) {
     if (!p) return -1;
-    return with_grad ? (p->have_step_costs ? 9 : 8) : 4;
+    if (!p->sharded) return with_grad ? (p->have_step_costs ? 9 : 8) : 4;
+    int levels = 0;
+    for (int c = p->nchunks; c > 1; c = (c + 1) / 2) ++levels;
+    if (levels == 0) levels = 0;
+    // forward: expm, tree, prefix, boundary, sweep; backward: [particular], boundary, suffix, boundary, sweep, expm, gather, finalize, pack
+    return with_grad ? 1 + levels + 3 + (p->have_step_costs ? 1 : 0) + 8 : 1 + levels + 3 + 2;
 }
 
 int qocb_time_resident(qocb_plan *p, int32_t with_grad, int32_t warmup, int32_t iters, int32_t flush_l2,
@@ -730,6 +848,69 @@ int qocb_time_resident(qocb_plan *p, int32_t with_grad, int32_t warmup, int32_t 
     if (ms_total) *ms_total = tot;
     if (stage_ms) for (int s = 0; s < 8; ++s) stage_ms[s] = st[s];
     return check_device_flag(p);
+}
+
+int qocb_flush_l2(qocb_plan *p) {
+    if (!p) return -1;
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const size_t flush_bytes = 256ull << 20;
+    if (p->flush.n == 0) CU_TRY(p, p->flush.alloc(flush_bytes / sizeof(double)));
+    CU_TRY(p, cudaMemsetAsync(p->flush.p, 0x5a, flush_bytes, p->stream));
+    return 0;
+}
+
+// ---- time-slice sharding phases ------------------------------------------------------------------------
+int qocb_shard_matrix_doubles(qocb_plan *p) { return p ? 2 * p->NP * p->NP : -1; }
+int qocb_shard_vector_doubles(qocb_plan *p) { return p ? p->pb.state_count * 2 * p->NP : -1; }
+
+int qocb_shard_forward_local(qocb_plan *p, int32_t with_grad, double *shardP_dev) {
+    if (!p || !shardP_dev) { set_error(p, "null argument"); return -1; }
+    if (!p->sharded) { set_error(p, "plan has no slice range"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    int rc = ready(p); if (rc) return rc;
+    rc = enqueue_expm_forward(p, with_grad != 0); if (rc) return rc;
+    return enqueue_shard_propagator(p, shardP_dev);
+}
+
+int qocb_shard_forward_finish(qocb_plan *p, const double *allP_dev, int32_t rank) {
+    if (!p || !allP_dev || rank < 0) { set_error(p, "bad argument"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const size_t sm = sweep_smem_bytes(p->NP, p->pb.state_count, p->ip_total);
+    k_prefix_states<<<1, kSweepThreads, sm, p->stream>>>(allP_dev, p->psi0.p, p->psi_in.p, rank, p->NP, p->pb.state_count);
+    CU_TRY(p, cudaGetLastError());
+    int rc = enqueue_state_forward(p, p->psi_in.p, nullptr); if (rc) return rc;
+    return enqueue_finalize(p);
+}
+
+int qocb_shard_backward_particular(qocb_plan *p, double *b_dev) {
+    if (!p || !b_dev) { set_error(p, "null argument"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    return enqueue_costate(p, nullptr, b_dev, true, false);
+}
+
+int qocb_shard_backward_finish(qocb_plan *p, const double *allP_dev, const double *allb_dev, int32_t rank, int32_t world) {
+    if (!p || !allP_dev || !allb_dev || rank < 0 || rank >= world) { set_error(p, "bad argument"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const size_t sm = sweep_smem_bytes(p->NP, p->pb.state_count, p->ip_total);
+    k_suffix_costates<<<1, kSweepThreads, sm, p->stream>>>(allP_dev, allb_dev, p->lam_in.p, rank, world, p->NP, p->pb.state_count);
+    CU_TRY(p, cudaGetLastError());
+    int rc = enqueue_costate(p, p->lam_in.p, nullptr, false, true); if (rc) return rc;
+    return enqueue_expm_backward(p, nullptr);
+}
+
+int qocb_shard_result_doubles(qocb_plan *p) {
+    return p ? p->pb.control_eval_count * p->pb.control_count + 1 + p->pb.state_count * 2 * p->NP : -1;
+}
+
+int qocb_shard_pack_result(qocb_plan *p, int32_t with_grad, double *result_dev) {
+    if (!p || !result_dev) { set_error(p, "null argument"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const int cnt = p->pb.control_eval_count * p->pb.control_count, VS = p->pb.state_count * 2 * p->NP;
+    const double *fin = p->owns_final ? p->psi.p + (size_t)(p->Nloc - 1) * VS : nullptr;
+    k_pack_result<<<(cnt + 1 + VS + 127) / 128, 128, 0, p->stream>>>(with_grad ? p->grad.p : nullptr, p->cost.p, fin,
+                                                                   result_dev, cnt, VS);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
 }
 
 // ---- standalone batched expm --------------------------------------------------------------------------

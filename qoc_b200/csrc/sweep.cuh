@@ -41,7 +41,12 @@ struct SweepArgs {
     double *psi, *lam;             // [E][N][S][2][NP]
     double *part;                  // [nchunks][S][2][NP]
     double *cost_part;             // [nchunks]
-    const double *psi0;            // [S][2][NP]
+    const double *psi_in;          // [S][2][NP] state entering the first local slice (psi0 unless time-sharded)
+    const double *lam_in;          // [S][2][NP] costate entering the last local state from later shards, or nullptr
+    double *b_out;                 // [S][2][NP] k_boundary_bwd also writes the costate at the first local state here
+    int j_off, Nglob;              // time sharding: global index of local slice 0; global system_eval_count.
+                                   // N above is the LOCAL state count (local slices + 1)
+    int add_final_seed;            // this shard owns the final state (seed of the final-step costs)
 };
 
 constexpr int kSweepThreads = 256;
@@ -177,7 +182,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_fwd(SweepArgs a) {
     const int NP = a.NP, S = a.S, VS = S * 2 * NP;
     double *sU = sm, *v0 = sm + 2 * NP * (NP + 1), *v1 = v0 + VS;
     const int e = blockIdx.x;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = a.psi0[i];
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = a.psi_in[i];
     __syncthreads();
     double *psi_e = a.psi + (size_t)e * a.N * VS;
     for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[i] = v0[i];
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_fwd(SweepArgs a) {
             for (int i = threadIdx.x; i < VS; i += kSweepThreads) v1[i] = psi_e[(size_t)k * VS + i];   // boundary state
             __syncthreads();
         }
-        const bool st = is_step_cost_state(k, a.ces), fin = (k == a.N - 1);
+        const bool st = is_step_cost_state(k + a.j_off, a.ces), fin = (k + a.j_off == a.Nglob - 1);
         if (a.nterms > 0 && (st || fin)) {
             cost_inner_products(a, v1, ip, st, fin);
             cost += cost_value(a, ip, st, fin);
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_bwd(SweepArgs a) {
         __syncthreads();
         matvec_smem<true>(v1, v0, sU, NP, S);                         // lam_j = U_j^T lam_{j+1}
         __syncthreads();
-        const bool st = is_step_cost_state(j, a.ces);
+        const bool st = is_step_cost_state(j + a.j_off, a.ces);
         if (a.nterms > 0 && st) {                                     // + seed_j (state j < N-1: step costs only)
             cost_inner_products(a, psi_e + (size_t)j * VS, ip, true, false);
             cost_add_seed(a, ip, v1, true, false);
@@ -271,10 +276,10 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_bwd(SweepArgs a, int
     const int e = blockIdx.x;
     const double *psi_e = a.psi + (size_t)e * a.N * VS;
     double *lam_e = a.lam + (size_t)e * a.N * VS;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = 0.;
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = a.lam_in ? a.lam_in[i] : 0.;
     __syncthreads();
-    if (a.nterms > 0) {
-        const bool st = is_step_cost_state(a.N - 1, a.ces);
+    if (a.nterms > 0 && a.add_final_seed) {
+        const bool st = is_step_cost_state(a.N - 1 + a.j_off, a.ces);
         cost_inner_products(a, psi_e + (size_t)(a.N - 1) * VS, ip, st, true);
         cost_add_seed(a, ip, v0, st, true);
     }
@@ -291,6 +296,47 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_bwd(SweepArgs a, int
         double *t = v0; v0 = v1; v1 = t;
         __syncthreads();
     }
+    if (a.b_out && e == 0)
+        for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.b_out[i] = v0[i];
+}
+
+// time sharding: state entering shard `rank` = P_{rank-1} ... P_0 psi0 (allP: [world][2*NP*NP]); grid = 1
+__global__ void __launch_bounds__(kSweepThreads) k_prefix_states(const double *allP, const double *psi0, double *psi_in,
+                                                                 int rank, int NP, int S) {
+    extern __shared__ double sm[];
+    const int VS = S * 2 * NP;
+    double *sU = sm, *v0 = sm + 2 * NP * (NP + 1), *v1 = v0 + VS;
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = psi0[i];
+    __syncthreads();
+    for (int r = 0; r < rank; ++r) {
+        load_mat_sweep(sU, allP + (size_t)r * 2 * NP * NP, NP);
+        __syncthreads();
+        matvec_smem<false>(v1, v0, sU, NP, S);
+        __syncthreads();
+        double *t = v0; v0 = v1; v1 = t;
+    }
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_in[i] = v0[i];
+}
+
+// time sharding: costate entering shard `rank` from the later shards: lam_in(world-1) = 0,
+// lam_in(g) = P_{g+1}^T lam_in(g+1) + b_{g+1}   (allb: [world][S][2][NP]); grid = 1
+__global__ void __launch_bounds__(kSweepThreads) k_suffix_costates(const double *allP, const double *allb, double *lam_in,
+                                                                   int rank, int world, int NP, int S) {
+    extern __shared__ double sm[];
+    const int VS = S * 2 * NP;
+    double *sU = sm, *v0 = sm + 2 * NP * (NP + 1), *v1 = v0 + VS;
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = 0.;
+    __syncthreads();
+    for (int r = world - 1; r > rank; --r) {
+        load_mat_sweep(sU, allP + (size_t)r * 2 * NP * NP, NP);
+        __syncthreads();
+        matvec_smem<true>(v1, v0, sU, NP, S);
+        __syncthreads();
+        for (int i = threadIdx.x; i < VS; i += kSweepThreads) v1[i] += allb[(size_t)r * VS + i];
+        __syncthreads();
+        double *t = v0; v0 = v1; v1 = t;
+    }
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_in[i] = v0[i];
 }
 
 }  // namespace qocb
