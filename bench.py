@@ -301,6 +301,8 @@ def run_b200(args, name):
             # parity gate on the same controls (bounded: first `sample` slices)
             out["parity"] = parity_gate(p, min(sample, 64), std, SchroedingerPlan, pol)
         print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
     plan.close()
     if world > 1:
         dist.destroy_process_group()

@@ -104,7 +104,15 @@ class CudaShardEngine(object):
         return self.plan.launch_count(with_grad)
 
     def close(self):
+        # free the exchange tensors while the plan stream still exists: torch's caching allocator records an event
+        # on every stream a block was used on when the block is released
+        if getattr(self, "plan", None) is None:
+            return
+        self.stream.synchronize()
+        self.P = self.b = self.result = None
+        self.torch.cuda.synchronize(self.dev)
         self.plan.close()
+        self.plan = None
 
 
 class TorchDistComm(object):
@@ -213,4 +221,10 @@ class ShardedSchroedingerPlan(object):
         return self.engine.launch_count(with_grad)
 
     def close(self):
+        if self.engine is None:
+            return
+        self.engine.stream.synchronize()
+        self.all_p = self.all_b = self.host = None
+        self.torch.cuda.synchronize()
         self.engine.close()
+        self.engine = None
