@@ -306,6 +306,29 @@ template <class C> int launch_backward(qocb_plan *p, const KArgs &a) {
     return 0;
 }
 
+// run `stmt` with the compile-time constant NPc bound to the plan's padded dimension
+#define SWEEP_NP(np, stmt)                                   \
+    do {                                                     \
+        switch (np) {                                        \
+            case 8: { constexpr int NPc = 8; stmt; } break;   \
+            case 16: { constexpr int NPc = 16; stmt; } break; \
+            case 32: { constexpr int NPc = 32; stmt; } break; \
+            case 64: { constexpr int NPc = 64; stmt; } break; \
+        }                                                    \
+    } while (0)
+
+template <int NP> cudaError_t set_sweep_attrs(int big) {
+    cudaError_t e;
+    const auto A = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if ((e = cudaFuncSetAttribute(k_boundary_fwd<NP>, A, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_sweep_fwd<NP>, A, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_sweep_bwd<NP, true>, A, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_sweep_bwd<NP, false>, A, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_boundary_bwd<NP>, A, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_prefix_states<NP>, A, big)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_suffix_costates<NP>, A, big);
+}
+
 using C8 = Cfg<8, 1, 1>;
 using C16 = Cfg<16, 2, 2>;
 using C32 = Cfg<32, 2, 2>;
@@ -415,9 +438,9 @@ int enqueue_state_forward(qocb_plan *p, const double *psi_in_dev, cudaEvent_t mi
     SweepArgs sa = make_sargs(p);
     sa.psi_in = psi_in_dev;
     const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
-    k_boundary_fwd<<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa);
+    SWEEP_NP(p->NP, (k_boundary_fwd<NPc><<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa)));
     if (mid) cudaEventRecord(mid, p->stream);
-    k_sweep_fwd<<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
+    SWEEP_NP(p->NP, (k_sweep_fwd<NPc><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa)));
     CU_TRY(p, cudaGetLastError());
     return 0;
 }
@@ -428,9 +451,9 @@ int enqueue_costate(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, b
     SweepArgs sa = make_sargs(p);
     sa.lam_in = lam_in_dev; sa.b_out = b_out_dev;
     const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
-    if (do_particular && p->have_step_costs) k_sweep_bwd<true><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
-    k_boundary_bwd<<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa, p->have_step_costs ? 1 : 0);
-    if (do_sweeps) k_sweep_bwd<false><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa);
+    if (do_particular && p->have_step_costs) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, true><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa)));
+    SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa, p->have_step_costs ? 1 : 0)));
+    if (do_sweeps) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, false><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa)));
     CU_TRY(p, cudaGetLastError());
     return 0;
 }
@@ -534,7 +557,9 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     int occ = dispatch(NP, [] { return occupancy_fwd<C8>(); }, [] { return occupancy_fwd<C16>(); },
                        [] { return occupancy_fwd<C32>(); }, [] { return occupancy_fwd<C64>(); });
     int cpm = pb->chunks_per_member;
-    if (cpm <= 0) cpm = (p->num_sms * occ + E - 1) / E;
+    // automatic: fill the machine, but keep the sequential chunk-boundary pass (one step per chunk) short: beyond
+    // two CTAs per SM the extra boundary steps cost more than the expm kernels gain at small dims
+    if (cpm <= 0) cpm = (p->num_sms * std::min(occ, 2) + E - 1) / E;
     cpm = std::max(1, std::min(cpm, Nm1));
     p->nchunks = cpm * E;
     std::vector<int> cb(p->nchunks + 1), mc0(E + 1);
@@ -622,13 +647,9 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     // sweep kernels may need > 48 KB of dynamic shared memory
     {
         const int big = 200 * 1024;
-        PTRY(cudaFuncSetAttribute(k_boundary_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        PTRY(cudaFuncSetAttribute(k_sweep_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        PTRY(cudaFuncSetAttribute(k_sweep_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        PTRY(cudaFuncSetAttribute(k_sweep_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        PTRY(cudaFuncSetAttribute(k_boundary_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        PTRY(cudaFuncSetAttribute(k_prefix_states, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        PTRY(cudaFuncSetAttribute(k_suffix_costates, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        cudaError_t ae = cudaSuccess;
+        SWEEP_NP(NP, (ae = set_sweep_attrs<NPc>(big)));
+        PTRY(ae);
     }
 #undef PTRY
     *out = p;
@@ -876,7 +897,7 @@ int qocb_shard_forward_finish(qocb_plan *p, const double *allP_dev, int32_t rank
     if (!p || !allP_dev || rank < 0) { set_error(p, "bad argument"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
     const size_t sm = sweep_smem_bytes(p->NP, p->pb.state_count, p->ip_total);
-    k_prefix_states<<<1, kSweepThreads, sm, p->stream>>>(allP_dev, p->psi0.p, p->psi_in.p, rank, p->NP, p->pb.state_count);
+    SWEEP_NP(p->NP, (k_prefix_states<NPc><<<1, kSweepThreads, sm, p->stream>>>(allP_dev, p->psi0.p, p->psi_in.p, rank, p->pb.state_count)));
     CU_TRY(p, cudaGetLastError());
     int rc = enqueue_state_forward(p, p->psi_in.p, nullptr); if (rc) return rc;
     return enqueue_finalize(p);
@@ -892,7 +913,7 @@ int qocb_shard_backward_finish(qocb_plan *p, const double *allP_dev, const doubl
     if (!p || !allP_dev || !allb_dev || rank < 0 || rank >= world) { set_error(p, "bad argument"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
     const size_t sm = sweep_smem_bytes(p->NP, p->pb.state_count, p->ip_total);
-    k_suffix_costates<<<1, kSweepThreads, sm, p->stream>>>(allP_dev, allb_dev, p->lam_in.p, rank, world, p->NP, p->pb.state_count);
+    SWEEP_NP(p->NP, (k_suffix_costates<NPc><<<1, kSweepThreads, sm, p->stream>>>(allP_dev, allb_dev, p->lam_in.p, rank, world, p->pb.state_count)));
     CU_TRY(p, cudaGetLastError());
     int rc = enqueue_costate(p, p->lam_in.p, nullptr, false, true); if (rc) return rc;
     return enqueue_expm_backward(p, nullptr);

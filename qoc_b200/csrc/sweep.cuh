@@ -49,32 +49,61 @@ struct SweepArgs {
     int add_final_seed;            // this shard owns the final state (seed of the final-step costs)
 };
 
-constexpr int kSweepThreads = 256;
+constexpr int kSweepThreads = 512;
 
-__device__ __forceinline__ void load_mat_sweep(double *sU, const double *gU, int NP) {
-    const int LDS = NP + 1, PL = NP * LDS;
-    for (int idx = threadIdx.x; idx < 2 * NP * NP; idx += kSweepThreads) {
-        const int plane = idx / (NP * NP), rem = idx % (NP * NP);
-        sU[plane * PL + (rem / NP) * LDS + (rem % NP)] = gU[idx];
+// ---- matrix pipeline: U_j staged global -> shared with 16-byte cp.async (LDGSTS), double buffered ---------------
+// Shared layout: planar, row stride LDS = NP + 2 doubles (rows stay 16-byte aligned).  With two lanes per output
+// (k-split) both access patterns are bank-conflict free for 64-bit loads:
+//   U   v : lane -> (a = lane / 2,  ks = lane % 2), b = 2 i + ks : bank = (2 a + ks) mod 16
+//   U^T v : lane -> (a = lane % 16, ks = lane / 16), b = 2 i + ks : a half-warp reads 16 consecutive doubles
+template <int NP> struct SwL {
+    static constexpr int LDS = NP + 2, PL = NP * LDS, MAT = 2 * PL;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int NP>
+__device__ __forceinline__ void prefetch_mat(double *sU, const double *gU) {
+    constexpr int RCH = NP / 2;                                     // 16-byte chunks per row
+    for (int idx = threadIdx.x; idx < NP * NP; idx += kSweepThreads) {   // 2 planes * NP rows * NP/2 chunks
+        const int plane = idx / (NP * RCH), rem = idx % (NP * RCH);
+        const int row = rem / RCH, cc = rem % RCH;
+        cp_async16(sU + plane * SwL<NP>::PL + row * SwL<NP>::LDS + cc * 2, gU + (size_t)idx * 2);
     }
 }
 
-// out[s][a] = sum_b U[a][b] in[s][b]   (TRANS: sum_b U[b][a] in[s][b]);  sU padded NP+1, vectors in smem
-template <bool TRANS>
-__device__ __forceinline__ void matvec_smem(double *out, const double *in, const double *sU, int NP, int S) {
-    const int LDS = NP + 1, PL = NP * LDS;
-    for (int o = threadIdx.x; o < S * NP; o += kSweepThreads) {
-        const int s = o / NP, a = o % NP;
+// out[s][a] = sum_b U[a][b] in[s][b]   (TRANS: sum_b U[b][a] in[s][b]); vectors planar [s][2][NP] in shared memory
+template <int NP, bool TRANS>
+__device__ __forceinline__ void matvec_smem(double *out, const double *in, const double *sU, int S) {
+    constexpr int LDS = SwL<NP>::LDS, PL = SwL<NP>::PL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ks = TRANS ? (lane >> 4) : (lane & 1);
+    const int sub = TRANS ? (lane & 15) : (lane >> 1);
+    for (int base = warp * 16; base < S * NP; base += (kSweepThreads / 32) * 16) {      // warp-uniform trip count
+        const int o = base + sub;
+        const bool live = o < S * NP;
+        const int oo = live ? o : 0;
+        const int s = oo / NP, a = oo % NP;
         const double *vr = in + s * 2 * NP, *vi = vr + NP;
         double xr = 0., xi = 0., yr = 0., yi = 0.;
-        for (int b = 0; b < NP; ++b) {
+#pragma unroll 8
+        for (int i = 0; i < NP / 2; ++i) {
+            const int b = 2 * i + ks;
             const int idx = TRANS ? (b * LDS + a) : (a * LDS + b);
             const double ur = sU[idx], ui = sU[PL + idx];
-            xr = fma(ur, vr[b], xr); yr = fma(ui, vi[b], yr);
-            xi = fma(ur, vi[b], xi); yi = fma(ui, vr[b], yi);
+            const double br = vr[b], bi = vi[b];
+            xr = fma(ur, br, xr); yr = fma(ui, bi, yr);
+            xi = fma(ur, bi, xi); yi = fma(ui, br, yi);
         }
-        out[s * 2 * NP + a] = xr - yr;
-        out[s * 2 * NP + NP + a] = xi + yi;
+        double re = xr - yr, im = xi + yi;
+        re += __shfl_xor_sync(0xffffffffu, re, TRANS ? 16 : 1);
+        im += __shfl_xor_sync(0xffffffffu, im, TRANS ? 16 : 1);
+        if (live && ks == 0) { out[s * 2 * NP + a] = re; out[s * 2 * NP + NP + a] = im; }
     }
 }
 
@@ -171,172 +200,217 @@ __device__ void cost_add_seed(const SweepArgs &a, const double *ip, double *lam,
     __syncthreads();
 }
 
-// dynamic smem layout of the sweep kernels: U (2*NP*(NP+1)) | v0 (S*2*NP) | v1 (S*2*NP) | ip (2*ip_total)
+// dynamic smem layout of the sweep kernels: U x 2 (double buffer) | v0 (S*2*NP) | v1 (S*2*NP) | ip (2*ip_total)
 __host__ __device__ inline size_t sweep_smem_bytes(int NP, int S, int ip_total) {
-    return sizeof(double) * ((size_t)2 * NP * (NP + 1) + (size_t)4 * S * NP + (size_t)2 * (ip_total > 0 ? ip_total : 1));
+    return sizeof(double) * ((size_t)4 * NP * (NP + 2) + (size_t)4 * S * NP + (size_t)2 * (ip_total > 0 ? ip_total : 1));
 }
 
+template <int NP> struct SweepSmem {
+    double *U[2], *v0, *v1, *ip;
+    __device__ __forceinline__ SweepSmem(double *sm, int S) {
+        U[0] = sm; U[1] = sm + SwL<NP>::MAT;
+        v0 = sm + 2 * SwL<NP>::MAT; v1 = v0 + S * 2 * NP; ip = v1 + S * 2 * NP;
+    }
+    __device__ __forceinline__ void swap() { double *t = v0; v0 = v1; v1 = t; }
+};
+
 // (1) boundary states: psi[b_{c+1}] = P_c psi[b_c], sequential over the chunks of one member; grid = E
+template <int NP>
 __global__ void __launch_bounds__(kSweepThreads) k_boundary_fwd(SweepArgs a) {
-    extern __shared__ double sm[];
-    const int NP = a.NP, S = a.S, VS = S * 2 * NP;
-    double *sU = sm, *v0 = sm + 2 * NP * (NP + 1), *v1 = v0 + VS;
+    extern __shared__ __align__(16) double sm_raw[];
+    const int S = a.S, VS = S * 2 * NP;
+    SweepSmem<NP> sm(sm_raw, S);
     const int e = blockIdx.x;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = a.psi_in[i];
-    __syncthreads();
+    const int c0 = a.member_chunk0[e], c1 = a.member_chunk0[e + 1];
+    prefetch_mat<NP>(sm.U[0], a.chunkP + (size_t)c0 * 2 * NP * NP);
+    cp_async_commit();
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = a.psi_in[i];
     double *psi_e = a.psi + (size_t)e * a.N * VS;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[i] = v0[i];
-    for (int c = a.member_chunk0[e]; c < a.member_chunk0[e + 1]; ++c) {
-        load_mat_sweep(sU, a.chunkP + (size_t)c * 2 * NP * NP, NP);
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[i] = a.psi_in[i];
+    for (int c = c0; c < c1; ++c) {
+        const int buf = (c - c0) & 1;
+        if (c + 1 < c1) prefetch_mat<NP>(sm.U[buf ^ 1], a.chunkP + (size_t)(c + 1) * 2 * NP * NP);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
-        matvec_smem<false>(v1, v0, sU, NP, S);
+        matvec_smem<NP, false>(sm.v1, sm.v0, sm.U[buf], S);
         __syncthreads();
         const int kend = a.chunk_begin[c + 1] - e * (a.N - 1);      // state index at the end of chunk c
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[(size_t)kend * VS + i] = v1[i];
-        double *t = v0; v0 = v1; v1 = t;
-        __syncthreads();
+        for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[(size_t)kend * VS + i] = sm.v1[i];
+        sm.swap();
     }
+    cp_async_wait<0>();
 }
 
 // (2) local forward sweeps + cost values; grid = nchunks
+template <int NP>
 __global__ void __launch_bounds__(kSweepThreads) k_sweep_fwd(SweepArgs a) {
-    extern __shared__ double sm[];
-    const int NP = a.NP, S = a.S, VS = S * 2 * NP;
-    double *sU = sm, *v0 = sm + 2 * NP * (NP + 1), *v1 = v0 + VS, *ip = v1 + VS;
+    extern __shared__ __align__(16) double sm_raw[];
+    const int S = a.S, VS = S * 2 * NP;
+    SweepSmem<NP> sm(sm_raw, S);
     const int c = blockIdx.x;
     const int wb = a.chunk_begin[c], we = a.chunk_begin[c + 1];
     const int e = wb / (a.N - 1), jb = wb - e * (a.N - 1), je = we - e * (a.N - 1);
+    const double *gU = a.U + (size_t)(e * (a.N - 1)) * 2 * NP * NP;
     double *psi_e = a.psi + (size_t)e * a.N * VS;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = psi_e[(size_t)jb * VS + i];
+    if (jb + 1 < je) prefetch_mat<NP>(sm.U[0], gU + (size_t)jb * 2 * NP * NP);
+    cp_async_commit();
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = psi_e[(size_t)jb * VS + i];
     __syncthreads();
     double cost = 0.;
     for (int j = jb; j < je; ++j) {
         const int k = j + 1;                                          // state produced by slice j
+        const int buf = (j - jb) & 1;
         if (k < je) {
-            load_mat_sweep(sU, a.U + (size_t)(e * (a.N - 1) + j) * 2 * NP * NP, NP);
+            if (k + 1 < je) prefetch_mat<NP>(sm.U[buf ^ 1], gU + (size_t)k * 2 * NP * NP);
+            cp_async_commit();
+            cp_async_wait<1>();
             __syncthreads();
-            matvec_smem<false>(v1, v0, sU, NP, S);
+            matvec_smem<NP, false>(sm.v1, sm.v0, sm.U[buf], S);
             __syncthreads();
-            for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[(size_t)k * VS + i] = v1[i];
+            for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[(size_t)k * VS + i] = sm.v1[i];
         } else {
-            for (int i = threadIdx.x; i < VS; i += kSweepThreads) v1[i] = psi_e[(size_t)k * VS + i];   // boundary state
+            for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v1[i] = psi_e[(size_t)k * VS + i];   // boundary state
             __syncthreads();
         }
         const bool st = is_step_cost_state(k + a.j_off, a.ces), fin = (k + a.j_off == a.Nglob - 1);
         if (a.nterms > 0 && (st || fin)) {
-            cost_inner_products(a, v1, ip, st, fin);
-            cost += cost_value(a, ip, st, fin);
+            cost_inner_products(a, sm.v1, sm.ip, st, fin);
+            cost += cost_value(a, sm.ip, st, fin);
         }
-        double *t = v0; v0 = v1; v1 = t;
+        sm.swap();
         __syncthreads();
     }
+    cp_async_wait<0>();
     if (threadIdx.x == 0) a.cost_part[c] = cost;
 }
 
 // (3a/3c) local backward sweeps.  PARTICULAR: zero incoming costate, result -> part[c], nothing stored.
 // otherwise: incoming lam[je] read from the lam array (written by k_boundary_bwd), lam[j] stored for j in (jb, je).
-template <bool PARTICULAR>
+template <int NP, bool PARTICULAR>
 __global__ void __launch_bounds__(kSweepThreads) k_sweep_bwd(SweepArgs a) {
-    extern __shared__ double sm[];
-    const int NP = a.NP, S = a.S, VS = S * 2 * NP;
-    double *sU = sm, *v0 = sm + 2 * NP * (NP + 1), *v1 = v0 + VS, *ip = v1 + VS;
+    extern __shared__ __align__(16) double sm_raw[];
+    const int S = a.S, VS = S * 2 * NP;
+    SweepSmem<NP> sm(sm_raw, S);
     const int c = blockIdx.x;
     const int wb = a.chunk_begin[c], we = a.chunk_begin[c + 1];
     const int e = wb / (a.N - 1), jb = wb - e * (a.N - 1), je = we - e * (a.N - 1);
+    const double *gU = a.U + (size_t)(e * (a.N - 1)) * 2 * NP * NP;
     const double *psi_e = a.psi + (size_t)e * a.N * VS;
     double *lam_e = a.lam + (size_t)e * a.N * VS;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = PARTICULAR ? 0. : lam_e[(size_t)je * VS + i];
-    __syncthreads();
     const int jstop = PARTICULAR ? jb : jb + 1;
+    if (je - 1 >= jstop) prefetch_mat<NP>(sm.U[0], gU + (size_t)(je - 1) * 2 * NP * NP);
+    cp_async_commit();
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = PARTICULAR ? 0. : lam_e[(size_t)je * VS + i];
+    __syncthreads();
     for (int j = je - 1; j >= jstop; --j) {
-        load_mat_sweep(sU, a.U + (size_t)(e * (a.N - 1) + j) * 2 * NP * NP, NP);
+        const int buf = (je - 1 - j) & 1;
+        if (j - 1 >= jstop) prefetch_mat<NP>(sm.U[buf ^ 1], gU + (size_t)(j - 1) * 2 * NP * NP);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
-        matvec_smem<true>(v1, v0, sU, NP, S);                         // lam_j = U_j^T lam_{j+1}
+        matvec_smem<NP, true>(sm.v1, sm.v0, sm.U[buf], S);            // lam_j = U_j^T lam_{j+1}
         __syncthreads();
         const bool st = is_step_cost_state(j + a.j_off, a.ces);
         if (a.nterms > 0 && st) {                                     // + seed_j (state j < N-1: step costs only)
-            cost_inner_products(a, psi_e + (size_t)j * VS, ip, true, false);
-            cost_add_seed(a, ip, v1, true, false);
+            cost_inner_products(a, psi_e + (size_t)j * VS, sm.ip, true, false);
+            cost_add_seed(a, sm.ip, sm.v1, true, false);
         }
         if (!PARTICULAR)
-            for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)j * VS + i] = v1[i];
-        double *t = v0; v0 = v1; v1 = t;
+            for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)j * VS + i] = sm.v1[i];
+        sm.swap();
         __syncthreads();
     }
+    cp_async_wait<0>();
     if (PARTICULAR)
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.part[(size_t)c * VS + i] = v0[i];
+        for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.part[(size_t)c * VS + i] = sm.v0[i];
 }
 
 // (3b) boundary costates, sequential over the chunks of one member (last to first); grid = E.
-// lam[N-1] = seed_{N-1};  lam[b_c] = P_c^T lam[b_{c+1}] + part_c
+// lam[N-1] = lam_in + seed_{N-1};  lam[b_c] = P_c^T lam[b_{c+1}] + part_c
+template <int NP>
 __global__ void __launch_bounds__(kSweepThreads) k_boundary_bwd(SweepArgs a, int have_part) {
-    extern __shared__ double sm[];
-    const int NP = a.NP, S = a.S, VS = S * 2 * NP;
-    double *sU = sm, *v0 = sm + 2 * NP * (NP + 1), *v1 = v0 + VS, *ip = v1 + VS;
+    extern __shared__ __align__(16) double sm_raw[];
+    const int S = a.S, VS = S * 2 * NP;
+    SweepSmem<NP> sm(sm_raw, S);
     const int e = blockIdx.x;
+    const int c0 = a.member_chunk0[e], c1 = a.member_chunk0[e + 1];
     const double *psi_e = a.psi + (size_t)e * a.N * VS;
     double *lam_e = a.lam + (size_t)e * a.N * VS;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = a.lam_in ? a.lam_in[i] : 0.;
+    prefetch_mat<NP>(sm.U[0], a.chunkP + (size_t)(c1 - 1) * 2 * NP * NP);
+    cp_async_commit();
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = a.lam_in ? a.lam_in[i] : 0.;
     __syncthreads();
     if (a.nterms > 0 && a.add_final_seed) {
         const bool st = is_step_cost_state(a.N - 1 + a.j_off, a.ces);
-        cost_inner_products(a, psi_e + (size_t)(a.N - 1) * VS, ip, st, true);
-        cost_add_seed(a, ip, v0, st, true);
+        cost_inner_products(a, psi_e + (size_t)(a.N - 1) * VS, sm.ip, st, true);
+        cost_add_seed(a, sm.ip, sm.v0, st, true);
     }
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)(a.N - 1) * VS + i] = v0[i];
-    for (int c = a.member_chunk0[e + 1] - 1; c >= a.member_chunk0[e]; --c) {
-        load_mat_sweep(sU, a.chunkP + (size_t)c * 2 * NP * NP, NP);
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)(a.N - 1) * VS + i] = sm.v0[i];
+    for (int c = c1 - 1; c >= c0; --c) {
+        const int buf = (c1 - 1 - c) & 1;
+        if (c - 1 >= c0) prefetch_mat<NP>(sm.U[buf ^ 1], a.chunkP + (size_t)(c - 1) * 2 * NP * NP);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
-        matvec_smem<true>(v1, v0, sU, NP, S);
+        matvec_smem<NP, true>(sm.v1, sm.v0, sm.U[buf], S);
         __syncthreads();
         if (have_part)
-            for (int i = threadIdx.x; i < VS; i += kSweepThreads) v1[i] += a.part[(size_t)c * VS + i];
+            for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v1[i] += a.part[(size_t)c * VS + i];
         const int kbeg = a.chunk_begin[c] - e * (a.N - 1);
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)kbeg * VS + i] = v1[i];
-        double *t = v0; v0 = v1; v1 = t;
         __syncthreads();
+        for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)kbeg * VS + i] = sm.v1[i];
+        sm.swap();
     }
+    cp_async_wait<0>();
+    __syncthreads();
     if (a.b_out && e == 0)
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.b_out[i] = v0[i];
+        for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.b_out[i] = sm.v0[i];
 }
 
 // time sharding: state entering shard `rank` = P_{rank-1} ... P_0 psi0 (allP: [world][2*NP*NP]); grid = 1
+template <int NP>
 __global__ void __launch_bounds__(kSweepThreads) k_prefix_states(const double *allP, const double *psi0, double *psi_in,
-                                                                 int rank, int NP, int S) {
-    extern __shared__ double sm[];
+                                                                 int rank, int S) {
+    extern __shared__ __align__(16) double sm_raw[];
     const int VS = S * 2 * NP;
-    double *sU = sm, *v0 = sm + 2 * NP * (NP + 1), *v1 = v0 + VS;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = psi0[i];
+    SweepSmem<NP> sm(sm_raw, S);
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = psi0[i];
     __syncthreads();
     for (int r = 0; r < rank; ++r) {
-        load_mat_sweep(sU, allP + (size_t)r * 2 * NP * NP, NP);
+        prefetch_mat<NP>(sm.U[0], allP + (size_t)r * 2 * NP * NP);
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncthreads();
-        matvec_smem<false>(v1, v0, sU, NP, S);
+        matvec_smem<NP, false>(sm.v1, sm.v0, sm.U[0], S);
         __syncthreads();
-        double *t = v0; v0 = v1; v1 = t;
+        sm.swap();
     }
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_in[i] = v0[i];
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_in[i] = sm.v0[i];
 }
 
 // time sharding: costate entering shard `rank` from the later shards: lam_in(world-1) = 0,
 // lam_in(g) = P_{g+1}^T lam_in(g+1) + b_{g+1}   (allb: [world][S][2][NP]); grid = 1
+template <int NP>
 __global__ void __launch_bounds__(kSweepThreads) k_suffix_costates(const double *allP, const double *allb, double *lam_in,
-                                                                   int rank, int world, int NP, int S) {
-    extern __shared__ double sm[];
+                                                                   int rank, int world, int S) {
+    extern __shared__ __align__(16) double sm_raw[];
     const int VS = S * 2 * NP;
-    double *sU = sm, *v0 = sm + 2 * NP * (NP + 1), *v1 = v0 + VS;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) v0[i] = 0.;
+    SweepSmem<NP> sm(sm_raw, S);
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = 0.;
     __syncthreads();
     for (int r = world - 1; r > rank; --r) {
-        load_mat_sweep(sU, allP + (size_t)r * 2 * NP * NP, NP);
+        prefetch_mat<NP>(sm.U[0], allP + (size_t)r * 2 * NP * NP);
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncthreads();
-        matvec_smem<true>(v1, v0, sU, NP, S);
+        matvec_smem<NP, true>(sm.v1, sm.v0, sm.U[0], S);
         __syncthreads();
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) v1[i] += allb[(size_t)r * VS + i];
+        for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v1[i] += allb[(size_t)r * VS + i];
         __syncthreads();
-        double *t = v0; v0 = v1; v1 = t;
+        sm.swap();
     }
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_in[i] = v0[i];
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_in[i] = sm.v0[i];
 }
 
 }  // namespace qocb
