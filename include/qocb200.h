@@ -135,6 +135,49 @@ int qocb_expm_vjp_batched(int32_t n, int64_t batch, const double *a, const doubl
 /* device-resident timing of the batched expm: returns ms per launch (best of `iters`) */
 int qocb_expm_batched_time(int32_t n, int64_t batch, double norm_scale, int32_t iters, double *ms_best, int32_t device);
 
+/* ---- Lindblad path: _evaluate_lindblad_discrete (qoc/core/lindbladdiscrete.py:357-441) and its jacobian (:322) -------
+   Densities are [D][n][n] complex128, interleaved (NumPy C order).  H(x) = H0 + sum_r x_r A_r as above; the dissipator is
+   sum_l gamma_l (L_l rho L_l^dag - 1/2 {L_l^dag L_l, rho}) with time-independent (gamma_l, L_l).  Each of the N-1
+   intervals is a fresh adaptive Dormand-Prince 5(4) integration (qoc/core/mathmethods.py:352-480). */
+typedef struct qocb_lplan qocb_lplan;
+
+typedef struct {
+    int32_t hilbert_size;        /* n */
+    int32_t density_count;       /* D */
+    int32_t control_count;       /* KR real control channels (0 with have_hamiltonian = 0) */
+    int32_t control_eval_count;  /* M */
+    int32_t system_eval_count;   /* N */
+    int32_t cost_eval_step;
+    int32_t lindblad_count;      /* L (0: lindblad_data = None) */
+    int32_t have_hamiltonian;    /* 0: hamiltonian = None (lindbladdiscrete.py:480-484) */
+    int32_t device;
+    int32_t max_rk_steps;        /* capacity of the accepted-step tape of one evaluation; 0 = automatic */
+    int32_t reserved0, reserved1;
+    double evolution_time;
+} qocb_lindblad_problem;
+
+#define QOCB_LCOST_TARGET 0   /* w * (1 - sum_d |tr(T_d^dag rho_d)| / (D n))        targetdensityinfidelity.py:60-66 */
+#define QOCB_LCOST_FORBID 1   /* w * sum_d (1/F_d) sum_f |tr(F_df^dag rho_d) / n|^2  forbiddensities.py:67-85        */
+
+int qocb_lindblad_create(const qocb_lindblad_problem *problem, qocb_lplan **plan_out);
+int qocb_lindblad_destroy(qocb_lplan *plan);
+const char *qocb_lindblad_last_error(const qocb_lplan *plan);
+/* h0: [n][n] (NULL without hamiltonian); a_ops: [KR][n][n]; gammas: [L]; lops: [L][n][n] */
+int qocb_lindblad_set_operators(qocb_lplan *plan, const double *h0, const double *a_ops, const double *gammas,
+                                const double *lops);
+int qocb_lindblad_set_densities(qocb_lplan *plan, const double *rho0);
+/* mats: [D][fmax][n][n]; counts: [D] or NULL; weight = cost_multiplier / normalisation; step_cost as above */
+int qocb_lindblad_add_cost(qocb_lplan *plan, int32_t kind, int32_t step_cost, double weight, const double *mats,
+                           const int32_t *counts, int32_t fmax);
+/* controls: [M][KR]; final_densities: [D][n][n] or NULL; grad: [M][KR] */
+int qocb_lindblad_cost(qocb_lplan *plan, const double *controls, double *cost, double *final_densities);
+int qocb_lindblad_cost_and_grad(qocb_lplan *plan, const double *controls, double *cost, double *grad,
+                                double *final_densities);
+/* stats[0] = Runge-Kutta attempts, stats[1] = accepted steps of the last evaluation */
+int qocb_lindblad_stats(qocb_lplan *plan, int64_t *stats);
+/* densities at every system step of the last evaluation: [N][D][n][n] (save_intermediate_densities payload) */
+int qocb_lindblad_get_densities(qocb_lplan *plan, double *densities);
+
 const char *qocb_version(void);
 
 #ifdef __cplusplus

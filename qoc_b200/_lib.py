@@ -14,8 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqocb200.so")
 CSRC = os.path.join(_HERE, "csrc")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
 
 EXPORTS = [
     "qocb_plan_create", "qocb_plan_destroy", "qocb_last_error", "qocb_set_operators", "qocb_set_states",
@@ -25,7 +25,9 @@ EXPORTS = [
     "qocb_expm_batched_time", "qocb_version", "qocb_flush_l2", "qocb_shard_matrix_doubles",
     "qocb_shard_vector_doubles", "qocb_shard_forward_local", "qocb_shard_forward_finish",
     "qocb_shard_backward_particular", "qocb_shard_backward_finish", "qocb_shard_result_doubles",
-    "qocb_shard_pack_result",
+    "qocb_shard_pack_result", "qocb_lindblad_create", "qocb_lindblad_destroy", "qocb_lindblad_last_error",
+    "qocb_lindblad_set_operators", "qocb_lindblad_set_densities", "qocb_lindblad_add_cost", "qocb_lindblad_cost",
+    "qocb_lindblad_cost_and_grad", "qocb_lindblad_stats", "qocb_lindblad_get_densities",
 ]
 
 
@@ -36,6 +38,15 @@ class Problem(C.Structure):
                 ("cost_eval_step", C.c_int32), ("ensemble_count", C.c_int32), ("device", C.c_int32),
                 ("store_tape", C.c_int32), ("chunks_per_member", C.c_int32), ("slice_begin", C.c_int32),
                 ("slice_end", C.c_int32), ("reserved", C.c_int32),
+                ("evolution_time", C.c_double)]
+
+
+class LindbladProblem(C.Structure):
+    """mirror of `qocb_lindblad_problem` (include/qocb200.h)."""
+    _fields_ = [("hilbert_size", C.c_int32), ("density_count", C.c_int32), ("control_count", C.c_int32),
+                ("control_eval_count", C.c_int32), ("system_eval_count", C.c_int32), ("cost_eval_step", C.c_int32),
+                ("lindblad_count", C.c_int32), ("have_hamiltonian", C.c_int32), ("device", C.c_int32),
+                ("max_rk_steps", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
                 ("evolution_time", C.c_double)]
 
 
@@ -52,11 +63,26 @@ def needs_build():
 
 
 def build_library(force=False, verbose=False):
-    """nvcc cross-compiles for sm_100a without a GPU."""
+    """nvcc cross-compiles for sm_100a without a GPU.  One object per .cu (compiled in parallel), then a link."""
     if not force and not needs_build():
         return LIB_PATH
     cus = [s for s in sources() if s.endswith(".cu")]
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + cus
+    hdrs = [s for s in sources() if s.endswith(".cuh")] + [os.path.join(os.path.dirname(_HERE), "include", "qocb200.h")]
+    newest_hdr = max(os.path.getmtime(h) for h in hdrs)
+    procs, objs = [], []
+    for cu in cus:
+        obj = cu[:-3] + ".o"
+        objs.append(obj)
+        if (not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(cu), newest_hdr)):
+            continue
+        cmd = ["nvcc"] + COMPILE_FLAGS + ["-c", "-o", obj, cu]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    cmd = ["nvcc"] + LINK_FLAGS + ["-o", LIB_PATH] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
@@ -101,6 +127,17 @@ def load():
     lib.qocb_expm_vjp_batched.argtypes = [i32, i64, vp, vp, vp, vp, i32]
     lib.qocb_expm_batched_time.argtypes = [i32, i64, dbl, i32, vp, i32]
     lib.qocb_version.restype = C.c_char_p
+    lib.qocb_lindblad_create.argtypes = [C.POINTER(LindbladProblem), C.POINTER(vp)]
+    lib.qocb_lindblad_destroy.argtypes = [vp]
+    lib.qocb_lindblad_last_error.argtypes = [vp]
+    lib.qocb_lindblad_last_error.restype = C.c_char_p
+    lib.qocb_lindblad_set_operators.argtypes = [vp, vp, vp, vp, vp]
+    lib.qocb_lindblad_set_densities.argtypes = [vp, vp]
+    lib.qocb_lindblad_add_cost.argtypes = [vp, i32, i32, dbl, vp, vp, i32]
+    lib.qocb_lindblad_cost.argtypes = [vp, vp, vp, vp]
+    lib.qocb_lindblad_cost_and_grad.argtypes = [vp, vp, vp, vp, vp]
+    lib.qocb_lindblad_stats.argtypes = [vp, vp]
+    lib.qocb_lindblad_get_densities.argtypes = [vp, vp]
     lib.qocb_flush_l2.argtypes = [vp]
     lib.qocb_shard_matrix_doubles.argtypes = [vp]
     lib.qocb_shard_vector_doubles.argtypes = [vp]

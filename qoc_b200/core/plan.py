@@ -211,3 +211,136 @@ class SchroedingerPlan(object):
             self.close()
         except Exception:
             pass
+
+
+# --- Lindblad --------------------------------------------------------------------------------------------
+def extract_lindblad_structure(lindblad_data, evolution_time):
+    """(gammas [L], operators [L x n x n]) of a time-independent `lindblad_data(time)` callable
+    (qoc/core/lindbladdiscrete.py:486-492); time-dependent dissipation raises NotImplementedError."""
+    if lindblad_data is None:
+        return None, None
+    g0, o0 = lindblad_data(0.0)
+    g1, o1 = lindblad_data(0.37 * evolution_time)
+    g0, o0 = np.asarray(g0, dtype=np.float64), np.asarray(o0, dtype=np.complex128)
+    if not (np.allclose(g0, np.asarray(g1), rtol=_PROBE_RTOL, atol=0) and
+            np.allclose(o0, np.asarray(o1), rtol=_PROBE_RTOL, atol=_PROBE_RTOL)):
+        raise NotImplementedError("time-dependent lindblad_data callables are not supported by the CUDA path yet "
+                                  "(no CPU fallback)")
+    if o0.ndim != 3 or g0.shape[0] != o0.shape[0]:
+        raise ValueError("lindblad_data(time) must return (dissipators [L], operators [L x n x n])")
+    return np.ascontiguousarray(g0), np.ascontiguousarray(o0)
+
+
+class LindbladPlan(object):
+    """Device plan for `_evaluate_lindblad_discrete` and its jacobian (qoc/core/lindbladdiscrete.py:357-441, :322).
+
+    Gradient semantics: the discrete adjoint of the Dormand-Prince map on the realised (accepted) step grid.  The
+    reference's autograd tape also differentiates the step-size controller; those terms are rounding noise (see
+    oracle/lindblad_adjoint_model.py and DESIGN.md section 5) and are deliberately not reproduced."""
+
+    def __init__(self, initial_densities, costs, evolution_time, system_eval_count, hamiltonian=None,
+                 lindblad_data=None, control_eval_count=0, control_count=0, complex_controls=False, cost_eval_step=1,
+                 interpolation_policy=InterpolationPolicy.LINEAR, device=0, max_rk_steps=0, structure=None):
+        if interpolation_policy != InterpolationPolicy.LINEAR:
+            raise ValueError("The interpolation policy {} is not implemented for this method."
+                             "".format(interpolation_policy))
+        self.lib = _lib.load()
+        rho0 = np.ascontiguousarray(initial_densities, dtype=np.complex128)
+        self.D, self.n = rho0.shape[0], rho0.shape[1]
+        self.K, self.M, self.N = int(control_count), int(control_eval_count), int(system_eval_count)
+        self.complex_controls = bool(complex_controls)
+        self.have_h = hamiltonian is not None
+        self.KR = self.K * (2 if self.complex_controls else 1) if self.have_h else 0
+        self.costs = list(costs)
+        h0 = a_ops = None
+        if self.have_h:
+            if structure is None:
+                structure = extract_hamiltonian_structure(hamiltonian, self.K, self.complex_controls, evolution_time)
+            h0, a_ops = structure
+            if h0.shape[0] != self.n:
+                raise ValueError("hamiltonian size {} does not match the densities' hilbert size {}".format(h0.shape[0], self.n))
+        gammas, lops = extract_lindblad_structure(lindblad_data, evolution_time)
+        self.L = 0 if gammas is None else gammas.shape[0]
+        pb = _lib.LindbladProblem(hilbert_size=self.n, density_count=self.D, control_count=self.KR,
+                                  control_eval_count=self.M if self.KR else 0, system_eval_count=self.N,
+                                  cost_eval_step=int(cost_eval_step), lindblad_count=self.L,
+                                  have_hamiltonian=int(self.have_h), device=int(device), max_rk_steps=int(max_rk_steps),
+                                  reserved0=0, reserved1=0, evolution_time=float(evolution_time))
+        handle = ctypes.c_void_p()
+        rc = self.lib.qocb_lindblad_create(ctypes.byref(pb), ctypes.byref(handle))
+        if rc != 0:
+            raise RuntimeError("qoc_b200 CUDA Lindblad path failed (rc={}): {}".format(
+                rc, self.lib.qocb_lindblad_last_error(None).decode()))
+        self.handle = handle
+        h0c = None if h0 is None else np.ascontiguousarray(h0, dtype=np.complex128)
+        aoc = None if a_ops is None or self.KR == 0 else np.ascontiguousarray(a_ops, dtype=np.complex128)
+        self._check(self.lib.qocb_lindblad_set_operators(handle, _lib.ptr(h0c), _lib.ptr(aoc), _lib.ptr(gammas), _lib.ptr(lops)))
+        self._check(self.lib.qocb_lindblad_set_densities(handle, _lib.ptr(rho0)))
+        self.control_costs = []
+        for c in self.costs:
+            terms = c.device_terms_density(self.D, self.n) if hasattr(c, "device_terms_density") else []
+            if not terms:
+                if not hasattr(c, "control_value_and_grad"):
+                    raise NotImplementedError("cost {} has no CUDA descriptor for the Lindblad path".format(c))
+                self.control_costs.append(c)
+            for kind, step, weight, mats, counts in terms:
+                mats = np.ascontiguousarray(mats, dtype=np.complex128)
+                cnt = None if counts is None else np.ascontiguousarray(counts, dtype=np.int32)
+                self._check(self.lib.qocb_lindblad_add_cost(handle, kind, step, float(weight), _lib.ptr(mats),
+                                                            None if cnt is None else cnt.ctypes.data_as(ctypes.c_void_p),
+                                                            mats.shape[1]))
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.qocb_lindblad_last_error(self.handle)
+            raise RuntimeError("qoc_b200 CUDA Lindblad path failed (rc={}): {}".format(rc, msg.decode() if msg else "?"))
+
+    _real_channels = SchroedingerPlan._real_channels
+    _control_costs = SchroedingerPlan._control_costs
+
+    def cost(self, controls):
+        x = self._real_channels(controls) if controls is not None else None
+        out = np.zeros(1)
+        fd = np.empty((self.D, self.n, self.n), dtype=np.complex128)
+        self._check(self.lib.qocb_lindblad_cost(self.handle, _lib.ptr(x), _lib.ptr(out), _lib.ptr(fd)))
+        extra, _ = self._control_costs(controls, False) if controls is not None else (0.0, None)
+        return float(out[0]) + extra, fd
+
+    def cost_and_grad(self, controls):
+        """(error, grads, final_densities); grads = dE/dRe(u) + i dE/dIm(u) for complex controls."""
+        x = self._real_channels(controls)
+        out = np.zeros(1)
+        fd = np.empty((self.D, self.n, self.n), dtype=np.complex128)
+        controls = np.asarray(controls)
+        if self.KR == 0:                                   # hamiltonian = None: the state costs do not see the controls
+            self._check(self.lib.qocb_lindblad_cost(self.handle, None, _lib.ptr(out), _lib.ptr(fd)))
+            grads = np.zeros(controls.shape, dtype=controls.dtype)
+        else:
+            g = np.zeros((self.M, self.KR))
+            self._check(self.lib.qocb_lindblad_cost_and_grad(self.handle, _lib.ptr(x), _lib.ptr(out), _lib.ptr(g), _lib.ptr(fd)))
+            grads = g[:, :self.K] + 1j * g[:, self.K:] if self.complex_controls else g
+        extra, extra_grad = self._control_costs(controls, True)
+        if extra_grad is not None:
+            grads = grads + extra_grad
+        return float(out[0]) + extra, grads, fd
+
+    def stats(self):
+        s = np.zeros(2, dtype=np.int64)
+        self._check(self.lib.qocb_lindblad_stats(self.handle, s.ctypes.data_as(ctypes.c_void_p)))
+        return {"attempts": int(s[0]), "accepted": int(s[1])}
+
+    def intermediate_densities(self):
+        buf = np.empty((self.N, self.D, self.n, self.n), dtype=np.complex128)
+        self._check(self.lib.qocb_lindblad_get_densities(self.handle, _lib.ptr(buf)))
+        return buf
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.qocb_lindblad_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -16,6 +16,7 @@ import numpy as np
 from qoc_b200.models.cost import Cost
 
 KIND_TARGET_COHERENT, KIND_TARGET_INCOHERENT, KIND_FORBID = 0, 1, 2
+LKIND_TARGET, LKIND_FORBID = 0, 1          # density costs (QOCB_LCOST_*)
 
 
 def _dag(x):
@@ -117,6 +118,11 @@ class TargetDensityInfidelity(Cost):
         fid = sum(np.abs(np.trace(p)) for p in prods) / (self.density_count * self.hilbert_size)
         return (1 - fid) / self._norm * self.cost_multiplier
 
+    def device_terms_density(self, density_count, hilbert_size):
+        mats = _dag(self.target_densities_dagger).reshape(self.density_count, 1, hilbert_size, hilbert_size)
+        return [(LKIND_TARGET, int(self.requires_step_evaluation), self.cost_multiplier / self._norm,
+                 np.ascontiguousarray(mats, dtype=np.complex128), None)]
+
 
 class TargetDensityInfidelityTime(TargetDensityInfidelity):
     """as above divided by cost_eval_count; evaluated on the final densities only because the reference sets
@@ -151,12 +157,23 @@ class ForbidDensities(Cost):
             total = total + np.sum(_abs2(ips)) / self.forbidden_densities_count[i]
         return total / self.cost_normalization_constant * self.cost_multiplier
 
+    def device_terms_density(self, density_count, hilbert_size):
+        fmax = int(self.forbidden_densities_count.max())
+        mats = np.zeros((density_count, fmax, hilbert_size, hilbert_size), dtype=np.complex128)
+        for d, fdag in enumerate(self.forbidden_densities_dagger):
+            mats[d, :fdag.shape[0]] = _dag(fdag)
+        return [(LKIND_FORBID, 1, self.cost_multiplier / self.cost_normalization_constant, mats,
+                 self.forbidden_densities_count.astype(np.int32))]
+
 
 # --- control-only costs: host value + analytic gradient -------------------------------------------------
 class _ControlCost(Cost):
     requires_step_evaluation = False
 
     def device_terms(self, state_count, hilbert_size):
+        return []
+
+    def device_terms_density(self, density_count, hilbert_size):
         return []
 
     def cost(self, controls, states, system_eval_step):
