@@ -36,7 +36,7 @@ struct Smem {
     double *X0, *X1, *X2;
     double *red;                // 64 + kMaxQ*kMaxKR*NWARP doubles of reduction scratch
     double *coef;               // [kMaxQ][kMaxKR]
-    int *piv;                   // [NP]
+    int *piv;                   // [NP] row permutation of the LU, then [8] pivots of the current panel
     __device__ __forceinline__ Smem(unsigned char *base) {
         double *d = reinterpret_cast<double *>(base);
         X0 = d; X1 = d + C::SMAT; X2 = d + 2 * C::SMAT;
@@ -45,7 +45,7 @@ struct Smem {
         piv = reinterpret_cast<int *>(coef + kMaxQ * kMaxKR);
     }
     static constexpr size_t bytes() {
-        return sizeof(double) * (3 * C::SMAT + 64 + kMaxQ * kMaxKR * C::NWARP + kMaxQ * kMaxKR) + sizeof(int) * C::NP;
+        return sizeof(double) * (3 * C::SMAT + 64 + kMaxQ * kMaxKR * C::NWARP + kMaxQ * kMaxKR) + sizeof(int) * (C::NP + 8);
     }
 };
 
@@ -256,17 +256,23 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
         sts2<C>(sm.X2, row, col, ve - uo);                              // Q
     });
     __syncthreads();
-    lu_factor_smem<C>(sm.X2, sm.piv, sm.red);
-    lu_solve_smem<C, false>(sm.X2, sm.piv, sm.X1);                      // R0 = Q^-1 P in X1
+    lu_factor_blocked<C>(sm.X2, sm.piv, sm.piv + C::NP);
+    lu_solve_blocked<C, false>(sm.X2, sm.piv, sm.X1, sm.X0);            // R0 = Q^-1 P in X0 (Y is dead)
     if (keep) {
-        s2g<C>(tape + (size_t)T_LU * C::GMAT, sm.X2);
+        s2g<C>(tape + (size_t)T_LU * C::GMAT, sm.X2);                   // LUi format (tile.cuh) + row permutation
         for (int c = threadIdx.x; c < C::NP; c += C::NT) piv_out[c] = sm.piv[c];
     }
+    const double *cur = sm.X0;
     for (int i = 0; i < s; ++i) {                                        // expm.py:249-250
-        if (keep && i < s_cap) s2g<C>(tape + (size_t)(T_R + i) * C::GMAT, sm.X1);
-        acc.zero(); mma_smem<C, false, false, false>(acc, sm.X1, sm.X1);
+        if (keep && i < s_cap) s2g<C>(tape + (size_t)(T_R + i) * C::GMAT, cur);
+        acc.zero(); mma_smem<C, false, false, false>(acc, cur, cur);
         __syncthreads();
         for_owned<C>([&](int ii, int jj, int row, int col) { sts2<C>(sm.X1, row, col, accv<C>(acc, ii, jj)); });
+        __syncthreads();
+        cur = sm.X1;
+    }
+    if (s == 0) {
+        for_owned<C>([&](int, int, int row, int col) { sts2<C>(sm.X1, row, col, lds2<C>(sm.X0, row, col)); });
         __syncthreads();
     }
     return s;
@@ -297,11 +303,11 @@ __device__ void pade_backward(const Smem<C> &sm, const double *tape, const int *
     for (int c = threadIdx.x; c < C::NP; c += C::NT) sm.piv[c] = tpiv[c];
     g2s<C>(sm.X1, s > 0 ? tape + (size_t)T_R * C::GMAT : gU);
     __syncthreads();
-    lu_solve_smem<C, true>(sm.X2, sm.piv, sm.X0);                        // X0 = pbar
-    acc.zero(); mma_smem<C, false, true, false>(acc, sm.X0, sm.X1);      // pbar R0^T = -qbar
+    lu_solve_blocked<C, true>(sm.X2, sm.piv, sm.X0, sm.X2);             // X2 = pbar = Q^-T rbar (over the dead LU)
+    acc.zero(); mma_smem<C, false, true, false>(acc, sm.X2, sm.X1);      // pbar R0^T = -qbar
     __syncthreads();
     for_owned<C>([&](int i, int j, int row, int col) {
-        const c2 pb = lds2<C>(sm.X0, row, col), t = accv<C>(acc, i, j);
+        const c2 pb = lds2<C>(sm.X2, row, col), t = accv<C>(acc, i, j);
         sts2<C>(sm.X0, row, col, pb + t);                               // uobar = pbar - qbar
         sts2<C>(sm.X2, row, col, pb - t);                               // vebar = pbar + qbar
     });

@@ -170,150 +170,253 @@ __device__ __forceinline__ cplx crecip(cplx a) {
     const double q = a.r / a.i, d = a.r * q + a.i; return {q / d, -1.0 / d};
 }
 
-// ---- LU with partial pivoting, in place on a shared-memory matrix ---------------------------------------
-// Follows zgesv's zgetf2 semantics (qoc/standard/functions/expm.py:246 -> numpy.linalg.solve -> LAPACK):
-// pivot = first row maximising |re| + |im| (izamax), unit-lower L stored below the diagonal.
-// red: shared scratch of >= 2 doubles; piv: shared int[NP].  Ends with a barrier.
-template <class C>
-__device__ void lu_factor_smem(double *__restrict__ Q, int *__restrict__ piv, double *__restrict__ red) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *Qr = Q, *Qi = Q + C::PLANE;
-    for (int k = 0; k < C::NP; ++k) {
-        if (warp == 0) {
-            double best = -1.0; int bi = k;
-            for (int i = k + lane; i < C::NP; i += 32) {
-                const double v = fabs(Qr[i * C::LD + k]) + fabs(Qi[i * C::LD + k]);
-                if (v > best) { best = v; bi = i; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_down_sync(0xffffffffu, best, o);
-                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
-            if (lane == 0) piv[k] = bi;
-        }
-        __syncthreads();
-        const int p = piv[k];
-        if (p != k) {
-            for (int c = tid; c < C::NP; c += C::NT) {
-                double t0 = Qr[k * C::LD + c]; Qr[k * C::LD + c] = Qr[p * C::LD + c]; Qr[p * C::LD + c] = t0;
-                t0 = Qi[k * C::LD + c]; Qi[k * C::LD + c] = Qi[p * C::LD + c]; Qi[p * C::LD + c] = t0;
-            }
-            __syncthreads();
-        }
-        const cplx inv = crecip({Qr[k * C::LD + k], Qi[k * C::LD + k]});
-        const int m = C::NP - k - 1;           // trailing size
-        // multipliers are formed on the fly from the unscaled column k; column k is scaled afterwards
-        for (int e = tid; e < m * m; e += C::NT) {
-            const int i = k + 1 + e / m, j = k + 1 + e % m;
-            const cplx l = cmul({Qr[i * C::LD + k], Qi[i * C::LD + k]}, inv);
-            const cplx u = {Qr[k * C::LD + j], Qi[k * C::LD + j]};
-            Qr[i * C::LD + j] -= l.r * u.r - l.i * u.i;
-            Qi[i * C::LD + j] -= l.r * u.i + l.i * u.r;
-        }
-        __syncthreads();
-        for (int i = k + 1 + tid; i < C::NP; i += C::NT) {
-            const cplx l = cmul({Qr[i * C::LD + k], Qi[i * C::LD + k]}, inv);
-            Qr[i * C::LD + k] = l.r; Qi[i * C::LD + k] = l.i;
-        }
-        // no barrier needed here: column k is not read again before the barrier after the next pivot search
-    }
-    __syncthreads();
+// ---- blocked LU with partial pivoting on a shared-memory matrix, FP64 tensor cores for everything but the panels --
+// Semantics of zgesv (qoc/standard/functions/expm.py:246 -> numpy.linalg.solve -> LAPACK zgetrf/zgetrs): row
+// pivoting with pivot = first row maximising |re| + |im| (izamax).  Block size 8 = one DMMA tile.
+//
+// Storage after lu_factor_blocked ("LUi" format, also what the reverse-pass tape holds):
+//   * off-diagonal blocks: L (below) and U (above) as usual;
+//   * every 8 x 8 diagonal block holds the INVERSES of its triangular factors: strictly lower part = strictly lower
+//     part of inv(L_kk) (unit diagonal implied), upper part incl. diagonal = inv(U_kk).  Triangular solves then are
+//     tile products only (trsm via inverted diagonal blocks), issued as DMMA like every other product;
+//   * perm[i] = source row of row i of the permuted matrix:  (Pi Q)[i] = Q[perm[i]],  Pi Q = L U.
+// Work split: warp 0 factors the 8-column panel (warp-synchronous, no block barrier inside); afterwards every warp
+// owns whole column tiles (row swaps, U12 = inv(L11) A12 and the trailing update of that column tile need only
+// __syncwarp), so one LU costs 2 block barriers per panel.  The solves are barrier-free: each warp carries its own
+// 8 right-hand-side columns through the whole forward and backward substitution.
+enum { MASK_NONE = 0, MASK_LINV = 1, MASK_UINV = 2 };
+
+// DMMA A-fragment element (row r0+g, k k0+t) of op(M); T: op = transpose.  Masks act on the STORED coordinates.
+template <class C, bool T, int MASK>
+__device__ __forceinline__ void ld_afrag(const double *M, int r0, int k0, int g, int t, double &re, double &im) {
+    const int r = r0 + g, k = k0 + t;
+    const int mr = T ? k : r, mc = T ? r : k;
+    re = M[mr * C::LD + mc]; im = M[C::PLANE + mr * C::LD + mc];
+    if (MASK == MASK_LINV) { if (mr == mc) { re = 1.0; im = 0.0; } else if (mr < mc) { re = 0.0; im = 0.0; } }
+    if (MASK == MASK_UINV) { if (mr > mc) { re = 0.0; im = 0.0; } }
 }
 
-// X <- Q^{-1} X (TRANS = false) or X <- Q^{-T} X (TRANS = true) with the factors from lu_factor_smem.
-// PARTS threads cooperate on one column of X (rows split mod PARTS); the pivot-row value is broadcast
-// inside the PARTS-lane group by shuffle, so no block barrier is needed inside the substitution loops.
+// acc (8 x 8 complex tile at rows ar0, cols bc0) += sign * op(A)[ar0:+8, ak0:+8] * B[bk0:+8, bc0:+8]
+template <class C, bool T, int MASK, bool NEG>
+__device__ __forceinline__ void tile_mma(c2 &acc, const double *A, int ar0, int ak0, const double *B, int bk0, int bc0) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        double ar, ai;
+        ld_afrag<C, T, MASK>(A, ar0, ak0 + 4 * ks, g, t, ar, ai);
+        if (NEG) { ar = -ar; ai = -ai; }
+        const int bidx = (bk0 + 4 * ks + t) * C::LD + bc0 + g;
+        const double br = B[bidx], bi = B[C::PLANE + bidx];
+        dmma884(acc.r0, acc.r1, ar, br);
+        dmma884(acc.i0, acc.i1, ar, bi);
+        dmma884(acc.r0, acc.r1, -ai, bi);
+        dmma884(acc.i0, acc.i1, ai, br);
+    }
+}
+template <class C> __device__ __forceinline__ c2 ld_ctile(const double *M, int r0, int c0) {
+    const int lane = threadIdx.x & 31;
+    return lds2<C>(M, r0 + (lane >> 2), c0 + (lane & 3) * 2);
+}
+template <class C> __device__ __forceinline__ void st_ctile(double *M, int r0, int c0, const c2 &v) {
+    const int lane = threadIdx.x & 31;
+    sts2<C>(M, r0 + (lane >> 2), c0 + (lane & 3) * 2, v);
+}
+
+// warp 0: unblocked LU with partial pivoting of the panel (rows j0.., columns j0..j0+7), then the in-place inversion
+// of the diagonal block's triangular factors.  piv8: shared int[8]; perm: shared int[NP].
+template <class C>
+__device__ void lu_panel_warp(double *Q, int *perm, int *piv8, int j0) {
+    const int lane = threadIdx.x & 31;
+    double *Qr = Q, *Qi = Q + C::PLANE;
+    for (int j = 0; j < 8; ++j) {
+        const int col = j0 + j;
+        double best = -1.0; int bi = col;
+        for (int r = col + lane; r < C::NP; r += 32) {
+            const double v = fabs(Qr[r * C::LD + col]) + fabs(Qi[r * C::LD + col]);
+            if (v > best) { best = v; bi = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        const int p = bi;
+        if (lane == 0) { piv8[j] = p; const int tp = perm[col]; perm[col] = perm[p]; perm[p] = tp; }
+        if (p != col && lane < 16) {
+            double *pl = Q + (lane >> 3) * C::PLANE;
+            const int c = j0 + (lane & 7);
+            const double t0 = pl[col * C::LD + c]; pl[col * C::LD + c] = pl[p * C::LD + c]; pl[p * C::LD + c] = t0;
+        }
+        __syncwarp();
+        const cplx inv = crecip({Qr[col * C::LD + col], Qi[col * C::LD + col]});
+        for (int r = col + 1 + lane; r < C::NP; r += 32) {
+            const cplx l = cmul({Qr[r * C::LD + col], Qi[r * C::LD + col]}, inv);
+            Qr[r * C::LD + col] = l.r; Qi[r * C::LD + col] = l.i;
+            for (int c = col + 1; c < j0 + 8; ++c) {
+                const double ur = Qr[col * C::LD + c], ui = Qi[col * C::LD + c];
+                Qr[r * C::LD + c] -= l.r * ur - l.i * ui;
+                Qi[r * C::LD + c] -= l.r * ui + l.i * ur;
+            }
+        }
+        __syncwarp();
+    }
+    // invert the diagonal block's factors: lanes 0-7 one column of inv(L_kk), lanes 8-15 one column of inv(U_kk)
+    cplx x[8];
+    const int c = lane & 7;
+    if (lane < 8) {
+        for (int r = 0; r < 8; ++r) x[r] = {r == c ? 1.0 : 0.0, 0.0};
+        for (int r = c + 1; r < 8; ++r) {
+            double sr = 0., si = 0.;
+            for (int k = c; k < r; ++k) {
+                const double lr = Qr[(j0 + r) * C::LD + j0 + k], li = Qi[(j0 + r) * C::LD + j0 + k];
+                sr += lr * x[k].r - li * x[k].i; si += lr * x[k].i + li * x[k].r;
+            }
+            x[r] = {-sr, -si};
+        }
+    } else if (lane < 16) {
+        for (int r = 0; r < 8; ++r) x[r] = {0.0, 0.0};
+        for (int r = c; r >= 0; --r) {
+            double sr = (r == c) ? 1.0 : 0.0, si = 0.;
+            for (int k = r + 1; k <= c; ++k) {
+                const double ur = Qr[(j0 + r) * C::LD + j0 + k], ui = Qi[(j0 + r) * C::LD + j0 + k];
+                sr -= ur * x[k].r - ui * x[k].i; si -= ur * x[k].i + ui * x[k].r;
+            }
+            x[r] = cmul({sr, si}, crecip({Qr[(j0 + r) * C::LD + j0 + r], Qi[(j0 + r) * C::LD + j0 + r]}));
+        }
+    }
+    __syncwarp();
+    if (lane < 8) {
+        for (int r = c + 1; r < 8; ++r) { Qr[(j0 + r) * C::LD + j0 + c] = x[r].r; Qi[(j0 + r) * C::LD + j0 + c] = x[r].i; }
+    } else if (lane < 16) {
+        for (int r = 0; r <= c; ++r) { Qr[(j0 + r) * C::LD + j0 + c] = x[r].r; Qi[(j0 + r) * C::LD + j0 + c] = x[r].i; }
+    }
+    __syncwarp();
+}
+
+// In-place blocked LU of Q (LUi format).  perm: shared int[NP]; piv8: shared int[8].  Ends with a barrier.
+template <class C>
+__device__ void lu_factor_blocked(double *Q, int *perm, int *piv8) {
+    constexpr int NB = C::NP / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < C::NP; i += C::NT) perm[i] = i;
+    __syncthreads();
+    for (int kb = 0; kb < NB; ++kb) {
+        const int j0 = kb * 8;
+        if (warp == 0) lu_panel_warp<C>(Q, perm, piv8, j0);
+        __syncthreads();
+        for (int ct = warp; ct < NB; ct += C::NWARP) {
+            if (ct == kb) continue;
+            if (lane < 16) {                                       // the panel's row swaps on this column tile
+                double *pl = Q + (lane >> 3) * C::PLANE;
+                const int c = ct * 8 + (lane & 7);
+                for (int j = 0; j < 8; ++j) {
+                    const int p = piv8[j], r = j0 + j;
+                    if (p != r) { const double t0 = pl[r * C::LD + c]; pl[r * C::LD + c] = pl[p * C::LD + c]; pl[p * C::LD + c] = t0; }
+                }
+            }
+            __syncwarp();
+            if (ct > kb) {
+                c2 u = czero();                                    // U12 = inv(L11) A12
+                tile_mma<C, false, MASK_LINV, false>(u, Q, j0, j0, Q, j0, ct * 8);
+                __syncwarp();
+                st_ctile<C>(Q, j0, ct * 8, u);
+                __syncwarp();
+                for (int rt = kb + 1; rt < NB; ++rt) {             // A22 -= L21 U12
+                    c2 a = ld_ctile<C>(Q, rt * 8, ct * 8);
+                    tile_mma<C, false, MASK_NONE, true>(a, Q, rt * 8, j0, Q, j0, ct * 8);
+                    st_ctile<C>(Q, rt * 8, ct * 8, a);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// X <- Q^{-1} B (TRANS = false) or Q^{-T} B (TRANS = true); LU in LUi format.  B is read from `B`, the result is
+// written to `X` (B != X: the row permutation is applied out of place).  Both end with a barrier.
 template <class C, bool TRANS>
-__device__ void lu_solve_smem(const double *__restrict__ LU, const int *__restrict__ piv, double *__restrict__ X) {
-    const int tid = threadIdx.x;
-    constexpr int P = C::PARTS;
-    const int c = tid / P, part = tid % P;
-    const int lane = tid & 31;
-    const int gbase = lane - part;               // first lane of this column group
-    const double *Lr = LU, *Li = LU + C::PLANE;
-    double *Xr = X, *Xi = X + C::PLANE;
-    if (!TRANS) {
-        if (part == 0)
-            for (int k = 0; k < C::NP; ++k) {
-                const int p = piv[k];
-                if (p != k) {
-                    double t0 = Xr[k * C::LD + c]; Xr[k * C::LD + c] = Xr[p * C::LD + c]; Xr[p * C::LD + c] = t0;
-                    t0 = Xi[k * C::LD + c]; Xi[k * C::LD + c] = Xi[p * C::LD + c]; Xi[p * C::LD + c] = t0;
+__device__ void lu_solve_blocked(const double *LU, const int *perm, double *B, double *X) {
+    constexpr int NB = C::NP / 8;
+    const int warp = threadIdx.x >> 5;
+    double *W = TRANS ? B : X;                                     // the substitutions run in place on W
+    if (!TRANS) {                                                  // X[i] = B[perm[i]]
+        for (int idx = threadIdx.x; idx < 2 * C::NP * (C::NP / 2); idx += C::NT) {
+            const int plane = idx / (C::NP * (C::NP / 2)), rem = idx % (C::NP * (C::NP / 2));
+            const int row = rem / (C::NP / 2), cc = rem % (C::NP / 2);
+            *reinterpret_cast<double2 *>(X + plane * C::PLANE + row * C::LD + 2 * cc) =
+                *reinterpret_cast<const double2 *>(B + plane * C::PLANE + perm[row] * C::LD + 2 * cc);
+        }
+        __syncthreads();
+    }
+    for (int ct = warp; ct < NB; ct += C::NWARP) {
+        const int c0 = ct * 8;
+        if (!TRANS) {
+            for (int kb = 0; kb < NB; ++kb) {                      // L z = b
+                c2 z = czero();
+                tile_mma<C, false, MASK_LINV, false>(z, LU, kb * 8, kb * 8, W, kb * 8, c0);
+                __syncwarp();
+                st_ctile<C>(W, kb * 8, c0, z);
+                __syncwarp();
+                for (int rt = kb + 1; rt < NB; ++rt) {
+                    c2 a = ld_ctile<C>(W, rt * 8, c0);
+                    tile_mma<C, false, MASK_NONE, true>(a, LU, rt * 8, kb * 8, W, kb * 8, c0);
+                    st_ctile<C>(W, rt * 8, c0, a);
                 }
+                __syncwarp();
             }
-        __syncwarp();
-        // L y = x (unit lower)
-        for (int k = 0; k < C::NP; ++k) {
-            double xr = 0., xi = 0.;
-            if (part == k % P) { xr = Xr[k * C::LD + c]; xi = Xi[k * C::LD + c]; }
-            xr = __shfl_sync(0xffffffffu, xr, gbase + k % P);
-            xi = __shfl_sync(0xffffffffu, xi, gbase + k % P);
-            int i = k + 1; i += ((part - i) % P + P) % P;
-            for (; i < C::NP; i += P) {
-                const double lr = Lr[i * C::LD + k], li = Li[i * C::LD + k];
-                Xr[i * C::LD + c] -= lr * xr - li * xi;
-                Xi[i * C::LD + c] -= lr * xi + li * xr;
-            }
-        }
-        // U z = y
-        for (int k = C::NP - 1; k >= 0; --k) {
-            double xr = 0., xi = 0.;
-            if (part == k % P) {
-                const cplx inv = crecip({Lr[k * C::LD + k], Li[k * C::LD + k]});
-                const cplx v = cmul({Xr[k * C::LD + c], Xi[k * C::LD + c]}, inv);
-                Xr[k * C::LD + c] = v.r; Xi[k * C::LD + c] = v.i; xr = v.r; xi = v.i;
-            }
-            xr = __shfl_sync(0xffffffffu, xr, gbase + k % P);
-            xi = __shfl_sync(0xffffffffu, xi, gbase + k % P);
-            for (int i = part; i < k; i += P) {
-                const double ur = Lr[i * C::LD + k], ui = Li[i * C::LD + k];
-                Xr[i * C::LD + c] -= ur * xr - ui * xi;
-                Xi[i * C::LD + c] -= ur * xi + ui * xr;
-            }
-        }
-    } else {
-        // U^T y = x : forward substitution with rows of U
-        for (int k = 0; k < C::NP; ++k) {
-            double xr = 0., xi = 0.;
-            if (part == k % P) {
-                const cplx inv = crecip({Lr[k * C::LD + k], Li[k * C::LD + k]});
-                const cplx v = cmul({Xr[k * C::LD + c], Xi[k * C::LD + c]}, inv);
-                Xr[k * C::LD + c] = v.r; Xi[k * C::LD + c] = v.i; xr = v.r; xi = v.i;
-            }
-            xr = __shfl_sync(0xffffffffu, xr, gbase + k % P);
-            xi = __shfl_sync(0xffffffffu, xi, gbase + k % P);
-            int i = k + 1; i += ((part - i) % P + P) % P;
-            for (; i < C::NP; i += P) {
-                const double ur = Lr[k * C::LD + i], ui = Li[k * C::LD + i];
-                Xr[i * C::LD + c] -= ur * xr - ui * xi;
-                Xi[i * C::LD + c] -= ur * xi + ui * xr;
-            }
-        }
-        // L^T z = y : backward substitution with rows of L (unit diagonal)
-        for (int k = C::NP - 1; k >= 0; --k) {
-            double xr = 0., xi = 0.;
-            if (part == k % P) { xr = Xr[k * C::LD + c]; xi = Xi[k * C::LD + c]; }
-            xr = __shfl_sync(0xffffffffu, xr, gbase + k % P);
-            xi = __shfl_sync(0xffffffffu, xi, gbase + k % P);
-            for (int i = part; i < k; i += P) {
-                const double lr = Lr[k * C::LD + i], li = Li[k * C::LD + i];
-                Xr[i * C::LD + c] -= lr * xr - li * xi;
-                Xi[i * C::LD + c] -= lr * xi + li * xr;
-            }
-        }
-        __syncwarp();
-        if (part == 0)
-            for (int k = C::NP - 1; k >= 0; --k) {
-                const int p = piv[k];
-                if (p != k) {
-                    double t0 = Xr[k * C::LD + c]; Xr[k * C::LD + c] = Xr[p * C::LD + c]; Xr[p * C::LD + c] = t0;
-                    t0 = Xi[k * C::LD + c]; Xi[k * C::LD + c] = Xi[p * C::LD + c]; Xi[p * C::LD + c] = t0;
+            for (int kb = NB - 1; kb >= 0; --kb) {                 // U x = z
+                c2 z = czero();
+                tile_mma<C, false, MASK_UINV, false>(z, LU, kb * 8, kb * 8, W, kb * 8, c0);
+                __syncwarp();
+                st_ctile<C>(W, kb * 8, c0, z);
+                __syncwarp();
+                for (int rt = 0; rt < kb; ++rt) {
+                    c2 a = ld_ctile<C>(W, rt * 8, c0);
+                    tile_mma<C, false, MASK_NONE, true>(a, LU, rt * 8, kb * 8, W, kb * 8, c0);
+                    st_ctile<C>(W, rt * 8, c0, a);
                 }
+                __syncwarp();
             }
+        } else {
+            for (int kb = 0; kb < NB; ++kb) {                      // U^T y = b
+                c2 z = czero();
+                tile_mma<C, true, MASK_UINV, false>(z, LU, kb * 8, kb * 8, W, kb * 8, c0);
+                __syncwarp();
+                st_ctile<C>(W, kb * 8, c0, z);
+                __syncwarp();
+                for (int rt = kb + 1; rt < NB; ++rt) {
+                    c2 a = ld_ctile<C>(W, rt * 8, c0);
+                    tile_mma<C, true, MASK_NONE, true>(a, LU, rt * 8, kb * 8, W, kb * 8, c0);
+                    st_ctile<C>(W, rt * 8, c0, a);
+                }
+                __syncwarp();
+            }
+            for (int kb = NB - 1; kb >= 0; --kb) {                 // L^T z = y
+                c2 z = czero();
+                tile_mma<C, true, MASK_LINV, false>(z, LU, kb * 8, kb * 8, W, kb * 8, c0);
+                __syncwarp();
+                st_ctile<C>(W, kb * 8, c0, z);
+                __syncwarp();
+                for (int rt = 0; rt < kb; ++rt) {
+                    c2 a = ld_ctile<C>(W, rt * 8, c0);
+                    tile_mma<C, true, MASK_NONE, true>(a, LU, rt * 8, kb * 8, W, kb * 8, c0);
+                    st_ctile<C>(W, rt * 8, c0, a);
+                }
+                __syncwarp();
+            }
+        }
     }
     __syncthreads();
+    if (TRANS) {                                                   // X[perm[i]] = W[i]
+        for (int idx = threadIdx.x; idx < 2 * C::NP * (C::NP / 2); idx += C::NT) {
+            const int plane = idx / (C::NP * (C::NP / 2)), rem = idx % (C::NP * (C::NP / 2));
+            const int row = rem / (C::NP / 2), cc = rem % (C::NP / 2);
+            *reinterpret_cast<double2 *>(X + plane * C::PLANE + perm[row] * C::LD + 2 * cc) =
+                *reinterpret_cast<const double2 *>(W + plane * C::PLANE + row * C::LD + 2 * cc);
+        }
+        __syncthreads();
+    }
 }
 
 // block-wide sum of NV doubles per thread -> result valid in all threads; red needs NV * NWARP doubles
