@@ -226,41 +226,74 @@ template <class C> __device__ __forceinline__ void st_ctile(double *M, int r0, i
 // of the diagonal block's triangular factors.  piv8: shared int[8]; perm: shared int[NP].
 template <class C>
 __device__ void lu_panel_warp(double *Q, int *perm, int *piv8, int j0) {
+    // Register-resident panel: lane owns panel rows j0 + lane (a) and j0 + lane + 32 (b).  Rows are not moved
+    // while the panel is factored; each row tracks the POSITION it would occupy under LAPACK's sequential swaps
+    // (pos), the pivot is found with one integer REDUX on the high word of |re| + |im| (ties inside 2^-20 are
+    // resolved towards the smaller row - any of them is an admissible pivot), and the pivot row is broadcast
+    // with shuffles.  Rows are written back to their final positions at the end.
+    constexpr bool TWO = C::NP > 32;
+    constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     double *Qr = Q, *Qi = Q + C::PLANE;
-    for (int j = 0; j < 8; ++j) {
-        const int col = j0 + j;
-        double best = -1.0; int bi = col;
-        for (int r = col + lane; r < C::NP; r += 32) {
-            const double v = fabs(Qr[r * C::LD + col]) + fabs(Qi[r * C::LD + col]);
-            if (v > best) { best = v; bi = r; }
-        }
+    const int ra = j0 + lane, rb = j0 + lane + 32;
+    const bool va = ra < C::NP, vb = TWO && rb < C::NP;
+    cplx pa[8], pb[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        const int p = bi;
-        if (lane == 0) { piv8[j] = p; const int tp = perm[col]; perm[col] = perm[p]; perm[p] = tp; }
-        if (p != col && lane < 16) {
-            double *pl = Q + (lane >> 3) * C::PLANE;
-            const int c = j0 + (lane & 7);
-            const double t0 = pl[col * C::LD + c]; pl[col * C::LD + c] = pl[p * C::LD + c]; pl[p * C::LD + c] = t0;
-        }
-        __syncwarp();
-        const cplx inv = crecip({Qr[col * C::LD + col], Qi[col * C::LD + col]});
-        for (int r = col + 1 + lane; r < C::NP; r += 32) {
-            const cplx l = cmul({Qr[r * C::LD + col], Qi[r * C::LD + col]}, inv);
-            Qr[r * C::LD + col] = l.r; Qi[r * C::LD + col] = l.i;
-            for (int c = col + 1; c < j0 + 8; ++c) {
-                const double ur = Qr[col * C::LD + c], ui = Qi[col * C::LD + c];
-                Qr[r * C::LD + c] -= l.r * ur - l.i * ui;
-                Qi[r * C::LD + c] -= l.r * ui + l.i * ur;
+    for (int c = 0; c < 8; ++c) {
+        pa[c] = va ? cplx{Qr[ra * C::LD + j0 + c], Qi[ra * C::LD + j0 + c]} : cplx{0., 0.};
+        pb[c] = vb ? cplx{Qr[rb * C::LD + j0 + c], Qi[rb * C::LD + j0 + c]} : cplx{0., 0.};
+    }
+    int posa = ra, posb = rb;
+    bool useda = !va, usedb = !vb;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ka = useda ? -1 : __double2hiint(fabs(pa[j].r) + fabs(pa[j].i));
+        const int kb = usedb ? -1 : __double2hiint(fabs(pb[j].r) + fabs(pb[j].i));
+        // smallest POSITION among the maxima, to follow izamax on the swapped matrix
+        const int kmax = __reduce_max_sync(FULL, max(ka, kb));
+        const int ca = (ka == kmax) ? posa : 0x7fffffff, cb = (kb == kmax) ? posb : 0x7fffffff;
+        const int q = __reduce_min_sync(FULL, min(ca, cb));                 // position of the pivot row
+        const bool mine_a = (!useda && posa == q), mine_b = (!usedb && posb == q);
+        const unsigned ba = __ballot_sync(FULL, mine_a), bb = __ballot_sync(FULL, mine_b);
+        const bool from_a = ba != 0u;
+        const int owner = __ffs(from_a ? ba : bb) - 1;
+        cplx u[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= j) {
+                const double sr = from_a ? pa[c].r : pb[c].r, si = from_a ? pa[c].i : pb[c].i;
+                u[c].r = __shfl_sync(FULL, sr, owner); u[c].i = __shfl_sync(FULL, si, owner);
             }
         }
-        __syncwarp();
+        // LAPACK swap of positions j0 + j and q
+        const int tgt = j0 + j;
+        if (posa == tgt && !mine_a) posa = q;
+        if (posb == tgt && !mine_b) posb = q;
+        if (mine_a) { posa = tgt; useda = true; }
+        if (mine_b) { posb = tgt; usedb = true; }
+        if (lane == 0) { piv8[j] = q; const int tp = perm[tgt]; perm[tgt] = perm[q]; perm[q] = tp; }
+        const double dn = 1.0 / (u[j].r * u[j].r + u[j].i * u[j].i);
+        const cplx inv = {u[j].r * dn, -u[j].i * dn};
+        if (!useda) {
+            const cplx l = cmul(pa[j], inv);
+            pa[j] = l;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) if (c > j) { pa[c].r -= l.r * u[c].r - l.i * u[c].i; pa[c].i -= l.r * u[c].i + l.i * u[c].r; }
+        }
+        if (TWO && !usedb) {
+            const cplx l = cmul(pb[j], inv);
+            pb[j] = l;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) if (c > j) { pb[c].r -= l.r * u[c].r - l.i * u[c].i; pb[c].i -= l.r * u[c].i + l.i * u[c].r; }
+        }
     }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (va) { Qr[posa * C::LD + j0 + c] = pa[c].r; Qi[posa * C::LD + j0 + c] = pa[c].i; }
+        if (vb) { Qr[posb * C::LD + j0 + c] = pb[c].r; Qi[posb * C::LD + j0 + c] = pb[c].i; }
+    }
+    __syncwarp();
     // invert the diagonal block's factors: lanes 0-7 one column of inv(L_kk), lanes 8-15 one column of inv(U_kk)
     cplx x[8];
     const int c = lane & 7;
