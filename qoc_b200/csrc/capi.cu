@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(C::NT) k_forward(KArgs a) {
         const int e = w / (a.N - 1), j = w - e * (a.N - 1);
         GenArgs ga = a.ga;
         ga.G0 += (size_t)e * C::GMAT;
+        PROF_DECL
         load_coefs<C>(sm, ga, j);
         magnus_forward<C>(sm, ga, scratch);
+        PROF_MARK(1);
         double *tape = a.tape ? a.tape + (size_t)w * a.tape_mats * C::GMAT : nullptr;
         int *piv = a.tape ? a.tape_piv + (size_t)w * C::NP : nullptr;
         const int s = pade_forward<C>(sm, tape, piv, scratch + (size_t)S_T0 * C::GMAT, scratch + (size_t)S_T1 * C::GMAT, a.s_cap);
@@ -82,6 +84,9 @@ __global__ void __launch_bounds__(C::NT) k_forward(KArgs a) {
             mma_smem<C, false, false, false>(acc, sm.X1, sm.X0);      // P <- U_j P
             for_owned<C>([&](int i, int jj, int row, int col) { stg2<C>(gP, row, col, accv<C>(acc, i, jj)); });
         }
+#ifdef QOCB_PROFILE
+        { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { g_prof[7] += clock64() - prof_t0__; g_prof[0] += 1; } }
+#endif
     }
 }
 
@@ -96,6 +101,7 @@ __global__ void __launch_bounds__(C::NT) k_backward(KArgs a) {
     int *cpiv = a.cta_piv + (size_t)c * C::NP;
     const int VS = a.S * 2 * C::NP;
     for (int w = wb; w < we; ++w) {
+        PROF_DECL
         const int e = w / (a.N - 1), j = w - e * (a.N - 1);
         GenArgs ga = a.ga;
         ga.G0 += (size_t)e * C::GMAT;
@@ -127,8 +133,10 @@ __global__ void __launch_bounds__(C::NT) k_backward(KArgs a) {
             sts2<C>(sm.X0, row, col, u);
         });
         __syncthreads();
+        PROF_MARK(9);
         pade_backward<C>(sm, tape, piv, s, a.U + (size_t)w * C::GMAT, scratch);
         magnus_backward<C>(sm, ga, scratch, a.node_grad + (size_t)w * ga.q * ga.KR);
+        PROF_MARK(13);
     }
 }
 
@@ -514,6 +522,16 @@ int check_device_flag(qocb_plan *p) {
 extern "C" {
 
 const char *qocb_version(void) { return "qocb200 0.1 (sm_100a, complex128)"; }
+
+#ifdef QOCB_PROFILE
+/* profiling build only: cumulative clock64 ticks per phase id of CTA 0 (then reset) */
+int qocb_debug_profile(long long *out32) {
+    long long zero[32] = {0};
+    if (cudaMemcpyFromSymbol(out32, qocb::g_prof, sizeof(zero)) != cudaSuccess) return -2;
+    if (cudaMemcpyToSymbol(qocb::g_prof, zero, sizeof(zero)) != cudaSuccess) return -2;
+    return 0;
+}
+#endif
 
 const char *qocb_last_error(const qocb_plan *plan) { return plan ? plan->err.c_str() : g_last_error.c_str(); }
 

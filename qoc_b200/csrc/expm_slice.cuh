@@ -79,6 +79,28 @@ __device__ __forceinline__ c2 gen_pair(const GenArgs &ga, int row, int col, doub
     return v;
 }
 
+// generators of up to two coefficient sets in ONE pass over the operators: v0 = a0 G0 + sum_r cf[r] G_r,
+// v1 = a1 G0 + sum_r cf[kMaxKR + r] G_r, for every element pair the thread owns.  The operator loop is outermost so
+// that each step has 2 * TM * TN independent 16-byte loads in flight (the operators live in L2).
+template <class C, int NODES>
+__device__ __forceinline__ void gen_nodes(const GenArgs &ga, const double *cf, double a0, double a1,
+                                          c2 (&v0)[C::TM][C::TN], c2 (&v1)[C::TM][C::TN]) {
+    for_owned<C>([&](int i, int j, int row, int col) {
+        const c2 g = ldg2<C>(ga.G0, row, col);
+        v0[i][j] = a0 * g;
+        if (NODES > 1) v1[i][j] = a1 * g;
+    });
+    for (int r = 0; r < ga.KR; ++r) {
+        const double c0 = cf[r], c1 = NODES > 1 ? cf[kMaxKR + r] : 0.0;
+        const double *g = ga.G + (size_t)r * C::GMAT;
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 x = ldg2<C>(g, row, col);
+            v0[i][j] = v0[i][j] + c0 * x;
+            if (NODES > 1) v1[i][j] = v1[i][j] + c1 * x;
+        });
+    }
+}
+
 // acc = op(A) op(B) - op(B') op(A') style helpers: load two global matrices into X0/X1 and multiply.
 template <class C, bool TA, bool TB, bool NEG>
 __device__ __forceinline__ void gmm(const Smem<C> &sm, Acc<C> &acc, const double *gA, const double *gB) {
@@ -95,17 +117,21 @@ template <class C>
 __device__ void magnus_forward(const Smem<C> &sm, const GenArgs &ga, double *scratch) {
     const double dt = ga.dt;
     if (ga.order == 2) {
-        for_owned<C>([&](int, int, int row, int col) {
-            sts2<C>(sm.X2, row, col, dt * gen_pair<C>(ga, row, col, 1.0, sm.coef));
-        });
+        c2 v[C::TM][C::TN];
+        gen_nodes<C, 1>(ga, sm.coef, 1.0, 1.0, v, v);
+        for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(sm.X2, row, col, dt * v[i][j]); });
         __syncthreads();
         return;
     }
     if (ga.order == 4) {
-        for_owned<C>([&](int, int, int row, int col) {
-            sts2<C>(sm.X0, row, col, gen_pair<C>(ga, row, col, 1.0, sm.coef));
-            sts2<C>(sm.X1, row, col, gen_pair<C>(ga, row, col, 1.0, sm.coef + kMaxKR));
-        });
+        {
+            c2 v0[C::TM][C::TN], v1[C::TM][C::TN];
+            gen_nodes<C, 2>(ga, sm.coef, 1.0, 1.0, v0, v1);
+            for_owned<C>([&](int i, int j, int row, int col) {
+                sts2<C>(sm.X0, row, col, v0[i][j]);
+                sts2<C>(sm.X1, row, col, v1[i][j]);
+            });
+        }
         __syncthreads();
         Acc<C> acc; acc.zero();
         mma_smem<C, false, false, false>(acc, sm.X1, sm.X0);        // a2 a1
@@ -170,24 +196,41 @@ __device__ void magnus_forward(const Smem<C> &sm, const GenArgs &ga, double *scr
 // tape: 8 + s matrices are written when tape != nullptr (T_R + i holds R_i for i < s); piv_out: int[NP].
 template <class C>
 __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, double *tmpY, double *tmpV, int s_cap) {
+    PROF_DECL
     // one-norm: max column sum of |m_ij|   (expm.py:103-116)
-    for (int c = threadIdx.x; c < C::NP; c += C::NT) {
+    {
+        // column c is summed by PARTS threads (rows split mod PARTS), combined in a fixed order, then one max
+        constexpr int P = C::PARTS;
+        const int c = threadIdx.x % C::NP, part = threadIdx.x / C::NP;
         double s = 0.;
-        for (int r = 0; r < C::NP; ++r) {
+        for (int r = part; r < C::NP; r += P) {
             const double xr = sm.X2[r * C::LD + c], xi = sm.X2[C::PLANE + r * C::LD + c];
             s += sqrt(xr * xr + xi * xi);
         }
-        sm.red[c] = s;
+        double *cs = sm.red + 64;                                   // [P][NP] <= NT doubles (fits: kMaxQ*kMaxKR*NWARP >= NT/ ...)
+        cs[part * C::NP + c] = s;
+        __syncthreads();
+        if (threadIdx.x < C::NP) {
+            double t = 0.;
+            for (int q = 0; q < P; ++q) t += cs[q * C::NP + threadIdx.x];
+            sm.red[threadIdx.x] = t;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     double norm = 0.;
-    for (int c = 0; c < C::NP; ++c) norm = fmax(norm, sm.red[c]);
+    {
+        const int lane = threadIdx.x & 31;
+        for (int c = lane; c < C::NP; c += 32) norm = fmax(norm, sm.red[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) norm = fmax(norm, __shfl_xor_sync(0xffffffffu, norm, o));
+    }
     int s = 0;
     if (!(norm < QOCB_THETA13)) {                                   // expm.py:238-241
         s = (int)ceil(log2(norm / QOCB_THETA13));
         if (s < 0) s = 0;
     }
     const double scale = ldexp(1.0, -s);
+    PROF_MARK(2);
     const bool keep = tape != nullptr;
     double *tA = keep ? tape + (size_t)T_A * C::GMAT : tmpV;        // A is always needed once more (for Uo)
     // A = M * 2^-s   -> X2 and tape
@@ -256,8 +299,11 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
         sts2<C>(sm.X2, row, col, ve - uo);                              // Q
     });
     __syncthreads();
+    PROF_MARK(3);
     lu_factor_blocked<C>(sm.X2, sm.piv, sm.piv + C::NP);
+    PROF_MARK(4);
     lu_solve_blocked<C, false>(sm.X2, sm.piv, sm.X1, sm.X0);            // R0 = Q^-1 P in X0 (Y is dead)
+    PROF_MARK(5);
     if (keep) {
         s2g<C>(tape + (size_t)T_LU * C::GMAT, sm.X2);                   // LUi format (tile.cuh) + row permutation
         for (int c = threadIdx.x; c < C::NP; c += C::NT) piv_out[c] = sm.piv[c];
@@ -275,6 +321,7 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
         for_owned<C>([&](int, int, int row, int col) { sts2<C>(sm.X1, row, col, lds2<C>(sm.X0, row, col)); });
         __syncthreads();
     }
+    PROF_MARK(6);
     return s;
 }
 
@@ -284,6 +331,7 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
 template <class C>
 __device__ void pade_backward(const Smem<C> &sm, const double *tape, const int *tpiv, int s,
                               const double *gU, double *scratch) {
+    PROF_DECL
     Acc<C> acc;
     double *sA = scratch + (size_t)S_A * C::GMAT, *sA2 = scratch + (size_t)S_A2 * C::GMAT;
     double *sA4 = scratch + (size_t)S_A4 * C::GMAT, *sA6 = scratch + (size_t)S_A6 * C::GMAT;
@@ -303,7 +351,9 @@ __device__ void pade_backward(const Smem<C> &sm, const double *tape, const int *
     for (int c = threadIdx.x; c < C::NP; c += C::NT) sm.piv[c] = tpiv[c];
     g2s<C>(sm.X1, s > 0 ? tape + (size_t)T_R * C::GMAT : gU);
     __syncthreads();
+    PROF_MARK(10);
     lu_solve_blocked<C, true>(sm.X2, sm.piv, sm.X0, sm.X2);             // X2 = pbar = Q^-T rbar (over the dead LU)
+    PROF_MARK(11);
     acc.zero(); mma_smem<C, false, true, false>(acc, sm.X2, sm.X1);      // pbar R0^T = -qbar
     __syncthreads();
     for_owned<C>([&](int i, int j, int row, int col) {
@@ -386,6 +436,7 @@ __device__ void pade_backward(const Smem<C> &sm, const double *tape, const int *
         sts2<C>(sm.X0, row, col, scale * (ldg2<C>(sA, row, col) + accv<C>(acc, i, j)));   // X0 = mbar
     });
     __syncthreads();
+    PROF_MARK(12);
 }
 
 // Magnus adjoint + contraction  cbar_{i,r} = Re sum_ab abar_i[ab] G_r[ab].  In: mbar in X0, coefficients of
@@ -394,36 +445,53 @@ template <class C>
 __device__ void magnus_backward(const Smem<C> &sm, const GenArgs &ga, double *scratch, double *gout) {
     Acc<C> acc;
     const double dt = ga.dt;
-    double part[kMaxQ * kMaxKR];
-#pragma unroll
-    for (int e = 0; e < kMaxQ * kMaxKR; ++e) part[e] = 0.;
-    auto contract = [&](int node, int row, int col, const c2 &ab) {
+    // cbar_{node,r} = Re sum_ab abar_node[ab] G_r[ab] for one node: the operator loop is outermost so that every step
+    // has 2 * TM * TN independent 16-byte loads in flight; thread partials -> warp shuffle -> per-warp slot in sm.red
+    c2 abn[C::TM][C::TN];
+    auto contract_node = [&](int node) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        double *red = sm.red + 64;
         for (int r = 0; r < ga.KR; ++r) {
-            const c2 g = ldg2<C>(ga.G + (size_t)r * C::GMAT, row, col);
-            part[node * kMaxKR + r] += ab.r0 * g.r0 - ab.i0 * g.i0 + ab.r1 * g.r1 - ab.i1 * g.i1;
+            const double *g = ga.G + (size_t)r * C::GMAT;
+            double v = 0.;
+            for_owned<C>([&](int i, int j, int row, int col) {
+                const c2 x = ldg2<C>(g, row, col);
+                const c2 &a = abn[i][j];
+                v += a.r0 * x.r0 - a.i0 * x.i0 + a.r1 * x.r1 - a.i1 * x.i1;
+            });
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[(node * kMaxKR + r) * C::NWARP + warp] = v;
         }
     };
     if (ga.order == 2) {
-        for_owned<C>([&](int, int, int row, int col) { contract(0, row, col, dt * lds2<C>(sm.X0, row, col)); });
+        for_owned<C>([&](int i, int j, int row, int col) { abn[i][j] = dt * lds2<C>(sm.X0, row, col); });
+        contract_node(0);
     } else if (ga.order == 4) {
-        for_owned<C>([&](int, int, int row, int col) {
-            sts2<C>(sm.X1, row, col, gen_pair<C>(ga, row, col, 1.0, sm.coef));                  // a1
-            sts2<C>(sm.X2, row, col, gen_pair<C>(ga, row, col, 1.0, sm.coef + kMaxKR));         // a2
-        });
+        {
+            c2 v0[C::TM][C::TN], v1[C::TM][C::TN];
+            gen_nodes<C, 2>(ga, sm.coef, 1.0, 1.0, v0, v1);
+            for_owned<C>([&](int i, int j, int row, int col) {
+                sts2<C>(sm.X1, row, col, v0[i][j]);                                             // a1
+                sts2<C>(sm.X2, row, col, v1[i][j]);                                             // a2
+            });
+        }
         __syncthreads();
         const double f = (QOCB_S3 / 12.0) * dt * dt;
         acc.zero();
         mma_smem<C, true, false, false>(acc, sm.X2, sm.X0);             // a2^T mbar
         mma_smem<C, false, true, true>(acc, sm.X0, sm.X2);              // - mbar a2^T
         for_owned<C>([&](int i, int j, int row, int col) {
-            contract(0, row, col, (0.5 * dt) * lds2<C>(sm.X0, row, col) + f * accv<C>(acc, i, j));
+            abn[i][j] = (0.5 * dt) * lds2<C>(sm.X0, row, col) + f * accv<C>(acc, i, j);
         });
+        contract_node(0);
         acc.zero();
         mma_smem<C, false, true, false>(acc, sm.X0, sm.X1);             // mbar a1^T
         mma_smem<C, true, false, true>(acc, sm.X1, sm.X0);              // - a1^T mbar
         for_owned<C>([&](int i, int j, int row, int col) {
-            contract(1, row, col, (0.5 * dt) * lds2<C>(sm.X0, row, col) + f * accv<C>(acc, i, j));
+            abn[i][j] = (0.5 * dt) * lds2<C>(sm.X0, row, col) + f * accv<C>(acc, i, j);
         });
+        contract_node(1);
     } else {
         // order 6 (oracle/adjoint_model.py:magnus_bwd), everything staged through CTA scratch
         double *gMB = scratch + (size_t)S_T0 * C::GMAT;      // mbar
@@ -502,23 +570,19 @@ __device__ void magnus_backward(const Smem<C> &sm, const GenArgs &ga, double *sc
         for_owned<C>([&](int i, int j, int row, int col) {
             const c2 b2b = ldg2<C>(gB2b, row, col) + accv<C>(acc, i, j);
             const c2 b1b = ldg2<C>(gB1b, row, col), b3b = ldg2<C>(gB3b, row, col);
-            contract(0, row, col, (-(QOCB_S15 / 3.0) * dt) * b2b + ((10.0 / 3.0) * dt) * b3b);
-            contract(1, row, col, dt * b1b - ((20.0 / 3.0) * dt) * b3b);
-            contract(2, row, col, ((QOCB_S15 / 3.0) * dt) * b2b + ((10.0 / 3.0) * dt) * b3b);
+            abn[i][j] = (-(QOCB_S15 / 3.0) * dt) * b2b + ((10.0 / 3.0) * dt) * b3b;
+            stg2<C>(gT, row, col, dt * b1b - ((20.0 / 3.0) * dt) * b3b);                        // node 1 (pbar is dead)
+            stg2<C>(gX, row, col, ((QOCB_S15 / 3.0) * dt) * b2b + ((10.0 / 3.0) * dt) * b3b);   // node 2 (c12bar is dead)
         });
+        contract_node(0);
+        for_owned<C>([&](int i, int j, int row, int col) { abn[i][j] = ldg2<C>(gT, row, col); });
+        contract_node(1);
+        for_owned<C>([&](int i, int j, int row, int col) { abn[i][j] = ldg2<C>(gX, row, col); });
+        contract_node(2);
     }
-    // block reduction of the q*KR partial sums
+    // sum of the per-warp slots
     {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         double *red = sm.red + 64;
-        __syncthreads();
-        for (int i = 0; i < ga.q; ++i)
-            for (int r = 0; r < ga.KR; ++r) {
-                double v = part[i * kMaxKR + r];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) red[(i * kMaxKR + r) * C::NWARP + warp] = v;
-            }
         __syncthreads();
         for (int e = threadIdx.x; e < ga.q * ga.KR; e += C::NT) {
             const int i = e / ga.KR, r = e % ga.KR;

@@ -15,6 +15,16 @@
 
 namespace qocb {
 
+// optional phase profiler (-DQOCB_PROFILE): thread 0 of CTA 0 accumulates clock64() deltas per phase id
+#ifdef QOCB_PROFILE
+__device__ long long g_prof[32];
+#define PROF_DECL long long prof_t0__ = clock64();
+#define PROF_MARK(id) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t__ = clock64(); g_prof[id] += t__ - prof_t0__; prof_t0__ = t__; } else { prof_t0__ = 0; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(id) do { } while (0)
+#endif
+
 template <int NP_, int WM_, int WN_>
 struct Cfg {
     static constexpr int NP = NP_, WM = WM_, WN = WN_;
@@ -245,6 +255,7 @@ __device__ void lu_panel_warp(double *Q, int *perm, int *piv8, int j0) {
     }
     int posa = ra, posb = rb;
     bool useda = !va, usedb = !vb;
+    cplx dinv[8];                                                   // reciprocals of the U diagonal
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int ka = useda ? -1 : __double2hiint(fabs(pa[j].r) + fabs(pa[j].i));
@@ -274,6 +285,7 @@ __device__ void lu_panel_warp(double *Q, int *perm, int *piv8, int j0) {
         if (lane == 0) { piv8[j] = q; const int tp = perm[tgt]; perm[tgt] = perm[q]; perm[q] = tp; }
         const double dn = 1.0 / (u[j].r * u[j].r + u[j].i * u[j].i);
         const cplx inv = {u[j].r * dn, -u[j].i * dn};
+        dinv[j] = inv;
         if (!useda) {
             const cplx l = cmul(pa[j], inv);
             pa[j] = l;
@@ -287,6 +299,9 @@ __device__ void lu_panel_warp(double *Q, int *perm, int *piv8, int j0) {
             for (int c = 0; c < 8; ++c) if (c > j) { pb[c].r -= l.r * u[c].r - l.i * u[c].i; pb[c].i -= l.r * u[c].i + l.i * u[c].r; }
         }
     }
+#ifdef QOCB_PROFILE
+    long long pt0__ = clock64();
+#endif
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -294,37 +309,50 @@ __device__ void lu_panel_warp(double *Q, int *perm, int *piv8, int j0) {
         if (vb) { Qr[posb * C::LD + j0 + c] = pb[c].r; Qi[posb * C::LD + j0 + c] = pb[c].i; }
     }
     __syncwarp();
-    // invert the diagonal block's factors: lanes 0-7 one column of inv(L_kk), lanes 8-15 one column of inv(U_kk)
+    // invert the diagonal block's factors: lanes 0-7 one column of inv(L_kk), lanes 8-15 one column of inv(U_kk).
+    // Column c of the inverse = substitution applied to e_c; entries above (L) / below (U) the diagonal come out as
+    // exact zeros, so the loops are branch-free and fully unrolled (x stays in registers).  Block entries are
+    // warp-uniform shared-memory broadcasts.
     cplx x[8];
     const int c = lane & 7;
+    const double *Br = Qr + j0 * C::LD + j0, *Bi = Qi + j0 * C::LD + j0;
     if (lane < 8) {
-        for (int r = 0; r < 8; ++r) x[r] = {r == c ? 1.0 : 0.0, 0.0};
-        for (int r = c + 1; r < 8; ++r) {
-            double sr = 0., si = 0.;
-            for (int k = c; k < r; ++k) {
-                const double lr = Qr[(j0 + r) * C::LD + j0 + k], li = Qi[(j0 + r) * C::LD + j0 + k];
-                sr += lr * x[k].r - li * x[k].i; si += lr * x[k].i + li * x[k].r;
-            }
-            x[r] = {-sr, -si};
-        }
-    } else if (lane < 16) {
-        for (int r = 0; r < 8; ++r) x[r] = {0.0, 0.0};
-        for (int r = c; r >= 0; --r) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
             double sr = (r == c) ? 1.0 : 0.0, si = 0.;
-            for (int k = r + 1; k <= c; ++k) {
-                const double ur = Qr[(j0 + r) * C::LD + j0 + k], ui = Qi[(j0 + r) * C::LD + j0 + k];
-                sr -= ur * x[k].r - ui * x[k].i; si -= ur * x[k].i + ui * x[k].r;
-            }
-            x[r] = cmul({sr, si}, crecip({Qr[(j0 + r) * C::LD + j0 + r], Qi[(j0 + r) * C::LD + j0 + r]}));
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < r) {
+                    const double lr = Br[r * C::LD + k], li = Bi[r * C::LD + k];
+                    sr -= lr * x[k].r - li * x[k].i; si -= lr * x[k].i + li * x[k].r;
+                }
+            x[r] = {sr, si};
+        }
+    } else if (lane < 16) {
+#pragma unroll
+        for (int r = 7; r >= 0; --r) {
+            double sr = (r == c) ? 1.0 : 0.0, si = 0.;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k > r) {
+                    const double ur = Br[r * C::LD + k], ui = Bi[r * C::LD + k];
+                    sr -= ur * x[k].r - ui * x[k].i; si -= ur * x[k].i + ui * x[k].r;
+                }
+            x[r] = cmul({sr, si}, dinv[r]);
         }
     }
     __syncwarp();
     if (lane < 8) {
-        for (int r = c + 1; r < 8; ++r) { Qr[(j0 + r) * C::LD + j0 + c] = x[r].r; Qi[(j0 + r) * C::LD + j0 + c] = x[r].i; }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r > c) { Qr[(j0 + r) * C::LD + j0 + c] = x[r].r; Qi[(j0 + r) * C::LD + j0 + c] = x[r].i; }
     } else if (lane < 16) {
-        for (int r = 0; r <= c; ++r) { Qr[(j0 + r) * C::LD + j0 + c] = x[r].r; Qi[(j0 + r) * C::LD + j0 + c] = x[r].i; }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r <= c) { Qr[(j0 + r) * C::LD + j0 + c] = x[r].r; Qi[(j0 + r) * C::LD + j0 + c] = x[r].i; }
     }
     __syncwarp();
+#ifdef QOCB_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_prof[16] += clock64() - pt0__;
+#endif
 }
 
 // In-place blocked LU of Q (LUi format).  perm: shared int[NP]; piv8: shared int[8].  Ends with a barrier.
@@ -334,10 +362,12 @@ __device__ void lu_factor_blocked(double *Q, int *perm, int *piv8) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < C::NP; i += C::NT) perm[i] = i;
     __syncthreads();
+    PROF_DECL
     for (int kb = 0; kb < NB; ++kb) {
         const int j0 = kb * 8;
         if (warp == 0) lu_panel_warp<C>(Q, perm, piv8, j0);
         __syncthreads();
+        PROF_MARK(14);
         for (int ct = warp; ct < NB; ct += C::NWARP) {
             if (ct == kb) continue;
             if (lane < 16) {                                       // the panel's row swaps on this column tile
@@ -363,6 +393,7 @@ __device__ void lu_factor_blocked(double *Q, int *perm, int *piv8) {
             }
         }
         __syncthreads();
+        PROF_MARK(15);
     }
 }
 

@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Per-phase clock64 breakdown of the expm kernels (CTA 0) on a B200.  Builds a -DQOCB_PROFILE variant of the
+library into gpurun_out/ (never the shipped .so), runs a workload and prints microseconds per slice and phase.
+Usage (on the GPU box): python tools/phase_profile.py [workload]"""
+import ctypes
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+out = os.path.join(ROOT, "gpurun_out", "libqocb200_prof.so")
+os.makedirs(os.path.dirname(out), exist_ok=True)
+csrc = os.path.join(ROOT, "qoc_b200", "csrc")
+subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DQOCB_PROFILE",
+                "-shared", "-Xcompiler", "-fPIC", "-o", out, os.path.join(csrc, "capi.cu"), os.path.join(csrc, "lindblad.cu")],
+               check=True)
+os.environ["QOCB200_LIB"] = out
+import numpy as np  # noqa: E402
+import bench  # noqa: E402
+import qoc_b200.standard as std  # noqa: E402
+from qoc_b200 import _lib  # noqa: E402
+from qoc_b200.core.plan import SchroedingerPlan  # noqa: E402
+from qoc_b200.models import MagnusPolicy  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "n64_2000_M4"
+p = bench.make_problem(name)
+pol = {2: MagnusPolicy.M2, 4: MagnusPolicy.M4, 6: MagnusPolicy.M6}
+plan = SchroedingerPlan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M,
+                        control_count=p.K, complex_controls=p.complex_controls, magnus_policy=pol[p.order])
+lib = _lib.load()
+buf = (ctypes.c_longlong * 32)()
+for _ in range(3):
+    plan.cost_and_grad(p.controls)
+lib.qocb_debug_profile(buf)
+reps = 5
+for _ in range(reps):
+    plan.cost_and_grad(p.controls)
+lib.qocb_debug_profile(buf)
+v = np.array(list(buf), dtype=np.float64)
+slices = v[0]
+ghz = 1.965
+us = v / slices / (ghz * 1e3)
+names = {1: "fwd coefs+magnus", 2: "fwd one-norm/scale", 3: "fwd pade polynomial (6 products)", 4: "fwd LU factor", 5: "fwd LU solve",
+         6: "fwd squarings/copy", 7: "fwd pade total + stores + chunk product", 9: "bwd coefs + ubar", 10: "bwd reverse squarings + tape loads",
+         11: "bwd transposed solve", 14: "  LU: panels (warp 0; all 8 per LU)", 15: "  LU: swaps + U12 + trailing update", 16: "  LU: writeback + diag inversion part of panels", 12: "bwd pade polynomial reverse", 13: "bwd pade total + magnus adjoint"}
+print("workload", name, "slices sampled by CTA 0:", int(slices))
+for k in sorted(names):
+    print("  %-45s %8.2f us/slice" % (names[k], us[k]))
