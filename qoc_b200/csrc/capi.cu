@@ -277,13 +277,16 @@ struct qocb_plan {
     qocb_problem pb;
     int NP = 0, q = 0, nchunks = 0, tape_mats = 0, num_sms = 0;
     int j0 = 0, Nloc = 0;               // time sharding: first local slice (global index), local state count
+    // sweep coarsening: the state / costate sweeps run on chunks merged pairwise `levels` times (propagator tree);
+    // lvl_count[l] chunks at level l, their propagators at lvlP + lvl_off[l] matrices, boundaries at cb_lvl + cb_off[l]
+    int levels = 0, lvl_count[16] = {}, lvl_off[16] = {}, cb_off[16] = {};
     bool sharded = false, owns_final = true;
     bool ops_set = false, states_set = false, have_step_costs = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16] = {};
     DevBuf<double> G0, G, controls, itab_w, U, tape, scratch, cta_tape, chunkP, psi, lam, part, cost_part, psi0,
-        node_grad, grad, cost, csr_w, vecs, flush, redA, redB, psi_in, lam_in;
-    DevBuf<int> itab_idx, tape_piv, meta, cta_piv, chunk_begin, member_chunk0, csr_ptr, csr_idx, counts, err_flag;
+        node_grad, grad, cost, csr_w, vecs, flush, redA, redB, psi_in, lam_in, lvlP;
+    DevBuf<int> itab_idx, tape_piv, meta, cta_piv, chunk_begin, member_chunk0, csr_ptr, csr_idx, counts, err_flag, cb_lvl, mc0_lvl;
     DevBuf<CostTerm> terms;
     std::vector<CostTerm> h_terms;
     std::vector<double> h_vecs;
@@ -384,6 +387,11 @@ SweepArgs make_sargs(qocb_plan *p) {
     s.ces = p->pb.cost_eval_step; s.nterms = (int)p->h_terms.size(); s.ip_total = p->ip_total;
     s.terms = p->terms.p; s.vecs = p->vecs.p; s.counts = p->counts.p;
     s.U = p->U.p; s.chunkP = p->chunkP.p; s.chunk_begin = p->chunk_begin.p; s.member_chunk0 = p->member_chunk0.p;
+    if (p->levels > 0) {
+        s.chunkP = p->lvlP.p + (size_t)p->lvl_off[p->levels] * 2 * p->NP * p->NP;
+        s.chunk_begin = p->cb_lvl.p + p->cb_off[p->levels];
+        s.member_chunk0 = p->mc0_lvl.p + 2 * p->levels;
+    }
     s.psi = p->psi.p; s.lam = p->lam.p; s.part = p->part.p; s.cost_part = p->cost_part.p; s.psi_in = p->psi0.p;
     return s;
 }
@@ -408,24 +416,48 @@ template <class C> int launch_reduce(qocb_plan *p, const double *in, double *out
     return 0;
 }
 
+// the chunk-boundary passes are chains of dependent mat-vecs: spread the states over CTAs unless the member axis
+// already fills the machine
+int boundary_state_groups(const qocb_plan *p) {
+    const int S = p->pb.state_count;
+    if (p->pb.ensemble_count >= p->num_sms) return 1;
+    return std::min(S, 8);
+}
+
 int ready(qocb_plan *p) {
     if (!p->ops_set || !p->states_set) { set_error(p, "operators and states must be set before evaluation"); return -1; }
     return upload_costs(p);
 }
 
 // ---- pipeline phases (each only enqueues on the plan stream) -----------------------------------------------
+int reduce_level(qocb_plan *p, const double *in, double *out, int count) {
+    return dispatch(p->NP, [&] { return launch_reduce<C8>(p, in, out, count); }, [&] { return launch_reduce<C16>(p, in, out, count); },
+                    [&] { return launch_reduce<C32>(p, in, out, count); }, [&] { return launch_reduce<C64>(p, in, out, count); });
+}
+
 int enqueue_expm_forward(qocb_plan *p, bool with_grad) {
     KArgs ka = make_kargs(p);
     if (!with_grad) ka.tape = nullptr;
-    return dispatch(p->NP, [&] { return launch_forward<C8>(p, ka); }, [&] { return launch_forward<C16>(p, ka); },
-                    [&] { return launch_forward<C32>(p, ka); }, [&] { return launch_forward<C64>(p, ka); });
+    int rc = dispatch(p->NP, [&] { return launch_forward<C8>(p, ka); }, [&] { return launch_forward<C16>(p, ka); },
+                      [&] { return launch_forward<C32>(p, ka); }, [&] { return launch_forward<C64>(p, ka); });
+    if (rc) return rc;
+    // propagator tree up to the level the sweeps run on
+    const size_t GM = 2 * (size_t)p->NP * p->NP;
+    const double *in = p->chunkP.p;
+    for (int l = 1; l <= p->levels; ++l) {
+        double *out = p->lvlP.p + (size_t)p->lvl_off[l] * GM;
+        rc = reduce_level(p, in, out, p->lvl_count[l - 1]);
+        if (rc) return rc;
+        in = out;
+    }
+    return 0;
 }
 
 // product of all chunk propagators of this shard (member 0) -> out_dev[GMAT]
 int enqueue_shard_propagator(qocb_plan *p, double *out_dev) {
     const size_t GM = 2 * (size_t)p->NP * p->NP;
-    const double *in = p->chunkP.p;
-    int count = p->nchunks;
+    const double *in = p->levels > 0 ? p->lvlP.p + (size_t)p->lvl_off[p->levels] * GM : p->chunkP.p;   // continue the tree
+    int count = p->lvl_count[p->levels];
     double *bufs[2] = {p->redA.p, p->redB.p};
     int which = 0;
     if (count == 1) {
@@ -434,8 +466,7 @@ int enqueue_shard_propagator(qocb_plan *p, double *out_dev) {
     }
     while (count > 1) {
         double *out = (count <= 2) ? out_dev : bufs[which];
-        int rc = dispatch(p->NP, [&] { return launch_reduce<C8>(p, in, out, count); }, [&] { return launch_reduce<C16>(p, in, out, count); },
-                          [&] { return launch_reduce<C32>(p, in, out, count); }, [&] { return launch_reduce<C64>(p, in, out, count); });
+        int rc = reduce_level(p, in, out, count);
         if (rc) return rc;
         in = out; count = (count + 1) / 2; which ^= 1;
     }
@@ -446,9 +477,10 @@ int enqueue_state_forward(qocb_plan *p, const double *psi_in_dev, cudaEvent_t mi
     SweepArgs sa = make_sargs(p);
     sa.psi_in = psi_in_dev;
     const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
-    SWEEP_NP(p->NP, (k_boundary_fwd<NPc><<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa)));
+    const dim3 bgrid(sa.E, boundary_state_groups(p));
+    SWEEP_NP(p->NP, (k_boundary_fwd<NPc><<<bgrid, kSweepThreads, sw_smem, p->stream>>>(sa)));
     if (mid) cudaEventRecord(mid, p->stream);
-    SWEEP_NP(p->NP, (k_sweep_fwd<NPc><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa)));
+    SWEEP_NP(p->NP, (k_sweep_fwd<NPc><<<p->lvl_count[p->levels], kSweepThreads, sw_smem, p->stream>>>(sa)));
     CU_TRY(p, cudaGetLastError());
     return 0;
 }
@@ -459,9 +491,10 @@ int enqueue_costate(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, b
     SweepArgs sa = make_sargs(p);
     sa.lam_in = lam_in_dev; sa.b_out = b_out_dev;
     const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
-    if (do_particular && p->have_step_costs) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, true><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa)));
-    SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<sa.E, kSweepThreads, sw_smem, p->stream>>>(sa, p->have_step_costs ? 1 : 0)));
-    if (do_sweeps) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, false><<<p->nchunks, kSweepThreads, sw_smem, p->stream>>>(sa)));
+    if (do_particular && p->have_step_costs) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, true><<<p->lvl_count[p->levels], kSweepThreads, sw_smem, p->stream>>>(sa)));
+    const dim3 bgrid(sa.E, boundary_state_groups(p));
+    SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<bgrid, kSweepThreads, sw_smem, p->stream>>>(sa, p->have_step_costs ? 1 : 0)));
+    if (do_sweeps) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, false><<<p->lvl_count[p->levels], kSweepThreads, sw_smem, p->stream>>>(sa)));
     CU_TRY(p, cudaGetLastError());
     return 0;
 }
@@ -482,7 +515,7 @@ int enqueue_expm_backward(qocb_plan *p, cudaEvent_t mid) {
 }
 
 int enqueue_finalize(qocb_plan *p) {
-    k_finalize_cost<<<1, 32, 0, p->stream>>>(p->cost_part.p, p->nchunks, p->pb.ensemble_count, p->cost.p);
+    k_finalize_cost<<<1, 32, 0, p->stream>>>(p->cost_part.p, p->lvl_count[p->levels], p->pb.ensemble_count, p->cost.p);
     CU_TRY(p, cudaGetLastError());
     return 0;
 }
@@ -589,6 +622,44 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     PTRY(p->chunk_begin.alloc(cb.size())); PTRY(p->member_chunk0.alloc(mc0.size()));
     PTRY(cudaMemcpy(p->chunk_begin.p, cb.data(), sizeof(int) * cb.size(), cudaMemcpyHostToDevice));
     PTRY(cudaMemcpy(p->member_chunk0.p, mc0.data(), sizeof(int) * mc0.size(), cudaMemcpyHostToDevice));
+    // ---- sweep coarsening levels (single member only: pairs must not straddle members) -------------------
+    {
+        p->lvl_count[0] = p->nchunks;
+        std::vector<int> cbl, mcl = {0, p->nchunks};
+        std::vector<int> cur = cb;
+        int maxl = 0, off = 0;
+        p->cb_off[0] = 0; p->lvl_off[0] = 0;
+        if (E == 1)
+            while (p->lvl_count[maxl] > 1 && maxl < 15) {
+                const int cnt = p->lvl_count[maxl], nxt = (cnt + 1) / 2;
+                std::vector<int> nb(nxt + 1);
+                for (int i = 0; i < nxt; ++i) nb[i] = cur[2 * i];
+                nb[nxt] = cur[cnt];
+                ++maxl;
+                p->lvl_count[maxl] = nxt;
+                p->lvl_off[maxl] = off; off += nxt;
+                p->cb_off[maxl] = (int)cbl.size();
+                cbl.insert(cbl.end(), nb.begin(), nb.end());
+                mcl.push_back(0); mcl.push_back(nxt);
+                cur = nb;
+            }
+        // pick the level: boundary passes cost one step per chunk (two directions), local sweeps one step per slice of
+        // the longest chunk (two to three passes), every level one small product kernel
+        const double r = (double)NP / 64.0;
+        const double t_b = 0.4 + 1.4 * r * r, t_s = 0.8 + 2.8 * r * r, t_l = 4.0 + 8.0 * r * r * r;
+        int best = 0; double best_t = 1e300;
+        for (int l = 0; l <= maxl; ++l) {
+            const double len = (double)Nm1 / p->lvl_count[l];
+            const double t = 2.0 * p->lvl_count[l] * t_b + 2.5 * len * t_s + l * t_l;
+            if (t < best_t) { best_t = t; best = l; }
+        }
+        if (pb->chunks_per_member > 0) best = 0;            // explicit chunking: no coarsening
+        p->levels = best;
+        PTRY(p->lvlP.alloc((size_t)std::max(1, off) * GM));
+        PTRY(p->cb_lvl.alloc(std::max<size_t>(1, cbl.size()))); PTRY(p->mc0_lvl.alloc(mcl.size()));
+        if (!cbl.empty()) PTRY(cudaMemcpy(p->cb_lvl.p, cbl.data(), sizeof(int) * cbl.size(), cudaMemcpyHostToDevice));
+        PTRY(cudaMemcpy(p->mc0_lvl.p, mcl.data(), sizeof(int) * mcl.size(), cudaMemcpyHostToDevice));
+    }
     // ---- interpolation table (qoc/core/mathmethods.py:36-67 on linspace(0, T, M), programstate.py:41) ----
     {
         const double T = pb->evolution_time, dt = T / (pb->system_eval_count - 1);
@@ -856,10 +927,9 @@ int qocb_get_propagators(qocb_plan *p, double *props) {
 
 int qocb_launch_count(qocb_plan *p, int32_t with_grad) {
     if (!p) return -1;
-    if (!p->sharded) return with_grad ? (p->have_step_costs ? 9 : 8) : 4;
+    if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->levels;
     int levels = 0;
     for (int c = p->nchunks; c > 1; c = (c + 1) / 2) ++levels;
-    if (levels == 0) levels = 0;
     // forward: expm, tree, prefix, boundary, sweep; backward: [particular], boundary, suffix, boundary, sweep, expm, gather, finalize, pack
     return with_grad ? 1 + levels + 3 + (p->have_step_costs ? 1 : 0) + 8 : 1 + levels + 3 + 2;
 }

@@ -172,15 +172,17 @@ __device__ double cost_value(const SweepArgs &a, const double *ip, bool step_sta
 }
 
 // lam[s][a] += d cost / d psi_s[a] in autograd's convention (d/dx - i d/dy):  sum coef * conj(v[a])
-__device__ void cost_add_seed(const SweepArgs &a, const double *ip, double *lam, bool step_state, bool final_state) {
+__device__ void cost_add_seed(const SweepArgs &a, const double *ip, double *lam, bool step_state, bool final_state,
+                              int sb = 0, int sc = -1) {
+    if (sc < 0) sc = a.S;                                  // lam holds states [sb, sb + sc) only
     for (int t = 0; t < a.nterms; ++t) {
         const CostTerm tm = a.terms[t];
         if (!((tm.step && step_state) || (!tm.step && final_state))) continue;
         double tr = 0., ti = 0.;
         if (tm.kind == 0)
             for (int s = 0; s < a.S; ++s) { tr += ip[2 * (tm.ip_off + s * tm.fmax)]; ti += ip[2 * (tm.ip_off + s * tm.fmax) + 1]; }
-        for (int o = threadIdx.x; o < a.S * a.NP; o += kSweepThreads) {
-            const int s = o / a.NP, b = o % a.NP;
+        for (int o = threadIdx.x; o < sc * a.NP; o += kSweepThreads) {
+            const int sl = o / a.NP, s = sb + sl, b = o % a.NP;
             const int F = a.counts[tm.cnt_off + s];
             double sr = 0., si = 0.;
             for (int f = 0; f < F; ++f) {
@@ -193,8 +195,8 @@ __device__ void cost_add_seed(const SweepArgs &a, const double *ip, double *lam,
                 sr += cr * vr - ci * vi;
                 si += cr * vi + ci * vr;
             }
-            lam[s * 2 * a.NP + b] += sr;
-            lam[s * 2 * a.NP + a.NP + b] += si;
+            lam[sl * 2 * a.NP + b] += sr;
+            lam[sl * 2 * a.NP + a.NP + b] += si;
         }
     }
     __syncthreads();
@@ -214,19 +216,23 @@ template <int NP> struct SweepSmem {
     __device__ __forceinline__ void swap() { double *t = v0; v0 = v1; v1 = t; }
 };
 
-// (1) boundary states: psi[b_{c+1}] = P_c psi[b_c], sequential over the chunks of one member; grid = E
+// (1) boundary states: psi[b_{c+1}] = P_c psi[b_c], sequential over the chunks of one member; grid = (E, state groups):
+// the pass is a chain of dependent mat-vecs whose per-step time is bound by reading the 32 n^2-byte propagator once per
+// state from shared memory, so the states are spread over CTAs (no coupling between states in this pass)
 template <int NP>
 __global__ void __launch_bounds__(kSweepThreads) k_boundary_fwd(SweepArgs a) {
     extern __shared__ __align__(16) double sm_raw[];
-    const int S = a.S, VS = S * 2 * NP;
+    const int spg = (a.S + gridDim.y - 1) / gridDim.y, sb = blockIdx.y * spg;
+    const int S = min(spg, a.S - sb), VS = S * 2 * NP, VSA = a.S * 2 * NP, off = sb * 2 * NP;
+    if (S <= 0) return;
     SweepSmem<NP> sm(sm_raw, S);
     const int e = blockIdx.x;
     const int c0 = a.member_chunk0[e], c1 = a.member_chunk0[e + 1];
     prefetch_mat<NP>(sm.U[0], a.chunkP + (size_t)c0 * 2 * NP * NP);
     cp_async_commit();
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = a.psi_in[i];
-    double *psi_e = a.psi + (size_t)e * a.N * VS;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[i] = a.psi_in[i];
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = a.psi_in[off + i];
+    double *psi_e = a.psi + (size_t)e * a.N * VSA + off;
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[i] = a.psi_in[off + i];
     for (int c = c0; c < c1; ++c) {
         const int buf = (c - c0) & 1;
         if (c + 1 < c1) prefetch_mat<NP>(sm.U[buf ^ 1], a.chunkP + (size_t)(c + 1) * 2 * NP * NP);
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_fwd(SweepArgs a) {
         matvec_smem<NP, false>(sm.v1, sm.v0, sm.U[buf], S);
         __syncthreads();
         const int kend = a.chunk_begin[c + 1] - e * (a.N - 1);      // state index at the end of chunk c
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[(size_t)kend * VS + i] = sm.v1[i];
+        for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[(size_t)kend * VSA + i] = sm.v1[i];
         sm.swap();
     }
     cp_async_wait<0>();
@@ -326,27 +332,29 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_bwd(SweepArgs a) {
         for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.part[(size_t)c * VS + i] = sm.v0[i];
 }
 
-// (3b) boundary costates, sequential over the chunks of one member (last to first); grid = E.
+// (3b) boundary costates, sequential over the chunks of one member (last to first); grid = (E, state groups).
 // lam[N-1] = lam_in + seed_{N-1};  lam[b_c] = P_c^T lam[b_{c+1}] + part_c
 template <int NP>
 __global__ void __launch_bounds__(kSweepThreads) k_boundary_bwd(SweepArgs a, int have_part) {
     extern __shared__ __align__(16) double sm_raw[];
-    const int S = a.S, VS = S * 2 * NP;
+    const int spg = (a.S + gridDim.y - 1) / gridDim.y, sb = blockIdx.y * spg;
+    const int S = min(spg, a.S - sb), VS = S * 2 * NP, VSA = a.S * 2 * NP, off = sb * 2 * NP;
+    if (S <= 0) return;
     SweepSmem<NP> sm(sm_raw, S);
     const int e = blockIdx.x;
     const int c0 = a.member_chunk0[e], c1 = a.member_chunk0[e + 1];
-    const double *psi_e = a.psi + (size_t)e * a.N * VS;
-    double *lam_e = a.lam + (size_t)e * a.N * VS;
+    const double *psi_e = a.psi + (size_t)e * a.N * VSA;
+    double *lam_e = a.lam + (size_t)e * a.N * VSA + off;
     prefetch_mat<NP>(sm.U[0], a.chunkP + (size_t)(c1 - 1) * 2 * NP * NP);
     cp_async_commit();
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = a.lam_in ? a.lam_in[i] : 0.;
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = a.lam_in ? a.lam_in[off + i] : 0.;
     __syncthreads();
-    if (a.nterms > 0 && a.add_final_seed) {
+    if (a.nterms > 0 && a.add_final_seed) {                         // inner products of ALL states (coherent sums)
         const bool st = is_step_cost_state(a.N - 1 + a.j_off, a.ces);
-        cost_inner_products(a, psi_e + (size_t)(a.N - 1) * VS, sm.ip, st, true);
-        cost_add_seed(a, sm.ip, sm.v0, st, true);
+        cost_inner_products(a, psi_e + (size_t)(a.N - 1) * VSA, sm.ip, st, true);
+        cost_add_seed(a, sm.ip, sm.v0, st, true, sb, S);
     }
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)(a.N - 1) * VS + i] = sm.v0[i];
+    for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)(a.N - 1) * VSA + i] = sm.v0[i];
     for (int c = c1 - 1; c >= c0; --c) {
         const int buf = (c1 - 1 - c) & 1;
         if (c - 1 >= c0) prefetch_mat<NP>(sm.U[buf ^ 1], a.chunkP + (size_t)(c - 1) * 2 * NP * NP);
@@ -356,16 +364,16 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_bwd(SweepArgs a, int
         matvec_smem<NP, true>(sm.v1, sm.v0, sm.U[buf], S);
         __syncthreads();
         if (have_part)
-            for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v1[i] += a.part[(size_t)c * VS + i];
+            for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v1[i] += a.part[(size_t)c * VSA + off + i];
         const int kbeg = a.chunk_begin[c] - e * (a.N - 1);
         __syncthreads();
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)kbeg * VS + i] = sm.v1[i];
+        for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)kbeg * VSA + i] = sm.v1[i];
         sm.swap();
     }
     cp_async_wait<0>();
     __syncthreads();
     if (a.b_out && e == 0)
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.b_out[i] = sm.v0[i];
+        for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.b_out[off + i] = sm.v0[i];
 }
 
 // time sharding: state entering shard `rank` = P_{rank-1} ... P_0 psi0 (allP: [world][2*NP*NP]); grid = 1
