@@ -10,12 +10,20 @@
 #include "../../include/qocb200.h"
 #include "expm_slice.cuh"
 #include "sweep.cuh"
+#include "large.cuh"
 
 using namespace qocb;
 
 namespace {
 
 thread_local std::string g_last_error;
+
+inline double kB_host(int i) {
+    static const double b[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
+                                 129060195264000., 10559470521600., 670442572800., 33522128640., 1323241920.,
+                                 40840800., 960960., 16380., 182., 1.};
+    return b[i];
+}
 
 #define CU_TRY(plan, expr)                                                                              \
     do {                                                                                                \
@@ -236,6 +244,7 @@ int pad_dim(int n) {
     if (n <= 16) return 16;
     if (n <= 32) return 32;
     if (n <= 64) return 64;
+    if (n <= 512) return n;          // large-dimension path (large.cuh): dense n x n, no padding
     return -1;
 }
 
@@ -273,8 +282,26 @@ template <class T> struct DevBuf {
 
 }  // namespace
 
+namespace {
+// work arrays of the large-dimension path, each [batch][n*n] double2
+enum { LA1 = 0, LA2N, LM, LA2, LA4, LA6, LW1, LX1, LY, LVE, LUO, LP, LQ, LT, LR0, LRS0,
+       LRB = LRS0 + qocb::kLgMaxSq, LQB, LUOB, LVEB, LAB, LYB, LA6B, LA4B, LA2B, LTB, LXB, LA1B, LA2NB, LCOUNT };
+
+struct LargeImpl {
+    int n = 0, nn = 0, B = 0;
+    cublasHandle_t blas = nullptr;
+    DevBuf<double2> G0, G, work, treeA, treeB;
+    DevBuf<double2 *> ptrQ, ptrP, ptrRB;
+    DevBuf<int> piv, info, sarr;
+    std::vector<int> h_s;
+    double2 *arr(int i) { return work.p + (size_t)i * B * nn; }
+    ~LargeImpl() { if (blas) cublasDestroy(blas); }
+};
+}  // namespace
+
 struct qocb_plan {
     qocb_problem pb;
+    LargeImpl *large = nullptr;
     int NP = 0, q = 0, nchunks = 0, tape_mats = 0, num_sms = 0;
     int j0 = 0, Nloc = 0;               // time sharding: first local slice (global index), local state count
     // sweep coarsening: the state / costate sweeps run on chunks merged pairwise `levels` times (propagator tree);
@@ -294,6 +321,7 @@ struct qocb_plan {
     int ip_total = 0;
     double *h_pinned = nullptr;         // [M*KR controls | M*KR grad | 1 cost]
     std::string err;
+    ~qocb_plan() { delete large; }
 };
 
 namespace {
@@ -429,6 +457,231 @@ int ready(qocb_plan *p) {
     return upload_costs(p);
 }
 
+// ==== large-dimension path (n > 64): batched level-3 pipeline, see large.cuh ======================================
+#define BL_TRY(p, expr) do { cublasStatus_t s__ = (expr); if (s__ != CUBLAS_STATUS_SUCCESS) { char b__[256]; snprintf(b__, sizeof(b__), "%s failed: cuBLAS status %d (%s:%d)", #expr, (int)s__, __FILE__, __LINE__); set_error(p, b__); return -2; } } while (0)
+
+inline int lg_blocks(size_t tot) { return (int)std::min<size_t>((tot + 255) / 256, 148 * 16); }
+
+// row-major C = alpha op(A) op(B) + beta C over `batch` matrices (strides in elements)
+int lg_gemm(qocb_plan *p, bool ta, bool tb, const double2 *A, const double2 *B, double2 *C, double alpha, double beta, int batch,
+            long long sA = -1, long long sB = -1, long long sC = -1) {
+    LargeImpl *L = p->large;
+    const int n = L->n;
+    if (sA < 0) sA = L->nn; if (sB < 0) sB = L->nn; if (sC < 0) sC = L->nn;
+    const cuDoubleComplex a = make_cuDoubleComplex(alpha, 0.), b = make_cuDoubleComplex(beta, 0.);
+    BL_TRY(p, cublasZgemmStridedBatched(L->blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, n, n, n, &a,
+                                        reinterpret_cast<const cuDoubleComplex *>(B), n, sB,
+                                        reinterpret_cast<const cuDoubleComplex *>(A), n, sA, &b,
+                                        reinterpret_cast<cuDoubleComplex *>(C), n, sC, batch));
+    return 0;
+}
+int lg_axpby(qocb_plan *p, double2 *out, double al, const double2 *x, double be, const double2 *y, double ga, const double2 *z, int batch) {
+    const size_t tot = (size_t)batch * p->large->nn;
+    k_lg_axpby<<<lg_blocks(tot), 256, 0, p->stream>>>(out, al, x, be, y, ga, z, tot);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+int lg_copy(qocb_plan *p, double2 *dst, const double2 *src, int batch) {
+    CU_TRY(p, cudaMemcpyAsync(dst, src, sizeof(double2) * (size_t)batch * p->large->nn, cudaMemcpyDeviceToDevice, p->stream));
+    return 0;
+}
+
+int large_init(qocb_plan *p) {
+    LargeImpl *L = new LargeImpl();
+    p->large = L;
+    const int n = p->pb.hilbert_size;
+    L->n = n; L->nn = n * n;
+    const int Lsl = p->Nloc - 1;
+    const size_t per = (size_t)LCOUNT * L->nn * sizeof(double2);
+    L->B = (int)std::max<size_t>(1, std::min<size_t>((size_t)Lsl, std::min<size_t>(256, ((size_t)6 << 30) / per)));
+    BL_TRY(p, cublasCreate(&L->blas));
+    BL_TRY(p, cublasSetStream(L->blas, p->stream));
+    CU_TRY(p, L->G0.alloc(L->nn)); CU_TRY(p, L->G.alloc((size_t)std::max(1, p->pb.control_count) * L->nn));
+    CU_TRY(p, L->work.alloc((size_t)LCOUNT * L->B * L->nn));
+    CU_TRY(p, L->piv.alloc((size_t)L->B * n)); CU_TRY(p, L->info.alloc(L->B)); CU_TRY(p, L->sarr.alloc(L->B));
+    CU_TRY(p, L->ptrQ.alloc(L->B)); CU_TRY(p, L->ptrP.alloc(L->B)); CU_TRY(p, L->ptrRB.alloc(L->B));
+    std::vector<double2 *> hq(L->B), hp(L->B), hr(L->B);
+    for (int b = 0; b < L->B; ++b) { hq[b] = L->arr(LQ) + (size_t)b * L->nn; hp[b] = L->arr(LP) + (size_t)b * L->nn; hr[b] = L->arr(LRB) + (size_t)b * L->nn; }
+    CU_TRY(p, cudaMemcpy(L->ptrQ.p, hq.data(), sizeof(double2 *) * L->B, cudaMemcpyHostToDevice));
+    CU_TRY(p, cudaMemcpy(L->ptrP.p, hp.data(), sizeof(double2 *) * L->B, cudaMemcpyHostToDevice));
+    CU_TRY(p, cudaMemcpy(L->ptrRB.p, hr.data(), sizeof(double2 *) * L->B, cudaMemcpyHostToDevice));
+    if (p->sharded) { CU_TRY(p, L->treeA.alloc((size_t)((Lsl + 1) / 2) * L->nn)); CU_TRY(p, L->treeB.alloc((size_t)((Lsl + 3) / 4) * L->nn)); }
+    L->h_s.resize(L->B);
+    const int big = 200 * 1024;
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_sweep_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_sweep_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_suffix, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    return 0;
+}
+
+// forward intermediates of slices [jb, jb + Bc); keep: also R0 and the squaring inputs for the reverse pass.
+// smax_out: largest squaring count of the batch.  Leaves U_j in arr(LP).
+int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_out) {
+    LargeImpl *L = p->large;
+    const int nn = L->nn, order = p->pb.magnus_order;
+    const size_t tot = (size_t)Bc * nn;
+    const double dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
+    LgCoef cf{p->controls.p, p->itab_idx.p, p->itab_w.p, p->pb.control_count, p->q};
+    k_lg_assemble<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA1), L->arr(LA2N), L->G0.p, L->G.p, cf, jb, Bc, nn);
+    int rc;
+    if (order == 2) { rc = lg_axpby(p, L->arr(LM), dt, L->arr(LA1), 0., nullptr, 0., nullptr, Bc); if (rc) return rc; }
+    else {
+        rc = lg_gemm(p, false, false, L->arr(LA2N), L->arr(LA1), L->arr(LT), 1., 0., Bc); if (rc) return rc;      // a2 a1
+        rc = lg_gemm(p, false, false, L->arr(LA1), L->arr(LA2N), L->arr(LT), -1., 1., Bc); if (rc) return rc;     // - a1 a2
+        k_lg_axpby<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LM), 0.5 * dt, L->arr(LA1), 0.5 * dt, L->arr(LA2N), (QOCB_S3 / 12.0) * dt * dt, L->arr(LT), tot);
+    }
+    k_lg_norm_scale<<<Bc, 256, 0, p->stream>>>(L->arr(LM), L->sarr.p, L->n);
+    CU_TRY(p, cudaMemcpyAsync(L->h_s.data(), L->sarr.p, sizeof(int) * Bc, cudaMemcpyDeviceToHost, p->stream));
+    rc = lg_gemm(p, false, false, L->arr(LM), L->arr(LM), L->arr(LA2), 1., 0., Bc); if (rc) return rc;
+    rc = lg_gemm(p, false, false, L->arr(LA2), L->arr(LA2), L->arr(LA4), 1., 0., Bc); if (rc) return rc;
+    rc = lg_gemm(p, false, false, L->arr(LA2), L->arr(LA4), L->arr(LA6), 1., 0., Bc); if (rc) return rc;
+    k_lg_poly<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA2), L->arr(LA4), L->arr(LA6), L->arr(LW1), L->arr(LX1), L->arr(LY), L->arr(LVE), L->n, tot);
+    rc = lg_gemm(p, false, false, L->arr(LA6), L->arr(LW1), L->arr(LY), 1., 1., Bc); if (rc) return rc;
+    rc = lg_gemm(p, false, false, L->arr(LA6), L->arr(LX1), L->arr(LVE), 1., 1., Bc); if (rc) return rc;
+    rc = lg_gemm(p, false, false, L->arr(LM), L->arr(LY), L->arr(LUO), 1., 0., Bc); if (rc) return rc;
+    k_lg_pq<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LVE), L->arr(LUO), L->arr(LP), L->arr(LQ), tot);
+    CU_TRY(p, cudaGetLastError());
+    BL_TRY(p, cublasZgetrfBatched(L->blas, L->n, reinterpret_cast<cuDoubleComplex **>(L->ptrQ.p), L->n, L->piv.p, L->info.p, Bc));
+    int hinfo = 0;
+    BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_N, L->n, L->n, reinterpret_cast<const cuDoubleComplex *const *>(L->ptrQ.p), L->n, L->piv.p,
+                                  reinterpret_cast<cuDoubleComplex **>(L->ptrP.p), L->n, &hinfo, Bc));   // R0 = P Q^-1 (row-major)
+    if (keep) { rc = lg_copy(p, L->arr(LR0), L->arr(LP), Bc); if (rc) return rc; }
+    CU_TRY(p, cudaStreamSynchronize(p->stream));                    // squaring counts of the batch
+    int smax = 0;
+    for (int b = 0; b < Bc; ++b) smax = std::max(smax, L->h_s[b]);
+    if (keep && smax > kLgMaxSq) { set_error(p, "scaling count exceeds the reverse-pass capacity of the large-dimension path"); return -4; }
+    for (int i = 0; i < smax; ++i) {
+        if (keep) { rc = lg_copy(p, L->arr(LRS0 + i), L->arr(LP), Bc); if (rc) return rc; }
+        rc = lg_gemm(p, false, false, L->arr(LP), L->arr(LP), L->arr(LT), 1., 0., Bc); if (rc) return rc;
+        k_lg_select<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LP), L->arr(LT), L->sarr.p, i, nn, tot);
+    }
+    CU_TRY(p, cudaGetLastError());
+    *smax_out = smax;
+    return 0;
+}
+
+int lg_expm_all(qocb_plan *p) {
+    LargeImpl *L = p->large;
+    const int Lsl = p->Nloc - 1;
+    for (int jb = 0; jb < Lsl; jb += L->B) {
+        const int Bc = std::min(L->B, Lsl - jb);
+        int smax = 0;
+        int rc = lg_forward_batch(p, jb, Bc, false, &smax); if (rc) return rc;
+        rc = lg_copy(p, reinterpret_cast<double2 *>(p->U.p) + (size_t)jb * L->nn, L->arr(LP), Bc); if (rc) return rc;
+    }
+    return 0;
+}
+
+LgSweep lg_sweep_args(qocb_plan *p) {
+    LgSweep g;
+    g.a = make_sargs(p);
+    g.a.NP = p->large->n;
+    g.U = reinterpret_cast<const double2 *>(p->U.p);
+    g.cost = p->cost.p;
+    return g;
+}
+size_t lg_sweep_smem(qocb_plan *p) {
+    return sizeof(double) * ((size_t)4 * p->pb.state_count * p->large->n + 2 * (size_t)std::max(1, p->ip_total));
+}
+
+int lg_backward_all(qocb_plan *p) {
+    LargeImpl *L = p->large;
+    const int Lsl = p->Nloc - 1, nn = L->nn, order = p->pb.magnus_order, n = L->n;
+    const double dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
+    for (int jb = 0; jb < Lsl; jb += L->B) {
+        const int Bc = std::min(L->B, Lsl - jb);
+        const size_t tot = (size_t)Bc * nn;
+        int smax = 0;
+        int rc = lg_forward_batch(p, jb, Bc, true, &smax); if (rc) return rc;
+        double2 *RB = L->arr(LRB), *T = L->arr(LT), *M = L->arr(LM);
+        k_lg_ubar<<<lg_blocks(tot), 256, 0, p->stream>>>(RB, p->psi.p, p->lam.p, jb, Bc, n, p->pb.state_count);
+        for (int i = smax - 1; i >= 0; --i) {                      // R_{i+1} = R_i^2
+            rc = lg_gemm(p, false, true, RB, L->arr(LRS0 + i), T, 1., 0., Bc); if (rc) return rc;
+            rc = lg_gemm(p, true, false, L->arr(LRS0 + i), RB, T, 1., 1., Bc); if (rc) return rc;
+            k_lg_select<<<lg_blocks(tot), 256, 0, p->stream>>>(RB, T, L->sarr.p, i, nn, tot);
+        }
+        int hinfo = 0;                                             // pbar = rbar Q^-T
+        BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_T, n, n, reinterpret_cast<const cuDoubleComplex *const *>(L->ptrQ.p), n, L->piv.p,
+                                      reinterpret_cast<cuDoubleComplex **>(L->ptrRB.p), n, &hinfo, Bc));
+        rc = lg_gemm(p, true, false, L->arr(LR0), RB, L->arr(LQB), -1., 0., Bc); if (rc) return rc;       // qbar = -R0^T pbar
+        rc = lg_axpby(p, L->arr(LUOB), 1., RB, -1., L->arr(LQB), 0., nullptr, Bc); if (rc) return rc;
+        rc = lg_axpby(p, L->arr(LVEB), 1., RB, 1., L->arr(LQB), 0., nullptr, Bc); if (rc) return rc;
+        rc = lg_gemm(p, false, true, L->arr(LUOB), L->arr(LY), L->arr(LAB), 1., 0., Bc); if (rc) return rc;  // abar = uobar Y^T
+        rc = lg_gemm(p, true, false, M, L->arr(LUOB), L->arr(LYB), 1., 0., Bc); if (rc) return rc;           // ybar = A^T uobar
+        rc = lg_axpby(p, L->arr(LA6B), kB_host(7), L->arr(LYB), kB_host(6), L->arr(LVEB), 0., nullptr, Bc); if (rc) return rc;
+        rc = lg_axpby(p, L->arr(LA4B), kB_host(5), L->arr(LYB), kB_host(4), L->arr(LVEB), 0., nullptr, Bc); if (rc) return rc;
+        rc = lg_axpby(p, L->arr(LA2B), kB_host(3), L->arr(LYB), kB_host(2), L->arr(LVEB), 0., nullptr, Bc); if (rc) return rc;
+        rc = lg_gemm(p, false, true, L->arr(LYB), L->arr(LW1), L->arr(LA6B), 1., 1., Bc); if (rc) return rc;
+        rc = lg_gemm(p, false, true, L->arr(LVEB), L->arr(LX1), L->arr(LA6B), 1., 1., Bc); if (rc) return rc;
+        rc = lg_gemm(p, true, false, L->arr(LA6), L->arr(LYB), L->arr(LTB), 1., 0., Bc); if (rc) return rc;  // w1bar
+        rc = lg_gemm(p, true, false, L->arr(LA6), L->arr(LVEB), L->arr(LXB), 1., 0., Bc); if (rc) return rc; // x1bar
+        rc = lg_axpby(p, L->arr(LA6B), 1., L->arr(LA6B), kB_host(13), L->arr(LTB), kB_host(12), L->arr(LXB), Bc); if (rc) return rc;
+        rc = lg_axpby(p, L->arr(LA4B), 1., L->arr(LA4B), kB_host(11), L->arr(LTB), kB_host(10), L->arr(LXB), Bc); if (rc) return rc;
+        rc = lg_axpby(p, L->arr(LA2B), 1., L->arr(LA2B), kB_host(9), L->arr(LTB), kB_host(8), L->arr(LXB), Bc); if (rc) return rc;
+        rc = lg_gemm(p, false, true, L->arr(LA6B), L->arr(LA4), L->arr(LA2B), 1., 1., Bc); if (rc) return rc;
+        rc = lg_gemm(p, true, false, L->arr(LA2), L->arr(LA6B), L->arr(LA4B), 1., 1., Bc); if (rc) return rc;
+        rc = lg_gemm(p, false, true, L->arr(LA4B), L->arr(LA2), L->arr(LA2B), 1., 1., Bc); if (rc) return rc;
+        rc = lg_gemm(p, true, false, L->arr(LA2), L->arr(LA4B), L->arr(LA2B), 1., 1., Bc); if (rc) return rc;
+        rc = lg_gemm(p, false, true, L->arr(LA2B), M, L->arr(LAB), 1., 1., Bc); if (rc) return rc;
+        rc = lg_gemm(p, true, false, M, L->arr(LA2B), L->arr(LAB), 1., 1., Bc); if (rc) return rc;
+        k_lg_unscale<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LAB), L->sarr.p, nn, tot);                // mbar
+        double2 *AB = L->arr(LAB);
+        if (order == 2) { rc = lg_axpby(p, L->arr(LA1B), dt, AB, 0., nullptr, 0., nullptr, Bc); if (rc) return rc; }
+        else {
+            const double f = (QOCB_S3 / 12.0) * dt * dt;
+            rc = lg_gemm(p, false, true, AB, L->arr(LA1), T, 1., 0., Bc); if (rc) return rc;                 // a2bar
+            rc = lg_gemm(p, true, false, L->arr(LA1), AB, T, -1., 1., Bc); if (rc) return rc;
+            rc = lg_axpby(p, L->arr(LA2NB), 0.5 * dt, AB, f, T, 0., nullptr, Bc); if (rc) return rc;
+            rc = lg_gemm(p, true, false, L->arr(LA2N), AB, T, 1., 0., Bc); if (rc) return rc;                // a1bar
+            rc = lg_gemm(p, false, true, AB, L->arr(LA2N), T, -1., 1., Bc); if (rc) return rc;
+            rc = lg_axpby(p, L->arr(LA1B), 0.5 * dt, AB, f, T, 0., nullptr, Bc); if (rc) return rc;
+        }
+        if (p->pb.control_count > 0)
+            k_lg_contract<<<dim3(Bc, p->q), 256, 0, p->stream>>>(L->arr(LA1B), L->arr(LA2NB), L->G.p, p->node_grad.p, jb, nn, p->pb.control_count, p->q);
+        CU_TRY(p, cudaGetLastError());
+    }
+    const int totg = p->pb.control_eval_count * p->pb.control_count;
+    if (totg > 0)
+        k_gather_grad<<<(totg + 127) / 128, 128, 0, p->stream>>>(p->csr_ptr.p, p->csr_idx.p, p->csr_w.p, p->node_grad.p, p->grad.p,
+                                                               p->pb.control_eval_count, p->pb.control_count, p->q, p->Nloc - 1, 1);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+int lg_eval(qocb_plan *p, bool with_grad) {
+    int rc = lg_expm_all(p); if (rc) return rc;
+    LgSweep g = lg_sweep_args(p);
+    g.a.psi_in = p->psi0.p;
+    k_lg_sweep_fwd<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(g);
+    if (with_grad) {
+        k_lg_sweep_bwd<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(g, 1);
+        CU_TRY(p, cudaGetLastError());
+        rc = lg_backward_all(p); if (rc) return rc;
+    }
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+// product of all local propagators (pairwise tree of batched GEMMs) -> out_dev[n*n] (interleaved)
+int lg_shard_propagator(qocb_plan *p, double2 *out_dev) {
+    LargeImpl *L = p->large;
+    const int nn = L->nn;
+    const double2 *in = reinterpret_cast<const double2 *>(p->U.p);
+    int count = p->Nloc - 1;
+    double2 *bufs[2] = {L->treeA.p, L->treeB.p};
+    int which = 0;
+    if (count == 1) return lg_copy(p, out_dev, in, 1);
+    while (count > 1) {
+        double2 *out = (count <= 2) ? out_dev : bufs[which];
+        const int pairs = count / 2;
+        int rc = lg_gemm(p, false, false, in + nn, in, out, 1., 0., pairs, 2LL * nn, 2LL * nn, nn); if (rc) return rc;   // later * earlier
+        if (count & 1) { rc = lg_copy(p, out + (size_t)pairs * nn, in + (size_t)(count - 1) * nn, 1); if (rc) return rc; }
+        in = out; count = (count + 1) / 2; which ^= 1;
+    }
+    return 0;
+}
+
 // ---- pipeline phases (each only enqueues on the plan stream) -----------------------------------------------
 int reduce_level(qocb_plan *p, const double *in, double *out, int count) {
     return dispatch(p->NP, [&] { return launch_reduce<C8>(p, in, out, count); }, [&] { return launch_reduce<C16>(p, in, out, count); },
@@ -526,6 +779,11 @@ int enqueue_eval(qocb_plan *p, bool with_grad, cudaEvent_t *ev) {
     int rc = ready(p); if (rc) return rc;
     auto rec = [&](int i) { if (ev) cudaEventRecord(ev[i], p->stream); };
     rec(0);
+    if (p->large) {
+        rc = lg_eval(p, with_grad); if (rc) return rc;
+        for (int i = 1; i < 8; ++i) rec(i);
+        return 0;
+    }
     rc = enqueue_expm_forward(p, with_grad); if (rc) return rc;
     rec(1);
     rc = enqueue_state_forward(p, p->psi0.p, ev ? ev[2] : nullptr); if (rc) return rc;
@@ -574,7 +832,10 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     if (!pb || !out) { set_error((qocb_plan *)nullptr, "null argument"); return -1; }
     *out = nullptr;
     const int NP = pad_dim(pb->hilbert_size);
-    if (pb->hilbert_size < 1 || NP < 0) { set_error((qocb_plan *)nullptr, "hilbert_size must be in [1, 64] in this build (larger dims: not implemented yet)"); return -1; }
+    if (pb->hilbert_size < 1 || NP < 0) { set_error((qocb_plan *)nullptr, "hilbert_size must be in [1, 512]"); return -1; }
+    const bool is_large = NP > 64;
+    if (is_large && pb->magnus_order == 6) { set_error((qocb_plan *)nullptr, "Magnus M6 is not implemented for hilbert_size > 64"); return -1; }
+    if (is_large && pb->ensemble_count != 1) { set_error((qocb_plan *)nullptr, "ensembles are not implemented for hilbert_size > 64"); return -1; }
     if (pb->magnus_order != 2 && pb->magnus_order != 4 && pb->magnus_order != 6) { set_error((qocb_plan *)nullptr, "magnus_order must be 2, 4 or 6"); return -1; }
     if (pb->system_eval_count < 2) { set_error((qocb_plan *)nullptr, "system_eval_count must be >= 2"); return -1; }
     if (pb->control_count < 0 || pb->control_count > kMaxKR) { set_error((qocb_plan *)nullptr, "control_count (real channels) must be in [0, 16]"); return -1; }
@@ -605,13 +866,14 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     const int KR = pb->control_count, S = pb->state_count, q = p->q;
     const size_t GM = 2 * (size_t)NP * NP;
     // ---- chunks -------------------------------------------------------------------------------------
-    int occ = dispatch(NP, [] { return occupancy_fwd<C8>(); }, [] { return occupancy_fwd<C16>(); },
-                       [] { return occupancy_fwd<C32>(); }, [] { return occupancy_fwd<C64>(); });
-    int cpm = pb->chunks_per_member;
+    int occ = is_large ? 1 : dispatch(NP, [] { return occupancy_fwd<C8>(); }, [] { return occupancy_fwd<C16>(); },
+                                      [] { return occupancy_fwd<C32>(); }, [] { return occupancy_fwd<C64>(); });
+    int cpm = is_large ? 1 : pb->chunks_per_member;
     // automatic: fill the machine, but keep the sequential chunk-boundary pass (one step per chunk) short: beyond
     // two CTAs per SM the extra boundary steps cost more than the expm kernels gain at small dims
     if (cpm <= 0) cpm = (p->num_sms * std::min(occ, 2) + E - 1) / E;
     cpm = std::max(1, std::min(cpm, Nm1));
+    if (is_large) cpm = 1;
     p->nchunks = cpm * E;
     std::vector<int> cb(p->nchunks + 1), mc0(E + 1);
     for (int e = 0; e < E; ++e) {
@@ -653,7 +915,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
             const double t = 2.0 * p->lvl_count[l] * t_b + 2.5 * len * t_s + l * t_l;
             if (t < best_t) { best_t = t; best = l; }
         }
-        if (pb->chunks_per_member > 0) best = 0;            // explicit chunking: no coarsening
+        if (pb->chunks_per_member > 0 || is_large) best = 0;   // explicit chunking: no coarsening
         p->levels = best;
         PTRY(p->lvlP.alloc((size_t)std::max(1, off) * GM));
         PTRY(p->cb_lvl.alloc(std::max<size_t>(1, cbl.size()))); PTRY(p->mc0_lvl.alloc(mcl.size()));
@@ -709,7 +971,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     PTRY(p->G0.alloc((size_t)E * GM)); PTRY(p->G.alloc(std::max<size_t>(1, (size_t)KR) * GM));
     PTRY(p->controls.alloc(std::max<size_t>(1, (size_t)M * KR)));
     PTRY(p->U.alloc(W * GM));
-    if (pb->store_tape) {
+    if (pb->store_tape && !is_large) {
         cudaError_t e = p->tape.alloc(W * p->tape_mats * GM);
         if (e != cudaSuccess) { cudaGetLastError(); p->tape.release(); }       // fall back to recompute mode on the GPU
         else PTRY(p->tape_piv.alloc(W * NP));
@@ -739,6 +1001,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
         cudaError_t ae = cudaSuccess;
         SWEEP_NP(NP, (ae = set_sweep_attrs<NPc>(big)));
         PTRY(ae);
+        if (is_large && large_init(p) != 0) return fail(-2);
     }
 #undef PTRY
     *out = p;
@@ -760,6 +1023,20 @@ int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
     CU_TRY(p, cudaSetDevice(p->pb.device));
     const int n = p->pb.hilbert_size, NP = p->NP, E = p->pb.ensemble_count, KR = p->pb.control_count;
     const size_t GM = 2 * (size_t)NP * NP;
+    if (p->large) {                                    // interleaved generators G = -1j * H
+        auto gen = [&](const double *src, double2 *dst_dev) -> cudaError_t {
+            std::vector<double> g(2 * (size_t)n * n);
+            for (size_t e = 0; e < (size_t)n * n; ++e) { g[2 * e] = src[2 * e + 1]; g[2 * e + 1] = -src[2 * e]; }
+            return cudaMemcpy(dst_dev, g.data(), sizeof(double) * g.size(), cudaMemcpyHostToDevice);
+        };
+        CU_TRY(p, gen(h0, p->large->G0.p));
+        if (KR > 0) {
+            if (!a_ops) { set_error(p, "a_ops is null but control_count > 0"); return -1; }
+            for (int r = 0; r < KR; ++r) CU_TRY(p, gen(a_ops + (size_t)r * 2 * n * n, p->large->G.p + (size_t)r * n * n));
+        }
+        p->ops_set = true;
+        return 0;
+    }
     std::vector<double> buf((size_t)std::max(E, KR) * GM);
     for (int e = 0; e < E; ++e) to_planar(h0 + (size_t)e * 2 * n * n, buf.data() + (size_t)e * GM, n, NP, true);
     CU_TRY(p, cudaMemcpy(p->G0.p, buf.data(), sizeof(double) * E * GM, cudaMemcpyHostToDevice));
@@ -918,6 +1195,10 @@ int qocb_get_propagators(qocb_plan *p, double *props) {
     const size_t W = (size_t)p->pb.ensemble_count * (p->Nloc - 1), GM = 2 * (size_t)NP * NP;
     std::vector<double> buf(GM);
     CU_TRY(p, cudaStreamSynchronize(p->stream));
+    if (p->large) {
+        CU_TRY(p, cudaMemcpy(props, p->U.p, sizeof(double) * W * GM, cudaMemcpyDeviceToHost));
+        return 0;
+    }
     for (size_t w = 0; w < W; ++w) {
         CU_TRY(p, cudaMemcpy(buf.data(), p->U.p + w * GM, sizeof(double) * GM, cudaMemcpyDeviceToHost));
         from_planar(buf.data(), props + w * 2 * n * n, n, NP);
@@ -927,6 +1208,11 @@ int qocb_get_propagators(qocb_plan *p, double *props) {
 
 int qocb_launch_count(qocb_plan *p, int32_t with_grad) {
     if (!p) return -1;
+    if (p->large) {
+        const int batches = (p->Nloc - 2 + p->large->B) / p->large->B;
+        const int fwd = p->pb.magnus_order == 4 ? 14 : 11;                   // own kernels + library calls per batch
+        return batches * (fwd + (with_grad ? fwd + (p->pb.magnus_order == 4 ? 38 : 30) : 0)) + (with_grad ? 3 : 1);
+    }
     if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->levels;
     int levels = 0;
     for (int c = p->nchunks; c > 1; c = (c + 1) / 2) ++levels;
@@ -977,6 +1263,10 @@ int qocb_shard_forward_local(qocb_plan *p, int32_t with_grad, double *shardP_dev
     if (!p->sharded) { set_error(p, "plan has no slice range"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
     int rc = ready(p); if (rc) return rc;
+    if (p->large) {
+        rc = lg_expm_all(p); if (rc) return rc;
+        return lg_shard_propagator(p, reinterpret_cast<double2 *>(shardP_dev));
+    }
     rc = enqueue_expm_forward(p, with_grad != 0); if (rc) return rc;
     return enqueue_shard_propagator(p, shardP_dev);
 }
@@ -984,6 +1274,15 @@ int qocb_shard_forward_local(qocb_plan *p, int32_t with_grad, double *shardP_dev
 int qocb_shard_forward_finish(qocb_plan *p, const double *allP_dev, int32_t rank) {
     if (!p || !allP_dev || rank < 0) { set_error(p, "bad argument"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
+    if (p->large) {
+        k_lg_prefix<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(reinterpret_cast<const double2 *>(allP_dev), p->psi0.p, p->psi_in.p, rank,
+                                                                   p->large->n, p->pb.state_count);
+        LgSweep g = lg_sweep_args(p);
+        g.a.psi_in = p->psi_in.p;
+        k_lg_sweep_fwd<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(g);
+        CU_TRY(p, cudaGetLastError());
+        return 0;
+    }
     const size_t sm = sweep_smem_bytes(p->NP, p->pb.state_count, p->ip_total);
     SWEEP_NP(p->NP, (k_prefix_states<NPc><<<1, kSweepThreads, sm, p->stream>>>(allP_dev, p->psi0.p, p->psi_in.p, rank, p->pb.state_count)));
     CU_TRY(p, cudaGetLastError());
@@ -994,12 +1293,28 @@ int qocb_shard_forward_finish(qocb_plan *p, const double *allP_dev, int32_t rank
 int qocb_shard_backward_particular(qocb_plan *p, double *b_dev) {
     if (!p || !b_dev) { set_error(p, "null argument"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
+    if (p->large) {
+        LgSweep g = lg_sweep_args(p);
+        g.a.lam_in = nullptr; g.a.b_out = b_dev;
+        k_lg_sweep_bwd<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(g, 0);
+        CU_TRY(p, cudaGetLastError());
+        return 0;
+    }
     return enqueue_costate(p, nullptr, b_dev, true, false);
 }
 
 int qocb_shard_backward_finish(qocb_plan *p, const double *allP_dev, const double *allb_dev, int32_t rank, int32_t world) {
     if (!p || !allP_dev || !allb_dev || rank < 0 || rank >= world) { set_error(p, "bad argument"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
+    if (p->large) {
+        k_lg_suffix<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(reinterpret_cast<const double2 *>(allP_dev), allb_dev, p->lam_in.p, rank, world,
+                                                                   p->large->n, p->pb.state_count);
+        LgSweep g = lg_sweep_args(p);
+        g.a.lam_in = p->lam_in.p; g.a.b_out = nullptr;
+        k_lg_sweep_bwd<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(g, 1);
+        CU_TRY(p, cudaGetLastError());
+        return lg_backward_all(p);
+    }
     const size_t sm = sweep_smem_bytes(p->NP, p->pb.state_count, p->ip_total);
     SWEEP_NP(p->NP, (k_suffix_costates<NPc><<<1, kSweepThreads, sm, p->stream>>>(allP_dev, allb_dev, p->lam_in.p, rank, world, p->pb.state_count)));
     CU_TRY(p, cudaGetLastError());
@@ -1064,7 +1379,7 @@ extern "C" {
 int qocb_expm_batched(int32_t n, int64_t batch, const double *a, double *out, int32_t device) {
     if (!a || !out || batch < 1) { set_error((qocb_plan *)nullptr, "bad argument"); return -1; }
     const int NP = pad_dim(n);
-    if (NP < 0) { set_error((qocb_plan *)nullptr, "n must be in [1, 64] in this build"); return -1; }
+    if (NP < 0 || NP > 64) { set_error((qocb_plan *)nullptr, "the standalone batched expm hooks cover n in [1, 64]"); return -1; }
     if (cudaSetDevice(device) != cudaSuccess) { set_error((qocb_plan *)nullptr, "cudaSetDevice failed (no CPU path)"); return -2; }
     return dispatch(NP, [&] { return expm_batched_impl<C8>(n, batch, a, nullptr, out, nullptr); },
                     [&] { return expm_batched_impl<C16>(n, batch, a, nullptr, out, nullptr); },
@@ -1076,7 +1391,7 @@ int qocb_expm_vjp_batched(int32_t n, int64_t batch, const double *a, const doubl
                           int32_t device) {
     if (!a || !out || !ubar || !abar || batch < 1) { set_error((qocb_plan *)nullptr, "bad argument"); return -1; }
     const int NP = pad_dim(n);
-    if (NP < 0) { set_error((qocb_plan *)nullptr, "n must be in [1, 64] in this build"); return -1; }
+    if (NP < 0 || NP > 64) { set_error((qocb_plan *)nullptr, "the standalone batched expm hooks cover n in [1, 64]"); return -1; }
     if (cudaSetDevice(device) != cudaSuccess) { set_error((qocb_plan *)nullptr, "cudaSetDevice failed (no CPU path)"); return -2; }
     return dispatch(NP, [&] { return expm_batched_impl<C8>(n, batch, a, ubar, out, abar); },
                     [&] { return expm_batched_impl<C16>(n, batch, a, ubar, out, abar); },
@@ -1143,7 +1458,7 @@ extern "C" {
 int qocb_expm_batched_time(int32_t n, int64_t batch, double norm_scale, int32_t iters, double *ms_best, int32_t device) {
     if (!ms_best || batch < 1) return -1;
     const int NP = pad_dim(n);
-    if (NP < 0) { set_error((qocb_plan *)nullptr, "n must be in [1, 64] in this build"); return -1; }
+    if (NP < 0 || NP > 64) { set_error((qocb_plan *)nullptr, "the standalone batched expm hooks cover n in [1, 64]"); return -1; }
     if (cudaSetDevice(device) != cudaSuccess) { set_error((qocb_plan *)nullptr, "cudaSetDevice failed (no CPU path)"); return -2; }
     return dispatch(NP, [&] { return expm_time_impl<C8>(n, batch, norm_scale, iters, ms_best); },
                     [&] { return expm_time_impl<C16>(n, batch, norm_scale, iters, ms_best); },

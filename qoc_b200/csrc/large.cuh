@@ -1,0 +1,288 @@
+// large.cuh - GRAPE hot path for Hilbert dimensions above 64 (up to 512), where one matrix set no longer fits the
+// shared memory of one CTA.  Same algorithm as expm_slice.cuh / sweep.cuh (qoc/core/schroedingerdiscrete.py:356-502,
+// qoc/core/mathmethods.py:72-122, qoc/standard/functions/expm.py:210-252 and the reverse of that graph), organised as
+// BATCHED level-3 work over many time slices at once:
+//   * every matrix product is one strided-batched complex GEMM over the slices of a batch (this round: cuBLAS ZGEMM,
+//     93 % of the FP64 DMMA peak at n = 256 - a plain library GEMM; the fused sm_100a tile kernel of the n <= 64 path does
+//     not apply because the operands live in HBM/L2);
+//   * the Pade denominator solve is cuBLAS batched LU (zgetrf/zgetrs).  The forward uses R = P Q^-1 (P and Q are
+//     polynomials in A and commute, so this equals the reference's Q^-1 P) because that form needs no transposes in
+//     row-major storage; the reverse pass differentiates exactly this form;
+//   * everything else - generator assembly from interpolated controls, Magnus combination, one-norm / scaling, the Pade
+//     polynomial combinations, squaring selection, rank-S cotangent seeds, Magnus adjoint, contraction with the control
+//     operators, state / costate sweeps with the fused cost reductions - are kernels of this file.
+// The reverse pass recomputes the forward intermediates per batch (no tape across the evaluation), so memory stays
+// O(batch) + the propagators.  Magnus M2 and M4 only (M6 at n > 64: not implemented, fails loudly).
+// Matrices are interleaved complex128 (double2), row-major, dense n x n; state vectors stay planar ([s][2][n]) so the
+// cost reductions of sweep.cuh are shared.
+#pragma once
+#include <cublas_v2.h>
+
+namespace qocb {
+
+constexpr int kLgThreads = kSweepThreads;      // the shared cost helpers stride by kSweepThreads
+constexpr int kLgMaxSq = 6;                    // squarings kept per batch for the reverse pass
+
+struct LgCoef {                                // interpolation of the controls at the Magnus nodes of the local slices
+    const double *controls; const int *itab_idx; const double *itab_w; int KR, q;
+};
+
+__device__ __forceinline__ double lg_coef(const LgCoef &c, int j, int i, int r) {
+    const int o = (j * c.q + i) * 2;
+    return c.controls[c.itab_idx[o] * c.KR + r] * c.itab_w[o] + c.controls[c.itab_idx[o + 1] * c.KR + r] * c.itab_w[o + 1];
+}
+
+// node generators a_i[b] = G0 + sum_r c_{j,i,r} G_r for the slices j = j_begin + b of a batch
+__global__ void k_lg_assemble(double2 *a1, double2 *a2, const double2 *G0, const double2 *G, LgCoef c, int j_begin, int B, int nn) {
+    const size_t tot = (size_t)B * nn;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / nn), e = (int)(t - (size_t)b * nn);
+        const double2 g0 = G0[e];
+        double2 v1 = g0, v2 = g0;
+        for (int r = 0; r < c.KR; ++r) {
+            const double2 g = G[(size_t)r * nn + e];
+            const double c1 = lg_coef(c, j_begin + b, 0, r);
+            v1.x += c1 * g.x; v1.y += c1 * g.y;
+            if (c.q > 1) { const double c2 = lg_coef(c, j_begin + b, 1, r); v2.x += c2 * g.x; v2.y += c2 * g.y; }
+        }
+        a1[t] = v1;
+        if (c.q > 1) a2[t] = v2;
+    }
+}
+
+// out = alpha x + beta y + gamma z (any of y, z may be null)
+__global__ void k_lg_axpby(double2 *out, double alpha, const double2 *x, double beta, const double2 *y, double gamma, const double2 *z, size_t tot) {
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        double2 v = make_double2(alpha * x[t].x, alpha * x[t].y);
+        if (y) { v.x += beta * y[t].x; v.y += beta * y[t].y; }
+        if (z) { v.x += gamma * z[t].x; v.y += gamma * z[t].y; }
+        out[t] = v;
+    }
+}
+
+// one-norm, squaring count and scaling per slice (expm.py:103-116, :229-241); one CTA per slice, in place
+__global__ void __launch_bounds__(256) k_lg_norm_scale(double2 *A, int *sarr, int n) {
+    __shared__ double red[256];
+    double2 *a = A + (size_t)blockIdx.x * n * n;
+    double best = 0.;
+    for (int c = threadIdx.x; c < n; c += 256) {
+        double s = 0.;
+        for (int r = 0; r < n; ++r) { const double2 v = a[(size_t)r * n + c]; s += sqrt(v.x * v.x + v.y * v.y); }
+        best = fmax(best, s);
+    }
+    red[threadIdx.x] = best;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]); __syncthreads(); }
+    const double norm = red[0];
+    int s = 0;
+    if (!(norm < QOCB_THETA13)) { s = (int)ceil(log2(norm / QOCB_THETA13)); if (s < 0) s = 0; }
+    if (threadIdx.x == 0) sarr[blockIdx.x] = s;
+    const double scale = ldexp(1.0, -s);
+    for (int e = threadIdx.x; e < n * n; e += 256) { a[e].x *= scale; a[e].y *= scale; }
+}
+
+// W1, X1 and the additive parts of Y and Ve (expm.py:153-159)
+__global__ void k_lg_poly(const double2 *A2, const double2 *A4, const double2 *A6, double2 *W1, double2 *X1, double2 *Y, double2 *Ve, int n, size_t tot) {
+    const int nn = n * n;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(t % nn);
+        const bool diag = (e / n) == (e % n);
+        const double2 a2 = A2[t], a4 = A4[t], a6 = A6[t];
+        W1[t] = make_double2(kB[13] * a6.x + kB[11] * a4.x + kB[9] * a2.x, kB[13] * a6.y + kB[11] * a4.y + kB[9] * a2.y);
+        X1[t] = make_double2(kB[12] * a6.x + kB[10] * a4.x + kB[8] * a2.x, kB[12] * a6.y + kB[10] * a4.y + kB[8] * a2.y);
+        Y[t] = make_double2(kB[7] * a6.x + kB[5] * a4.x + kB[3] * a2.x + (diag ? kB[1] : 0.), kB[7] * a6.y + kB[5] * a4.y + kB[3] * a2.y);
+        Ve[t] = make_double2(kB[6] * a6.x + kB[4] * a4.x + kB[2] * a2.x + (diag ? kB[0] : 0.), kB[6] * a6.y + kB[4] * a4.y + kB[2] * a2.y);
+    }
+}
+
+// P = Ve + Uo, Q = Ve - Uo
+__global__ void k_lg_pq(const double2 *Ve, const double2 *Uo, double2 *P, double2 *Q, size_t tot) {
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const double2 v = Ve[t], u = Uo[t];
+        P[t] = make_double2(v.x + u.x, v.y + u.y);
+        Q[t] = make_double2(v.x - u.x, v.y - u.y);
+    }
+}
+
+// dst[b] = (level < s_b) ? src[b] : dst[b]   (squaring / reverse-squaring selection per slice)
+__global__ void k_lg_select(double2 *dst, const double2 *src, const int *sarr, int level, int nn, size_t tot) {
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x)
+        if (level < sarr[t / nn]) dst[t] = src[t];
+}
+
+// x[b] *= 2^-s_b
+__global__ void k_lg_unscale(double2 *x, const int *sarr, int nn, size_t tot) {
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const double f = ldexp(1.0, -sarr[t / nn]);
+        x[t].x *= f; x[t].y *= f;
+    }
+}
+
+// ubar[b][a][c] = sum_s lam_{j+1,s}[a] psi_{j,s}[c]  (cotangent of U_j from states = U_j psi); vectors planar [step][s][2][n]
+__global__ void k_lg_ubar(double2 *ubar, const double *psi, const double *lam, int j_begin, int B, int n, int S) {
+    const int nn = n * n;
+    const size_t tot = (size_t)B * nn, VS = (size_t)S * 2 * n;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / nn), e = (int)(t - (size_t)b * nn), a = e / n, c = e - a * n;
+        const double *p = psi + (size_t)(j_begin + b) * VS, *l = lam + (size_t)(j_begin + b + 1) * VS;
+        double sr = 0., si = 0.;
+        for (int s = 0; s < S; ++s) {
+            const double lr = l[s * 2 * n + a], li = l[s * 2 * n + n + a], pr = p[s * 2 * n + c], pi = p[s * 2 * n + n + c];
+            sr += lr * pr - li * pi; si += lr * pi + li * pr;
+        }
+        ubar[t] = make_double2(sr, si);
+    }
+}
+
+// node_grad[(j*q + i)*KR + r] = Re sum_e abar_i[b][e] G_r[e]; one CTA per (slice of the batch, node)
+__global__ void __launch_bounds__(256) k_lg_contract(const double2 *ab1, const double2 *ab2, const double2 *G, double *node_grad,
+                                                     int j_begin, int nn, int KR, int q) {
+    __shared__ double red[256];
+    const int b = blockIdx.x, i = blockIdx.y;
+    const double2 *ab = (i == 0 ? ab1 : ab2) + (size_t)b * nn;
+    for (int r = 0; r < KR; ++r) {
+        const double2 *g = G + (size_t)r * nn;
+        double s = 0.;
+        for (int e = threadIdx.x; e < nn; e += 256) s += ab[e].x * g[e].x - ab[e].y * g[e].y;
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+        if (threadIdx.x == 0) node_grad[((size_t)(j_begin + b) * q + i) * KR + r] = red[0];
+        __syncthreads();
+    }
+}
+
+// ---- state / costate sweeps: one persistent CTA walks the local slices; the propagator streams from HBM / L2 ----------
+// out[s][a] = sum_b U[a][b] in[s][b]: one warp per row, lanes along the contiguous index; states in groups of four
+__device__ void lg_matvec(double *out, const double *in, const double2 *U, int n, int S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = kLgThreads / 32;
+    for (int s0 = 0; s0 < S; s0 += 4) {
+        const int sc = min(4, S - s0);
+        for (int a = warp; a < n; a += NW) {
+            double ar[4] = {0., 0., 0., 0.}, ai[4] = {0., 0., 0., 0.};
+            for (int b = lane; b < n; b += 32) {
+                const double2 u = U[(size_t)a * n + b];
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    if (s < sc) {
+                        const double vr = in[(s0 + s) * 2 * n + b], vi = in[(s0 + s) * 2 * n + n + b];
+                        ar[s] += u.x * vr - u.y * vi; ai[s] += u.x * vi + u.y * vr;
+                    }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { ar[s] += __shfl_xor_sync(0xffffffffu, ar[s], o); ai[s] += __shfl_xor_sync(0xffffffffu, ai[s], o); }
+                if (lane == 0 && s < sc) { out[(s0 + s) * 2 * n + a] = ar[s]; out[(s0 + s) * 2 * n + n + a] = ai[s]; }
+            }
+        }
+    }
+    __syncthreads();
+}
+// out[s][a] = sum_b U[b][a] in[s][b]: one thread per column (coalesced along a)
+__device__ void lg_matvec_t(double *out, const double *in, const double2 *U, int n, int S) {
+    for (int s0 = 0; s0 < S; s0 += 4) {
+        const int sc = min(4, S - s0);
+        for (int a = threadIdx.x; a < n; a += kLgThreads) {
+            double ar[4] = {0., 0., 0., 0.}, ai[4] = {0., 0., 0., 0.};
+#pragma unroll 4
+            for (int b = 0; b < n; ++b) {
+                const double2 u = U[(size_t)b * n + a];
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    if (s < sc) {
+                        const double vr = in[(s0 + s) * 2 * n + b], vi = in[(s0 + s) * 2 * n + n + b];
+                        ar[s] += u.x * vr - u.y * vi; ai[s] += u.x * vi + u.y * vr;
+                    }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (s < sc) { out[(s0 + s) * 2 * n + a] = ar[s]; out[(s0 + s) * 2 * n + n + a] = ai[s]; }
+        }
+    }
+    __syncthreads();
+}
+
+struct LgSweep {
+    SweepArgs a;            // NP = n, N = local state count, j_off, Nglob, cost tables, psi / lam / psi_in / lam_in / b_out
+    const double2 *U;       // [N-1][n*n]
+    double *cost;
+};
+
+// psi[0] = psi_in; psi[k+1] = U_k psi[k]; cost values of the local states (k > 0)
+__global__ void __launch_bounds__(kLgThreads) k_lg_sweep_fwd(LgSweep g) {
+    extern __shared__ __align__(16) double sm_raw[];
+    const SweepArgs &a = g.a;
+    const int n = a.NP, S = a.S, VS = S * 2 * n;
+    double *v0 = sm_raw, *v1 = v0 + VS, *ip = v1 + VS;
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) { v0[i] = a.psi_in[i]; a.psi[i] = a.psi_in[i]; }
+    __syncthreads();
+    double cost = 0.;
+    for (int k = 1; k < a.N; ++k) {
+        lg_matvec(v1, v0, g.U + (size_t)(k - 1) * n * n, n, S);
+        for (int i = threadIdx.x; i < VS; i += kLgThreads) a.psi[(size_t)k * VS + i] = v1[i];
+        const bool st = is_step_cost_state(k + a.j_off, a.ces), fin = (k + a.j_off == a.Nglob - 1);
+        if (a.nterms > 0 && (st || fin)) {
+            cost_inner_products(a, v1, ip, st, fin);
+            cost += cost_value(a, ip, st, fin);
+        }
+        double *t = v0; v0 = v1; v1 = t;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *g.cost = cost;
+}
+
+// lam[N-1] = lam_in + final seed; lam[j] = U_j^T lam[j+1] + seed_j.  store = 0: only the costate at local state 0 is
+// written (to b_out) - the particular part of the time-sharded recursion
+__global__ void __launch_bounds__(kLgThreads) k_lg_sweep_bwd(LgSweep g, int store) {
+    extern __shared__ __align__(16) double sm_raw[];
+    const SweepArgs &a = g.a;
+    const int n = a.NP, S = a.S, VS = S * 2 * n;
+    double *v0 = sm_raw, *v1 = v0 + VS, *ip = v1 + VS;
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) v0[i] = a.lam_in ? a.lam_in[i] : 0.;
+    __syncthreads();
+    if (a.nterms > 0 && a.add_final_seed) {
+        const bool st = is_step_cost_state(a.N - 1 + a.j_off, a.ces);
+        cost_inner_products(a, a.psi + (size_t)(a.N - 1) * VS, ip, st, true);
+        cost_add_seed(a, ip, v0, st, true);
+    }
+    if (store) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.lam[(size_t)(a.N - 1) * VS + i] = v0[i];
+    for (int j = a.N - 2; j >= 0; --j) {
+        lg_matvec_t(v1, v0, g.U + (size_t)j * n * n, n, S);
+        if (a.nterms > 0 && is_step_cost_state(j + a.j_off, a.ces)) {
+            cost_inner_products(a, a.psi + (size_t)j * VS, ip, true, false);
+            cost_add_seed(a, ip, v1, true, false);
+        }
+        if (store) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.lam[(size_t)j * VS + i] = v1[i];
+        double *t = v0; v0 = v1; v1 = t;
+        __syncthreads();
+    }
+    if (a.b_out) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.b_out[i] = v0[i];
+}
+
+// time sharding: psi_in = P_{rank-1} .. P_0 psi0   /   lam_in = sum over later shards (see sweep.cuh)
+__global__ void __launch_bounds__(kLgThreads) k_lg_prefix(const double2 *allP, const double *psi0, double *psi_in, int rank, int n, int S) {
+    extern __shared__ __align__(16) double sm_raw[];
+    const int VS = S * 2 * n;
+    double *v0 = sm_raw, *v1 = v0 + VS;
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) v0[i] = psi0[i];
+    __syncthreads();
+    for (int r = 0; r < rank; ++r) { lg_matvec(v1, v0, allP + (size_t)r * n * n, n, S); double *t = v0; v0 = v1; v1 = t; }
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) psi_in[i] = v0[i];
+}
+__global__ void __launch_bounds__(kLgThreads) k_lg_suffix(const double2 *allP, const double *allb, double *lam_in, int rank, int world, int n, int S) {
+    extern __shared__ __align__(16) double sm_raw[];
+    const int VS = S * 2 * n;
+    double *v0 = sm_raw, *v1 = v0 + VS;
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) v0[i] = 0.;
+    __syncthreads();
+    for (int r = world - 1; r > rank; --r) {
+        lg_matvec_t(v1, v0, allP + (size_t)r * n * n, n, S);
+        for (int i = threadIdx.x; i < VS; i += kLgThreads) v1[i] += allb[(size_t)r * VS + i];
+        __syncthreads();
+        double *t = v0; v0 = v1; v1 = t;
+    }
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) lam_in[i] = v0[i];
+}
+
+}  // namespace qocb

@@ -13,7 +13,7 @@ out = os.path.join(ROOT, "gpurun_out", "libqocb200_prof.so")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 csrc = os.path.join(ROOT, "qoc_b200", "csrc")
 subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DQOCB_PROFILE",
-                "-shared", "-Xcompiler", "-fPIC", "-o", out, os.path.join(csrc, "capi.cu"), os.path.join(csrc, "lindblad.cu")],
+                "-shared", "-Xcompiler", "-fPIC", "-lcublas", "-o", out, os.path.join(csrc, "capi.cu"), os.path.join(csrc, "lindblad.cu")],
                check=True)
 os.environ["QOCB200_LIB"] = out
 import numpy as np  # noqa: E402
