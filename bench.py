@@ -40,13 +40,18 @@ FP64_TENSOR_PEAK_TFLOPS = 37.1   # measured on this pool's B200: DMMA m8n8k4 iss
 #                                  (profiles/r01_microbench_fp64.jsonl); MEASURED_PEAKS.json has no FP64 entry
 
 WORKLOADS = {
-    # name: (n, slices, K, S, order, complex_controls, F)
+    # name: (n, slices, K, S, order, complex_controls, F[, ensemble members])
     "n64_2000_M4": (64, 2000, 4, 4, 4, False, 0),
     "cfg3_n60_2000_M4": (60, 2000, 2, 4, 4, True, 6),
     "cfg1_n2_10_M2": (2, 10, 1, 1, 2, True, 0),
     "n32_2000_M4": (32, 2000, 4, 4, 4, False, 0),
     "n16_2000_M4": (16, 2000, 4, 4, 4, False, 0),
     "n8_2000_M2": (8, 2000, 2, 2, 2, False, 0),
+    "n128_2000_M4": (128, 2000, 4, 4, 4, False, 0),
+    "cfg4_n256_10000_M4": (256, 10000, 4, 4, 4, False, 0),
+    "n256_1250_M4": (256, 1250, 4, 4, 4, False, 0),                     # one rank's share of cfg4 at 8 GPUs
+    "cfg5_n32_500_S64_E1024_M2": (32, 500, 2, 64, 2, False, 0, 1024),
+    "cfg5_n32_500_S64_E128_M2": (32, 500, 2, 64, 2, False, 0, 128),      # one rank's share of cfg5 at 8 GPUs
 }
 
 
@@ -108,8 +113,16 @@ class ClockSampler(object):
 
 
 def make_problem(name):
-    n, slices, K, S, order, cc, F = WORKLOADS[name]
-    return Problem(n, slices, K, S, order, complex_controls=cc, F=F, seed=0)
+    w = WORKLOADS[name]
+    n, slices, K, S, order, cc, F = w[:7]
+    p = Problem(n, slices, K, S, order, complex_controls=cc, F=F, seed=0)
+    p.E = w[7] if len(w) > 7 else 1
+    p.drifts = None
+    if p.E > 1:                         # H0^(e) = H0 + delta_e Z, delta_e ~ N(0, 0.1^2)
+        rng = np.random.default_rng(12345)
+        z = np.diag(np.linspace(-1, 1, n)).astype(np.complex128) * np.abs(p.h0).max()
+        p.drifts = np.stack([p.h0 + d * z for d in rng.normal(0, 0.1, p.E)])
+    return p
 
 
 def oracle_time(p, sample_slices, reps, threads):
@@ -133,6 +146,13 @@ def oracle_time(p, sample_slices, reps, threads):
     return float(np.median(times[1:]))
 
 
+def cpu_sample(p, want):
+    """bounded CPU sample: slices of ONE ensemble member; the cost per slice grows as n^3"""
+    slices = p.N - 1
+    cap = want if p.n <= 64 else (40 if p.n <= 128 else 12)
+    return max(4, min(slices, cap))
+
+
 def pick_threads(p):
     """the oracle's BLAS threading can hurt at small n: calibrate 1 thread vs all cores on a
     few slices and use the faster."""
@@ -149,13 +169,13 @@ def run_reference(args, name):
     p = make_problem(name)
     slices = p.N - 1
     threads, t1, ta = pick_threads(p)
-    sample = max(4, min(slices, int(args.ref_slices)))
+    sample = cpu_sample(p, int(args.ref_slices))
     for _ in range(args.warmup):
         oracle_time(p, min(sample, 8), 0 + 1, threads)
     t0 = time.perf_counter()
     per = []
     for _ in range(args.steps):
-        per.append(oracle_time(p, sample, 1, threads) * slices / sample)
+        per.append(oracle_time(p, sample, 1, threads) * slices / sample * p.E)
     wall = time.perf_counter() - t0
     sec = float(np.mean(per))
     val = 1.0 / sec
@@ -164,7 +184,7 @@ def run_reference(args, name):
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64)",
            "data": "synthetic", "config": workload_config(name, p),
            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
-                            "sample": "%d of %d slices per step (fwd+bwd), scaled linearly; oracle = torch complex128 "
+                            "sample": "%d of %d slices (of one ensemble member) per step (fwd+bwd), scaled linearly; oracle = torch complex128 "
                                       "restatement of the reference (autograd absent in this image); 1 thread %.3fs vs %d "
                                       "threads %.3fs on an 8-slice calibration" % (sample, slices, t1, os.cpu_count() or 1, ta)},
            "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -173,7 +193,7 @@ def run_reference(args, name):
 
 
 def workload_config(name, p):
-    return {"workload": name, "hilbert_dim": p.n, "slices": p.N - 1, "controls": p.K,
+    return {"workload": name, "hilbert_dim": p.n, "slices": p.N - 1, "controls": p.K, "ensemble_members": p.E,
             "complex_controls": p.complex_controls, "states": p.S, "magnus": "M%d" % p.order,
             "costs": "TargetStateInfidelity" + ("+ForbidStates" if p.F else ""),
             "l2": "working set (propagators + tape) > 126 MB L2 and a 256 MiB flush write between timed iterations"}
@@ -197,7 +217,15 @@ def run_b200(args, name):
     p = make_problem(name)
     slices = p.N - 1
     kw = {}
-    if world > 1:
+    if p.E > 1:                          # ensembles shard by members (independent units, weak in members per rank? no:
+        kw["store_tape"] = False         # strong - the member set is fixed), time slices stay whole
+        if world > 1:
+            from qoc_b200.core.sharded import EnsembleShardedPlan as PlanCls
+            kw["ensemble_drifts"] = p.drifts
+        else:
+            PlanCls = SchroedingerPlan
+            kw["ensemble_drifts"] = p.drifts
+    elif world > 1:
         from qoc_b200.core.sharded import ShardedSchroedingerPlan as PlanCls
     else:
         PlanCls = SchroedingerPlan
@@ -237,13 +265,16 @@ def run_b200(args, name):
     KR = plan.KR
     h2d = p.M * KR * 8
     d2h = p.M * KR * 8 + 8 + plan.E * p.S * p.n * 16
+    if p.n > 64:
+        stage_names_note = "n > 64: stages are not split (batched pipeline)"
     fwd_f, bwd_f = flops_per_slice(p.n, p.S, p.order)
     names = ["expm_fwd", "boundary_fwd", "sweep_fwd", "sweep_bwd", "expm_bwd", "gather", "finalize", "spare"]
     stage_ms = {k: float(v) / args.steps for k, v in zip(names, stages)}
-    total_flops = (fwd_f + bwd_f) * slices
-    if world == 1:
+    total_flops = (fwd_f + bwd_f) * slices * p.E
+    fwd_f, bwd_f = fwd_f * p.E, bwd_f * p.E
+    if world == 1 or p.E > 1:
         dom = max(("expm_fwd", "expm_bwd"), key=lambda k: stage_ms[k])
-        dom_flops = (fwd_f if dom == "expm_fwd" else bwd_f) * slices
+        dom_flops = (fwd_f if dom == "expm_fwd" else bwd_f) * slices / (world if p.E > 1 else 1)
         achieved = dom_flops / (stage_ms[dom] * 1e-3) / 1e12
         dom_name = "k_backward" if dom == "expm_bwd" else "k_forward"
     else:       # no per-kernel split across the collectives: whole evaluation, per GPU
@@ -267,7 +298,7 @@ def run_b200(args, name):
                         "whole_eval_tflops": total_flops / (ms_per_step * 1e-3) / 1e12,
                         "whole_eval_frac": total_flops / (ms_per_step * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS / world},
            "stage_ms": stage_ms, "clocks": clocks, "cost": err}
-    if args.check and world > 1:
+    if args.check and world > 1 and p.E == 1:
         ok = True
         if rank == 0:
             ref = SchroedingerPlan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M,
@@ -291,15 +322,16 @@ def run_b200(args, name):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads, t1, ta = pick_threads(p)
-            sample = min(slices, args.cpu_slices)
-            sec = oracle_time(p, sample, 3, threads) * slices / sample
+            sample = cpu_sample(p, args.cpu_slices)
+            sec = oracle_time(p, sample, 3, threads) * slices / sample * p.E
             out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "evals/s", "cores": threads, "kind": "port",
-                                   "sample": "%d of %d slices (fwd+bwd), median of 3 after 1 warm-up, scaled linearly; "
+                                   "sample": "%d of %d slices of one ensemble member (fwd+bwd), median of 3 after 1 warm-up, scaled linearly; "
                                              "1 thread %.3fs vs %d threads %.3fs on an 8-slice calibration; published "
                                              "reference figure: 0.187 evals/s at n=64 x 1000 slices on 1 core i7-6700K "
                                              "(report.tex:110)" % (sample, slices, t1, os.cpu_count() or 1, ta)}
             # parity gate on the same controls (bounded: first `sample` slices)
-            out["parity"] = parity_gate(p, min(sample, 64), std, SchroedingerPlan, pol)
+            if p.E == 1:
+                out["parity"] = parity_gate(p, min(sample, 64 if p.n <= 64 else 8), std, SchroedingerPlan, pol)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

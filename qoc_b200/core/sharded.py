@@ -228,3 +228,55 @@ class ShardedSchroedingerPlan(object):
         self.torch.cuda.synchronize()
         self.engine.close()
         self.engine = None
+
+
+class EnsembleShardedPlan(object):
+    """robust-control ensembles (build-side extension): members that differ in the drift are
+    independent units, so they are block-partitioned across the ranks with no data-path exchange; one all-reduce of
+    [cost, gradient] (weighted by the members each rank holds) ends the evaluation.  Cost = mean over members."""
+
+    def __init__(self, hamiltonian, initial_states, costs, evolution_time, system_eval_count, ensemble_drifts, device=0,
+                 group=None, **kw):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        drifts = np.asarray(ensemble_drifts)
+        self.E_total = drifts.shape[0]
+        b = slice_bounds(self.E_total, self.world)
+        self.member_range = (b[self.rank], b[self.rank + 1])
+        self.plan = SchroedingerPlan(hamiltonian, initial_states, costs, evolution_time, system_eval_count,
+                                     ensemble_drifts=drifts[b[self.rank]:b[self.rank + 1]], device=device, **kw)
+        p = self.plan
+        self.KR, self.K, self.M, self.S, self.n, self.E = p.KR, p.K, p.M, p.S, p.n, p.E
+        self.complex_controls = p.complex_controls
+        self.weight = float(p.E) / self.E_total
+        self.dev = torch.device("cuda", device)
+        self.buf = torch.zeros(p.M * p.KR + 1, dtype=torch.float64, device=self.dev)
+
+    def upload(self, controls):
+        self.plan.upload(controls)
+
+    def cost_and_grad(self, controls):
+        """(mean cost, gradient of the mean cost, final states of the LOCAL members)."""
+        err, grads, finals = self.plan.cost_and_grad(controls)
+        g = np.concatenate([grads.real, grads.imag], axis=1) if self.complex_controls else np.asarray(grads)
+        host = np.concatenate([g.ravel(), [err]]) * self.weight
+        self.buf.copy_(self.torch.from_numpy(host))
+        self.dist.all_reduce(self.buf, group=self.group)
+        out = self.buf.cpu().numpy()
+        g = out[:-1].reshape(self.M, self.KR)
+        grads = g[:, :self.K] + 1j * g[:, self.K:] if self.complex_controls else g
+        return float(out[-1]), grads, finals
+
+    def time_resident(self, with_grad=True, warmup=3, iters=10, flush_l2=True):
+        """device time of the local members (no exchange inside the device-resident pipeline: the members are independent;
+        the caller takes the max over ranks)."""
+        return self.plan.time_resident(with_grad, warmup, iters, flush_l2)
+
+    def launch_count(self, with_grad=True):
+        return self.plan.launch_count(with_grad)
+
+    def close(self):
+        self.buf = None
+        self.plan.close()

@@ -290,10 +290,11 @@ enum { LA1 = 0, LA2N, LM, LA2, LA4, LA6, LW1, LX1, LY, LVE, LUO, LP, LQ, LT, LR0
 struct LargeImpl {
     int n = 0, nn = 0, B = 0;
     cublasHandle_t blas = nullptr;
-    DevBuf<double2> G0, G, work, treeA, treeB;
+    DevBuf<double2> G0, G, work, treeA, treeB, UT, lvl, PT, allPT;
     DevBuf<double2 *> ptrQ, ptrP, ptrRB;
-    DevBuf<int> piv, info, sarr;
+    DevBuf<int> piv, info, sarr, cb;
     std::vector<int> h_s;
+    int lstar = 0, nchunks = 0, lvl_count[24] = {}, lvl_off[24] = {};   // pairwise propagator tree levels 0..lstar
     double2 *arr(int i) { return work.p + (size_t)i * B * nn; }
     ~LargeImpl() { if (blas) cublasDestroy(blas); }
 };
@@ -505,11 +506,35 @@ int large_init(qocb_plan *p) {
     CU_TRY(p, cudaMemcpy(L->ptrQ.p, hq.data(), sizeof(double2 *) * L->B, cudaMemcpyHostToDevice));
     CU_TRY(p, cudaMemcpy(L->ptrP.p, hp.data(), sizeof(double2 *) * L->B, cudaMemcpyHostToDevice));
     CU_TRY(p, cudaMemcpy(L->ptrRB.p, hr.data(), sizeof(double2 *) * L->B, cudaMemcpyHostToDevice));
-    if (p->sharded) { CU_TRY(p, L->treeA.alloc((size_t)((Lsl + 1) / 2) * L->nn)); CU_TRY(p, L->treeB.alloc((size_t)((Lsl + 3) / 4) * L->nn)); }
+    // chunk level of the sweeps: first level of the pairwise tree with at most 160 propagators
+    L->lvl_count[0] = Lsl;
+    int off = 0;
+    while (L->lvl_count[L->lstar] > 160) {
+        const int nxt = (L->lvl_count[L->lstar] + 1) / 2;
+        ++L->lstar;
+        L->lvl_count[L->lstar] = nxt; L->lvl_off[L->lstar] = off; off += nxt;
+    }
+    L->nchunks = L->lvl_count[L->lstar];
+    {
+        std::vector<int> cb(L->nchunks + 1);
+        for (int c = 0; c < L->nchunks; ++c) cb[c] = (int)std::min<long long>((long long)c << L->lstar, Lsl);
+        cb[L->nchunks] = Lsl;
+        CU_TRY(p, L->cb.alloc(cb.size()));
+        CU_TRY(p, cudaMemcpy(L->cb.p, cb.data(), sizeof(int) * cb.size(), cudaMemcpyHostToDevice));
+    }
+    CU_TRY(p, L->UT.alloc((size_t)Lsl * L->nn));
+    CU_TRY(p, L->lvl.alloc((size_t)std::max(1, off) * L->nn));
+    if (L->lstar > 0) CU_TRY(p, L->PT.alloc((size_t)L->nchunks * L->nn));
+    const size_t VSl = (size_t)p->pb.state_count * 2 * n;
+    CU_TRY(p, p->part.alloc((size_t)L->nchunks * VSl)); CU_TRY(p, p->cost_part.alloc(L->nchunks));
+    if (p->sharded) { CU_TRY(p, L->treeA.alloc((size_t)((L->nchunks + 1) / 2) * L->nn)); CU_TRY(p, L->treeB.alloc((size_t)((L->nchunks + 3) / 4) * L->nn)); }
     L->h_s.resize(L->B);
     const int big = 200 * 1024;
     CU_TRY(p, cudaFuncSetAttribute(k_lg_sweep_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU_TRY(p, cudaFuncSetAttribute(k_lg_sweep_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_sweep_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_sweep_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_boundary_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_boundary_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(p, cudaFuncSetAttribute(k_lg_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(p, cudaFuncSetAttribute(k_lg_suffix, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     return 0;
@@ -570,15 +595,33 @@ int lg_expm_all(qocb_plan *p) {
         int rc = lg_forward_batch(p, jb, Bc, false, &smax); if (rc) return rc;
         rc = lg_copy(p, reinterpret_cast<double2 *>(p->U.p) + (size_t)jb * L->nn, L->arr(LP), Bc); if (rc) return rc;
     }
+    // transposed copies for the costate sweeps; pairwise product tree up to the chunk level of the sweeps
+    const double2 *U = reinterpret_cast<const double2 *>(p->U.p);
+    k_lg_transpose<<<148 * 8, dim3(16, 16), 0, p->stream>>>(L->UT.p, U, L->n, Lsl);
+    const double2 *in = U;
+    for (int l = 1; l <= L->lstar; ++l) {
+        double2 *out = L->lvl.p + (size_t)L->lvl_off[l] * L->nn;
+        const int count = L->lvl_count[l - 1], pairs = count / 2;
+        int rc = lg_gemm(p, false, false, in + L->nn, in, out, 1., 0., pairs, 2LL * L->nn, 2LL * L->nn, L->nn); if (rc) return rc;
+        if (count & 1) { rc = lg_copy(p, out + (size_t)pairs * L->nn, in + (size_t)(count - 1) * L->nn, 1); if (rc) return rc; }
+        in = out;
+    }
+    if (L->lstar > 0) k_lg_transpose<<<148 * 8, dim3(16, 16), 0, p->stream>>>(L->PT.p, in, L->n, L->nchunks);
+    CU_TRY(p, cudaGetLastError());
     return 0;
 }
 
 LgSweep lg_sweep_args(qocb_plan *p) {
     LgSweep g;
     g.a = make_sargs(p);
-    g.a.NP = p->large->n;
+    LargeImpl *L = p->large;
+    g.a.NP = L->n;
+    g.a.chunk_begin = L->cb.p;
     g.U = reinterpret_cast<const double2 *>(p->U.p);
-    g.cost = p->cost.p;
+    g.UT = L->UT.p;
+    g.P = L->lstar > 0 ? L->lvl.p + (size_t)L->lvl_off[L->lstar] * L->nn : g.U;
+    g.PT = L->lstar > 0 ? L->PT.p : L->UT.p;
+    g.nchunks = L->nchunks;
     return g;
 }
 size_t lg_sweep_smem(qocb_plan *p) {
@@ -649,17 +692,35 @@ int lg_backward_all(qocb_plan *p) {
     return 0;
 }
 
+int lg_states_forward(qocb_plan *p, const double *psi_in_dev) {
+    LgSweep g = lg_sweep_args(p);
+    g.a.psi_in = psi_in_dev;
+    const size_t sm = lg_sweep_smem(p);
+    k_lg_boundary_fwd<<<1, kLgThreads, sm, p->stream>>>(g);
+    k_lg_sweep_fwd<<<g.nchunks, kLgThreads, sm, p->stream>>>(g);
+    k_finalize_cost<<<1, 32, 0, p->stream>>>(p->cost_part.p, g.nchunks, 1, p->cost.p);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+int lg_costates(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, bool do_particular, bool do_sweeps) {
+    LgSweep g = lg_sweep_args(p);
+    g.a.lam_in = lam_in_dev; g.a.b_out = b_out_dev;
+    const size_t sm = lg_sweep_smem(p);
+    if (do_particular && p->have_step_costs) k_lg_sweep_bwd<true><<<g.nchunks, kLgThreads, sm, p->stream>>>(g);
+    k_lg_boundary_bwd<<<1, kLgThreads, sm, p->stream>>>(g, p->have_step_costs ? 1 : 0);
+    if (do_sweeps) k_lg_sweep_bwd<false><<<g.nchunks, kLgThreads, sm, p->stream>>>(g);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
 int lg_eval(qocb_plan *p, bool with_grad) {
     int rc = lg_expm_all(p); if (rc) return rc;
-    LgSweep g = lg_sweep_args(p);
-    g.a.psi_in = p->psi0.p;
-    k_lg_sweep_fwd<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(g);
+    rc = lg_states_forward(p, p->psi0.p); if (rc) return rc;
     if (with_grad) {
-        k_lg_sweep_bwd<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(g, 1);
-        CU_TRY(p, cudaGetLastError());
+        rc = lg_costates(p, nullptr, nullptr, true, true); if (rc) return rc;
         rc = lg_backward_all(p); if (rc) return rc;
     }
-    CU_TRY(p, cudaGetLastError());
     return 0;
 }
 
@@ -667,8 +728,8 @@ int lg_eval(qocb_plan *p, bool with_grad) {
 int lg_shard_propagator(qocb_plan *p, double2 *out_dev) {
     LargeImpl *L = p->large;
     const int nn = L->nn;
-    const double2 *in = reinterpret_cast<const double2 *>(p->U.p);
-    int count = p->Nloc - 1;
+    const double2 *in = L->lstar > 0 ? L->lvl.p + (size_t)L->lvl_off[L->lstar] * nn : reinterpret_cast<const double2 *>(p->U.p);
+    int count = L->nchunks;
     double2 *bufs[2] = {L->treeA.p, L->treeB.p};
     int which = 0;
     if (count == 1) return lg_copy(p, out_dev, in, 1);
@@ -1277,11 +1338,8 @@ int qocb_shard_forward_finish(qocb_plan *p, const double *allP_dev, int32_t rank
     if (p->large) {
         k_lg_prefix<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(reinterpret_cast<const double2 *>(allP_dev), p->psi0.p, p->psi_in.p, rank,
                                                                    p->large->n, p->pb.state_count);
-        LgSweep g = lg_sweep_args(p);
-        g.a.psi_in = p->psi_in.p;
-        k_lg_sweep_fwd<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(g);
         CU_TRY(p, cudaGetLastError());
-        return 0;
+        return lg_states_forward(p, p->psi_in.p);
     }
     const size_t sm = sweep_smem_bytes(p->NP, p->pb.state_count, p->ip_total);
     SWEEP_NP(p->NP, (k_prefix_states<NPc><<<1, kSweepThreads, sm, p->stream>>>(allP_dev, p->psi0.p, p->psi_in.p, rank, p->pb.state_count)));
@@ -1293,13 +1351,7 @@ int qocb_shard_forward_finish(qocb_plan *p, const double *allP_dev, int32_t rank
 int qocb_shard_backward_particular(qocb_plan *p, double *b_dev) {
     if (!p || !b_dev) { set_error(p, "null argument"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
-    if (p->large) {
-        LgSweep g = lg_sweep_args(p);
-        g.a.lam_in = nullptr; g.a.b_out = b_dev;
-        k_lg_sweep_bwd<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(g, 0);
-        CU_TRY(p, cudaGetLastError());
-        return 0;
-    }
+    if (p->large) return lg_costates(p, nullptr, b_dev, true, false);
     return enqueue_costate(p, nullptr, b_dev, true, false);
 }
 
@@ -1307,12 +1359,12 @@ int qocb_shard_backward_finish(qocb_plan *p, const double *allP_dev, const doubl
     if (!p || !allP_dev || !allb_dev || rank < 0 || rank >= world) { set_error(p, "bad argument"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
     if (p->large) {
-        k_lg_suffix<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(reinterpret_cast<const double2 *>(allP_dev), allb_dev, p->lam_in.p, rank, world,
-                                                                   p->large->n, p->pb.state_count);
-        LgSweep g = lg_sweep_args(p);
-        g.a.lam_in = p->lam_in.p; g.a.b_out = nullptr;
-        k_lg_sweep_bwd<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(g, 1);
+        LargeImpl *L = p->large;
+        if (L->allPT.n < (size_t)world * L->nn) CU_TRY(p, L->allPT.alloc((size_t)world * L->nn));
+        k_lg_transpose<<<world * 64, dim3(16, 16), 0, p->stream>>>(L->allPT.p, reinterpret_cast<const double2 *>(allP_dev), L->n, world);
+        k_lg_suffix<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(L->allPT.p, allb_dev, p->lam_in.p, rank, world, L->n, p->pb.state_count);
         CU_TRY(p, cudaGetLastError());
+        int rc = lg_costates(p, p->lam_in.p, nullptr, false, true); if (rc) return rc;
         return lg_backward_all(p);
     }
     const size_t sm = sweep_smem_bytes(p->NP, p->pb.state_count, p->ip_total);

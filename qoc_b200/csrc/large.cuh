@@ -152,75 +152,121 @@ __global__ void __launch_bounds__(256) k_lg_contract(const double2 *ab1, const d
     }
 }
 
-// ---- state / costate sweeps: one persistent CTA walks the local slices; the propagator streams from HBM / L2 ----------
-// out[s][a] = sum_b U[a][b] in[s][b]: one warp per row, lanes along the contiguous index; states in groups of four
-__device__ void lg_matvec(double *out, const double *in, const double2 *U, int n, int S) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = kLgThreads / 32;
+// ---- state / costate sweeps -----------------------------------------------------------------------------------------
+// Same three-step chunk scheme as sweep.cuh (boundary pass over chunk propagators, independent local sweeps; affine
+// recursion with particular parts backwards); the chunk propagators are one level of the batched pairwise GEMM tree.
+// Every mat-vec streams its n x n matrix from HBM / L2: one warp per row with the rows of four passes in flight
+// (register prefetch).  The costate sweeps read explicitly transposed copies U_j^T, P_c^T, so both directions use the
+// coalesced row-streaming kernel.
+__global__ void k_lg_transpose(double2 *dst, const double2 *src, int n, int batch) {
+    __shared__ double2 tile[16][17];
+    const int tiles = (n + 15) / 16;
+    const size_t nn = (size_t)n * n;
+    for (int w = blockIdx.x; w < batch * tiles * tiles; w += gridDim.x) {
+        const int b = w / (tiles * tiles), t = w % (tiles * tiles), tr = t / tiles, tc = t % tiles;
+        const int r = tr * 16 + threadIdx.y, c = tc * 16 + threadIdx.x;
+        if (r < n && c < n) tile[threadIdx.y][threadIdx.x] = src[b * nn + (size_t)r * n + c];
+        __syncthreads();
+        const int r2 = tc * 16 + threadIdx.y, c2 = tr * 16 + threadIdx.x;
+        if (r2 < n && c2 < n) dst[b * nn + (size_t)r2 * n + c2] = tile[threadIdx.x][threadIdx.y];
+        __syncthreads();
+    }
+}
+
+// out[s][a] = sum_b U[a][b] in[s][b]; vectors planar [s][2][n] in shared memory; ends with a barrier
+template <int NPL>          // double2 per lane per row: n <= 32 * NPL
+__device__ void lg_matvec_rows(double *out, const double *in, const double2 *U, int n, int S) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = kLgThreads / 32, D = NPL <= 8 ? 4 : 2;
     for (int s0 = 0; s0 < S; s0 += 4) {
         const int sc = min(4, S - s0);
-        for (int a = warp; a < n; a += NW) {
-            double ar[4] = {0., 0., 0., 0.}, ai[4] = {0., 0., 0., 0.};
-            for (int b = lane; b < n; b += 32) {
-                const double2 u = U[(size_t)a * n + b];
+        for (int a0 = warp; a0 < n; a0 += NW * D) {
+            double2 u[D][NPL];
 #pragma unroll
-                for (int s = 0; s < 4; ++s)
-                    if (s < sc) {
-                        const double vr = in[(s0 + s) * 2 * n + b], vi = in[(s0 + s) * 2 * n + n + b];
-                        ar[s] += u.x * vr - u.y * vi; ai[s] += u.x * vi + u.y * vr;
-                    }
+            for (int d = 0; d < D; ++d) {
+                const int a = a0 + d * NW;
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) {
+                    const int c = lane + 32 * k;
+                    u[d][k] = (a < n && c < n) ? U[(size_t)a * n + c] : make_double2(0., 0.);
+                }
             }
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
+            for (int d = 0; d < D; ++d) {
+                const int a = a0 + d * NW;
+                double ar[4] = {0., 0., 0., 0.}, ai[4] = {0., 0., 0., 0.};
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { ar[s] += __shfl_xor_sync(0xffffffffu, ar[s], o); ai[s] += __shfl_xor_sync(0xffffffffu, ai[s], o); }
-                if (lane == 0 && s < sc) { out[(s0 + s) * 2 * n + a] = ar[s]; out[(s0 + s) * 2 * n + n + a] = ai[s]; }
+                for (int k = 0; k < NPL; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c < n) {
+#pragma unroll
+                        for (int s = 0; s < 4; ++s)
+                            if (s < sc) {
+                                const double vr = in[(s0 + s) * 2 * n + c], vi = in[(s0 + s) * 2 * n + n + c];
+                                ar[s] += u[d][k].x * vr - u[d][k].y * vi; ai[s] += u[d][k].x * vi + u[d][k].y * vr;
+                            }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { ar[s] += __shfl_xor_sync(0xffffffffu, ar[s], o); ai[s] += __shfl_xor_sync(0xffffffffu, ai[s], o); }
+                    if (lane == 0 && s < sc && a < n) { out[(s0 + s) * 2 * n + a] = ar[s]; out[(s0 + s) * 2 * n + n + a] = ai[s]; }
+                }
             }
         }
     }
     __syncthreads();
 }
-// out[s][a] = sum_b U[b][a] in[s][b]: one thread per column (coalesced along a)
-__device__ void lg_matvec_t(double *out, const double *in, const double2 *U, int n, int S) {
-    for (int s0 = 0; s0 < S; s0 += 4) {
-        const int sc = min(4, S - s0);
-        for (int a = threadIdx.x; a < n; a += kLgThreads) {
-            double ar[4] = {0., 0., 0., 0.}, ai[4] = {0., 0., 0., 0.};
-#pragma unroll 4
-            for (int b = 0; b < n; ++b) {
-                const double2 u = U[(size_t)b * n + a];
-#pragma unroll
-                for (int s = 0; s < 4; ++s)
-                    if (s < sc) {
-                        const double vr = in[(s0 + s) * 2 * n + b], vi = in[(s0 + s) * 2 * n + n + b];
-                        ar[s] += u.x * vr - u.y * vi; ai[s] += u.x * vi + u.y * vr;
-                    }
-            }
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                if (s < sc) { out[(s0 + s) * 2 * n + a] = ar[s]; out[(s0 + s) * 2 * n + n + a] = ai[s]; }
-        }
-    }
-    __syncthreads();
+__device__ __forceinline__ void lg_matvec(double *out, const double *in, const double2 *U, int n, int S) {
+    if (n <= 128) lg_matvec_rows<4>(out, in, U, n, S);
+    else if (n <= 256) lg_matvec_rows<8>(out, in, U, n, S);
+    else lg_matvec_rows<16>(out, in, U, n, S);
 }
 
 struct LgSweep {
-    SweepArgs a;            // NP = n, N = local state count, j_off, Nglob, cost tables, psi / lam / psi_in / lam_in / b_out
-    const double2 *U;       // [N-1][n*n]
-    double *cost;
+    SweepArgs a;            // NP = n, N = local state count, chunk tables, cost tables, psi / lam / part / cost_part, ...
+    const double2 *U, *UT;  // [N-1][n*n] propagators and their transposes
+    const double2 *P, *PT;  // [nchunks][n*n] chunk propagators and their transposes
+    int nchunks;
 };
 
-// psi[0] = psi_in; psi[k+1] = U_k psi[k]; cost values of the local states (k > 0)
+// (1) boundary states; grid = 1
+__global__ void __launch_bounds__(kLgThreads) k_lg_boundary_fwd(LgSweep g) {
+    extern __shared__ __align__(16) double sm_raw[];
+    const SweepArgs &a = g.a;
+    const int n = a.NP, S = a.S, VS = S * 2 * n;
+    double *v0 = sm_raw, *v1 = v0 + VS;
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) { v0[i] = a.psi_in[i]; a.psi[i] = a.psi_in[i]; }
+    __syncthreads();
+    for (int c = 0; c < g.nchunks; ++c) {
+        lg_matvec(v1, v0, g.P + (size_t)c * n * n, n, S);
+        const int kend = a.chunk_begin[c + 1];
+        for (int i = threadIdx.x; i < VS; i += kLgThreads) a.psi[(size_t)kend * VS + i] = v1[i];
+        double *t = v0; v0 = v1; v1 = t;
+        __syncthreads();
+    }
+}
+
+// (2) local forward sweeps + cost values; grid = nchunks
 __global__ void __launch_bounds__(kLgThreads) k_lg_sweep_fwd(LgSweep g) {
     extern __shared__ __align__(16) double sm_raw[];
     const SweepArgs &a = g.a;
     const int n = a.NP, S = a.S, VS = S * 2 * n;
     double *v0 = sm_raw, *v1 = v0 + VS, *ip = v1 + VS;
-    for (int i = threadIdx.x; i < VS; i += kLgThreads) { v0[i] = a.psi_in[i]; a.psi[i] = a.psi_in[i]; }
+    const int c = blockIdx.x, jb = a.chunk_begin[c], je = a.chunk_begin[c + 1];
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) v0[i] = a.psi[(size_t)jb * VS + i];
     __syncthreads();
     double cost = 0.;
-    for (int k = 1; k < a.N; ++k) {
-        lg_matvec(v1, v0, g.U + (size_t)(k - 1) * n * n, n, S);
-        for (int i = threadIdx.x; i < VS; i += kLgThreads) a.psi[(size_t)k * VS + i] = v1[i];
+    for (int j = jb; j < je; ++j) {
+        const int k = j + 1;
+        if (k < je) {
+            lg_matvec(v1, v0, g.U + (size_t)j * n * n, n, S);
+            for (int i = threadIdx.x; i < VS; i += kLgThreads) a.psi[(size_t)k * VS + i] = v1[i];
+        } else {
+            for (int i = threadIdx.x; i < VS; i += kLgThreads) v1[i] = a.psi[(size_t)k * VS + i];
+            __syncthreads();
+        }
         const bool st = is_step_cost_state(k + a.j_off, a.ces), fin = (k + a.j_off == a.Nglob - 1);
         if (a.nterms > 0 && (st || fin)) {
             cost_inner_products(a, v1, ip, st, fin);
@@ -229,12 +275,35 @@ __global__ void __launch_bounds__(kLgThreads) k_lg_sweep_fwd(LgSweep g) {
         double *t = v0; v0 = v1; v1 = t;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *g.cost = cost;
+    if (threadIdx.x == 0) a.cost_part[c] = cost;
 }
 
-// lam[N-1] = lam_in + final seed; lam[j] = U_j^T lam[j+1] + seed_j.  store = 0: only the costate at local state 0 is
-// written (to b_out) - the particular part of the time-sharded recursion
-__global__ void __launch_bounds__(kLgThreads) k_lg_sweep_bwd(LgSweep g, int store) {
+// (3a/3c) local backward sweeps; grid = nchunks
+template <bool PARTICULAR>
+__global__ void __launch_bounds__(kLgThreads) k_lg_sweep_bwd(LgSweep g) {
+    extern __shared__ __align__(16) double sm_raw[];
+    const SweepArgs &a = g.a;
+    const int n = a.NP, S = a.S, VS = S * 2 * n;
+    double *v0 = sm_raw, *v1 = v0 + VS, *ip = v1 + VS;
+    const int c = blockIdx.x, jb = a.chunk_begin[c], je = a.chunk_begin[c + 1];
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) v0[i] = PARTICULAR ? 0. : a.lam[(size_t)je * VS + i];
+    __syncthreads();
+    const int jstop = PARTICULAR ? jb : jb + 1;
+    for (int j = je - 1; j >= jstop; --j) {
+        lg_matvec(v1, v0, g.UT + (size_t)j * n * n, n, S);
+        if (a.nterms > 0 && is_step_cost_state(j + a.j_off, a.ces)) {
+            cost_inner_products(a, a.psi + (size_t)j * VS, ip, true, false);
+            cost_add_seed(a, ip, v1, true, false);
+        }
+        if (!PARTICULAR) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.lam[(size_t)j * VS + i] = v1[i];
+        double *t = v0; v0 = v1; v1 = t;
+        __syncthreads();
+    }
+    if (PARTICULAR) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.part[(size_t)c * VS + i] = v0[i];
+}
+
+// (3b) boundary costates; grid = 1
+__global__ void __launch_bounds__(kLgThreads) k_lg_boundary_bwd(LgSweep g, int have_part) {
     extern __shared__ __align__(16) double sm_raw[];
     const SweepArgs &a = g.a;
     const int n = a.NP, S = a.S, VS = S * 2 * n;
@@ -246,21 +315,19 @@ __global__ void __launch_bounds__(kLgThreads) k_lg_sweep_bwd(LgSweep g, int stor
         cost_inner_products(a, a.psi + (size_t)(a.N - 1) * VS, ip, st, true);
         cost_add_seed(a, ip, v0, st, true);
     }
-    if (store) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.lam[(size_t)(a.N - 1) * VS + i] = v0[i];
-    for (int j = a.N - 2; j >= 0; --j) {
-        lg_matvec_t(v1, v0, g.U + (size_t)j * n * n, n, S);
-        if (a.nterms > 0 && is_step_cost_state(j + a.j_off, a.ces)) {
-            cost_inner_products(a, a.psi + (size_t)j * VS, ip, true, false);
-            cost_add_seed(a, ip, v1, true, false);
-        }
-        if (store) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.lam[(size_t)j * VS + i] = v1[i];
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) a.lam[(size_t)(a.N - 1) * VS + i] = v0[i];
+    for (int c = g.nchunks - 1; c >= 0; --c) {
+        lg_matvec(v1, v0, g.PT + (size_t)c * n * n, n, S);
+        if (have_part) { for (int i = threadIdx.x; i < VS; i += kLgThreads) v1[i] += a.part[(size_t)c * VS + i]; __syncthreads(); }
+        const int kbeg = a.chunk_begin[c];
+        for (int i = threadIdx.x; i < VS; i += kLgThreads) a.lam[(size_t)kbeg * VS + i] = v1[i];
         double *t = v0; v0 = v1; v1 = t;
         __syncthreads();
     }
     if (a.b_out) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.b_out[i] = v0[i];
 }
 
-// time sharding: psi_in = P_{rank-1} .. P_0 psi0   /   lam_in = sum over later shards (see sweep.cuh)
+// time sharding: psi_in = P_{rank-1} .. P_0 psi0   /   lam_in from the later shards (allPT: transposed shard propagators)
 __global__ void __launch_bounds__(kLgThreads) k_lg_prefix(const double2 *allP, const double *psi0, double *psi_in, int rank, int n, int S) {
     extern __shared__ __align__(16) double sm_raw[];
     const int VS = S * 2 * n;
@@ -270,14 +337,14 @@ __global__ void __launch_bounds__(kLgThreads) k_lg_prefix(const double2 *allP, c
     for (int r = 0; r < rank; ++r) { lg_matvec(v1, v0, allP + (size_t)r * n * n, n, S); double *t = v0; v0 = v1; v1 = t; }
     for (int i = threadIdx.x; i < VS; i += kLgThreads) psi_in[i] = v0[i];
 }
-__global__ void __launch_bounds__(kLgThreads) k_lg_suffix(const double2 *allP, const double *allb, double *lam_in, int rank, int world, int n, int S) {
+__global__ void __launch_bounds__(kLgThreads) k_lg_suffix(const double2 *allPT, const double *allb, double *lam_in, int rank, int world, int n, int S) {
     extern __shared__ __align__(16) double sm_raw[];
     const int VS = S * 2 * n;
     double *v0 = sm_raw, *v1 = v0 + VS;
     for (int i = threadIdx.x; i < VS; i += kLgThreads) v0[i] = 0.;
     __syncthreads();
     for (int r = world - 1; r > rank; --r) {
-        lg_matvec_t(v1, v0, allP + (size_t)r * n * n, n, S);
+        lg_matvec(v1, v0, allPT + (size_t)r * n * n, n, S);
         for (int i = threadIdx.x; i < VS; i += kLgThreads) v1[i] += allb[(size_t)r * VS + i];
         __syncthreads();
         double *t = v0; v0 = v1; v1 = t;

@@ -20,6 +20,7 @@ CASES = [
     (72, 11, 2, 3, 4, True, 2, 1.0, 2, True),
     (96, 7, 1, 4, 4, False, 3, 8.0, 1, False),
     (130, 5, 2, 2, 4, True, 0, 30.0, 1, False),
+    (68, 401, 2, 2, 2, False, 2, 1.0, 7, True),          # > 160 slices: sweeps run on a coarser level of the propagator tree
 ]
 
 
@@ -47,13 +48,13 @@ def test_large_dim_vs_oracle(case):
     plan.close()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_large_dim_sharded(world):
+@pytest.mark.parametrize("world,slices", [(2, 13), (3, 13), (2, 700)])
+def test_large_dim_sharded(world, slices):
     import qoc_b200.standard as std
     from oracle import qoc_oracle as orc
     from qoc_b200.core.sharded import CudaShardEngine
     from qoc_b200.models import MagnusPolicy
-    n, slices, K, S, cc = 80, 13, 2, 3, True
+    n, K, S, cc = 80 if slices < 100 else 66, 2, 3, True
     p = Problem(n, slices, K, S, 4, complex_controls=cc, F=2, seed=3, stiff=8.0, cost_eval_step=2, step_target=True)
     kw = dict(control_eval_count=p.M, control_count=K, complex_controls=cc, magnus_policy=MagnusPolicy.M4, cost_eval_step=2)
     engines = [CudaShardEngine(r, world, p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, **kw) for r in range(world)]
