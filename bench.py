@@ -112,6 +112,15 @@ class ClockSampler(object):
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(workload, kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
 def make_problem(name):
     w = WORKLOADS[name]
     n, slices, K, S, order, cc, F = w[:7]
@@ -217,8 +226,7 @@ def run_b200(args, name):
     p = make_problem(name)
     slices = p.N - 1
     kw = {}
-    if p.E > 1:                          # ensembles shard by members (independent units, weak in members per rank? no:
-        kw["store_tape"] = False         # strong - the member set is fixed), time slices stay whole
+    if p.E > 1:                          # ensembles shard by members (independent units; the member set is fixed: strong)
         if world > 1:
             from qoc_b200.core.sharded import EnsembleShardedPlan as PlanCls
             kw["ensemble_drifts"] = p.drifts
@@ -291,7 +299,7 @@ def run_b200(args, name):
            "gpu_launches": plan.launch_count(True) * args.steps,
            "roofline": {"bound": "tensor", "kernel": dom_name,
                         "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                        "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": None,
+                        "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": ncu_traffic(name, dom_name),
                         "peak_source": "FP64 DMMA pipe measured on this pool (profiles/r01_microbench_fp64.jsonl); "
                                        "MEASURED_PEAKS.json has HBM and bf16 only",
                         "algorithmic_flops_per_launch": dom_flops,

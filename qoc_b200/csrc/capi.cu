@@ -1032,11 +1032,6 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     PTRY(p->G0.alloc((size_t)E * GM)); PTRY(p->G.alloc(std::max<size_t>(1, (size_t)KR) * GM));
     PTRY(p->controls.alloc(std::max<size_t>(1, (size_t)M * KR)));
     PTRY(p->U.alloc(W * GM));
-    if (pb->store_tape && !is_large) {
-        cudaError_t e = p->tape.alloc(W * p->tape_mats * GM);
-        if (e != cudaSuccess) { cudaGetLastError(); p->tape.release(); }       // fall back to recompute mode on the GPU
-        else PTRY(p->tape_piv.alloc(W * NP));
-    }
     PTRY(p->meta.alloc(W));
     PTRY(p->scratch.alloc((size_t)p->nchunks * S_COUNT * GM));
     PTRY(p->cta_tape.alloc((size_t)p->nchunks * (8 + kCtaTapeR) * GM));
@@ -1063,6 +1058,18 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
         SWEEP_NP(NP, (ae = set_sweep_attrs<NPc>(big)));
         PTRY(ae);
         if (is_large && large_init(p) != 0) return fail(-2);
+    }
+    // the reverse-pass tape goes last: if it does not fit beside everything else (and 4 GiB of head-room), the plan
+    // runs in recompute mode on the GPU instead
+    if (pb->store_tape && !is_large) {
+        size_t free_b = 0, total_b = 0;
+        PTRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = W * p->tape_mats * GM * sizeof(double) + W * NP * sizeof(int);
+        if (need + ((size_t)4 << 30) <= free_b) {
+            cudaError_t e = p->tape.alloc(W * p->tape_mats * GM);
+            if (e != cudaSuccess) { cudaGetLastError(); p->tape.release(); }
+            else PTRY(p->tape_piv.alloc(W * NP));
+        }
     }
 #undef PTRY
     *out = p;
