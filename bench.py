@@ -366,19 +366,105 @@ def parity_gate(p, sample, std, Plan, pol):
             "grad_rel_err": float(np.linalg.norm(grads - o_grad) / np.linalg.norm(o_grad)), "tolerance": 1e-10}
 
 
+# ---- Lindblad workloads (cfg2 and a denser variant): one step = one cost+gradient of the adaptive RKDP5 path -------------
+LINDBLAD_WORKLOADS = {
+    # name: (n, D, intervals, T, gamma, max control norm)
+    "cfg2_lindblad_n2": (2, 1, 1, 10.0, 1e-3, 5.0),              # examples/1_transmon_pi_dechoerence.py:22-60
+    "lindblad_n8_D2_N5": (8, 2, 4, 4.0, 5e-2, 1.0),
+}
+
+
+def lindblad_problem(name):
+    n, D, intervals, T, gamma, mx = LINDBLAD_WORKLOADS[name]
+    rng = np.random.default_rng(0)
+    a = np.diag(np.sqrt(np.arange(1, n)), 1).astype(np.complex128)
+    h0 = np.diag(np.arange(n) - (n - 1) / 2.0).astype(np.complex128) * (1.0 if n == 2 else 0.7)
+    M = 11
+    controls = (0.1 * mx * (1 - 1j) / np.sqrt(2)) * np.ones((M, 1), dtype=np.complex128)     # flat initial guess (common.py:110-142)
+    if n > 2:
+        controls = controls + 0.05 * (rng.standard_normal((M, 1)) + 1j * rng.standard_normal((M, 1)))
+    rho0 = np.zeros((D, n, n), dtype=np.complex128)
+    targ = np.zeros((D, n, n), dtype=np.complex128)
+    for d in range(D):
+        rho0[d, d, d] = 1.0
+        targ[d, d + 1, d + 1] = 1.0
+    return dict(n=n, D=D, N=intervals + 1, T=T, M=M, h0=h0, drive=a[None], controls=controls, gam=np.array([gamma]),
+                lops=a[None], rho0=rho0, targ=targ)
+
+
+def run_lindblad(args, name):
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the GRAPE hot path has no CPU fallback")
+    import qoc_b200.standard as std
+    from oracle import qoc_oracle as orc
+    from qoc_b200.core.plan import LindbladPlan
+    from tests.problems import numpy_hamiltonian
+    q = lindblad_problem(name)
+    plan = LindbladPlan(q["rho0"], [std.TargetDensityInfidelity(q["targ"])], q["T"], q["N"],
+                        hamiltonian=numpy_hamiltonian(q["h0"], q["drive"], True), lindblad_data=lambda t: (q["gam"], q["lops"]),
+                        control_eval_count=q["M"], control_count=1, complex_controls=True)
+    for _ in range(max(3, args.warmup)):
+        plan.cost_and_grad(q["controls"])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        err, grads, finals = plan.cost_and_grad(q["controls"])
+    sec = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    st = plan.stats()
+    if args.impl == "reference":
+        return
+    torch.set_num_threads(1)
+    ocosts = [orc.TargetDensityInfidelity(q["targ"])]
+    oh, old = orc.make_hamiltonian(q["h0"], q["drive"], True), orc.make_lindblad_data(q["gam"], q["lops"])
+    t1 = time.perf_counter()
+    o_err, o_grad, o_fin = orc.lindblad_cost_and_grad(q["controls"], oh, old, q["rho0"], ocosts, q["T"], q["N"], freeze_steps=True)
+    cpu_sec = time.perf_counter() - t1
+    # RHS evaluations: 7 per attempt (forward) + reverse replay of the accepted steps (7 recomputed + 7 adjoint)
+    nn = q["n"] ** 2
+    rhs_flops = 8.0 * q["n"] ** 3 * (2 + 2 * len(q["gam"])) * q["D"]
+    flops = rhs_flops * (7 * st["attempts"] + 14 * st["accepted"])
+    out = {"metric": "grape_cost_grad_evals_per_sec", "value": 1.0 / sec, "unit": "evals/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": max(3, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "replicas only",
+           "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+           "config": {"workload": name, "hilbert_dim": q["n"], "densities": q["D"], "intervals": q["N"] - 1,
+                      "rk_attempts": st["attempts"], "rk_accepted": st["accepted"],
+                      "l2": "latency-bound persistent CTA; working set in shared memory"},
+           "e2e": {"value": 1.0 / sec, "unit": "evals/s", "h2d_bytes_per_step": q["M"] * 2 * 8,
+                   "d2h_bytes_per_step": q["M"] * 2 * 8 + 8 + q["D"] * nn * 16},
+           "gpu_launches": 2 * args.steps,
+           "roofline": {"bound": "tensor", "kernel": "k_lindblad_forward + k_lindblad_backward", "achieved": flops / sec / 1e12,
+                        "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": flops / sec / 1e12 / FP64_TENSOR_PEAK_TFLOPS,
+                        "traffic": None, "note": "sequential adaptive integration on one SM: latency-bound by construction"},
+           "clocks": clocks, "cost": err,
+           "cpu_baseline": {"value": 1.0 / cpu_sec, "unit": "evals/s", "cores": 1, "kind": "port",
+                            "sample": "one full cost+gradient evaluation of the oracle (torch, frozen step grid)"},
+           "parity": {"cost_abs_err": abs(err - o_err), "grad_rel_err_vs_frozen_oracle":
+                      float(np.linalg.norm(grads - o_grad) / np.linalg.norm(o_grad)), "tolerance": "1e-9 / 1e-7 (DESIGN.md section 5)"}}
+    print(json.dumps(out))
+    plan.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="n64_2000_M4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="n64_2000_M4", choices=sorted(WORKLOADS) + sorted(LINDBLAD_WORKLOADS))
     ap.add_argument("--cpu-slices", type=int, default=400, help="slices of the bounded CPU-baseline sample")
     ap.add_argument("--ref-slices", type=int, default=100, help="slices per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check", action="store_true", help="N > 1: compare the sharded result with the unsharded CUDA path (and the oracle for n <= 16)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload in LINDBLAD_WORKLOADS:
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_lindblad(args, args.workload)
+        return
     if args.impl == "reference":
         run_reference(args, args.workload)
     else:
