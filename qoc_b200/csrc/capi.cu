@@ -54,6 +54,7 @@ struct KArgs {
     const double *psi, *lam;    // [E][N][S][2][NP]
     double *node_grad;          // [E*(N-1)][q][KR]
     int S;
+    int lowrank;                // 1: use the rank-S reverse pass where it applies (QOCB_NO_LOWRANK=1 disables it)
     int *err_flag;
 };
 
@@ -126,23 +127,33 @@ __global__ void __launch_bounds__(C::NT) k_backward(KArgs a) {
             tape = ctape; piv = cpiv;
             __syncthreads();
         }
-        // ubar = sum_s lam_{j+1,s} psi_{j,s}^T   (cotangent of U_j from states = U_j psi)
         const double *psi = a.psi + ((size_t)e * a.N + j) * VS;
         const double *lam = a.lam + ((size_t)e * a.N + j + 1) * VS;
-        for_owned<C>([&](int, int, int row, int col) {
-            c2 u = czero();
-            for (int s_ = 0; s_ < a.S; ++s_) {
-                const double lr = lam[s_ * 2 * C::NP + row], li = lam[s_ * 2 * C::NP + C::NP + row];
-                const double2 pr = *reinterpret_cast<const double2 *>(psi + s_ * 2 * C::NP + col);
-                const double2 pi = *reinterpret_cast<const double2 *>(psi + s_ * 2 * C::NP + C::NP + col);
-                u.r0 += lr * pr.x - li * pi.x; u.i0 += lr * pi.x + li * pr.x;
-                u.r1 += lr * pr.y - li * pi.y; u.i1 += lr * pi.y + li * pr.y;
+        bool done = false;
+        if constexpr (C::NP == 64 && C::NWARP == 8) {
+            if (a.S <= 4 && s == 0 && a.lowrank) {                     // rank-S reverse pass (lowrank.cuh)
+                PROF_MARK(9);
+                pade_backward_lowrank<C>(sm, tape, piv, psi, psi + VS, lam, a.S);
+                done = true;
             }
-            sts2<C>(sm.X0, row, col, u);
-        });
-        __syncthreads();
-        PROF_MARK(9);
-        pade_backward<C>(sm, tape, piv, s, a.U + (size_t)w * C::GMAT, scratch);
+        }
+        if (!done) {
+            // ubar = sum_s lam_{j+1,s} psi_{j,s}^T   (cotangent of U_j from states = U_j psi)
+            for_owned<C>([&](int, int, int row, int col) {
+                c2 u = czero();
+                for (int s_ = 0; s_ < a.S; ++s_) {
+                    const double lr = lam[s_ * 2 * C::NP + row], li = lam[s_ * 2 * C::NP + C::NP + row];
+                    const double2 pr = *reinterpret_cast<const double2 *>(psi + s_ * 2 * C::NP + col);
+                    const double2 pi = *reinterpret_cast<const double2 *>(psi + s_ * 2 * C::NP + C::NP + col);
+                    u.r0 += lr * pr.x - li * pi.x; u.i0 += lr * pi.x + li * pr.x;
+                    u.r1 += lr * pr.y - li * pi.y; u.i1 += lr * pi.y + li * pr.y;
+                }
+                sts2<C>(sm.X0, row, col, u);
+            });
+            __syncthreads();
+            PROF_MARK(9);
+            pade_backward<C>(sm, tape, piv, s, a.U + (size_t)w * C::GMAT, scratch);
+        }
         magnus_backward<C>(sm, ga, scratch, a.node_grad + (size_t)w * ga.q * ga.KR);
         PROF_MARK(13);
     }
@@ -405,6 +416,7 @@ KArgs make_kargs(qocb_plan *p) {
     a.scratch = p->scratch.p; a.cta_tape = p->cta_tape.p; a.cta_piv = p->cta_piv.p; a.chunkP = p->chunkP.p;
     a.psi = p->psi.p; a.lam = p->lam.p; a.node_grad = p->node_grad.p; a.S = p->pb.state_count;
     a.err_flag = p->err_flag.p;
+    { const char *nl = getenv("QOCB_NO_LOWRANK"); a.lowrank = (nl && nl[0] == '1') ? 0 : 1; }
     return a;
 }
 

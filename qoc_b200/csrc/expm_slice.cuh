@@ -12,6 +12,7 @@
 // live on a "tape" in global memory (per slice when stored, per CTA when recomputed).
 #pragma once
 #include "tile.cuh"
+#include "lowrank.cuh"
 
 namespace qocb {
 
@@ -435,6 +436,168 @@ __device__ void pade_backward(const Smem<C> &sm, const double *tape, const int *
     for_owned<C>([&](int i, int j, int row, int col) {
         sts2<C>(sm.X0, row, col, scale * (ldg2<C>(sA, row, col) + accv<C>(acc, i, j)));   // X0 = mbar
     });
+    __syncthreads();
+    PROF_MARK(12);
+}
+
+// Reverse pass of the Pade graph for a rank-S cotangent ubar = sum_s lam1_s psi_s^T without squarings (lowrank.cuh).
+// In: tape of the slice, psi = psi_j, psi1 = psi_{j+1}, lam1 = lam_{j+1} (planar [s][2][NP]).  Out: mbar in X0.
+template <class C>
+__device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, const int *tperm, const double *psi,
+                                      const double *psi1, const double *lam1, int S) {
+    static_assert(C::NP == 64 && C::NWARP == 8, "low-rank reverse pass is laid out for NP = 64 with 8 warps");
+    PROF_DECL
+    constexpr int NP = C::NP, LD = LR_LD, PL = LR_PL, TLD = LR_TLD, TPL = LR_TPL;
+    double *X0 = sm.X0, *LEFT = sm.X1, *TMP = sm.X1 + 2 * LR_PL, *RIGHT = sm.X2, *EL = sm.X2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = lane & 3;
+    const int frow = warp * 8 + (lane >> 2);                       // row of this lane's C-fragment elements
+    // ---- stage 0: [0 | lam] -> LEFT[:, 0:8], [p | m] -> TMP[:, 0:8]; LUi -> X0
+    for (int e = threadIdx.x; e < NP * 4; e += C::NT) {
+        const int row = e >> 2, c = e & 3;
+        const bool on = c < S;
+        const double lr = on ? lam1[c * 2 * NP + row] : 0., li = on ? lam1[c * 2 * NP + NP + row] : 0.;
+        const double pr = on ? psi[c * 2 * NP + row] : 0., pi = on ? psi[c * 2 * NP + NP + row] : 0.;
+        const double qr = on ? psi1[c * 2 * NP + row] : 0., qi = on ? psi1[c * 2 * NP + NP + row] : 0.;
+        LEFT[row * LD + c] = 0.; LEFT[PL + row * LD + c] = 0.;
+        LEFT[row * LD + 4 + c] = lr; LEFT[PL + row * LD + 4 + c] = li;
+        TMP[row * TLD + c] = pr + qr; TMP[TPL + row * TLD + c] = pi + qi;
+        TMP[row * TLD + 4 + c] = pr - qr; TMP[TPL + row * TLD + 4 + c] = pi - qi;
+    }
+    g2s<C>(X0, tape + (size_t)T_LU * C::GMAT);
+    for (int c = threadIdx.x; c < NP; c += C::NT) sm.piv[c] = tperm[c];
+    __syncthreads();
+    // ---- stage 1: l = Q^-T lam (thin solve), row un-permutation through RIGHT
+    lu_solve_thin_T<C>(X0, LEFT);
+    for (int e = threadIdx.x; e < NP * 4; e += C::NT) {
+        const int row = e >> 2, c = e & 3, pr = sm.piv[row];
+        RIGHT[pr * LD + c] = LEFT[row * LD + 4 + c]; RIGHT[PL + pr * LD + c] = LEFT[PL + row * LD + 4 + c];
+    }
+    g2s<C>(X0, tape + (size_t)T_Y * C::GMAT);
+    __syncthreads();
+    for (int e = threadIdx.x; e < NP * 4; e += C::NT) {
+        const int row = e >> 2, c = e & 3;
+        LEFT[row * LD + 4 + c] = RIGHT[row * LD + c]; LEFT[PL + row * LD + 4 + c] = RIGHT[PL + row * LD + c];
+    }
+    // ---- stage 2: yp = Y p -> TMP[:, 8:12]
+    {
+        const c2 v = thin_tile<C, false, TLD, TPL>(X0, TMP, warp, 0);
+        if (t < 2) {
+            *reinterpret_cast<double2 *>(TMP + frow * TLD + 8 + 2 * t) = make_double2(v.r0, v.r1);
+            *reinterpret_cast<double2 *>(TMP + TPL + frow * TLD + 8 + 2 * t) = make_double2(v.i0, v.i1);
+        }
+    }
+    __syncthreads();
+    g2s<C>(X0, tape + (size_t)T_A * C::GMAT);
+    __syncthreads();
+    // ---- stage 3: a = A^T l -> LEFT[:, 0:4]
+    {
+        const c2 v = thin_tile<C, true, LD, PL>(X0, LEFT, warp, 0);
+        __syncthreads();
+        if (t >= 2) {
+            *reinterpret_cast<double2 *>(LEFT + frow * LD + 2 * (t - 2)) = make_double2(v.r0, v.r1);
+            *reinterpret_cast<double2 *>(LEFT + PL + frow * LD + 2 * (t - 2)) = make_double2(v.i0, v.i1);
+        }
+    }
+    g2s<C>(X0, tape + (size_t)T_W1 * C::GMAT);
+    // R4, R2 and the polynomial blocks of R6 (elementwise from p, m)
+    for (int e = threadIdx.x; e < NP * 4; e += C::NT) {
+        const int row = e >> 2, c = e & 3;
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+            const double pv = TMP[pl * TPL + row * TLD + c], mv = TMP[pl * TPL + row * TLD + 4 + c];
+            double *R = RIGHT + pl * PL + row * LD;
+            R[0 + c] = kB[3] * pv; R[4 + c] = kB[2] * mv; R[8 + c] = kB[9] * pv; R[12 + c] = kB[8] * mv;      // R2 -> X_a
+            R[16 + c] = kB[5] * pv; R[20 + c] = kB[4] * mv; R[24 + c] = kB[11] * pv; R[28 + c] = kB[10] * mv;  // R4 -> X_b
+            R[40 + c] = kB[13] * pv; R[44 + c] = kB[12] * mv;                                                  // R6 blocks 2, 3
+        }
+    }
+    __syncthreads();
+    // ---- stage 4: c1 = b7 p + W1 p -> RIGHT[:, 32:36]
+    {
+        const c2 v = thin_tile<C, false, TLD, TPL>(X0, TMP, warp, 0);
+        if (t < 2) {
+            const double2 pr = *reinterpret_cast<const double2 *>(TMP + frow * TLD + 2 * t);
+            const double2 pi = *reinterpret_cast<const double2 *>(TMP + TPL + frow * TLD + 2 * t);
+            *reinterpret_cast<double2 *>(RIGHT + frow * LD + 32 + 2 * t) = make_double2(v.r0 + kB[7] * pr.x, v.r1 + kB[7] * pr.y);
+            *reinterpret_cast<double2 *>(RIGHT + PL + frow * LD + 32 + 2 * t) = make_double2(v.i0 + kB[7] * pi.x, v.i1 + kB[7] * pi.y);
+        }
+    }
+    __syncthreads();
+    g2s<C>(X0, tape + (size_t)T_X1 * C::GMAT);
+    __syncthreads();
+    // ---- stage 5: c2 = b6 m + X1 m -> RIGHT[:, 36:40]
+    {
+        const c2 v = thin_tile<C, false, TLD, TPL>(X0, TMP, warp, 0);
+        if (t >= 2) {
+            const double2 mr = *reinterpret_cast<const double2 *>(TMP + frow * TLD + 2 * t);
+            const double2 mi = *reinterpret_cast<const double2 *>(TMP + TPL + frow * TLD + 2 * t);
+            *reinterpret_cast<double2 *>(RIGHT + frow * LD + 32 + 2 * t) = make_double2(v.r0 + kB[6] * mr.x, v.r1 + kB[6] * mr.y);
+            *reinterpret_cast<double2 *>(RIGHT + PL + frow * LD + 32 + 2 * t) = make_double2(v.i0 + kB[6] * mi.x, v.i1 + kB[6] * mi.y);
+        }
+    }
+    __syncthreads();
+    g2s<C>(X0, tape + (size_t)T_A6 * C::GMAT);
+    __syncthreads();
+    // ---- stage 6: [A6^T a | A6^T l] -> LEFT[:, 8:16]
+    st_thin<LD, PL>(LEFT, warp * 8, 8, thin_tile<C, true, LD, PL>(X0, LEFT, warp, 0));
+    __syncthreads();
+    g2s<C>(X0, tape + (size_t)T_A4 * C::GMAT);
+    __syncthreads();
+    // ---- stage 7: X_a += A4 R6
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct) {
+        c2 acc = ld_thin<LD, PL>(RIGHT, warp * 8, ct * 8);
+        for (int kt = 0; kt < NP / 8; ++kt) tile_mma_thin<C, false, MASK_NONE, false, LD, PL>(acc, X0, warp * 8, kt * 8, RIGHT, kt * 8, 32 + ct * 8);
+        st_thin<LD, PL>(RIGHT, warp * 8, ct * 8, acc);
+    }
+    __syncthreads();
+    g2s<C>(X0, tape + (size_t)T_A2 * C::GMAT);
+    __syncthreads();
+    // ---- stage 8a: X_a += A2 R4 (R4 = the untouched X_b block)
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct) {
+        c2 acc = ld_thin<LD, PL>(RIGHT, warp * 8, ct * 8);
+        for (int kt = 0; kt < NP / 8; ++kt) tile_mma_thin<C, false, MASK_NONE, false, LD, PL>(acc, X0, warp * 8, kt * 8, RIGHT, kt * 8, 16 + ct * 8);
+        st_thin<LD, PL>(RIGHT, warp * 8, ct * 8, acc);
+    }
+    __syncthreads();
+    // ---- stage 8b: X_b += A2 R6;  Lb2 = A2^T Lb
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct) {
+        c2 acc = ld_thin<LD, PL>(RIGHT, warp * 8, 16 + ct * 8);
+        for (int kt = 0; kt < NP / 8; ++kt) tile_mma_thin<C, false, MASK_NONE, false, LD, PL>(acc, X0, warp * 8, kt * 8, RIGHT, kt * 8, 32 + ct * 8);
+        st_thin<LD, PL>(RIGHT, warp * 8, 16 + ct * 8, acc);
+        st_thin<LD, PL>(LEFT, warp * 8, 16 + ct * 8, thin_tile<C, true, LD, PL>(X0, LEFT, warp, ct * 8));
+    }
+    __syncthreads();
+    // ---- stage 8c: Lb3 = A2^T Lb2
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct) st_thin<LD, PL>(LEFT, warp * 8, 32 + ct * 8, thin_tile<C, true, LD, PL>(X0, LEFT, warp, 16 + ct * 8));
+    __syncthreads();
+    // ---- stage 9: a2bar = [Lb Lb2 Lb3] [X_a X_b X_c]^T -> X0
+    Acc<C> acc;
+    acc.zero();
+    mma_lowrank<C, LD, PL, LD, PL>(acc, LEFT, 0, RIGHT, 0, 48);
+    for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(X0, row, col, accv<C>(acc, i, j)); });
+    __syncthreads();
+    for (int e = threadIdx.x; e < NP * 4; e += C::NT) {             // keep l and yp for the rank-S term
+        const int row = e >> 2, c = e & 3;
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+            EL[pl * TPL + row * TLD + c] = LEFT[pl * PL + row * LD + 4 + c];
+            EL[pl * TPL + row * TLD + 4 + c] = TMP[pl * TPL + row * TLD + 8 + c];
+        }
+    }
+    __syncthreads();
+    g2s<C>(sm.X1, tape + (size_t)T_A * C::GMAT);
+    __syncthreads();
+    // ---- stage 10: mbar = l yp^T + a2bar A^T + A^T a2bar
+    acc.zero();
+    mma_lowrank<C, TLD, TPL, TLD, TPL>(acc, EL, 0, EL, 4, 4);
+    mma_smem<C, false, true, false>(acc, X0, sm.X1);
+    mma_smem<C, true, false, false>(acc, sm.X1, X0);
+    __syncthreads();
+    for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(X0, row, col, accv<C>(acc, i, j)); });
     __syncthreads();
     PROF_MARK(12);
 }
