@@ -11,6 +11,7 @@
 #include "expm_slice.cuh"
 #include "sweep.cuh"
 #include "large.cuh"
+#include "zgemm.cuh"
 
 using namespace qocb;
 
@@ -306,6 +307,7 @@ struct LargeImpl {
     DevBuf<int> piv, info, sarr, cb;
     std::vector<int> h_s;
     int lstar = 0, nchunks = 0, lvl_count[24] = {}, lvl_off[24] = {};   // pairwise propagator tree levels 0..lstar
+    bool use_cublas_gemm = false;       // QOCB_LARGE_CUBLAS=1: library ZGEMM instead of zgemm.cuh (A/B comparison)
     double2 *arr(int i) { return work.p + (size_t)i * B * nn; }
     ~LargeImpl() { if (blas) cublasDestroy(blas); }
 };
@@ -481,6 +483,16 @@ int lg_gemm(qocb_plan *p, bool ta, bool tb, const double2 *A, const double2 *B, 
     LargeImpl *L = p->large;
     const int n = L->n;
     if (sA < 0) sA = L->nn; if (sB < 0) sB = L->nn; if (sC < 0) sC = L->nn;
+    if (!L->use_cublas_gemm) {                         // own DMMA tile kernel (zgemm.cuh)
+        const int tiles = (n + 63) / 64;
+        const dim3 grid(tiles * tiles, batch);
+        if (!ta && !tb) k_zgemm<false, false><<<grid, ZG_NT, kZgemmSmem, p->stream>>>(A, B, C, n, alpha, beta, sA, sB, sC);
+        else if (ta && !tb) k_zgemm<true, false><<<grid, ZG_NT, kZgemmSmem, p->stream>>>(A, B, C, n, alpha, beta, sA, sB, sC);
+        else if (!ta && tb) k_zgemm<false, true><<<grid, ZG_NT, kZgemmSmem, p->stream>>>(A, B, C, n, alpha, beta, sA, sB, sC);
+        else k_zgemm<true, true><<<grid, ZG_NT, kZgemmSmem, p->stream>>>(A, B, C, n, alpha, beta, sA, sB, sC);
+        CU_TRY(p, cudaGetLastError());
+        return 0;
+    }
     const cuDoubleComplex a = make_cuDoubleComplex(alpha, 0.), b = make_cuDoubleComplex(beta, 0.);
     BL_TRY(p, cublasZgemmStridedBatched(L->blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, n, n, n, &a,
                                         reinterpret_cast<const cuDoubleComplex *>(B), n, sB,
@@ -507,6 +519,11 @@ int large_init(qocb_plan *p) {
     const int Lsl = p->Nloc - 1;
     const size_t per = (size_t)LCOUNT * L->nn * sizeof(double2);
     L->B = (int)std::max<size_t>(1, std::min<size_t>((size_t)Lsl, std::min<size_t>(256, ((size_t)6 << 30) / per)));
+    { const char *e = getenv("QOCB_LARGE_CUBLAS"); L->use_cublas_gemm = e && e[0] == '1'; }
+    CU_TRY(p, cudaFuncSetAttribute(k_zgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZgemmSmem));
+    CU_TRY(p, cudaFuncSetAttribute(k_zgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZgemmSmem));
+    CU_TRY(p, cudaFuncSetAttribute(k_zgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZgemmSmem));
+    CU_TRY(p, cudaFuncSetAttribute(k_zgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZgemmSmem));
     BL_TRY(p, cublasCreate(&L->blas));
     BL_TRY(p, cublasSetStream(L->blas, p->stream));
     CU_TRY(p, L->G0.alloc(L->nn)); CU_TRY(p, L->G.alloc((size_t)std::max(1, p->pb.control_count) * L->nn));

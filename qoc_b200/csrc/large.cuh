@@ -2,10 +2,10 @@
 // shared memory of one CTA.  Same algorithm as expm_slice.cuh / sweep.cuh (qoc/core/schroedingerdiscrete.py:356-502,
 // qoc/core/mathmethods.py:72-122, qoc/standard/functions/expm.py:210-252 and the reverse of that graph), organised as
 // BATCHED level-3 work over many time slices at once:
-//   * every matrix product is one strided-batched complex GEMM over the slices of a batch (this round: cuBLAS ZGEMM,
-//     93 % of the FP64 DMMA peak at n = 256 - a plain library GEMM; the fused sm_100a tile kernel of the n <= 64 path does
-//     not apply because the operands live in HBM/L2);
-//   * the Pade denominator solve is cuBLAS batched LU (zgetrf/zgetrs).  The forward uses R = P Q^-1 (P and Q are
+//   * every matrix product is one strided-batched complex GEMM over the slices of a batch: the DMMA tile kernel of
+//     zgemm.cuh (64 x 64 tiles, cp.async double-buffered K panels; ~85 % of cuBLAS ZGEMM on this pipeline;
+//     QOCB_LARGE_CUBLAS=1 switches to the library GEMM for A/B comparison);
+//   * the Pade denominator solve is cuBLAS batched LU (zgetrf/zgetrs) - the one library call left on this path.  The forward uses R = P Q^-1 (P and Q are
 //     polynomials in A and commute, so this equals the reference's Q^-1 P) because that form needs no transposes in
 //     row-major storage; the reverse pass differentiates exactly this form;
 //   * everything else - generator assembly from interpolated controls, Magnus combination, one-norm / scaling, the Pade
