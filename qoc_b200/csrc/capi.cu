@@ -308,7 +308,25 @@ struct LargeImpl {
     std::vector<int> h_s;
     int lstar = 0, nchunks = 0, lvl_count[24] = {}, lvl_off[24] = {};   // pairwise propagator tree levels 0..lstar
     bool use_cublas_gemm = false;       // QOCB_LARGE_CUBLAS=1: library ZGEMM instead of zgemm.cuh (A/B comparison)
-    double2 *arr(int i) { return work.p + (size_t)i * B * nn; }
+    // reverse-pass tape (stored when it fits): M, A2, A4, A6, Y, LU(Q), R0 of every local slice + pivots + squaring counts.
+    // tj >= 0 redirects those work arrays (and pivots / counts / LU pointers) to the tape entries of slices tj, tj+1, ...
+    DevBuf<double2> tape;
+    DevBuf<int> tpiv, tsarr;
+    DevBuf<double2 *> tptrQ;
+    bool taped = false;
+    int tj = -1, Lsl = 0;
+    std::vector<char> batch_taped;
+    static int tslot(int id) {
+        switch (id) { case LM: return 0; case LA2: return 1; case LA4: return 2; case LA6: return 3; case LY: return 4; case LQ: return 5; case LR0: return 6; }
+        return -1;
+    }
+    double2 *arr(int i) {
+        const int ts = tj >= 0 ? tslot(i) : -1;
+        return ts >= 0 ? tape.p + ((size_t)ts * Lsl + tj) * nn : work.p + (size_t)i * B * nn;
+    }
+    int *cur_piv() { return tj >= 0 ? tpiv.p + (size_t)tj * n : piv.p; }
+    int *cur_sarr() { return tj >= 0 ? tsarr.p + tj : sarr.p; }
+    double2 **cur_ptrQ() { return tj >= 0 ? tptrQ.p + tj : ptrQ.p; }
     ~LargeImpl() { if (blas) cublasDestroy(blas); }
 };
 }  // namespace
@@ -558,6 +576,21 @@ int large_init(qocb_plan *p) {
     CU_TRY(p, p->part.alloc((size_t)L->nchunks * VSl)); CU_TRY(p, p->cost_part.alloc(L->nchunks));
     if (p->sharded) { CU_TRY(p, L->treeA.alloc((size_t)((L->nchunks + 1) / 2) * L->nn)); CU_TRY(p, L->treeB.alloc((size_t)((L->nchunks + 3) / 4) * L->nn)); }
     L->h_s.resize(L->B);
+    L->Lsl = Lsl;
+    L->batch_taped.assign((Lsl + L->B - 1) / L->B, 0);
+    if (p->pb.store_tape) {
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(p, cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (size_t)7 * Lsl * L->nn * sizeof(double2) + (size_t)Lsl * (n + 1) * sizeof(int) + (size_t)Lsl * sizeof(double2 *);
+        if (need + ((size_t)6 << 30) <= free_b) {
+            CU_TRY(p, L->tape.alloc((size_t)7 * Lsl * L->nn)); CU_TRY(p, L->tpiv.alloc((size_t)Lsl * n)); CU_TRY(p, L->tsarr.alloc(Lsl));
+            CU_TRY(p, L->tptrQ.alloc(Lsl));
+            std::vector<double2 *> hq2(Lsl);
+            for (int j = 0; j < Lsl; ++j) hq2[j] = L->tape.p + ((size_t)LargeImpl::tslot(LQ) * Lsl + j) * L->nn;
+            CU_TRY(p, cudaMemcpy(L->tptrQ.p, hq2.data(), sizeof(double2 *) * Lsl, cudaMemcpyHostToDevice));
+            L->taped = true;
+        }
+    }
     const int big = 200 * 1024;
     CU_TRY(p, cudaFuncSetAttribute(k_lg_sweep_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(p, cudaFuncSetAttribute(k_lg_sweep_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -585,8 +618,8 @@ int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_out) {
         rc = lg_gemm(p, false, false, L->arr(LA1), L->arr(LA2N), L->arr(LT), -1., 1., Bc); if (rc) return rc;     // - a1 a2
         k_lg_axpby<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LM), 0.5 * dt, L->arr(LA1), 0.5 * dt, L->arr(LA2N), (QOCB_S3 / 12.0) * dt * dt, L->arr(LT), tot);
     }
-    k_lg_norm_scale<<<Bc, 256, 0, p->stream>>>(L->arr(LM), L->sarr.p, L->n);
-    CU_TRY(p, cudaMemcpyAsync(L->h_s.data(), L->sarr.p, sizeof(int) * Bc, cudaMemcpyDeviceToHost, p->stream));
+    k_lg_norm_scale<<<Bc, 256, 0, p->stream>>>(L->arr(LM), L->cur_sarr(), L->n);
+    CU_TRY(p, cudaMemcpyAsync(L->h_s.data(), L->cur_sarr(), sizeof(int) * Bc, cudaMemcpyDeviceToHost, p->stream));
     rc = lg_gemm(p, false, false, L->arr(LM), L->arr(LM), L->arr(LA2), 1., 0., Bc); if (rc) return rc;
     rc = lg_gemm(p, false, false, L->arr(LA2), L->arr(LA2), L->arr(LA4), 1., 0., Bc); if (rc) return rc;
     rc = lg_gemm(p, false, false, L->arr(LA2), L->arr(LA4), L->arr(LA6), 1., 0., Bc); if (rc) return rc;
@@ -596,11 +629,11 @@ int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_out) {
     rc = lg_gemm(p, false, false, L->arr(LM), L->arr(LY), L->arr(LUO), 1., 0., Bc); if (rc) return rc;
     k_lg_pq<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LVE), L->arr(LUO), L->arr(LP), L->arr(LQ), tot);
     CU_TRY(p, cudaGetLastError());
-    BL_TRY(p, cublasZgetrfBatched(L->blas, L->n, reinterpret_cast<cuDoubleComplex **>(L->ptrQ.p), L->n, L->piv.p, L->info.p, Bc));
+    BL_TRY(p, cublasZgetrfBatched(L->blas, L->n, reinterpret_cast<cuDoubleComplex **>(L->cur_ptrQ()), L->n, L->cur_piv(), L->info.p, Bc));
     int hinfo = 0;
-    BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_N, L->n, L->n, reinterpret_cast<const cuDoubleComplex *const *>(L->ptrQ.p), L->n, L->piv.p,
+    BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_N, L->n, L->n, reinterpret_cast<const cuDoubleComplex *const *>(L->cur_ptrQ()), L->n, L->cur_piv(),
                                   reinterpret_cast<cuDoubleComplex **>(L->ptrP.p), L->n, &hinfo, Bc));   // R0 = P Q^-1 (row-major)
-    if (keep) { rc = lg_copy(p, L->arr(LR0), L->arr(LP), Bc); if (rc) return rc; }
+    if (keep || L->tj >= 0) { rc = lg_copy(p, L->arr(LR0), L->arr(LP), Bc); if (rc) return rc; }
     CU_TRY(p, cudaStreamSynchronize(p->stream));                    // squaring counts of the batch
     int smax = 0;
     for (int b = 0; b < Bc; ++b) smax = std::max(smax, L->h_s[b]);
@@ -608,7 +641,7 @@ int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_out) {
     for (int i = 0; i < smax; ++i) {
         if (keep) { rc = lg_copy(p, L->arr(LRS0 + i), L->arr(LP), Bc); if (rc) return rc; }
         rc = lg_gemm(p, false, false, L->arr(LP), L->arr(LP), L->arr(LT), 1., 0., Bc); if (rc) return rc;
-        k_lg_select<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LP), L->arr(LT), L->sarr.p, i, nn, tot);
+        k_lg_select<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LP), L->arr(LT), L->cur_sarr(), i, nn, tot);
     }
     CU_TRY(p, cudaGetLastError());
     *smax_out = smax;
@@ -621,7 +654,11 @@ int lg_expm_all(qocb_plan *p) {
     for (int jb = 0; jb < Lsl; jb += L->B) {
         const int Bc = std::min(L->B, Lsl - jb);
         int smax = 0;
-        int rc = lg_forward_batch(p, jb, Bc, false, &smax); if (rc) return rc;
+        L->tj = L->taped ? jb : -1;                                 // forward intermediates go straight to the tape
+        int rc = lg_forward_batch(p, jb, Bc, false, &smax);
+        L->tj = -1;
+        if (rc) return rc;
+        L->batch_taped[jb / L->B] = (L->taped && smax == 0) ? 1 : 0;   // batches with squarings are recomputed
         rc = lg_copy(p, reinterpret_cast<double2 *>(p->U.p) + (size_t)jb * L->nn, L->arr(LP), Bc); if (rc) return rc;
     }
     // transposed copies for the costate sweeps; pairwise product tree up to the chunk level of the sweeps
@@ -664,17 +701,27 @@ int lg_backward_all(qocb_plan *p) {
     for (int jb = 0; jb < Lsl; jb += L->B) {
         const int Bc = std::min(L->B, Lsl - jb);
         const size_t tot = (size_t)Bc * nn;
-        int smax = 0;
-        int rc = lg_forward_batch(p, jb, Bc, true, &smax); if (rc) return rc;
+        int smax = 0, rc = 0;
+        if (L->batch_taped[jb / L->B]) {
+            // taped batch: only the cheap elementwise pieces are rebuilt (node generators for the Magnus adjoint, W1, X1)
+            L->tj = jb;
+            LgCoef cf{p->controls.p, p->itab_idx.p, p->itab_w.p, p->pb.control_count, p->q};
+            k_lg_assemble<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA1), L->arr(LA2N), L->G0.p, L->G.p, cf, jb, Bc, nn);
+            k_lg_poly<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA2), L->arr(LA4), L->arr(LA6), L->arr(LW1), L->arr(LX1), L->arr(LT), L->arr(LVE), L->n, tot);
+        } else {
+            L->tj = -1;
+            rc = lg_forward_batch(p, jb, Bc, true, &smax); if (rc) return rc;
+        }
+        struct TjReset { LargeImpl *l; ~TjReset() { l->tj = -1; } } tj_reset{L};
         double2 *RB = L->arr(LRB), *T = L->arr(LT), *M = L->arr(LM);
         k_lg_ubar<<<lg_blocks(tot), 256, 0, p->stream>>>(RB, p->psi.p, p->lam.p, jb, Bc, n, p->pb.state_count);
         for (int i = smax - 1; i >= 0; --i) {                      // R_{i+1} = R_i^2
             rc = lg_gemm(p, false, true, RB, L->arr(LRS0 + i), T, 1., 0., Bc); if (rc) return rc;
             rc = lg_gemm(p, true, false, L->arr(LRS0 + i), RB, T, 1., 1., Bc); if (rc) return rc;
-            k_lg_select<<<lg_blocks(tot), 256, 0, p->stream>>>(RB, T, L->sarr.p, i, nn, tot);
+            k_lg_select<<<lg_blocks(tot), 256, 0, p->stream>>>(RB, T, L->cur_sarr(), i, nn, tot);
         }
         int hinfo = 0;                                             // pbar = rbar Q^-T
-        BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_T, n, n, reinterpret_cast<const cuDoubleComplex *const *>(L->ptrQ.p), n, L->piv.p,
+        BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_T, n, n, reinterpret_cast<const cuDoubleComplex *const *>(L->cur_ptrQ()), n, L->cur_piv(),
                                       reinterpret_cast<cuDoubleComplex **>(L->ptrRB.p), n, &hinfo, Bc));
         rc = lg_gemm(p, true, false, L->arr(LR0), RB, L->arr(LQB), -1., 0., Bc); if (rc) return rc;       // qbar = -R0^T pbar
         rc = lg_axpby(p, L->arr(LUOB), 1., RB, -1., L->arr(LQB), 0., nullptr, Bc); if (rc) return rc;
@@ -697,7 +744,7 @@ int lg_backward_all(qocb_plan *p) {
         rc = lg_gemm(p, true, false, L->arr(LA2), L->arr(LA4B), L->arr(LA2B), 1., 1., Bc); if (rc) return rc;
         rc = lg_gemm(p, false, true, L->arr(LA2B), M, L->arr(LAB), 1., 1., Bc); if (rc) return rc;
         rc = lg_gemm(p, true, false, M, L->arr(LA2B), L->arr(LAB), 1., 1., Bc); if (rc) return rc;
-        k_lg_unscale<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LAB), L->sarr.p, nn, tot);                // mbar
+        k_lg_unscale<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LAB), L->cur_sarr(), nn, tot);                // mbar
         double2 *AB = L->arr(LAB);
         if (order == 2) { rc = lg_axpby(p, L->arr(LA1B), dt, AB, 0., nullptr, 0., nullptr, Bc); if (rc) return rc; }
         else {
