@@ -27,7 +27,7 @@
 
 namespace {
 
-constexpr int LNT = 256;              // threads of the persistent CTA
+constexpr int LNT = 256;              // max threads of the persistent CTA (32 for tiny problems: barriers become warp-wide)
 constexpr int kMaxKRL = 16;
 
 __device__ __constant__ double cA[6][5] = {
@@ -67,12 +67,9 @@ struct LArgs {
     long long *stats;                           // attempts, accepted
     int *err_flag;
     double2 *work;                              // global work arrays (used when the working set exceeds shared memory)
-    int work_in_smem;
+    int work_in_smem, ops_in_smem;
     double *grad;                               // [M][KR]
 };
-
-__device__ __forceinline__ double2 cmul2(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ double2 cadd2(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 
 // block-wide sum, result in all threads
 __device__ double block_sum(double v, double *red) {
@@ -83,7 +80,7 @@ __device__ double block_sum(double v, double *red) {
     if (lane == 0) red[warp] = v;
     __syncthreads();
     double s = 0.;
-    for (int w = 0; w < LNT / 32; ++w) s += red[w];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
     return s;
 }
 
@@ -98,7 +95,7 @@ template <int OP> __device__ __forceinline__ double2 elem(const double2 *m, int 
 template <int OPA, int OPB, bool ACC>
 __device__ void bmm(double2 *out, const double2 *A, int sA, const double2 *B, int sB, int n, int D, double alpha) {
     const int nn = n * n;
-    for (int e = threadIdx.x; e < D * nn; e += LNT) {
+    for (int e = threadIdx.x; e < D * nn; e += blockDim.x) {
         const int d = e / nn, r = e - d * nn, i = r / n, j = r - i * n;
         const double2 *a = A + (size_t)d * sA, *b = B + (size_t)d * sB;
         double sr = 0., si = 0.;
@@ -120,7 +117,11 @@ struct Ctx {
     double *red;            // reduction scratch
     double *coef;           // interpolated controls [KR], then slot for (i0, i1, w)
     int *loc;               // i0, i1
-    __device__ Ctx(const LArgs &a_) : a(a_) {}
+    // operators, rates, controls and control times: shared-memory copies when they fit (a.ops_in_smem), else global
+    const double2 *H0, *Aops, *Lops, *Khalf;
+    const double *gam, *controls, *xs;
+    __device__ Ctx(const LArgs &a_) : a(a_), H0(a_.H0), Aops(a_.Aops), Lops(a_.Lops), Khalf(a_.Khalf), gam(a_.gam),
+                                      controls(a_.controls), xs(a_.xs) {}
 };
 
 // controls at time t (qoc/core/mathmethods.py:36-67 on control_eval_times) and the effective generators
@@ -130,27 +131,27 @@ __device__ void set_time(Ctx &c, double t) {
     if (a.have_h && a.KR > 0) {
         if (threadIdx.x == 0) {
             int i0, i1;
-            if (t <= a.xs[0]) { i0 = 0; i1 = 1; }
-            else if (t >= a.xs[a.M - 1]) { i0 = a.M - 2; i1 = a.M - 1; }
-            else { i1 = 0; while (!(t <= a.xs[i1])) ++i1; i0 = i1 - 1; }
+            if (t <= c.xs[0]) { i0 = 0; i1 = 1; }
+            else if (t >= c.xs[a.M - 1]) { i0 = a.M - 2; i1 = a.M - 1; }
+            else { i1 = 0; while (!(t <= c.xs[i1])) ++i1; i0 = i1 - 1; }
             c.loc[0] = i0; c.loc[1] = i1;
         }
         __syncthreads();
         const int i0 = c.loc[0], i1 = c.loc[1];
-        for (int r = threadIdx.x; r < a.KR; r += LNT) {
-            const double y0 = a.controls[i0 * a.KR + r], y1 = a.controls[i1 * a.KR + r];
-            c.coef[r] = y0 + ((y1 - y0) / (a.xs[i1] - a.xs[i0])) * (t - a.xs[i0]);
+        for (int r = threadIdx.x; r < a.KR; r += blockDim.x) {
+            const double y0 = c.controls[i0 * a.KR + r], y1 = c.controls[i1 * a.KR + r];
+            c.coef[r] = y0 + ((y1 - y0) / (c.xs[i1] - c.xs[i0])) * (t - c.xs[i0]);
         }
         __syncthreads();
     }
-    for (int e = threadIdx.x; e < nn; e += LNT) {
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
         double2 h = make_double2(0., 0.);
         if (a.have_h) {
-            h = a.H0[e];
-            for (int r = 0; r < a.KR; ++r) { const double2 g = a.Aops[(size_t)r * nn + e]; h.x += c.coef[r] * g.x; h.y += c.coef[r] * g.y; }
+            h = c.H0[e];
+            for (int r = 0; r < a.KR; ++r) { const double2 g = c.Aops[(size_t)r * nn + e]; h.x += c.coef[r] * g.x; h.y += c.coef[r] * g.y; }
         }
         double2 k = make_double2(0., 0.);
-        if (a.L > 0) k = a.Khalf[e];
+        if (a.L > 0) k = c.Khalf[e];
         c.A1[e] = make_double2(h.y - k.x, -h.x - k.y);     // -i h - k
         c.A2[e] = make_double2(-h.y - k.x, h.x - k.y);     // +i h - k
     }
@@ -165,8 +166,8 @@ __device__ void rhs(Ctx &c, double t, const double2 *rho, double2 *out) {
     bmm<0, 0, false>(out, c.A1, 0, rho, nn, a.n, a.D, 1.0);
     bmm<0, 0, true>(out, rho, nn, c.A2, 0, a.n, a.D, 1.0);
     for (int l = 0; l < a.L; ++l) {
-        bmm<0, 0, false>(c.tmp, a.Lops + (size_t)l * nn, 0, rho, nn, a.n, a.D, 1.0);
-        bmm<0, 3, true>(out, c.tmp, nn, a.Lops + (size_t)l * nn, 0, a.n, a.D, a.gam[l]);
+        bmm<0, 0, false>(c.tmp, c.Lops + (size_t)l * nn, 0, rho, nn, a.n, a.D, 1.0);
+        bmm<0, 3, true>(out, c.tmp, nn, c.Lops + (size_t)l * nn, 0, a.n, a.D, c.gam[l]);
     }
 }
 
@@ -178,14 +179,14 @@ __device__ void rhs_vjp(Ctx &c, double t, const double2 *rho, const double2 *rba
     bmm<1, 0, true>(rho_bar, c.A1, 0, rbar, nn, n, a.D, 1.0);
     bmm<0, 1, true>(rho_bar, rbar, nn, c.A2, 0, n, a.D, 1.0);
     for (int l = 0; l < a.L; ++l) {
-        bmm<0, 2, false>(c.tmp, rbar, nn, a.Lops + (size_t)l * nn, 0, n, a.D, 1.0);
-        bmm<1, 0, true>(rho_bar, a.Lops + (size_t)l * nn, 0, c.tmp, nn, n, a.D, a.gam[l]);
+        bmm<0, 2, false>(c.tmp, rbar, nn, c.Lops + (size_t)l * nn, 0, n, a.D, 1.0);
+        bmm<1, 0, true>(rho_bar, c.Lops + (size_t)l * nn, 0, c.tmp, nn, n, a.D, c.gam[l]);
     }
     if (a.have_h && a.KR > 0) {
         // hbar = -i sum_d (rbar_d rho_d^T - rho_d^T rbar_d);  cbar_r = Re sum_ab hbar_ab (A_r)_ab
         double part[kMaxKRL];
         for (int r = 0; r < a.KR; ++r) part[r] = 0.;
-        for (int e = threadIdx.x; e < nn; e += LNT) {
+        for (int e = threadIdx.x; e < nn; e += blockDim.x) {
             const int i = e / n, j = e - i * n;
             double sr = 0., si = 0.;
             for (int d = 0; d < a.D; ++d) {
@@ -199,12 +200,12 @@ __device__ void rhs_vjp(Ctx &c, double t, const double2 *rho, const double2 *rba
             }
             const double hr = si, hi = -sr;                                    // -i (sr + i si)
             for (int r = 0; r < a.KR; ++r) {
-                const double2 g = a.Aops[(size_t)r * nn + e];
+                const double2 g = c.Aops[(size_t)r * nn + e];
                 part[r] += hr * g.x - hi * g.y;
             }
         }
         const int i0 = c.loc[0], i1 = c.loc[1];
-        const double w = (t - a.xs[i0]) / (a.xs[i1] - a.xs[i0]);
+        const double w = (t - c.xs[i0]) / (c.xs[i1] - c.xs[i0]);
         for (int r = 0; r < a.KR; ++r) {
             const double cb = block_sum(part[r], c.red);
             if (threadIdx.x == 0) {
@@ -218,7 +219,7 @@ __device__ void rhs_vjp(Ctx &c, double t, const double2 *rho, const double2 *rba
 
 __device__ double rms_of(const double2 *x, int count, double *red) {
     double s = 0.;
-    for (int e = threadIdx.x; e < count; e += LNT) s += x[e].x * x[e].x + x[e].y * x[e].y;
+    for (int e = threadIdx.x; e < count; e += blockDim.x) s += x[e].x * x[e].x + x[e].y * x[e].y;
     return sqrt(block_sum(s, red) / count);
 }
 
@@ -226,7 +227,7 @@ __device__ double rms_of(const double2 *x, int count, double *red) {
 __device__ double rk_attempt(Ctx &c, double x0, double h, const double2 *y0, double2 *const *k, double2 *ytmp, double2 *y1) {
     const int DE = c.a.D * c.a.n * c.a.n;
     for (int i = 1; i < 6; ++i) {
-        for (int e = threadIdx.x; e < DE; e += LNT) {
+        for (int e = threadIdx.x; e < DE; e += blockDim.x) {
             double2 acc = make_double2(0., 0.);
             for (int j = 0; j < i; ++j) { acc.x += cA[i][j] * k[j][e].x; acc.y += cA[i][j] * k[j][e].y; }
             ytmp[e] = make_double2(y0[e].x + h * acc.x, y0[e].y + h * acc.y);
@@ -234,7 +235,7 @@ __device__ double rk_attempt(Ctx &c, double x0, double h, const double2 *y0, dou
         __syncthreads();
         rhs(c, x0 + cC[i] * h, ytmp, k[i]);
     }
-    for (int e = threadIdx.x; e < DE; e += LNT) {
+    for (int e = threadIdx.x; e < DE; e += blockDim.x) {
         double2 acc = make_double2(0., 0.);
         for (int j = 0; j < 6; ++j) { acc.x += cB[j] * k[j][e].x; acc.y += cB[j] * k[j][e].y; }
         y1[e] = make_double2(y0[e].x + h * acc.x, y0[e].y + h * acc.y);
@@ -242,7 +243,7 @@ __device__ double rk_attempt(Ctx &c, double x0, double h, const double2 *y0, dou
     __syncthreads();
     rhs(c, x0 + h, y1, k[6]);
     double s = 0.;
-    for (int e = threadIdx.x; e < DE; e += LNT) {
+    for (int e = threadIdx.x; e < DE; e += blockDim.x) {
         double2 acc = make_double2(0., 0.);
         for (int j = 0; j < 7; ++j) { acc.x += cBH[j] * k[j][e].x; acc.y += cBH[j] * k[j][e].y; }
         const double er = (y1[e].x - (y0[e].x + h * acc.x)) / L_ATOL, ei = (y1[e].y - (y0[e].y + h * acc.y)) / L_ATOL;
@@ -266,7 +267,7 @@ __device__ double density_costs(Ctx &c, const double2 *rho, bool step_state, boo
             for (int f = 0; f < F; ++f) {
                 const double2 *m = a.mats + ((size_t)tm.mat_off + (size_t)d * tm.fmax + f) * nn;
                 double zr = 0., zi = 0.;                       // tr(M^dagger rho) = sum conj(M_ab) rho_ab
-                for (int e = threadIdx.x; e < nn; e += LNT) {
+                for (int e = threadIdx.x; e < nn; e += blockDim.x) {
                     const double2 x = m[e], y = rho[(size_t)d * nn + e];
                     zr += x.x * y.x + x.y * y.y; zi += x.x * y.y - x.y * y.x;
                 }
@@ -284,7 +285,7 @@ __device__ double density_costs(Ctx &c, const double2 *rho, bool step_state, boo
                     cr = kf * ir; ci = -kf * ii;
                 }
                 if (seed)
-                    for (int e = threadIdx.x; e < nn; e += LNT) {
+                    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
                         const double2 x = m[e];                // conj(M) = (x.x, -x.y)
                         seed[(size_t)d * nn + e].x += cr * x.x + ci * x.y;
                         seed[(size_t)d * nn + e].y += -cr * x.y + ci * x.x;
@@ -312,6 +313,22 @@ __device__ void carve(const LArgs &a, unsigned char *smem, Ctx &c, Work &w, int 
     c.red = d; d += 32;
     c.coef = d; d += kMaxKRL;
     c.loc = reinterpret_cast<int *>(d); d += 2;
+    if (a.ops_in_smem) {                           // the sequential loop re-reads these every stage: keep them on chip
+        auto stage = [&](const double *src, int count) {
+            double *dst = d;
+            for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+            d += (count + 1) & ~1;
+            return dst;
+        };
+        c.H0 = reinterpret_cast<const double2 *>(stage(reinterpret_cast<const double *>(a.H0), 2 * nn));
+        c.Khalf = reinterpret_cast<const double2 *>(stage(reinterpret_cast<const double *>(a.Khalf), 2 * nn));
+        c.Aops = reinterpret_cast<const double2 *>(stage(reinterpret_cast<const double *>(a.Aops), 2 * nn * max(a.KR, 1)));
+        c.Lops = reinterpret_cast<const double2 *>(stage(reinterpret_cast<const double *>(a.Lops), 2 * nn * max(a.L, 1)));
+        c.gam = stage(a.gam, max(a.L, 1));
+        c.controls = stage(a.controls, max(a.M * a.KR, 1));
+        c.xs = stage(a.xs, max(a.M, 1));
+        __syncthreads();
+    }
     double2 *base = a.work_in_smem ? reinterpret_cast<double2 *>(d) : a.work;
     c.tmp = base;
     for (int i = 0; i < narr; ++i) w.p[i] = base + (size_t)(i + 1) * DE;
@@ -325,14 +342,14 @@ __global__ void __launch_bounds__(LNT) k_lindblad_forward(LArgs a, int keep_tape
     const int DE = a.D * a.n * a.n;
     double2 *y = w.p[0], *y1 = w.p[1], *ytmp = w.p[2], *out = w.p[3];
     double2 *k[7] = {w.p[4], w.p[5], w.p[6], w.p[7], w.p[8], w.p[9], w.p[10]};
-    for (int e = threadIdx.x; e < DE; e += LNT) y[e] = a.rho0[e];
+    for (int e = threadIdx.x; e < DE; e += blockDim.x) y[e] = a.rho0[e];
     __syncthreads();
     const double dt = a.T / (a.N - 1);
     double cost = 0.;
     long long attempts = 0, accepted = 0;
     int ntape = 0;
     for (int step = 0; step < a.N; ++step) {
-        for (int e = threadIdx.x; e < DE; e += LNT) a.states[(size_t)step * DE + e] = y[e];
+        for (int e = threadIdx.x; e < DE; e += blockDim.x) a.states[(size_t)step * DE + e] = y[e];
         const bool st = is_cost_step(step, a.ces), fin = step == a.N - 1;
         if (a.nterms > 0 && (st || fin)) cost += density_costs(c, y, st, fin, nullptr);
         if (threadIdx.x == 0) a.first[step] = ntape;
@@ -342,11 +359,11 @@ __global__ void __launch_bounds__(LNT) k_lindblad_forward(LArgs a, int keep_tape
         rhs(c, t0, y, k[0]);
         const double d0 = rms_of(y, DE, c.red), d1 = rms_of(k[0], DE, c.red);
         const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        for (int e = threadIdx.x; e < DE; e += LNT) ytmp[e] = make_double2(y[e].x + h0 * k[0][e].x, y[e].y + h0 * k[0][e].y);
+        for (int e = threadIdx.x; e < DE; e += blockDim.x) ytmp[e] = make_double2(y[e].x + h0 * k[0][e].x, y[e].y + h0 * k[0][e].y);
         __syncthreads();
         rhs(c, t0 + h0, ytmp, k[1]);
         double s = 0.;
-        for (int e = threadIdx.x; e < DE; e += LNT) { const double dr = k[1][e].x - k[0][e].x, di = k[1][e].y - k[0][e].y; s += dr * dr + di * di; }
+        for (int e = threadIdx.x; e < DE; e += blockDim.x) { const double dr = k[1][e].x - k[0][e].x, di = k[1][e].y - k[0][e].y; s += dr * dr + di * di; }
         const double d2 = sqrt(block_sum(s, c.red) / DE) / h0;
         const double mx = fmax(d1, d2);
         const double h1 = (mx <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / mx, 1.0 / 6.0);
@@ -374,12 +391,12 @@ __global__ void __launch_bounds__(LNT) k_lindblad_forward(LArgs a, int keep_tape
                 if (ntape >= a.cap) { if (threadIdx.x == 0) *a.err_flag = 1; }
                 else {
                     if (threadIdx.x == 0) { a.tape_x[ntape] = xc; a.tape_h[ntape] = h; }
-                    for (int e = threadIdx.x; e < DE; e += LNT) { a.tape_y[(size_t)ntape * DE + e] = y[e]; a.tape_k1[(size_t)ntape * DE + e] = k[0][e]; }
+                    for (int e = threadIdx.x; e < DE; e += blockDim.x) { a.tape_y[(size_t)ntape * DE + e] = y[e]; a.tape_k1[(size_t)ntape * DE + e] = k[0][e]; }
                 }
             }
             if (xc <= tf && tf <= xn) {                                  // dense output (mathmethods.py:263-304)
                 const double hh = xn - xc, th = (tf - xc) / hh;
-                for (int e = threadIdx.x; e < DE; e += LNT) {
+                for (int e = threadIdx.x; e < DE; e += blockDim.x) {
                     double o[2];
                     for (int q = 0; q < 2; ++q) {
                         const double y0v = q ? y[e].y : y[e].x, y1v = q ? y1[e].y : y1[e].x;
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(LNT) k_lindblad_forward(LArgs a, int keep_tape
             xc = xn; h = hn;
         }
         if (threadIdx.x == 0) a.hit[step] = hit_idx;
-        for (int e = threadIdx.x; e < DE; e += LNT) y[e] = out[e];
+        for (int e = threadIdx.x; e < DE; e += blockDim.x) y[e] = out[e];
         __syncthreads();
     }
     if (threadIdx.x == 0) { *a.cost = cost; a.stats[0] = attempts; a.stats[1] = accepted; }
@@ -415,22 +432,22 @@ __global__ void __launch_bounds__(LNT) k_lindblad_backward(LArgs a) {
     double2 *k[7] = {w.p[0], w.p[1], w.p[2], w.p[3], w.p[4], w.p[5], w.p[6]};
     double2 *kb[7] = {w.p[7], w.p[8], w.p[9], w.p[10], w.p[11], w.p[12], w.p[13]};
     double2 *y1 = w.p[14], *ytmp = w.p[15], *y0b = w.p[16], *y1b = w.p[17], *zb = w.p[18], *rbar = w.p[19], *k1b_next = w.p[20];
-    for (int e = threadIdx.x; e < a.M * a.KR; e += LNT) a.grad[e] = 0.;
-    for (int e = threadIdx.x; e < DE; e += LNT) rbar[e] = make_double2(0., 0.);
+    for (int e = threadIdx.x; e < a.M * a.KR; e += blockDim.x) a.grad[e] = 0.;
+    for (int e = threadIdx.x; e < DE; e += blockDim.x) rbar[e] = make_double2(0., 0.);
     __syncthreads();
     if (a.nterms > 0) density_costs(c, a.states + (size_t)(a.N - 1) * DE, is_cost_step(a.N - 1, a.ces), true, rbar);
     for (int step = a.N - 2; step >= 0; --step) {
         const int first = a.first[step], last = a.hit[step];
         const double tf = step * (a.T / (a.N - 1)) + a.T / (a.N - 1);
-        for (int e = threadIdx.x; e < DE; e += LNT) k1b_next[e] = make_double2(0., 0.);
+        for (int e = threadIdx.x; e < DE; e += blockDim.x) k1b_next[e] = make_double2(0., 0.);
         // rbar: cotangent of the interval's output; becomes ybar_next after the dense-output step
         for (int i = last; i >= first; --i) {
             const double x0 = a.tape_x[i], h = a.tape_h[i];
             const double2 *y0 = a.tape_y + (size_t)i * DE;
-            for (int e = threadIdx.x; e < DE; e += LNT) k[0][e] = a.tape_k1[(size_t)i * DE + e];
+            for (int e = threadIdx.x; e < DE; e += blockDim.x) k[0][e] = a.tape_k1[(size_t)i * DE + e];
             __syncthreads();
             rk_attempt(c, x0, h, y0, k, ytmp, y1);
-            for (int e = threadIdx.x; e < DE; e += LNT) {
+            for (int e = threadIdx.x; e < DE; e += blockDim.x) {
                 for (int j = 0; j < 6; ++j) kb[j][e] = make_double2(0., 0.);
                 kb[6][e] = k1b_next[e];
                 y0b[e] = make_double2(0., 0.);
@@ -438,7 +455,7 @@ __global__ void __launch_bounds__(LNT) k_lindblad_backward(LArgs a) {
             if (i == last) {                                              // out = dense(...), seed rbar
                 const double th = (tf - x0) / h;
                 const double c2 = th, c3 = th - th * th, c4 = th * th - th * th * th, c5 = th * th - 2.0 * th * th * th + th * th * th * th;
-                for (int e = threadIdx.x; e < DE; e += LNT) {
+                for (int e = threadIdx.x; e < DE; e += blockDim.x) {
                     const double2 ob = rbar[e];
                     const double f0 = 1.0 - c2 + c3 - 2.0 * c4, f1 = c2 - c3 + 2.0 * c4;
                     y0b[e] = make_double2(f0 * ob.x, f0 * ob.y);
@@ -449,19 +466,19 @@ __global__ void __launch_bounds__(LNT) k_lindblad_backward(LArgs a) {
                     for (int j = 0; j < 7; ++j) { const double gj = h * cD[j] * c5; kb[j][e].x += gj * ob.x; kb[j][e].y += gj * ob.y; }
                 }
             } else {
-                for (int e = threadIdx.x; e < DE; e += LNT) y1b[e] = rbar[e];      // ybar_next
+                for (int e = threadIdx.x; e < DE; e += blockDim.x) y1b[e] = rbar[e];      // ybar_next
             }
             __syncthreads();
             // ks[6] = rhs(x0 + h, y1)
             rhs_vjp(c, x0 + h, y1, kb[6], y1b);
             // y1 = y0 + h sum b_j k_j
-            for (int e = threadIdx.x; e < DE; e += LNT) {
+            for (int e = threadIdx.x; e < DE; e += blockDim.x) {
                 y0b[e].x += y1b[e].x; y0b[e].y += y1b[e].y;
                 for (int j = 0; j < 6; ++j) { kb[j][e].x += h * cB[j] * y1b[e].x; kb[j][e].y += h * cB[j] * y1b[e].y; }
             }
             __syncthreads();
             for (int s = 5; s >= 1; --s) {
-                for (int e = threadIdx.x; e < DE; e += LNT) {
+                for (int e = threadIdx.x; e < DE; e += blockDim.x) {
                     double2 acc = make_double2(0., 0.);
                     for (int j = 0; j < s; ++j) { acc.x += cA[s][j] * k[j][e].x; acc.y += cA[s][j] * k[j][e].y; }
                     ytmp[e] = make_double2(y0[e].x + h * acc.x, y0[e].y + h * acc.y);
@@ -469,13 +486,13 @@ __global__ void __launch_bounds__(LNT) k_lindblad_backward(LArgs a) {
                 }
                 __syncthreads();
                 rhs_vjp(c, x0 + cC[s] * h, ytmp, kb[s], zb);
-                for (int e = threadIdx.x; e < DE; e += LNT) {
+                for (int e = threadIdx.x; e < DE; e += blockDim.x) {
                     y0b[e].x += zb[e].x; y0b[e].y += zb[e].y;
                     for (int j = 0; j < s; ++j) { kb[j][e].x += h * cA[s][j] * zb[e].x; kb[j][e].y += h * cA[s][j] * zb[e].y; }
                 }
                 __syncthreads();
             }
-            for (int e = threadIdx.x; e < DE; e += LNT) { rbar[e] = y0b[e]; k1b_next[e] = kb[0][e]; }
+            for (int e = threadIdx.x; e < DE; e += blockDim.x) { rbar[e] = y0b[e]; k1b_next[e] = kb[0][e]; }
             __syncthreads();
         }
         // k1 of the interval's first step = rhs(t0, y_in)
@@ -513,7 +530,7 @@ struct qocb_lplan {
     Buf<DTerm> terms;
     std::vector<DTerm> h_terms; std::vector<double2> h_mats; std::vector<int> h_counts;
     size_t smem_fwd = 0, smem_bwd = 0;
-    int in_smem_fwd = 0, in_smem_bwd = 0;
+    int in_smem_fwd = 0, in_smem_bwd = 0, ops_in_smem = 0;
     std::string err;
 };
 
@@ -530,7 +547,7 @@ LArgs make_largs(qocb_lplan *p) {
     a.xs = p->xs.p; a.rho0 = p->rho0.p; a.terms = p->terms.p; a.mats = p->mats.p; a.counts = p->counts.p;
     a.states = p->states.p; a.cost = p->cost.p; a.tape_x = p->tape_x.p; a.tape_h = p->tape_h.p; a.tape_y = p->tape_y.p;
     a.tape_k1 = p->tape_k1.p; a.first = p->first.p; a.hit = p->hit.p; a.stats = p->stats.p; a.err_flag = p->err_flag.p;
-    a.work = p->work.p; a.work_in_smem = 0; a.grad = p->grad.p;
+    a.work = p->work.p; a.work_in_smem = 0; a.ops_in_smem = p->ops_in_smem; a.grad = p->grad.p;
     return a;
 }
 
@@ -560,10 +577,12 @@ int run_lindblad(qocb_lplan *p, const double *controls, bool with_grad, double *
     LTRY(p, cudaMemsetAsync(p->err_flag.p, 0, sizeof(int), p->stream));
     LArgs a = make_largs(p);
     a.work_in_smem = p->in_smem_fwd;
-    k_lindblad_forward<<<1, LNT, p->smem_fwd, p->stream>>>(a, with_grad ? 1 : 0);
+    const int DEl = p->pb.density_count * p->pb.hilbert_size * p->pb.hilbert_size;
+    const int nt = DEl <= 64 ? 32 : (DEl <= 256 ? 128 : LNT);
+    k_lindblad_forward<<<1, nt, p->smem_fwd, p->stream>>>(a, with_grad ? 1 : 0);
     if (with_grad && cnt) {
         a.work_in_smem = p->in_smem_bwd;
-        k_lindblad_backward<<<1, LNT, p->smem_bwd, p->stream>>>(a);
+        k_lindblad_backward<<<1, nt, p->smem_bwd, p->stream>>>(a);
     }
     LTRY(p, cudaGetLastError());
     int flag = 0;
@@ -618,8 +637,11 @@ int qocb_lindblad_create(const qocb_lindblad_problem *pb, qocb_lplan **out) {
         for (int m = 0; m < M; ++m) xs[m] = (M == 1) ? 0.0 : (m == M - 1 ? T : m * (T / (M - 1)));
         CTRY(cudaMemcpy(p->xs.p, xs.data(), sizeof(double) * M, cudaMemcpyHostToDevice));
     }
-    const size_t fixed = sizeof(double) * (4 * (size_t)nn + 32 + kMaxKRL + 2);
+    size_t fixed = sizeof(double) * (4 * (size_t)nn + 32 + kMaxKRL + 2);
     const size_t limit = 200 * 1024;
+    const size_t ops_doubles = 2 * (size_t)nn * (2 + std::max(KR, 1) + std::max(L, 1)) + std::max(L, 1) + std::max(M * KR, 1) + std::max(M, 1) + 16;
+    p->ops_in_smem = ops_doubles * sizeof(double) <= 48 * 1024;
+    if (p->ops_in_smem) fixed += ops_doubles * sizeof(double);
     const size_t need_f = fixed + sizeof(double2) * 13 * DE, need_b = fixed + sizeof(double2) * 23 * DE;
     p->in_smem_fwd = need_f <= limit; p->in_smem_bwd = need_b <= limit;
     p->smem_fwd = p->in_smem_fwd ? need_f : fixed; p->smem_bwd = p->in_smem_bwd ? need_b : fixed;

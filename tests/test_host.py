@@ -191,3 +191,25 @@ def test_program_state_fields():
     assert [c.name for c in ps.step_costs] == ["forbid_states"]
     assert ps.controls_shape == (6, 1) and ps.program_type == ProgramType.GRAPE
     assert ps.save_intermediate_states_ is False
+
+
+def test_autograd_primitive_registration_with_stub(monkeypatch):
+    """HIPS autograd is absent from this image: check the `primitive` + `defvjp` wiring of
+    make_autograd_primitive against a stub of autograd.extend (hard part 8)."""
+    import sys
+    import types
+    from qoc_b200.standard.utils import make_autograd_primitive
+    registry = {}
+    ext = types.ModuleType("autograd.extend")
+    ext.primitive = lambda f: f
+    ext.defvjp = lambda f, *vjps: registry.setdefault(f, vjps)
+    ag = types.ModuleType("autograd")
+    ag.extend = ext
+    monkeypatch.setitem(sys.modules, "autograd", ag)
+    monkeypatch.setitem(sys.modules, "autograd.extend", ext)
+    grad = np.array([[1.0 - 2.0j], [0.5 + 0.25j]])
+    f = make_autograd_primitive(lambda controls: (3.5, grad))
+    assert f(np.zeros((2, 1), dtype=complex)) == 3.5
+    (vjp_maker,) = registry[f]
+    vjp = vjp_maker(3.5, np.zeros((2, 1), dtype=complex))
+    assert np.array_equal(vjp(2.0), 2.0 * grad)            # cotangent of the scalar cost times the stored gradient
