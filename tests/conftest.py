@@ -16,6 +16,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
 
 
+def pytest_sessionstart(session):
+    """the C-ABI library is a build artefact (git-ignored): compile it when a fresh checkout has none"""
+    try:
+        from qoc_b200 import _lib
+        if not os.path.exists(_lib.LIB_PATH):
+            _lib.build_library(verbose=True)
+    except Exception as exc:                      # the tests that need it will fail loudly
+        print("qoc_b200: could not build libqocb200.so:", exc)
+
+
 def _cuda_available():
     try:
         import torch
