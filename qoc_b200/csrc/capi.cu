@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(C::NT) k_forward(KArgs a) {
         const int e = w / (a.N - 1), j = w - e * (a.N - 1);
         GenArgs ga = a.ga;
         ga.G0 += (size_t)e * C::GMAT;
+        ga.C0 += (size_t)e * ga.KR * C::GMAT;
         PROF_DECL
         load_coefs<C>(sm, ga, j);
         magnus_forward<C>(sm, ga, scratch);
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(C::NT) k_backward(KArgs a) {
         const int e = w / (a.N - 1), j = w - e * (a.N - 1);
         GenArgs ga = a.ga;
         ga.G0 += (size_t)e * C::GMAT;
+        ga.C0 += (size_t)e * ga.KR * C::GMAT;
         load_coefs<C>(sm, ga, j);
         const double *tape; const int *piv; int s;
         if (a.tape && a.meta[w] <= a.s_cap) {
@@ -340,10 +342,10 @@ struct qocb_plan {
     // lvl_count[l] chunks at level l, their propagators at lvlP + lvl_off[l] matrices, boundaries at cb_lvl + cb_off[l]
     int levels = 0, lvl_count[16] = {}, lvl_off[16] = {}, cb_off[16] = {};
     bool sharded = false, owns_final = true;
-    bool ops_set = false, states_set = false, have_step_costs = false;
+    bool ops_set = false, states_set = false, have_step_costs = false, comm_ok = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16] = {};
-    DevBuf<double> G0, G, controls, itab_w, U, tape, scratch, cta_tape, chunkP, psi, lam, part, cost_part, psi0,
+    DevBuf<double> C0, Cs, G0, G, controls, itab_w, U, tape, scratch, cta_tape, chunkP, psi, lam, part, cost_part, psi0,
         node_grad, grad, cost, csr_w, vecs, flush, redA, redB, psi_in, lam_in, lvlP;
     DevBuf<int> itab_idx, tape_piv, meta, cta_piv, chunk_begin, member_chunk0, csr_ptr, csr_idx, counts, err_flag, cb_lvl, mc0_lvl;
     DevBuf<CostTerm> terms;
@@ -428,6 +430,7 @@ KArgs make_kargs(qocb_plan *p) {
     a.ga.G0 = p->G0.p; a.ga.G = p->G.p; a.ga.controls = p->controls.p;
     a.ga.itab_idx = p->itab_idx.p; a.ga.itab_w = p->itab_w.p;
     a.ga.KR = p->pb.control_count; a.ga.q = p->q; a.ga.order = p->pb.magnus_order;
+    a.ga.C0 = p->C0.p; a.ga.Cs = p->Cs.p; a.ga.comm = p->comm_ok ? 1 : 0;
     a.ga.dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
     a.N = p->Nloc; a.E = p->pb.ensemble_count;
     a.s_cap = kStoredTapeR; a.tape_mats = p->tape_mats;
@@ -1188,6 +1191,47 @@ int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
         if (!a_ops) { set_error(p, "a_ops is null but control_count > 0"); return -1; }
         for (int r = 0; r < KR; ++r) to_planar(a_ops + (size_t)r * 2 * n * n, buf.data() + (size_t)r * GM, n, NP, true);
         CU_TRY(p, cudaMemcpy(p->G.p, buf.data(), sizeof(double) * KR * GM, cudaMemcpyHostToDevice));
+    }
+    // commutators of the generators G = -1j H for the product-free Magnus M4: C0[e][r] = [G0_e, G_r], Cs[s<r] = [G_s, G_r]
+    p->comm_ok = false;
+    { const char *nc = getenv("QOCB_NO_COMM"); if (p->pb.magnus_order == 4 && KR <= kMaxCommKR && !(nc && nc[0] == '1')) p->comm_ok = true; }
+    if (p->comm_ok) {
+        typedef std::vector<double> Mat;                           // interleaved complex n x n
+        auto gen = [&](const double *h) { Mat g(2 * (size_t)n * n); for (size_t i = 0; i < (size_t)n * n; ++i) { g[2 * i] = h[2 * i + 1]; g[2 * i + 1] = -h[2 * i]; } return g; };
+        auto comm = [&](const Mat &x, const Mat &y) {
+            Mat c(2 * (size_t)n * n, 0.0);
+            for (int i = 0; i < n; ++i)
+                for (int k = 0; k < n; ++k) {
+                    const double xr = x[2 * ((size_t)i * n + k)], xi = x[2 * ((size_t)i * n + k) + 1];
+                    const double yr = y[2 * ((size_t)i * n + k)], yi = y[2 * ((size_t)i * n + k) + 1];
+                    for (int j = 0; j < n; ++j) {
+                        const double br = y[2 * ((size_t)k * n + j)], bi = y[2 * ((size_t)k * n + j) + 1];
+                        const double ar = x[2 * ((size_t)k * n + j)], ai = x[2 * ((size_t)k * n + j) + 1];
+                        c[2 * ((size_t)i * n + j)] += (xr * br - xi * bi) - (yr * ar - yi * ai);
+                        c[2 * ((size_t)i * n + j) + 1] += (xr * bi + xi * br) - (yr * ai + yi * ar);
+                    }
+                }
+            return c;
+        };
+        std::vector<Mat> g(KR);
+        for (int r = 0; r < KR; ++r) g[r] = gen(a_ops + (size_t)r * 2 * n * n);
+        const int npair = KR * (KR - 1) / 2;
+        CU_TRY(p, p->C0.alloc(std::max<size_t>(1, (size_t)E * KR) * GM)); CU_TRY(p, p->Cs.alloc(std::max<size_t>(1, (size_t)npair) * GM));
+        std::vector<double> pl(GM);
+        for (int e = 0; e < E; ++e) {
+            const Mat g0 = gen(h0 + (size_t)e * 2 * n * n);
+            for (int r = 0; r < KR; ++r) {
+                const Mat c = comm(g0, g[r]);
+                to_planar(c.data(), pl.data(), n, NP, false);
+                CU_TRY(p, cudaMemcpy(p->C0.p + ((size_t)e * KR + r) * GM, pl.data(), sizeof(double) * GM, cudaMemcpyHostToDevice));
+            }
+        }
+        for (int s_ = 0; s_ < KR; ++s_)
+            for (int r = s_ + 1; r < KR; ++r) {
+                const Mat c = comm(g[s_], g[r]);
+                to_planar(c.data(), pl.data(), n, NP, false);
+                CU_TRY(p, cudaMemcpy(p->Cs.p + (size_t)comm_pair(s_, r, KR) * GM, pl.data(), sizeof(double) * GM, cudaMemcpyHostToDevice));
+            }
     }
     p->ops_set = true;
     return 0;

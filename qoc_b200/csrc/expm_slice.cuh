@@ -58,7 +58,13 @@ struct GenArgs {
     const double *itab_w;       // [N-1][q][2]
     int KR, q, order;
     double dt;
+    // Magnus M4 without matrix products: [a2, a1] and the adjoint's [a_i, G_r] are linear in the precomputed commutators
+    // C0[r] = [G0, G_r] (per member) and Cs[(s<r)] = [G_s, G_r]; enabled for KR <= kMaxCommKR
+    const double *C0, *Cs;
+    int comm;
 };
+constexpr int kMaxCommKR = 6;
+__host__ __device__ inline int comm_pair(int s, int r, int KR) { return s * KR - s * (s + 1) / 2 + (r - s - 1); }   // s < r
 
 // interpolated control coefficients of slice j at the Magnus nodes -> sm.coef[i*kMaxKR + r]
 template <class C>
@@ -121,6 +127,24 @@ __device__ void magnus_forward(const Smem<C> &sm, const GenArgs &ga, double *scr
         c2 v[C::TM][C::TN];
         gen_nodes<C, 1>(ga, sm.coef, 1.0, 1.0, v, v);
         for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(sm.X2, row, col, dt * v[i][j]); });
+        __syncthreads();
+        return;
+    }
+    if (ga.order == 4 && ga.comm) {
+        // M = dt G0 + sum_r dt/2 (c1_r + c2_r) G_r + f [ sum_r (c1_r - c2_r) C0_r + sum_{s<r} (c2_s c1_r - c2_r c1_s) C_sr ]
+        const double f = (QOCB_S3 / 12.0) * dt * dt;
+        const double *c1 = sm.coef, *cc2 = sm.coef + kMaxKR;
+        c2 v[C::TM][C::TN];
+        for_owned<C>([&](int i, int j, int row, int col) { v[i][j] = dt * ldg2<C>(ga.G0, row, col); });
+        auto axpy = [&](double w, const double *g) {
+            for_owned<C>([&](int i, int j, int row, int col) { v[i][j] = v[i][j] + w * ldg2<C>(g, row, col); });
+        };
+        for (int r = 0; r < ga.KR; ++r) axpy(0.5 * dt * (c1[r] + cc2[r]), ga.G + (size_t)r * C::GMAT);
+        for (int r = 0; r < ga.KR; ++r) axpy(f * (c1[r] - cc2[r]), ga.C0 + (size_t)r * C::GMAT);
+        for (int s_ = 0; s_ < ga.KR; ++s_)
+            for (int r = s_ + 1; r < ga.KR; ++r)
+                axpy(f * (cc2[s_] * c1[r] - cc2[r] * c1[s_]), ga.Cs + (size_t)comm_pair(s_, r, ga.KR) * C::GMAT);
+        for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(sm.X2, row, col, v[i][j]); });
         __syncthreads();
         return;
     }
@@ -630,6 +654,43 @@ __device__ void magnus_backward(const Smem<C> &sm, const GenArgs &ga, double *sc
     if (ga.order == 2) {
         for_owned<C>([&](int i, int j, int row, int col) { abn[i][j] = dt * lds2<C>(sm.X0, row, col); });
         contract_node(0);
+    } else if (ga.order == 4 && ga.comm) {
+        // cbar_{0,r} = <mbar, dt/2 G_r + f (C0_r + sum_s c2_s C_sr)>,  cbar_{1,r} = <mbar, dt/2 G_r - f (C0_r + sum_s c1_s C_sr)>
+        // (<X, Y> = Re sum X.Y): inner products of mbar with the precomputed matrices, no products
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, KR = ga.KR, NPAIR = KR * (KR - 1) / 2;
+        double *red = sm.red + 64;
+        for_owned<C>([&](int i, int j, int row, int col) { abn[i][j] = lds2<C>(sm.X0, row, col); });
+        auto dot = [&](const double *g, int slot) {
+            double v = 0.;
+            for_owned<C>([&](int i, int j, int row, int col) {
+                const c2 x = ldg2<C>(g, row, col);
+                const c2 &a = abn[i][j];
+                v += a.r0 * x.r0 - a.i0 * x.i0 + a.r1 * x.r1 - a.i1 * x.i1;
+            });
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[slot * C::NWARP + warp] = v;
+        };
+        __syncthreads();
+        for (int r = 0; r < KR; ++r) dot(ga.G + (size_t)r * C::GMAT, r);
+        for (int r = 0; r < KR; ++r) dot(ga.C0 + (size_t)r * C::GMAT, KR + r);
+        for (int pr = 0; pr < NPAIR; ++pr) dot(ga.Cs + (size_t)pr * C::GMAT, 2 * KR + pr);
+        __syncthreads();
+        const double f = (QOCB_S3 / 12.0) * dt * dt;
+        for (int e = threadIdx.x; e < 2 * KR; e += C::NT) {
+            const int node = e / KR, r = e % KR;
+            auto slot_sum = [&](int slot) { double t = 0.; for (int w = 0; w < C::NWARP; ++w) t += red[slot * C::NWARP + w]; return t; };
+            const double *cf = sm.coef + (node == 0 ? kMaxKR : 0);          // node 0 pairs with c2, node 1 with c1
+            double acc_k = slot_sum(KR + r);
+            for (int s_ = 0; s_ < KR; ++s_) {
+                if (s_ == r) continue;
+                const double k = s_ < r ? slot_sum(2 * KR + comm_pair(s_, r, KR)) : -slot_sum(2 * KR + comm_pair(r, s_, KR));
+                acc_k += cf[s_] * k;
+            }
+            gout[node * KR + r] = 0.5 * dt * slot_sum(r) + (node == 0 ? f : -f) * acc_k;
+        }
+        __syncthreads();
+        return;
     } else if (ga.order == 4) {
         {
             c2 v0[C::TM][C::TN], v1[C::TM][C::TN];
