@@ -475,6 +475,21 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
     double *X0 = sm.X0, *LEFT = sm.X1, *TMP = sm.X1 + 2 * LR_PL, *RIGHT = sm.X2, *EL = sm.X2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = lane & 3;
     const int frow = warp * 8 + (lane >> 2);                       // row of this lane's C-fragment elements
+    // register-staged prefetch of the next tape matrix: the loads fly while the current stage computes on X0
+    double2 pre[C::GMAT / 2 / C::NT];
+    auto pf_load = [&](const double *gm) {
+#pragma unroll
+        for (int i = 0; i < C::GMAT / 2 / C::NT; ++i) pre[i] = reinterpret_cast<const double2 *>(gm)[threadIdx.x + i * C::NT];
+    };
+    auto pf_store = [&](double *sdst) {
+#pragma unroll
+        for (int i = 0; i < C::GMAT / 2 / C::NT; ++i) {
+            const int idx = threadIdx.x + i * C::NT;
+            const int plane = idx / (C::GPLANE / 2), rem = idx - plane * (C::GPLANE / 2);
+            const int row = rem / (NP / 2), cc = rem - row * (NP / 2);
+            *reinterpret_cast<double2 *>(sdst + plane * C::PLANE + row * C::LD + cc * 2) = pre[i];
+        }
+    };
     // ---- stage 0: [0 | lam] -> LEFT[:, 0:8], [p | m] -> TMP[:, 0:8]; LUi -> X0
     for (int e = threadIdx.x; e < NP * 4; e += C::NT) {
         const int row = e >> 2, c = e & 3;
@@ -489,6 +504,7 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
     }
     g2s<C>(X0, tape + (size_t)T_LU * C::GMAT);
     for (int c = threadIdx.x; c < NP; c += C::NT) sm.piv[c] = tperm[c];
+    pf_load(tape + (size_t)T_Y * C::GMAT);
     __syncthreads();
     // ---- stage 1: l = Q^-T lam (thin solve), row un-permutation through RIGHT
     lu_solve_thin_T<C>(X0, LEFT);
@@ -496,7 +512,8 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
         const int row = e >> 2, c = e & 3, pr = sm.piv[row];
         RIGHT[pr * LD + c] = LEFT[row * LD + 4 + c]; RIGHT[PL + pr * LD + c] = LEFT[PL + row * LD + 4 + c];
     }
-    g2s<C>(X0, tape + (size_t)T_Y * C::GMAT);
+    pf_store(X0);                                                   // Y
+    pf_load(tape + (size_t)T_A * C::GMAT);
     __syncthreads();
     for (int e = threadIdx.x; e < NP * 4; e += C::NT) {
         const int row = e >> 2, c = e & 3;
@@ -511,7 +528,8 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
         }
     }
     __syncthreads();
-    g2s<C>(X0, tape + (size_t)T_A * C::GMAT);
+    pf_store(X0);                                                   // A
+    pf_load(tape + (size_t)T_W1 * C::GMAT);
     __syncthreads();
     // ---- stage 3: a = A^T l -> LEFT[:, 0:4]
     {
@@ -522,7 +540,8 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
             *reinterpret_cast<double2 *>(LEFT + PL + frow * LD + 2 * (t - 2)) = make_double2(v.i0, v.i1);
         }
     }
-    g2s<C>(X0, tape + (size_t)T_W1 * C::GMAT);
+    pf_store(X0);                                                   // W1
+    pf_load(tape + (size_t)T_X1 * C::GMAT);
     // R4, R2 and the polynomial blocks of R6 (elementwise from p, m)
     for (int e = threadIdx.x; e < NP * 4; e += C::NT) {
         const int row = e >> 2, c = e & 3;
@@ -547,7 +566,8 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
         }
     }
     __syncthreads();
-    g2s<C>(X0, tape + (size_t)T_X1 * C::GMAT);
+    pf_store(X0);                                                   // X1
+    pf_load(tape + (size_t)T_A6 * C::GMAT);
     __syncthreads();
     // ---- stage 5: c2 = b6 m + X1 m -> RIGHT[:, 36:40]
     {
@@ -560,12 +580,14 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
         }
     }
     __syncthreads();
-    g2s<C>(X0, tape + (size_t)T_A6 * C::GMAT);
+    pf_store(X0);                                                   // A6
+    pf_load(tape + (size_t)T_A4 * C::GMAT);
     __syncthreads();
     // ---- stage 6: [A6^T a | A6^T l] -> LEFT[:, 8:16]
     st_thin<LD, PL>(LEFT, warp * 8, 8, thin_tile<C, true, LD, PL>(X0, LEFT, warp, 0));
     __syncthreads();
-    g2s<C>(X0, tape + (size_t)T_A4 * C::GMAT);
+    pf_store(X0);                                                   // A4
+    pf_load(tape + (size_t)T_A2 * C::GMAT);
     __syncthreads();
     // ---- stage 7: X_a += A4 R6
 #pragma unroll
@@ -575,7 +597,7 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
         st_thin<LD, PL>(RIGHT, warp * 8, ct * 8, acc);
     }
     __syncthreads();
-    g2s<C>(X0, tape + (size_t)T_A2 * C::GMAT);
+    pf_store(X0);                                                   // A2
     __syncthreads();
     // ---- stage 8a: X_a += A2 R4 (R4 = the untouched X_b block)
 #pragma unroll
@@ -602,6 +624,7 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
     Acc<C> acc;
     acc.zero();
     mma_lowrank<C, LD, PL, LD, PL>(acc, LEFT, 0, RIGHT, 0, 48);
+    pf_load(tape + (size_t)T_A * C::GMAT);
     for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(X0, row, col, accv<C>(acc, i, j)); });
     __syncthreads();
     for (int e = threadIdx.x; e < NP * 4; e += C::NT) {             // keep l and yp for the rank-S term
@@ -613,7 +636,7 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
         }
     }
     __syncthreads();
-    g2s<C>(sm.X1, tape + (size_t)T_A * C::GMAT);
+    pf_store(sm.X1);                                                // A
     __syncthreads();
     // ---- stage 10: mbar = l yp^T + a2bar A^T + A^T a2bar
     acc.zero();
