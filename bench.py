@@ -65,15 +65,33 @@ def flops_per_slice(n, S, order, s=0):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML in a background thread
+    (a few ms per sample, so short timed regions still get samples); falls back to `nvidia-smi -lms` when pynvml is absent."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bit masks
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+               "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, device):
         self.device, self.proc, self.lines = device, None, []
+        self.nvml, self.samples, self.stop_flag, self.thread = None, [], False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.device]) if vis and vis.split(",")[self.device].isdigit() else self.device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -83,11 +101,38 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                try:
+                    pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((sm, mask, pw))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            sm = [x[0] for x in self.samples]
+            reasons = sorted(k for k, bit in self.REASONS.items() if any(x[1] & bit for x in self.samples))
+            pw = [x[2] for x in self.samples if x[2] is not None]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max,
+                    "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -109,7 +154,8 @@ class ClockSampler(object):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi"}
 
 
 def ncu_traffic(workload, kernel):
