@@ -286,3 +286,74 @@ def test_errors_are_loud():
     with pytest.raises(NotImplementedError):
         Plan(lambda c, t: p.h0 * (1 + t) + c[0] * p.drives[0], p.initial_states, [], p.T, p.N, control_eval_count=p.M,
              control_count=1, magnus_policy=pol[2])
+
+
+EDGE = [
+    # n, slices, K, S, order, complex, F, stiff, ces, step_target, label
+    (64, 1, 2, 1, 4, False, 0, 1.0, 1, False, "single_slice_S1_lowrank"),
+    (64, 9, 7, 3, 4, False, 1, 1.0, 1, False, "KR7_commutators_off"),
+    (64, 9, 4, 2, 4, True, 0, 1.0, 1, False, "KR8_complex_commutators_off"),
+    (64, 9, 2, 5, 4, True, 2, 1.0, 1, False, "S5_dense_reverse"),
+    (61, 7, 1, 4, 2, True, 4, 1.0, 3, True, "n61_M2_lowrank"),
+    (64, 8, 2, 4, 6, False, 0, 1.0, 1, False, "M6_lowrank"),
+    (64, 6, 2, 4, 4, False, 0, 6.0, 1, False, "mixed_s_lowrank_and_dense"),
+    (5, 1, 1, 1, 4, True, 1, 1.0, 1, True, "n5_single_slice"),
+]
+
+
+@pytest.mark.parametrize("case", EDGE, ids=lambda c: c[-1])
+def test_edge_cases_vs_oracle(case):
+    n, slices, K, S, order, cc, F, stiff, ces, step_target, _ = case
+    std, Plan, pol = product()
+    orc = oracle_mod()
+    p = Problem(n, slices, K, S, order, complex_controls=cc, F=F, seed=17 + n, stiff=stiff, cost_eval_step=ces,
+                step_target=step_target)
+    if case[-1] == "mixed_s_lowrank_and_dense":          # some slices need squarings (s > 0), some do not
+        p.controls[: p.M // 2] *= 0.02
+        p.h0 = p.h0 * 0.8
+    plan = Plan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M,
+                control_count=K, complex_controls=cc, magnus_policy=pol[order], cost_eval_step=ces)
+    err, grads, finals = plan.cost_and_grad(p.controls)
+    o_err, o_grad, o_fin = orc.schroedinger_cost_and_grad(p.controls, orc.make_hamiltonian(p.h0, p.drives, cc),
+                                                          p.initial_states, p.costs(orc), p.T, p.N, order=order,
+                                                          cost_eval_step=ces)
+    assert abs(err - o_err) <= RTOL * max(abs(o_err), 1e-3)
+    assert rel(finals, o_fin) < RTOL
+    assert rel(grads, o_grad) < RTOL, rel(grads, o_grad)
+    plan.close()
+
+
+def test_lowrank_and_commutator_paths_match_dense(monkeypatch):
+    """the rank-S reverse pass and the product-free Magnus M4 against the dense / product forms of the same kernels"""
+    std, Plan, pol = product()
+    p = Problem(64, 40, 4, 4, 4, complex_controls=False, F=2, seed=2)
+    kw = dict(control_eval_count=p.M, control_count=4, magnus_policy=pol[4])
+    plan = Plan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, **kw)
+    e1, g1, f1 = plan.cost_and_grad(p.controls)
+    plan.close()
+    monkeypatch.setenv("QOCB_NO_LOWRANK", "1")
+    monkeypatch.setenv("QOCB_NO_COMM", "1")
+    plan = Plan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, **kw)
+    e2, g2, f2 = plan.cost_and_grad(p.controls)
+    plan.close()
+    assert abs(e1 - e2) < 1e-13 and rel(f1, f2) < 1e-12 and rel(g1, g2) < 1e-11
+
+
+def test_ensemble_with_lowrank_path():
+    std, Plan, pol = product()
+    orc = oracle_mod()
+    p = Problem(64, 6, 2, 2, 4, complex_controls=False, F=0, seed=4)
+    rng = np.random.default_rng(8)
+    z = np.diag(np.linspace(-1, 1, 64)).astype(complex) * 0.05
+    drifts = np.stack([p.h0 + d * z for d in rng.normal(0, 1.0, 3)])
+    plan = Plan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M, control_count=2,
+                magnus_policy=pol[4], ensemble_drifts=drifts)
+    err, grads, _ = plan.cost_and_grad(p.controls)
+    o_err, o_grad = 0.0, 0.0
+    for e in range(3):
+        v, g, _ = orc.schroedinger_cost_and_grad(p.controls, orc.make_hamiltonian(drifts[e], p.drives, False),
+                                                 p.initial_states, p.costs(orc), p.T, p.N, order=4)
+        o_err += v / 3
+        o_grad = o_grad + g / 3
+    assert abs(err - o_err) <= RTOL * abs(o_err) and rel(grads, o_grad) < RTOL
+    plan.close()
