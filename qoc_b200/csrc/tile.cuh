@@ -232,6 +232,25 @@ template <class C> __device__ __forceinline__ void st_ctile(double *M, int r0, i
     sts2<C>(M, r0 + (lane >> 2), c0 + (lane & 3) * 2, v);
 }
 
+// W[rt] -= op(LU)[rt, kb] * W[kb] for the row tiles rt = r_begin, r_begin + r_step, ... < r_end of one column tile; two
+// row tiles per trip give the DMMA pipe independent accumulator chains
+template <class C, bool T>
+__device__ __forceinline__ void tile_update_rows(const double *LU, double *W, int kb, int c0, int r_begin, int r_end, int r_step) {
+    int rt = r_begin;
+    for (; rt + r_step < r_end; rt += 2 * r_step) {
+        c2 a = ld_ctile<C>(W, rt * 8, c0), b = ld_ctile<C>(W, (rt + r_step) * 8, c0);
+        tile_mma<C, T, MASK_NONE, true>(a, LU, rt * 8, kb * 8, W, kb * 8, c0);
+        tile_mma<C, T, MASK_NONE, true>(b, LU, (rt + r_step) * 8, kb * 8, W, kb * 8, c0);
+        st_ctile<C>(W, rt * 8, c0, a);
+        st_ctile<C>(W, (rt + r_step) * 8, c0, b);
+    }
+    if (rt < r_end) {
+        c2 a = ld_ctile<C>(W, rt * 8, c0);
+        tile_mma<C, T, MASK_NONE, true>(a, LU, rt * 8, kb * 8, W, kb * 8, c0);
+        st_ctile<C>(W, rt * 8, c0, a);
+    }
+}
+
 // warp 0: unblocked LU with partial pivoting of the panel (rows j0.., columns j0..j0+7), then the in-place inversion
 // of the diagonal block's triangular factors.  piv8: shared int[8]; perm: shared int[NP].
 template <class C>
@@ -385,11 +404,7 @@ __device__ void lu_factor_blocked(double *Q, int *perm, int *piv8) {
                 __syncwarp();
                 st_ctile<C>(Q, j0, ct * 8, u);
                 __syncwarp();
-                for (int rt = kb + 1; rt < NB; ++rt) {             // A22 -= L21 U12
-                    c2 a = ld_ctile<C>(Q, rt * 8, ct * 8);
-                    tile_mma<C, false, MASK_NONE, true>(a, Q, rt * 8, j0, Q, j0, ct * 8);
-                    st_ctile<C>(Q, rt * 8, ct * 8, a);
-                }
+                tile_update_rows<C, false>(Q, Q, kb, ct * 8, kb + 1, NB, 1);   // A22 -= L21 U12
             }
         }
         __syncthreads();
@@ -422,11 +437,7 @@ __device__ void lu_solve_blocked(const double *LU, const int *perm, double *B, d
                 __syncwarp();
                 st_ctile<C>(W, kb * 8, c0, z);
                 __syncwarp();
-                for (int rt = kb + 1; rt < NB; ++rt) {
-                    c2 a = ld_ctile<C>(W, rt * 8, c0);
-                    tile_mma<C, false, MASK_NONE, true>(a, LU, rt * 8, kb * 8, W, kb * 8, c0);
-                    st_ctile<C>(W, rt * 8, c0, a);
-                }
+                tile_update_rows<C, false>(LU, W, kb, c0, kb + 1, NB, 1);
                 __syncwarp();
             }
             for (int kb = NB - 1; kb >= 0; --kb) {                 // U x = z
@@ -435,11 +446,7 @@ __device__ void lu_solve_blocked(const double *LU, const int *perm, double *B, d
                 __syncwarp();
                 st_ctile<C>(W, kb * 8, c0, z);
                 __syncwarp();
-                for (int rt = 0; rt < kb; ++rt) {
-                    c2 a = ld_ctile<C>(W, rt * 8, c0);
-                    tile_mma<C, false, MASK_NONE, true>(a, LU, rt * 8, kb * 8, W, kb * 8, c0);
-                    st_ctile<C>(W, rt * 8, c0, a);
-                }
+                tile_update_rows<C, false>(LU, W, kb, c0, 0, kb, 1);
                 __syncwarp();
             }
         } else {
@@ -449,11 +456,7 @@ __device__ void lu_solve_blocked(const double *LU, const int *perm, double *B, d
                 __syncwarp();
                 st_ctile<C>(W, kb * 8, c0, z);
                 __syncwarp();
-                for (int rt = kb + 1; rt < NB; ++rt) {
-                    c2 a = ld_ctile<C>(W, rt * 8, c0);
-                    tile_mma<C, true, MASK_NONE, true>(a, LU, rt * 8, kb * 8, W, kb * 8, c0);
-                    st_ctile<C>(W, rt * 8, c0, a);
-                }
+                tile_update_rows<C, true>(LU, W, kb, c0, kb + 1, NB, 1);
                 __syncwarp();
             }
             for (int kb = NB - 1; kb >= 0; --kb) {                 // L^T z = y
@@ -462,11 +465,7 @@ __device__ void lu_solve_blocked(const double *LU, const int *perm, double *B, d
                 __syncwarp();
                 st_ctile<C>(W, kb * 8, c0, z);
                 __syncwarp();
-                for (int rt = 0; rt < kb; ++rt) {
-                    c2 a = ld_ctile<C>(W, rt * 8, c0);
-                    tile_mma<C, true, MASK_NONE, true>(a, LU, rt * 8, kb * 8, W, kb * 8, c0);
-                    st_ctile<C>(W, rt * 8, c0, a);
-                }
+                tile_update_rows<C, true>(LU, W, kb, c0, 0, kb, 1);
                 __syncwarp();
             }
         }
