@@ -354,6 +354,13 @@ struct qocb_plan {
     std::vector<int> h_counts;
     int ip_total = 0;
     double *h_pinned = nullptr;         // [M*KR controls | M*KR grad | 1 cost]
+    // CUDA graph of one whole host-facing evaluation (H2D controls, all kernels, D2H of gradient, cost, final states and the
+    // error flag): replayed by qocb_cost / qocb_cost_and_grad from the third call on - launch-bound small problems gain 2x
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    int host_calls[2] = {0, 0};
+    double *h_fin = nullptr;            // pinned [E][S][2][NP] final states
+    int *h_flag = nullptr;              // pinned device error flag
+    bool use_graph = true;
     std::string err;
     ~qocb_plan() { delete large; }
 };
@@ -1130,6 +1137,9 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     PTRY(cudaMemset(p->grad.p, 0, sizeof(double) * p->grad.n));
     PTRY(cudaMemset(p->psi.p, 0, sizeof(double) * p->psi.n)); PTRY(cudaMemset(p->lam.p, 0, sizeof(double) * p->lam.n));
     PTRY(cudaMallocHost(&p->h_pinned, sizeof(double) * (2 * std::max<size_t>(1, (size_t)M * KR) + 8)));
+    PTRY(cudaMallocHost(&p->h_fin, sizeof(double) * (size_t)E * S * 2 * NP));
+    PTRY(cudaMallocHost(&p->h_flag, sizeof(int)));
+    { const char *ng = getenv("QOCB_NO_GRAPH"); p->use_graph = !(ng && ng[0] == '1') && !is_large && !sliced; }
     // sweep kernels may need > 48 KB of dynamic shared memory
     {
         const int big = 200 * 1024;
@@ -1161,12 +1171,21 @@ int qocb_plan_destroy(qocb_plan *p) {
     if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->h_pinned) cudaFreeHost(p->h_pinned);
+    if (p->h_fin) cudaFreeHost(p->h_fin);
+    if (p->h_flag) cudaFreeHost(p->h_flag);
+    for (auto &g : p->gexec) if (g) cudaGraphExecDestroy(g);
     delete p;
     return 0;
 }
 
+static void drop_graphs(qocb_plan *p) {
+    for (auto &g : p->gexec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    p->host_calls[0] = p->host_calls[1] = 0;
+}
+
 int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
     if (!p || !h0) { set_error(p, "null argument"); return -1; }
+    drop_graphs(p);
     CU_TRY(p, cudaSetDevice(p->pb.device));
     const int n = p->pb.hilbert_size, NP = p->NP, E = p->pb.ensemble_count, KR = p->pb.control_count;
     const size_t GM = 2 * (size_t)NP * NP;
@@ -1254,6 +1273,7 @@ int qocb_set_states(qocb_plan *p, const double *psi0) {
 
 int qocb_clear_costs(qocb_plan *p) {
     if (!p) return -1;
+    drop_graphs(p);
     p->h_terms.clear(); p->h_vecs.clear(); p->h_counts.clear(); p->ip_total = 0; p->have_step_costs = false;
     p->terms.release();
     return 0;
@@ -1288,6 +1308,7 @@ int qocb_add_cost(qocb_plan *p, int32_t kind, int32_t step_cost, double weight, 
     p->h_terms.push_back(t);
     if (t.step) p->have_step_costs = true;
     p->terms.release();          // force re-upload
+    drop_graphs(p);
     return 0;
 }
 
@@ -1343,20 +1364,82 @@ static int fetch_final_states(qocb_plan *p, double *final_states) {
     return 0;
 }
 
-int qocb_cost(qocb_plan *p, const double *controls, double *cost, double *final_states) {
+// everything one host-facing evaluation puts on the stream, in capture-safe form (async copies through pinned buffers)
+static int enqueue_host_eval(qocb_plan *p, bool with_grad) {
+    const size_t cnt = (size_t)p->pb.control_eval_count * p->pb.control_count;
+    const size_t VS = (size_t)p->pb.state_count * 2 * p->NP;
+    const int N = p->Nloc, E = p->pb.ensemble_count;
+    double *hg = p->h_pinned + std::max<size_t>(1, cnt), *hc = hg + std::max<size_t>(1, cnt);
+    if (cnt) CU_TRY(p, cudaMemcpyAsync(p->controls.p, p->h_pinned, sizeof(double) * cnt, cudaMemcpyHostToDevice, p->stream));
+    int rc = enqueue_eval(p, with_grad, nullptr); if (rc) return rc;
+    if (with_grad && cnt) CU_TRY(p, cudaMemcpyAsync(hg, p->grad.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaMemcpyAsync(hc, p->cost.p, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaMemcpy2DAsync(p->h_fin, sizeof(double) * VS, p->psi.p + (size_t)(N - 1) * VS, sizeof(double) * N * VS,
+                                sizeof(double) * VS, E, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaMemcpyAsync(p->h_flag, p->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    return 0;
+}
+
+static int host_eval(qocb_plan *p, bool with_grad, const double *controls, double *cost, double *grad, double *final_states) {
     if (!p) return -1;
-    int rc = qocb_upload_controls(p, controls); if (rc) return rc;
-    rc = enqueue_eval(p, false, nullptr); if (rc) return rc;
-    rc = qocb_download_result(p, cost, nullptr); if (rc) return rc;
-    return fetch_final_states(p, final_states);
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    if (!p->use_graph) {
+        int rc = qocb_upload_controls(p, controls); if (rc) return rc;
+        rc = enqueue_eval(p, with_grad, nullptr); if (rc) return rc;
+        rc = qocb_download_result(p, cost, with_grad ? grad : nullptr); if (rc) return rc;
+        return fetch_final_states(p, final_states);
+    }
+    int rc = ready(p); if (rc) return rc;                          // synchronous uploads of changed cost tables: never captured
+    const size_t cnt = (size_t)p->pb.control_eval_count * p->pb.control_count;
+    if (cnt) {
+        if (!controls) { set_error(p, "controls is null"); return -1; }
+        std::memcpy(p->h_pinned, controls, sizeof(double) * cnt);
+    }
+    const int wg = with_grad ? 1 : 0;
+    if (p->gexec[wg]) {
+        CU_TRY(p, cudaGraphLaunch(p->gexec[wg], p->stream));
+    } else if (p->host_calls[wg]++ < 1) {
+        rc = enqueue_host_eval(p, with_grad); if (rc) return rc;    // first call: plain launches (function attributes, lazy init)
+    } else {
+        cudaGraph_t graph = nullptr;
+        CU_TRY(p, cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_host_eval(p, with_grad);
+        const cudaError_t ce = cudaStreamEndCapture(p->stream, &graph);
+        if (rc || ce != cudaSuccess || !graph) {                    // capture refused: fall back to plain launches for good
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            p->use_graph = false;
+            return host_eval(p, with_grad, controls, cost, grad, final_states);
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&p->gexec[wg], graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); p->gexec[wg] = nullptr; p->use_graph = false; return host_eval(p, with_grad, controls, cost, grad, final_states); }
+        CU_TRY(p, cudaGraphLaunch(p->gexec[wg], p->stream));
+    }
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    double *hg = p->h_pinned + std::max<size_t>(1, cnt), *hc = hg + std::max<size_t>(1, cnt);
+    if (with_grad && grad && cnt) std::memcpy(grad, hg, sizeof(double) * cnt);
+    if (cost) *cost = *hc;
+    if (*p->h_flag) { set_error(p, "device error flag set: scaling count exceeded the recompute tape capacity"); return -4; }
+    if (final_states) {
+        const int n = p->pb.hilbert_size, NP = p->NP, S = p->pb.state_count, E = p->pb.ensemble_count;
+        for (int e = 0; e < E; ++e)
+            for (int s_ = 0; s_ < S; ++s_)
+                for (int a = 0; a < n; ++a) {
+                    const double *b = p->h_fin + ((size_t)e * S + s_) * 2 * NP;
+                    final_states[2 * (((size_t)e * S + s_) * n + a)] = b[a];
+                    final_states[2 * (((size_t)e * S + s_) * n + a) + 1] = b[NP + a];
+                }
+    }
+    return 0;
+}
+
+int qocb_cost(qocb_plan *p, const double *controls, double *cost, double *final_states) {
+    return host_eval(p, false, controls, cost, nullptr, final_states);
 }
 
 int qocb_cost_and_grad(qocb_plan *p, const double *controls, double *cost, double *grad, double *final_states) {
-    if (!p) return -1;
-    int rc = qocb_upload_controls(p, controls); if (rc) return rc;
-    rc = enqueue_eval(p, true, nullptr); if (rc) return rc;
-    rc = qocb_download_result(p, cost, grad); if (rc) return rc;
-    return fetch_final_states(p, final_states);
+    return host_eval(p, true, controls, cost, grad, final_states);
 }
 
 int qocb_get_states(qocb_plan *p, double *states) {
