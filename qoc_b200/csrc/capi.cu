@@ -304,7 +304,7 @@ enum { LA1 = 0, LA2N, LM, LA2, LA4, LA6, LW1, LX1, LY, LVE, LUO, LP, LQ, LT, LR0
 struct LargeImpl {
     int n = 0, nn = 0, B = 0;
     cublasHandle_t blas = nullptr;
-    DevBuf<double2> G0, G, work, treeA, treeB, UT, lvl, PT, allPT;
+    DevBuf<double2> G0, G, C0, Cs, work, treeA, treeB, UT, lvl, PT, allPT;
     DevBuf<double2 *> ptrQ, ptrP, ptrRB;
     DevBuf<int> piv, info, sarr, cb;
     std::vector<int> h_s;
@@ -620,13 +620,17 @@ int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_out) {
     const size_t tot = (size_t)Bc * nn;
     const double dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
     LgCoef cf{p->controls.p, p->itab_idx.p, p->itab_w.p, p->pb.control_count, p->q};
-    k_lg_assemble<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA1), L->arr(LA2N), L->G0.p, L->G.p, cf, jb, Bc, nn);
     int rc;
+    if (order == 4 && p->comm_ok) {
+        k_lg_magnus4_comm<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LM), L->G0.p, L->G.p, L->C0.p, L->Cs.p, cf, jb, Bc, nn, dt);
+    } else {
+    k_lg_assemble<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA1), L->arr(LA2N), L->G0.p, L->G.p, cf, jb, Bc, nn);
     if (order == 2) { rc = lg_axpby(p, L->arr(LM), dt, L->arr(LA1), 0., nullptr, 0., nullptr, Bc); if (rc) return rc; }
     else {
         rc = lg_gemm(p, false, false, L->arr(LA2N), L->arr(LA1), L->arr(LT), 1., 0., Bc); if (rc) return rc;      // a2 a1
         rc = lg_gemm(p, false, false, L->arr(LA1), L->arr(LA2N), L->arr(LT), -1., 1., Bc); if (rc) return rc;     // - a1 a2
         k_lg_axpby<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LM), 0.5 * dt, L->arr(LA1), 0.5 * dt, L->arr(LA2N), (QOCB_S3 / 12.0) * dt * dt, L->arr(LT), tot);
+    }
     }
     k_lg_norm_scale<<<Bc, 256, 0, p->stream>>>(L->arr(LM), L->cur_sarr(), L->n);
     CU_TRY(p, cudaMemcpyAsync(L->h_s.data(), L->cur_sarr(), sizeof(int) * Bc, cudaMemcpyDeviceToHost, p->stream));
@@ -716,7 +720,8 @@ int lg_backward_all(qocb_plan *p) {
             // taped batch: only the cheap elementwise pieces are rebuilt (node generators for the Magnus adjoint, W1, X1)
             L->tj = jb;
             LgCoef cf{p->controls.p, p->itab_idx.p, p->itab_w.p, p->pb.control_count, p->q};
-            k_lg_assemble<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA1), L->arr(LA2N), L->G0.p, L->G.p, cf, jb, Bc, nn);
+            if (!(order == 4 && p->comm_ok))
+                k_lg_assemble<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA1), L->arr(LA2N), L->G0.p, L->G.p, cf, jb, Bc, nn);
             k_lg_poly<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA2), L->arr(LA4), L->arr(LA6), L->arr(LW1), L->arr(LX1), L->arr(LT), L->arr(LVE), L->n, tot);
         } else {
             L->tj = -1;
@@ -756,6 +761,14 @@ int lg_backward_all(qocb_plan *p) {
         rc = lg_gemm(p, true, false, M, L->arr(LA2B), L->arr(LAB), 1., 1., Bc); if (rc) return rc;
         k_lg_unscale<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LAB), L->cur_sarr(), nn, tot);                // mbar
         double2 *AB = L->arr(LAB);
+        if (order == 4 && p->comm_ok) {
+            if (p->pb.control_count > 0) {
+                LgCoef cf2{p->controls.p, p->itab_idx.p, p->itab_w.p, p->pb.control_count, p->q};
+                k_lg_contract_comm<<<Bc, 256, 0, p->stream>>>(AB, L->G.p, L->C0.p, L->Cs.p, cf2, p->node_grad.p, jb, nn, dt);
+            }
+            CU_TRY(p, cudaGetLastError());
+            continue;
+        }
         if (order == 2) { rc = lg_axpby(p, L->arr(LA1B), dt, AB, 0., nullptr, 0., nullptr, Bc); if (rc) return rc; }
         else {
             const double f = (QOCB_S3 / 12.0) * dt * dt;
@@ -1199,6 +1212,24 @@ int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
         if (KR > 0) {
             if (!a_ops) { set_error(p, "a_ops is null but control_count > 0"); return -1; }
             for (int r = 0; r < KR; ++r) CU_TRY(p, gen(a_ops + (size_t)r * 2 * n * n, p->large->G.p + (size_t)r * n * n));
+        }
+        p->comm_ok = false;
+        { const char *nc = getenv("QOCB_NO_COMM"); if (p->pb.magnus_order == 4 && KR <= kMaxCommKR && !(nc && nc[0] == '1')) p->comm_ok = true; }
+        if (p->comm_ok) {                                // commutators [G0, G_r], [G_s, G_r] on the device (own ZGEMM)
+            LargeImpl *L = p->large;
+            const int npair = KR * (KR - 1) / 2;
+            CU_TRY(p, L->C0.alloc((size_t)std::max(1, KR) * L->nn)); CU_TRY(p, L->Cs.alloc((size_t)std::max(1, npair) * L->nn));
+            for (int r = 0; r < KR; ++r) {
+                int rc = lg_gemm(p, false, false, L->G0.p, L->G.p + (size_t)r * L->nn, L->C0.p + (size_t)r * L->nn, 1., 0., 1); if (rc) return rc;
+                rc = lg_gemm(p, false, false, L->G.p + (size_t)r * L->nn, L->G0.p, L->C0.p + (size_t)r * L->nn, -1., 1., 1); if (rc) return rc;
+            }
+            for (int s_ = 0; s_ < KR; ++s_)
+                for (int r = s_ + 1; r < KR; ++r) {
+                    double2 *dst = L->Cs.p + (size_t)comm_pair(s_, r, KR) * L->nn;
+                    int rc = lg_gemm(p, false, false, L->G.p + (size_t)s_ * L->nn, L->G.p + (size_t)r * L->nn, dst, 1., 0., 1); if (rc) return rc;
+                    rc = lg_gemm(p, false, false, L->G.p + (size_t)r * L->nn, L->G.p + (size_t)s_ * L->nn, dst, -1., 1., 1); if (rc) return rc;
+                }
+            CU_TRY(p, cudaStreamSynchronize(p->stream));
         }
         p->ops_set = true;
         return 0;

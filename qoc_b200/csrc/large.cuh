@@ -50,6 +50,61 @@ __global__ void k_lg_assemble(double2 *a1, double2 *a2, const double2 *G0, const
     }
 }
 
+// product-free Magnus M4 (see expm_slice.cuh): M[b] = dt G0 + sum_r dt/2 (c1_r + c2_r) G_r
+//                                                    + f [ sum_r (c1_r - c2_r) C0_r + sum_{s<r} (c2_s c1_r - c2_r c1_s) C_sr ]
+__global__ void k_lg_magnus4_comm(double2 *M, const double2 *G0, const double2 *G, const double2 *C0, const double2 *Cs, LgCoef c,
+                                  int j_begin, int B, int nn, double dt) {
+    const size_t tot = (size_t)B * nn;
+    const double f = (QOCB_S3 / 12.0) * dt * dt;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / nn), e = (int)(t - (size_t)b * nn), j = j_begin + b;
+        double2 v = make_double2(dt * G0[e].x, dt * G0[e].y);
+        for (int r = 0; r < c.KR; ++r) {
+            const double c1 = lg_coef(c, j, 0, r), c2 = lg_coef(c, j, 1, r);
+            const double2 g = G[(size_t)r * nn + e], k = C0[(size_t)r * nn + e];
+            const double wg = 0.5 * dt * (c1 + c2), wk = f * (c1 - c2);
+            v.x += wg * g.x + wk * k.x; v.y += wg * g.y + wk * k.y;
+        }
+        for (int s_ = 0; s_ < c.KR; ++s_)
+            for (int r = s_ + 1; r < c.KR; ++r) {
+                const double w = f * (lg_coef(c, j, 1, s_) * lg_coef(c, j, 0, r) - lg_coef(c, j, 1, r) * lg_coef(c, j, 0, s_));
+                const double2 k = Cs[(size_t)comm_pair(s_, r, c.KR) * nn + e];
+                v.x += w * k.x; v.y += w * k.y;
+            }
+        M[t] = v;
+    }
+}
+
+// adjoint of the product-free Magnus M4: node_grad from inner products of mbar[b] with G_r, C0_r, C_sr; one CTA per slice
+__global__ void __launch_bounds__(256) k_lg_contract_comm(const double2 *mbar, const double2 *G, const double2 *C0, const double2 *Cs,
+                                                          LgCoef c, double *node_grad, int j_begin, int nn, double dt) {
+    __shared__ double red[256];
+    __shared__ double dots[2 * kMaxCommKR + kMaxCommKR * (kMaxCommKR - 1) / 2];
+    const int b = blockIdx.x, KR = c.KR, NPAIR = KR * (KR - 1) / 2, j = j_begin + b;
+    const double2 *m = mbar + (size_t)b * nn;
+    for (int q = 0; q < 2 * KR + NPAIR; ++q) {
+        const double2 *g = q < KR ? G + (size_t)q * nn : (q < 2 * KR ? C0 + (size_t)(q - KR) * nn : Cs + (size_t)(q - 2 * KR) * nn);
+        double s = 0.;
+        for (int e = threadIdx.x; e < nn; e += 256) s += m[e].x * g[e].x - m[e].y * g[e].y;
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+        if (threadIdx.x == 0) dots[q] = red[0];
+        __syncthreads();
+    }
+    const double f = (QOCB_S3 / 12.0) * dt * dt;
+    for (int e = threadIdx.x; e < 2 * KR; e += 256) {
+        const int node = e / KR, r = e % KR;
+        double acc = dots[KR + r];
+        for (int s_ = 0; s_ < KR; ++s_) {
+            if (s_ == r) continue;
+            const double k = s_ < r ? dots[2 * KR + comm_pair(s_, r, KR)] : -dots[2 * KR + comm_pair(r, s_, KR)];
+            acc += lg_coef(c, j, node == 0 ? 1 : 0, s_) * k;              // node 0 pairs with c2, node 1 with c1
+        }
+        node_grad[((size_t)j * 2 + node) * KR + r] = 0.5 * dt * dots[r] + (node == 0 ? f : -f) * acc;
+    }
+}
+
 // out = alpha x + beta y + gamma z (any of y, z may be null)
 __global__ void k_lg_axpby(double2 *out, double alpha, const double2 *x, double beta, const double2 *y, double gamma, const double2 *z, size_t tot) {
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
