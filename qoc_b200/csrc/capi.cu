@@ -304,8 +304,9 @@ enum { LA1 = 0, LA2N, LM, LA2, LA4, LA6, LW1, LX1, LY, LVE, LUO, LP, LQ, LT, LR0
 struct LargeImpl {
     int n = 0, nn = 0, B = 0;
     cublasHandle_t blas = nullptr;
-    DevBuf<double2> G0, G, C0, Cs, work, treeA, treeB, UT, lvl, PT, allPT;
-    DevBuf<double2 *> ptrQ, ptrP, ptrRB;
+    DevBuf<double2> G0, G, C0, Cs, work, treeA, treeB, UT, lvl, PT, allPT, lr;   // lr: thin buffers of the rank-S reverse pass
+    DevBuf<double2 *> ptrQ, ptrP, ptrRB, ptrPSI;
+    bool lowrank = false;
     DevBuf<int> piv, info, sarr, cb;
     std::vector<int> h_s;
     int lstar = 0, nchunks = 0, lvl_count[24] = {}, lvl_off[24] = {};   // pairwise propagator tree levels 0..lstar
@@ -505,6 +506,25 @@ int ready(qocb_plan *p) {
 
 inline int lg_blocks(size_t tot) { return (int)std::min<size_t>((tot + 255) / 256, 148 * 16); }
 
+// own DMMA GEMM, general shapes: C (m x nc, ldc) = alpha op(A) (m x k) op(B) (k x nc) + beta C over `batch` matrices
+int lg_gemm_rect(qocb_plan *p, bool ta, bool tb, const double2 *A, const double2 *B, double2 *C, int m, int nc, int k, int lda, int ldb,
+                 int ldc, double alpha, double beta, int batch, long long sA, long long sB, long long sC) {
+    const bool thin = nc <= 16;
+    const int bn = thin ? 16 : 64;
+    const dim3 grid(((m + 63) / 64) * ((nc + bn - 1) / bn), batch);
+#define ZG_LAUNCH(TA_, TB_, BN_) k_zgemm<TA_, TB_, BN_><<<grid, ZG_NT, ZgTile<BN_>::smem, p->stream>>>(A, B, C, m, nc, k, lda, ldb, ldc, alpha, beta, sA, sB, sC)
+    if (thin) {
+        if (!ta && !tb) ZG_LAUNCH(false, false, 16); else if (ta && !tb) ZG_LAUNCH(true, false, 16);
+        else if (!ta && tb) ZG_LAUNCH(false, true, 16); else ZG_LAUNCH(true, true, 16);
+    } else {
+        if (!ta && !tb) ZG_LAUNCH(false, false, 64); else if (ta && !tb) ZG_LAUNCH(true, false, 64);
+        else if (!ta && tb) ZG_LAUNCH(false, true, 64); else ZG_LAUNCH(true, true, 64);
+    }
+#undef ZG_LAUNCH
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
 // row-major C = alpha op(A) op(B) + beta C over `batch` matrices (strides in elements)
 int lg_gemm(qocb_plan *p, bool ta, bool tb, const double2 *A, const double2 *B, double2 *C, double alpha, double beta, int batch,
             long long sA = -1, long long sB = -1, long long sC = -1) {
@@ -512,14 +532,7 @@ int lg_gemm(qocb_plan *p, bool ta, bool tb, const double2 *A, const double2 *B, 
     const int n = L->n;
     if (sA < 0) sA = L->nn; if (sB < 0) sB = L->nn; if (sC < 0) sC = L->nn;
     if (!L->use_cublas_gemm) {                         // own DMMA tile kernel (zgemm.cuh)
-        const int tiles = (n + 63) / 64;
-        const dim3 grid(tiles * tiles, batch);
-        if (!ta && !tb) k_zgemm<false, false><<<grid, ZG_NT, kZgemmSmem, p->stream>>>(A, B, C, n, alpha, beta, sA, sB, sC);
-        else if (ta && !tb) k_zgemm<true, false><<<grid, ZG_NT, kZgemmSmem, p->stream>>>(A, B, C, n, alpha, beta, sA, sB, sC);
-        else if (!ta && tb) k_zgemm<false, true><<<grid, ZG_NT, kZgemmSmem, p->stream>>>(A, B, C, n, alpha, beta, sA, sB, sC);
-        else k_zgemm<true, true><<<grid, ZG_NT, kZgemmSmem, p->stream>>>(A, B, C, n, alpha, beta, sA, sB, sC);
-        CU_TRY(p, cudaGetLastError());
-        return 0;
+        return lg_gemm_rect(p, ta, tb, A, B, C, n, n, n, n, n, n, alpha, beta, batch, sA, sB, sC);
     }
     const cuDoubleComplex a = make_cuDoubleComplex(alpha, 0.), b = make_cuDoubleComplex(beta, 0.);
     BL_TRY(p, cublasZgemmStridedBatched(L->blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, n, n, n, &a,
@@ -548,10 +561,10 @@ int large_init(qocb_plan *p) {
     const size_t per = (size_t)LCOUNT * L->nn * sizeof(double2);
     L->B = (int)std::max<size_t>(1, std::min<size_t>((size_t)Lsl, std::min<size_t>(256, ((size_t)6 << 30) / per)));
     { const char *e = getenv("QOCB_LARGE_CUBLAS"); L->use_cublas_gemm = e && e[0] == '1'; }
-    CU_TRY(p, cudaFuncSetAttribute(k_zgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZgemmSmem));
-    CU_TRY(p, cudaFuncSetAttribute(k_zgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZgemmSmem));
-    CU_TRY(p, cudaFuncSetAttribute(k_zgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZgemmSmem));
-    CU_TRY(p, cudaFuncSetAttribute(k_zgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZgemmSmem));
+#define ZG_ATTR(TA_, TB_, BN_) CU_TRY(p, cudaFuncSetAttribute(k_zgemm<TA_, TB_, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZgTile<BN_>::smem))
+    ZG_ATTR(false, false, 64); ZG_ATTR(true, false, 64); ZG_ATTR(false, true, 64); ZG_ATTR(true, true, 64);
+    ZG_ATTR(false, false, 16); ZG_ATTR(true, false, 16); ZG_ATTR(false, true, 16); ZG_ATTR(true, true, 16);
+#undef ZG_ATTR
     BL_TRY(p, cublasCreate(&L->blas));
     BL_TRY(p, cublasSetStream(L->blas, p->stream));
     CU_TRY(p, L->G0.alloc(L->nn)); CU_TRY(p, L->G.alloc((size_t)std::max(1, p->pb.control_count) * L->nn));
@@ -585,6 +598,15 @@ int large_init(qocb_plan *p) {
     const size_t VSl = (size_t)p->pb.state_count * 2 * n;
     CU_TRY(p, p->part.alloc((size_t)L->nchunks * VSl)); CU_TRY(p, p->cost_part.alloc(L->nchunks));
     if (p->sharded) { CU_TRY(p, L->treeA.alloc((size_t)((L->nchunks + 1) / 2) * L->nn)); CU_TRY(p, L->treeB.alloc((size_t)((L->nchunks + 3) / 4) * L->nn)); }
+    // rank-S reverse pass (S <= 4): PSI [B][4][n], LAM / LAMP / PT [B][n][4], TMPV [B][n][16], LEFT / RIGHT [B][n][48]
+    { const char *nl = getenv("QOCB_NO_LOWRANK"); L->lowrank = p->pb.state_count <= 4 && !(nl && nl[0] == '1'); }
+    if (L->lowrank) {
+        CU_TRY(p, L->lr.alloc((size_t)L->B * n * (4 + 4 + 4 + 4 + 16 + 48 + 48)));
+        CU_TRY(p, L->ptrPSI.alloc(L->B));
+        std::vector<double2 *> hp2(L->B);
+        for (int b = 0; b < L->B; ++b) hp2[b] = L->lr.p + (size_t)b * 4 * n;
+        CU_TRY(p, cudaMemcpy(L->ptrPSI.p, hp2.data(), sizeof(double2 *) * L->B, cudaMemcpyHostToDevice));
+    }
     L->h_s.resize(L->B);
     L->Lsl = Lsl;
     L->batch_taped.assign((Lsl + L->B - 1) / L->B, 0);
@@ -729,6 +751,39 @@ int lg_backward_all(qocb_plan *p) {
         }
         struct TjReset { LargeImpl *l; ~TjReset() { l->tj = -1; } } tj_reset{L};
         double2 *RB = L->arr(LRB), *T = L->arr(LT), *M = L->arr(LM);
+        if (L->lowrank && smax == 0) {
+            // rank-S reverse pass: thin products through the own GEMM (64 x 16 tiles), one rank-48 recombination
+            const int S = p->pb.state_count;
+            const long long s4 = 4LL * n, s16 = 16LL * n, s48 = 48LL * n;
+            double2 *PSI = L->lr.p, *LAM = PSI + (size_t)L->B * 4 * n, *LAMP = LAM + (size_t)L->B * 4 * n, *PTt = LAMP + (size_t)L->B * 4 * n;
+            double2 *TMPV = PTt + (size_t)L->B * 4 * n, *LEFT = TMPV + (size_t)L->B * 16 * n, *RIGHT = LEFT + (size_t)L->B * 48 * n;
+            const size_t tot4 = (size_t)Bc * n * 4;
+            k_lr_load<<<lg_blocks(tot4), 256, 0, p->stream>>>(PSI, LAM, p->psi.p, p->lam.p, jb, Bc, n, S);
+            CU_TRY(p, cudaMemsetAsync(LEFT, 0, sizeof(double2) * (size_t)Bc * 48 * n, p->stream));
+            int hinfo2 = 0;                                        // psit = Q^-1 psi (columns = states)
+            BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_T, n, S, reinterpret_cast<const cuDoubleComplex *const *>(L->cur_ptrQ()), n, L->cur_piv(),
+                                          reinterpret_cast<cuDoubleComplex **>(L->ptrPSI.p), n, &hinfo2, Bc));
+            auto G = [&](bool ta, bool tb, const double2 *A_, const double2 *B_, double2 *C_, int m_, int nc_, int k_, int lda_, int ldb_, int ldc_,
+                         double be, long long sa, long long sb, long long sc) {
+                return lg_gemm_rect(p, ta, tb, A_, B_, C_, m_, nc_, k_, lda_, ldb_, ldc_, 1.0, be, Bc, sa, sb, sc);
+            };
+            rc = G(true, false, L->arr(LR0), LAM, LAMP, n, 4, n, n, 4, 4, 0., nn, s4, s4); if (rc) return rc;                 // lamp = R0^T lam
+            k_lr_fill<<<lg_blocks(tot4), 256, 0, p->stream>>>(PSI, LAM, LAMP, PTt, TMPV, LEFT, RIGHT, Bc, n);
+            rc = G(false, false, L->arr(LY), PTt, TMPV + 4, n, 4, n, n, 4, 16, 0., nn, s4, s16); if (rc) return rc;            // Y psit
+            rc = G(true, false, M, TMPV, LEFT, n, 4, n, n, 16, 48, 0., nn, s16, s48); if (rc) return rc;                       // a = A^T pl
+            rc = G(false, false, L->arr(LW1), PTt, RIGHT + 32, n, 4, n, n, 4, 48, 1., nn, s4, s48); if (rc) return rc;         // + W1 psit
+            rc = G(false, false, L->arr(LX1), PTt, RIGHT + 36, n, 4, n, n, 4, 48, 1., nn, s4, s48); if (rc) return rc;         // + X1 psit
+            rc = G(true, false, L->arr(LA6), LEFT, LEFT + 8, n, 8, n, n, 48, 48, 0., nn, s48, s48); if (rc) return rc;         // A6^T [a | ml]
+            rc = G(false, false, L->arr(LA4), RIGHT + 32, RIGHT, n, 16, n, n, 48, 48, 1., nn, s48, s48); if (rc) return rc;    // X_a += A4 R6
+            rc = G(false, false, L->arr(LA2), RIGHT + 16, RIGHT, n, 16, n, n, 48, 48, 1., nn, s48, s48); if (rc) return rc;    // X_a += A2 R4
+            rc = G(false, false, L->arr(LA2), RIGHT + 32, RIGHT + 16, n, 16, n, n, 48, 48, 1., nn, s48, s48); if (rc) return rc; // X_b += A2 R6
+            rc = G(true, false, L->arr(LA2), LEFT, LEFT + 16, n, 16, n, n, 48, 48, 0., nn, s48, s48); if (rc) return rc;       // Lb2
+            rc = G(true, false, L->arr(LA2), LEFT + 16, LEFT + 32, n, 16, n, n, 48, 48, 0., nn, s48, s48); if (rc) return rc;  // Lb3
+            rc = G(false, true, LEFT, RIGHT, L->arr(LA2B), n, n, 48, 48, 48, n, 0., s48, s48, nn); if (rc) return rc;          // a2bar
+            rc = G(false, true, TMPV, TMPV + 4, L->arr(LAB), n, n, 4, 16, 16, n, 0., s16, s16, nn); if (rc) return rc;         // pl (Y psit)^T
+            rc = lg_gemm(p, false, true, L->arr(LA2B), M, L->arr(LAB), 1., 1., Bc); if (rc) return rc;
+            rc = lg_gemm(p, true, false, M, L->arr(LA2B), L->arr(LAB), 1., 1., Bc); if (rc) return rc;
+        } else {
         k_lg_ubar<<<lg_blocks(tot), 256, 0, p->stream>>>(RB, p->psi.p, p->lam.p, jb, Bc, n, p->pb.state_count);
         for (int i = smax - 1; i >= 0; --i) {                      // R_{i+1} = R_i^2
             rc = lg_gemm(p, false, true, RB, L->arr(LRS0 + i), T, 1., 0., Bc); if (rc) return rc;
@@ -759,6 +814,7 @@ int lg_backward_all(qocb_plan *p) {
         rc = lg_gemm(p, true, false, L->arr(LA2), L->arr(LA4B), L->arr(LA2B), 1., 1., Bc); if (rc) return rc;
         rc = lg_gemm(p, false, true, L->arr(LA2B), M, L->arr(LAB), 1., 1., Bc); if (rc) return rc;
         rc = lg_gemm(p, true, false, M, L->arr(LA2B), L->arr(LAB), 1., 1., Bc); if (rc) return rc;
+        }
         k_lg_unscale<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LAB), L->cur_sarr(), nn, tot);                // mbar
         double2 *AB = L->arr(LAB);
         if (order == 4 && p->comm_ok) {

@@ -189,6 +189,41 @@ __global__ void k_lg_ubar(double2 *ubar, const double *psi, const double *lam, i
     }
 }
 
+// ---- rank-S reverse pass (see lowrank.cuh for the algebra; here with R = P Q^-1, so the common factor sits on the right):
+//   psit = Q^-1 psi,  lamp = R0^T lam,  pl = lam + lamp,  ml = lam - lamp,  a = A^T pl
+//   uobar = pl psit^T, vebar = ml psit^T, ybar = a psit^T, abar1 = pl (Y psit)^T
+//   Lb = [a, ml, A6^T a, A6^T ml],  R6 = [b7 psit + W1 psit, b6 psit + X1 psit, b13 psit, b12 psit],  R4, R2 likewise
+// PSI[b][4][n] holds psi^T (the right-hand sides of the thin solve), LAM[b][n][4] the costates as columns.
+__global__ void k_lr_load(double2 *PSI, double2 *LAM, const double *psi, const double *lam, int j_begin, int B, int n, int S) {
+    const size_t tot = (size_t)B * n * 4, VS = (size_t)S * 2 * n;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / (4 * n)), r = (int)(t % (4 * n)), s = r / n, a = r % n;
+        const double *p = psi + (size_t)(j_begin + b) * VS, *l = lam + (size_t)(j_begin + b + 1) * VS;
+        const bool on = s < S;
+        PSI[(size_t)b * 4 * n + (size_t)s * n + a] = on ? make_double2(p[s * 2 * n + a], p[s * 2 * n + n + a]) : make_double2(0., 0.);
+        LAM[((size_t)b * n + a) * 4 + s] = on ? make_double2(l[s * 2 * n + a], l[s * 2 * n + n + a]) : make_double2(0., 0.);
+    }
+}
+
+// from psit (PSI after the solve), lam, lamp: TMPV[:, 0:4] = pl, LEFT[:, 4:8] = ml, and the polynomial blocks of RIGHT
+__global__ void k_lr_fill(const double2 *PSI, const double2 *LAM, const double2 *LAMP, double2 *PT, double2 *TMPV, double2 *LEFT,
+                          double2 *RIGHT, int B, int n) {
+    const size_t tot = (size_t)B * n * 4;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / (4 * n)), r = (int)(t % (4 * n)), a = r / 4, s = r % 4;
+        const size_t row = (size_t)b * n + a;
+        const double2 x = PSI[(size_t)b * 4 * n + (size_t)s * n + a], l = LAM[row * 4 + s], lp = LAMP[row * 4 + s];
+        PT[row * 4 + s] = x;
+        TMPV[row * 16 + s] = make_double2(l.x + lp.x, l.y + lp.y);
+        LEFT[row * 48 + 4 + s] = make_double2(l.x - lp.x, l.y - lp.y);
+        double2 *R = RIGHT + row * 48;
+        const int cols[12] = {0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 44};
+        const int bi[12] = {3, 2, 9, 8, 5, 4, 11, 10, 7, 6, 13, 12};
+#pragma unroll
+        for (int q = 0; q < 12; ++q) R[cols[q] + s] = make_double2(kB[bi[q]] * x.x, kB[bi[q]] * x.y);
+    }
+}
+
 // node_grad[(j*q + i)*KR + r] = Re sum_e abar_i[b][e] G_r[e]; one CTA per (slice of the batch, node)
 __global__ void __launch_bounds__(256) k_lg_contract(const double2 *ab1, const double2 *ab2, const double2 *G, double *node_grad,
                                                      int j_begin, int nn, int KR, int q) {
