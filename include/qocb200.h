@@ -46,7 +46,8 @@ typedef struct {
     int32_t chunks_per_member;   /* 0 = automatic */
     int32_t slice_begin;         /* time-slice sharding: this plan owns slices [slice_begin, slice_end) of the N-1 */
     int32_t slice_end;           /* (both 0 = the whole pulse, unsharded).  See the qocb_shard_* calls below */
-    int32_t reserved;
+    int32_t channel_count;       /* KC: operator channels of a time-dependent hamiltonian (qocb_set_node_map);
+                                    0 = control_count (time-independent operators, one per real control channel) */
     double evolution_time;       /* T */
 } qocb_problem;
 
@@ -59,8 +60,15 @@ int qocb_plan_create(const qocb_problem *problem, qocb_plan **plan_out);
 int qocb_plan_destroy(qocb_plan *plan);
 const char *qocb_last_error(const qocb_plan *plan);           /* plan may be NULL: last creation error */
 
-/* H0: [E][n][n] complex (E = ensemble_count), A: [KR][n][n] complex */
+/* H0: [E][n][n] complex (E = ensemble_count), A: [KC][n][n] complex (KC = channel_count, or control_count if that is 0) */
 int qocb_set_operators(qocb_plan *plan, const double *h0, const double *a_ops);
+/* Time-dependent hamiltonian(controls, time) (the callable's `time` argument, qoc/core/schroedingerdiscrete.py:483-486),
+   affine in the controls: at Magnus node i of slice j
+       H = H0 + sum_c coef[j][i][c] A_c,   coef[j][i][c] = offset[j][i][c] + sum_r gain[j][i][c][r] x_r(t_ji),
+   x_r = interpolated real control channel r.  offset: [N-1][q][KC], gain: [N-1][q][KC][KR] for ALL N-1 slices (a plan
+   that owns a slice range reads its part); q = magnus_order / 2.  Requires channel_count > 0.  gain may be NULL when
+   control_count is 0.  The gradient returned by qocb_cost_and_grad stays [M][KR]. */
+int qocb_set_node_map(qocb_plan *plan, const double *offset, const double *gain);
 /* psi0: [S][n] complex */
 int qocb_set_states(qocb_plan *plan, const double *psi0);
 /* vectors: [S][fmax][n] complex; counts: [S] number of valid vectors per state (NULL = fmax for all);

@@ -19,7 +19,7 @@ LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompil
               "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 EXPORTS = [
-    "qocb_plan_create", "qocb_plan_destroy", "qocb_last_error", "qocb_set_operators", "qocb_set_states",
+    "qocb_plan_create", "qocb_plan_destroy", "qocb_last_error", "qocb_set_operators", "qocb_set_node_map", "qocb_set_states",
     "qocb_add_cost", "qocb_clear_costs", "qocb_cost", "qocb_cost_and_grad", "qocb_get_states",
     "qocb_get_propagators", "qocb_upload_controls", "qocb_run_resident", "qocb_sync", "qocb_download_result",
     "qocb_time_resident", "qocb_launch_count", "qocb_stream", "qocb_expm_batched", "qocb_expm_vjp_batched",
@@ -38,7 +38,7 @@ class Problem(C.Structure):
                 ("control_eval_count", C.c_int32), ("system_eval_count", C.c_int32), ("magnus_order", C.c_int32),
                 ("cost_eval_step", C.c_int32), ("ensemble_count", C.c_int32), ("device", C.c_int32),
                 ("store_tape", C.c_int32), ("chunks_per_member", C.c_int32), ("slice_begin", C.c_int32),
-                ("slice_end", C.c_int32), ("reserved", C.c_int32),
+                ("slice_end", C.c_int32), ("channel_count", C.c_int32),
                 ("evolution_time", C.c_double)]
 
 
@@ -109,6 +109,7 @@ def load():
     lib.qocb_last_error.argtypes = [vp]
     lib.qocb_last_error.restype = C.c_char_p
     lib.qocb_set_operators.argtypes = [vp, vp, vp]
+    lib.qocb_set_node_map.argtypes = [vp, vp, vp]
     lib.qocb_set_states.argtypes = [vp, vp]
     lib.qocb_add_cost.argtypes = [vp, i32, i32, dbl, vp, vp, i32]
     lib.qocb_clear_costs.argtypes = [vp]

@@ -9,8 +9,12 @@ What happens here, once per `grape_*` / `evolve_*` call:
     it.  The CUDA path needs the operator structure, so the callable is probed: H0 = h(0), A_k = h(e_k) - H0,
     B_k = h(i e_k) - H0 (complex controls), and real-linearity in (Re u, Im u) plus time-independence are
     verified with random probes.  Every hamiltonian in the reference's examples/tests has this form
-    (examples/0_transmon_pi.py:24-26, examples/tutorial.py:101-106, tests/test_core.py:529-531,582); anything
-    else raises NotImplementedError - there is no CPU fallback.
+    (examples/0_transmon_pi.py:24-26, examples/tutorial.py:101-106, tests/test_core.py:529-531,582).
+    A callable that uses its `time` argument is probed at every Magnus node of every
+    slice instead and expanded over a small operator basis (`extract_time_dependent_structure`): the device
+    then sees H = G0 + sum_c coef_c(node) A_c with per-node coefficients affine in the interpolated controls
+    (qocb_set_node_map).  Anything else (non-linear in the controls, more than 16 operator channels) raises
+    NotImplementedError - there is no CPU fallback.
   * cost recognition: the qoc cost classes provide device descriptors (`device_terms`) or, for control-only
     costs, an analytic host value+gradient (`control_value_and_grad`).
 """
@@ -24,30 +28,144 @@ from qoc_b200.models.enums import InterpolationPolicy, MagnusPolicy
 _PROBE_RTOL = 1e-10
 
 
-def extract_hamiltonian_structure(hamiltonian, control_count, complex_controls, evolution_time, hilbert_size=None,
-                                  seed=1234):
-    """Returns (h0 [n x n], a_ops [KR x n x n]) with H(x) = H0 + sum_r x_r A_r, x = [Re u, Im u]."""
-    rng = np.random.default_rng(seed)
-    t0, t1 = 0.0, 0.37 * evolution_time
-    if control_count == 0:
-        h0 = np.asarray(hamiltonian(None, t0), dtype=np.complex128)
-        h1 = np.asarray(hamiltonian(None, t1), dtype=np.complex128)
-        if not np.allclose(h0, h1, rtol=_PROBE_RTOL, atol=_PROBE_RTOL * max(1.0, np.abs(h0).max())):
-            raise NotImplementedError("time-dependent hamiltonian callables are not supported by the CUDA path yet")
-        return h0, np.zeros((0,) + h0.shape, dtype=np.complex128)
+_MAX_CHANNELS = 16          # kMaxKR of the CUDA kernels
+_NODES = {1: (0.5,), 2: (0.5 - np.sqrt(3.0) / 6, 0.5 + np.sqrt(3.0) / 6),
+          3: (0.5 - np.sqrt(15.0) / 10, 0.5, 0.5 + np.sqrt(15.0) / 10)}          # mathmethods.py:88,113-114,148-150
+
+
+def _unit_controls(control_count, complex_controls):
     dtype = np.complex128 if complex_controls else np.float64
     zero = np.zeros(control_count, dtype=dtype)
-    h0 = np.array(hamiltonian(zero, t0), dtype=np.complex128)
-    if h0.ndim != 2 or h0.shape[0] != h0.shape[1]:
-        raise ValueError("hamiltonian(controls, time) must return a square matrix")
-    ops = []
-    parts = (1.0, 1j) if complex_controls else (1.0,)
-    for part in parts:
+    units = []
+    for part in ((1.0, 1j) if complex_controls else (1.0,)):
         for k in range(control_count):
             e = zero.copy()
             e[k] = part
-            ops.append(np.array(hamiltonian(e, t0), dtype=np.complex128) - h0)
-    a_ops = np.stack(ops)
+            units.append(e)
+    return zero, units
+
+
+def _is_time_dependent(hamiltonian, zero, units, evolution_time):
+    times = (0.0, 0.37 * evolution_time, 0.731 * evolution_time)
+    for u in [zero] + units:
+        ref = np.asarray(hamiltonian(u, times[0]), dtype=np.complex128)
+        tol = _PROBE_RTOL * max(1.0, np.abs(ref).max())
+        for t in times[1:]:
+            if not np.allclose(np.asarray(hamiltonian(u, t), dtype=np.complex128), ref, rtol=_PROBE_RTOL, atol=tol):
+                return True
+    return False
+
+
+class _RealBasis(object):
+    """Streaming rank-revealing Gram-Schmidt of complex matrices over the REALS (the device coefficients are real):
+    `add(m)` returns the coefficient vector of m on the basis so far, extending the basis when the residual exceeds
+    1e-12 * scale.  Earlier samples have zero weight on later basis vectors by construction."""
+
+    def __init__(self, limit):
+        self.vecs, self.limit, self.scale = [], limit, 1.0
+
+    def add(self, m):
+        v = np.concatenate([m.real.ravel(), m.imag.ravel()])
+        self.scale = max(self.scale, np.abs(v).max())
+        coef = np.zeros(len(self.vecs) + 1)
+        r = v.copy()
+        for _ in range(2):                       # re-orthogonalise once
+            for k, b in enumerate(self.vecs):
+                c = np.dot(b, r)
+                coef[k] += c
+                r -= c * b
+        nr = np.linalg.norm(r)
+        if nr > 1e-12 * self.scale * np.sqrt(v.size):
+            if len(self.vecs) >= self.limit:
+                raise NotImplementedError(
+                    "the time dependence of this hamiltonian needs more than {} operator channels; not supported by "
+                    "the CUDA path (no CPU fallback)".format(self.limit))
+            self.vecs.append(r / nr)
+            coef[-1] = nr
+            return coef
+        return coef[:-1]
+
+    def matrices(self, shape):
+        half = shape[0] * shape[1]
+        return np.array([(b[:half] + 1j * b[half:]).reshape(shape) for b in self.vecs]).reshape((-1,) + tuple(shape))
+
+
+def extract_time_dependent_structure(hamiltonian, control_count, complex_controls, evolution_time, system_eval_count,
+                                     magnus_order, seed=1234):
+    """Structure of a `hamiltonian(controls, time)` that is affine in the controls at every time:
+    returns (G0, channels [KC x n x n], offset [N-1, q, KC], gain [N-1, q, KC, KR]) such that at Magnus node i of
+    slice j   H = G0 + sum_c (offset[j,i,c] + sum_r gain[j,i,c,r] x_r) channels[c],   x = [Re u, Im u].
+    The callable is evaluated at the node times the reference evaluates it at (schroedingerdiscrete.py:483-497);
+    one shared real operator basis serves the drift variation and every control operator, built in one streaming
+    pass (memory: the basis and the coefficients only)."""
+    q = magnus_order // 2
+    nsl = system_eval_count - 1
+    dt = evolution_time / nsl
+    times = np.array([[(j + c) * dt for c in _NODES[q]] for j in range(nsl)]).ravel()
+    zero, units = _unit_controls(control_count, complex_controls) if control_count else (None, [])
+    KR = len(units)
+    g0 = np.array(hamiltonian(zero, times[0]), dtype=np.complex128)
+    if g0.ndim != 2 or g0.shape[0] != g0.shape[1]:
+        raise ValueError("hamiltonian(controls, time) must return a square matrix")
+    basis = _RealBasis(_MAX_CHANNELS)
+    rows = []                                   # per node: [offset coefficients, gain coefficients of control 0, ...]
+    for t in times:
+        d = np.asarray(hamiltonian(zero, t), dtype=np.complex128)
+        row = [basis.add(d - g0)]
+        for e in units:
+            row.append(basis.add(np.asarray(hamiltonian(e, t), dtype=np.complex128) - d))
+        rows.append(row)
+    KC = len(basis.vecs)
+    if KC == 0:                                 # H == G0 at every node
+        return g0, np.zeros((KR,) + g0.shape, dtype=np.complex128)
+    channels = basis.matrices(g0.shape)
+    offset = np.zeros((len(times), KC))
+    gain = np.zeros((len(times), KC, KR))
+    for k, row in enumerate(rows):
+        offset[k, :len(row[0])] = row[0]
+        for r in range(KR):
+            gain[k, :len(row[1 + r]), r] = row[1 + r]
+    # affine in the controls?  (random controls at a few node times against the expansion)
+    rng = np.random.default_rng(seed)
+    scale = max(1.0, basis.scale, np.abs(g0).max())
+    for trial in range(4 if KR else 0):
+        k = int(rng.integers(len(times)))
+        u = rng.standard_normal(control_count) * (1.0 + trial)
+        if complex_controls:
+            u = u + 1j * rng.standard_normal(control_count) * (1.0 + trial)
+        x = np.concatenate([u.real, u.imag]) if complex_controls else u
+        model = g0 + np.tensordot(offset[k] + gain[k] @ x, channels, axes=(0, 0))
+        got = np.asarray(hamiltonian(u.astype(zero.dtype), times[k]), dtype=np.complex128)
+        if not np.allclose(got, model, rtol=0, atol=_PROBE_RTOL * scale * (1 + np.abs(x).sum())):
+            raise NotImplementedError(
+                "hamiltonian(controls, time) is not affine in (Re u, Im u); non-linear callables are not supported "
+                "by the CUDA path yet (no CPU fallback)")
+    return (g0, channels, np.ascontiguousarray(offset.reshape(nsl, q, KC)),
+            np.ascontiguousarray(gain.reshape(nsl, q, KC, KR)))
+
+
+def extract_hamiltonian_structure(hamiltonian, control_count, complex_controls, evolution_time, hilbert_size=None,
+                                  seed=1234, system_eval_count=None, magnus_order=None):
+    """Returns (h0 [n x n], a_ops [KR x n x n]) with H(x) = H0 + sum_r x_r A_r, x = [Re u, Im u]; for a callable
+    that depends on `time` (needs system_eval_count and magnus_order): the 4-tuple of
+    `extract_time_dependent_structure`."""
+    rng = np.random.default_rng(seed)
+    t0, t1 = 0.0, 0.37 * evolution_time
+    zero, units = _unit_controls(control_count, complex_controls) if control_count else (None, [])
+    if _is_time_dependent(hamiltonian, zero, units, evolution_time):
+        if system_eval_count is None or magnus_order is None:
+            raise NotImplementedError("time-dependent hamiltonian callables are not supported by this CUDA path yet "
+                                      "(no CPU fallback)")
+        return extract_time_dependent_structure(hamiltonian, control_count, complex_controls, evolution_time,
+                                                system_eval_count, magnus_order, seed)
+    if control_count == 0:
+        h0 = np.asarray(hamiltonian(None, t0), dtype=np.complex128)
+        return h0, np.zeros((0,) + h0.shape, dtype=np.complex128)
+    dtype = zero.dtype
+    h0 = np.array(hamiltonian(zero, t0), dtype=np.complex128)
+    if h0.ndim != 2 or h0.shape[0] != h0.shape[1]:
+        raise ValueError("hamiltonian(controls, time) must return a square matrix")
+    a_ops = np.stack([np.array(hamiltonian(e, t0), dtype=np.complex128) - h0 for e in units])
     scale = max(1.0, np.abs(h0).max(), np.abs(a_ops).max())
     for trial in range(3):
         u = rng.standard_normal(control_count) * (1.0 + trial)
@@ -59,9 +177,8 @@ def extract_hamiltonian_structure(hamiltonian, control_count, complex_controls, 
             got = np.asarray(hamiltonian(u.astype(dtype), t), dtype=np.complex128)
             if not np.allclose(got, model, rtol=0, atol=_PROBE_RTOL * scale * (1 + np.abs(x).sum())):
                 raise NotImplementedError(
-                    "hamiltonian(controls, time) is not of the form H0 + sum_k Re(u_k) A_k + Im(u_k) B_k with "
-                    "time-independent operators; general (non-linear or time-dependent) callables are not "
-                    "supported by the CUDA path yet (no CPU fallback)")
+                    "hamiltonian(controls, time) is not of the form H0 + sum_k Re(u_k) A_k + Im(u_k) B_k; non-linear "
+                    "callables are not supported by the CUDA path yet (no CPU fallback)")
     return h0, a_ops
 
 
@@ -90,8 +207,13 @@ class SchroedingerPlan(object):
         self.KR = self.K * (2 if self.complex_controls else 1)
         self.costs = list(costs)
         if structure is None:
-            structure = extract_hamiltonian_structure(hamiltonian, self.K, self.complex_controls, evolution_time)
-        h0, a_ops = structure
+            structure = extract_hamiltonian_structure(hamiltonian, self.K, self.complex_controls, evolution_time,
+                                                      system_eval_count=self.N, magnus_order=magnus_policy.order)
+        self.structure = structure
+        h0, a_ops = structure[0], structure[1]
+        node_map = structure[2:] if len(structure) == 4 else None
+        if node_map is not None and ensemble_drifts is not None:
+            raise NotImplementedError("ensemble drifts with a time-dependent hamiltonian are not supported")
         if h0.shape[0] != self.n:
             raise ValueError("hamiltonian size {} does not match the states' hilbert size {}".format(h0.shape[0], self.n))
         if ensemble_drifts is not None:          # build-side extension: members differ in the drift only
@@ -105,13 +227,18 @@ class SchroedingerPlan(object):
                           ensemble_count=self.E, device=int(device), store_tape=int(bool(store_tape)),
                           chunks_per_member=int(chunks_per_member),
                           slice_begin=0 if slice_range is None else int(slice_range[0]),
-                          slice_end=0 if slice_range is None else int(slice_range[1]), reserved=0,
+                          slice_end=0 if slice_range is None else int(slice_range[1]),
+                          channel_count=0 if node_map is None else int(a_ops.shape[0]),
                           evolution_time=float(evolution_time))
         handle = ctypes.c_void_p()
         _lib.check(self.lib.qocb_plan_create(ctypes.byref(pb), ctypes.byref(handle)))
         self.handle = handle
         a_ops = np.ascontiguousarray(a_ops, dtype=np.complex128)
-        _lib.check(self.lib.qocb_set_operators(handle, _lib.ptr(h0s), _lib.ptr(a_ops) if self.KR else None), handle)
+        _lib.check(self.lib.qocb_set_operators(handle, _lib.ptr(h0s), _lib.ptr(a_ops) if a_ops.shape[0] else None), handle)
+        if node_map is not None:
+            offset = np.ascontiguousarray(node_map[0], dtype=np.float64)
+            gain = np.ascontiguousarray(node_map[1], dtype=np.float64)
+            _lib.check(self.lib.qocb_set_node_map(handle, _lib.ptr(offset), _lib.ptr(gain) if self.KR else None), handle)
         psi0 = np.ascontiguousarray(initial_states.reshape(self.S, self.n), dtype=np.complex128)
         _lib.check(self.lib.qocb_set_states(handle, _lib.ptr(psi0)), handle)
         self.control_costs = []

@@ -179,6 +179,30 @@ __global__ void k_gather_grad(const int *csr_ptr, const int *csr_idx, const doub
     grad[t] = sum / E;
 }
 
+// time-dependent operators: channel coefficients of every local node from the interpolated controls,
+// coef[ji][c] = off[ji][c] + sum_r gain[ji][c][r] x_r(t_ji)
+__global__ void k_node_coefs(const double *controls, const int *itab_idx, const double *itab_w, const double *off, const double *gain,
+                             double *coef, int nodes, int KC, int KR) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nodes * KC) return;
+    const int ji = t / KC;
+    double v = off[t];
+    for (int r = 0; r < KR; ++r) {
+        const double x = controls[itab_idx[2 * ji] * KR + r] * itab_w[2 * ji] + controls[itab_idx[2 * ji + 1] * KR + r] * itab_w[2 * ji + 1];
+        v += gain[(size_t)t * KR + r] * x;
+    }
+    coef[t] = v;
+}
+// ... and the transpose for the gradient: gx[e][ji][r] = sum_c gain[ji][c][r] gc[e][ji][c]
+__global__ void k_node_grad_map(const double *gc, const double *gain, double *gx, int E, int nodes, int KC, int KR) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= E * nodes * KR) return;
+    const int r = t % KR, eji = t / KR, ji = eji % nodes;
+    double v = 0.;
+    for (int c = 0; c < KC; ++c) v += gain[((size_t)ji * KC + c) * KR + r] * gc[(size_t)eji * KC + c];
+    gx[t] = v;
+}
+
 __global__ void k_finalize_cost(const double *cost_part, int nchunks, int E, double *cost) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double s = 0.;
@@ -339,6 +363,10 @@ struct qocb_plan {
     LargeImpl *large = nullptr;
     int NP = 0, q = 0, nchunks = 0, tape_mats = 0, num_sms = 0;
     int j0 = 0, Nloc = 0;               // time sharding: first local slice (global index), local state count
+    // operator channels (KC = pb.control_count unless a node map is set): the kernels see KC coefficient channels;
+    // controls and gradients crossing the ABI keep pb.control_count real channels
+    int KC = 0;
+    bool mapped = false, map_set = false;
     // sweep coarsening: the state / costate sweeps run on chunks merged pairwise `levels` times (propagator tree);
     // lvl_count[l] chunks at level l, their propagators at lvlP + lvl_off[l] matrices, boundaries at cb_lvl + cb_off[l]
     int levels = 0, lvl_count[16] = {}, lvl_off[16] = {}, cb_off[16] = {};
@@ -347,7 +375,7 @@ struct qocb_plan {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16] = {};
     DevBuf<double> C0, Cs, G0, G, controls, itab_w, U, tape, scratch, cta_tape, chunkP, psi, lam, part, cost_part, psi0,
-        node_grad, grad, cost, csr_w, vecs, flush, redA, redB, psi_in, lam_in, lvlP;
+        node_grad, grad, cost, csr_w, vecs, flush, redA, redB, psi_in, lam_in, lvlP, nodecoef, map_off, map_gain, node_grad_x;
     DevBuf<int> itab_idx, tape_piv, meta, cta_piv, chunk_begin, member_chunk0, csr_ptr, csr_idx, counts, err_flag, cb_lvl, mc0_lvl;
     DevBuf<CostTerm> terms;
     std::vector<CostTerm> h_terms;
@@ -437,7 +465,8 @@ KArgs make_kargs(qocb_plan *p) {
     KArgs a;
     a.ga.G0 = p->G0.p; a.ga.G = p->G.p; a.ga.controls = p->controls.p;
     a.ga.itab_idx = p->itab_idx.p; a.ga.itab_w = p->itab_w.p;
-    a.ga.KR = p->pb.control_count; a.ga.q = p->q; a.ga.order = p->pb.magnus_order;
+    a.ga.KR = p->KC; a.ga.q = p->q; a.ga.order = p->pb.magnus_order;
+    a.ga.nodecoef = p->mapped ? p->nodecoef.p : nullptr;
     a.ga.C0 = p->C0.p; a.ga.Cs = p->Cs.p; a.ga.comm = p->comm_ok ? 1 : 0;
     a.ga.dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
     a.N = p->Nloc; a.E = p->pb.ensemble_count;
@@ -498,11 +527,35 @@ int boundary_state_groups(const qocb_plan *p) {
 
 int ready(qocb_plan *p) {
     if (!p->ops_set || !p->states_set) { set_error(p, "operators and states must be set before evaluation"); return -1; }
+    if (p->mapped && !p->map_set) { set_error(p, "channel_count > 0: qocb_set_node_map must be called before evaluation"); return -1; }
     return upload_costs(p);
 }
 
+// time-dependent operators: channel coefficients of the local nodes (first kernel of every evaluation) ...
+int enqueue_node_coefs(qocb_plan *p) {
+    if (!p->mapped) return 0;
+    const int nodes = (p->Nloc - 1) * p->q, tot = nodes * p->KC;
+    if (tot > 0)
+        k_node_coefs<<<(tot + 127) / 128, 128, 0, p->stream>>>(p->controls.p, p->itab_idx.p, p->itab_w.p, p->map_off.p, p->map_gain.p,
+                                                             p->nodecoef.p, nodes, p->KC, p->pb.control_count);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+// ... and the per-node gradient with respect to the interpolated controls, which k_gather_grad scatters to the control points
+int node_grad_for_gather(qocb_plan *p, const double **out) {
+    *out = p->node_grad.p;
+    if (!p->mapped) return 0;
+    const int nodes = (p->Nloc - 1) * p->q, E = p->pb.ensemble_count, tot = E * nodes * p->pb.control_count;
+    if (tot > 0)
+        k_node_grad_map<<<(tot + 127) / 128, 128, 0, p->stream>>>(p->node_grad.p, p->map_gain.p, p->node_grad_x.p, E, nodes, p->KC,
+                                                                p->pb.control_count);
+    CU_TRY(p, cudaGetLastError());
+    *out = p->node_grad_x.p;
+    return 0;
+}
+
 // ==== large-dimension path (n > 64): batched level-3 pipeline, see large.cuh ======================================
-#define BL_TRY(p, expr) do { cublasStatus_t s__ = (expr); if (s__ != CUBLAS_STATUS_SUCCESS) { char b__[256]; snprintf(b__, sizeof(b__), "%s failed: cuBLAS status %d (%s:%d)", #expr, (int)s__, __FILE__, __LINE__); set_error(p, b__); return -2; } } while (0)
+#define BL_TRY(p, expr) do { cublasStatus_t s__ = (expr); if (s__ != CUBLAS_STATUS_SUCCESS) { char b__[640]; snprintf(b__, sizeof(b__), "%s failed: cuBLAS status %d (%s:%d)", #expr, (int)s__, __FILE__, __LINE__); set_error(p, b__); return -2; } } while (0)
 
 inline int lg_blocks(size_t tot) { return (int)std::min<size_t>((tot + 255) / 256, 148 * 16); }
 
@@ -552,6 +605,44 @@ int lg_copy(qocb_plan *p, double2 *dst, const double2 *src, int batch) {
     return 0;
 }
 
+// out = alpha (a b - b a)
+int lg_comm(qocb_plan *p, const double2 *a, const double2 *b, double2 *out, double alpha, int batch) {
+    int rc = lg_gemm(p, false, false, a, b, out, alpha, 0., batch); if (rc) return rc;
+    return lg_gemm(p, false, false, b, a, out, -alpha, 1., batch);
+}
+// cotangents of c = a b - b a (unconjugated convention): abar (+)= alpha (cbar b^T - b^T cbar), bbar (+)= alpha (a^T cbar - cbar a^T);
+// beta = 0 overwrites, 1 accumulates; a null output is skipped
+int lg_comm_bwd(qocb_plan *p, const double2 *a, const double2 *b, const double2 *cbar, double2 *abar, double2 *bbar, double alpha,
+                double beta, int batch) {
+    int rc;
+    if (abar) {
+        rc = lg_gemm(p, false, true, cbar, b, abar, alpha, beta, batch); if (rc) return rc;
+        rc = lg_gemm(p, true, false, b, cbar, abar, -alpha, 1., batch); if (rc) return rc;
+    }
+    if (bbar) {
+        rc = lg_gemm(p, true, false, a, cbar, bbar, alpha, beta, batch); if (rc) return rc;
+        rc = lg_gemm(p, false, true, cbar, a, bbar, -alpha, 1., batch); if (rc) return rc;
+    }
+    return 0;
+}
+
+// Magnus M6 pieces of slices [jb, jb + Bc) (oracle/adjoint_model.py:magnus_fwd): b1 -> LA1, b2 -> LA2N, b3 -> LA1B,
+// c12 = [b1, b2] -> LA2NB, e = 2 b3 + c12 -> LTB, p = -20 b1 - b3 + c12 -> LA6B, qm = b2 - [b1, e] / 60 -> LA4B
+int lg_magnus6_pieces(qocb_plan *p, int jb, int Bc) {
+    LargeImpl *L = p->large;
+    const size_t tot = (size_t)Bc * L->nn;
+    const double dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
+    LgCoef cf{p->controls.p, p->itab_idx.p, p->itab_w.p, p->KC, p->q, p->mapped ? p->nodecoef.p : nullptr};
+    double2 *b1 = L->arr(LA1), *b2 = L->arr(LA2N), *b3 = L->arr(LA1B), *c12 = L->arr(LA2NB), *e = L->arr(LTB), *d = L->arr(LXB);
+    k_lg_assemble6<<<lg_blocks(tot), 256, 0, p->stream>>>(b1, b2, b3, L->G0.p, L->G.p, cf, jb, Bc, L->nn, dt);
+    CU_TRY(p, cudaGetLastError());
+    int rc = lg_comm(p, b1, b2, c12, 1., Bc); if (rc) return rc;
+    rc = lg_axpby(p, e, 2., b3, 1., c12, 0., nullptr, Bc); if (rc) return rc;
+    rc = lg_comm(p, b1, e, d, 1., Bc); if (rc) return rc;
+    rc = lg_axpby(p, L->arr(LA4B), 1., b2, -1.0 / 60.0, d, 0., nullptr, Bc); if (rc) return rc;
+    return lg_axpby(p, L->arr(LA6B), -20., b1, -1., b3, 1., c12, Bc);
+}
+
 int large_init(qocb_plan *p) {
     LargeImpl *L = new LargeImpl();
     p->large = L;
@@ -567,7 +658,7 @@ int large_init(qocb_plan *p) {
 #undef ZG_ATTR
     BL_TRY(p, cublasCreate(&L->blas));
     BL_TRY(p, cublasSetStream(L->blas, p->stream));
-    CU_TRY(p, L->G0.alloc(L->nn)); CU_TRY(p, L->G.alloc((size_t)std::max(1, p->pb.control_count) * L->nn));
+    CU_TRY(p, L->G0.alloc(L->nn)); CU_TRY(p, L->G.alloc((size_t)std::max(1, p->KC) * L->nn));
     CU_TRY(p, L->work.alloc((size_t)LCOUNT * L->B * L->nn));
     CU_TRY(p, L->piv.alloc((size_t)L->B * n)); CU_TRY(p, L->info.alloc(L->B)); CU_TRY(p, L->sarr.alloc(L->B));
     CU_TRY(p, L->ptrQ.alloc(L->B)); CU_TRY(p, L->ptrP.alloc(L->B)); CU_TRY(p, L->ptrRB.alloc(L->B));
@@ -641,14 +732,18 @@ int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_out) {
     const int nn = L->nn, order = p->pb.magnus_order;
     const size_t tot = (size_t)Bc * nn;
     const double dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
-    LgCoef cf{p->controls.p, p->itab_idx.p, p->itab_w.p, p->pb.control_count, p->q};
+    LgCoef cf{p->controls.p, p->itab_idx.p, p->itab_w.p, p->KC, p->q, p->mapped ? p->nodecoef.p : nullptr};
     int rc;
     if (order == 4 && p->comm_ok) {
         k_lg_magnus4_comm<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LM), L->G0.p, L->G.p, L->C0.p, L->Cs.p, cf, jb, Bc, nn, dt);
     } else {
-    k_lg_assemble<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA1), L->arr(LA2N), L->G0.p, L->G.p, cf, jb, Bc, nn);
+    if (order != 6) k_lg_assemble<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA1), L->arr(LA2N), L->G0.p, L->G.p, cf, jb, Bc, nn);
     if (order == 2) { rc = lg_axpby(p, L->arr(LM), dt, L->arr(LA1), 0., nullptr, 0., nullptr, Bc); if (rc) return rc; }
-    else {
+    else if (order == 6) {
+        rc = lg_magnus6_pieces(p, jb, Bc); if (rc) return rc;
+        rc = lg_comm(p, L->arr(LA6B), L->arr(LA4B), L->arr(LA2B), 1., Bc); if (rc) return rc;                     // [p, qm]
+        rc = lg_axpby(p, L->arr(LM), 1., L->arr(LA1), 0.5, L->arr(LA1B), 1.0 / 240.0, L->arr(LA2B), Bc); if (rc) return rc;
+    } else {
         rc = lg_gemm(p, false, false, L->arr(LA2N), L->arr(LA1), L->arr(LT), 1., 0., Bc); if (rc) return rc;      // a2 a1
         rc = lg_gemm(p, false, false, L->arr(LA1), L->arr(LA2N), L->arr(LT), -1., 1., Bc); if (rc) return rc;     // - a1 a2
         k_lg_axpby<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LM), 0.5 * dt, L->arr(LA1), 0.5 * dt, L->arr(LA2N), (QOCB_S3 / 12.0) * dt * dt, L->arr(LT), tot);
@@ -687,6 +782,7 @@ int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_out) {
 int lg_expm_all(qocb_plan *p) {
     LargeImpl *L = p->large;
     const int Lsl = p->Nloc - 1;
+    { int rc = enqueue_node_coefs(p); if (rc) return rc; }
     for (int jb = 0; jb < Lsl; jb += L->B) {
         const int Bc = std::min(L->B, Lsl - jb);
         int smax = 0;
@@ -741,8 +837,8 @@ int lg_backward_all(qocb_plan *p) {
         if (L->batch_taped[jb / L->B]) {
             // taped batch: only the cheap elementwise pieces are rebuilt (node generators for the Magnus adjoint, W1, X1)
             L->tj = jb;
-            LgCoef cf{p->controls.p, p->itab_idx.p, p->itab_w.p, p->pb.control_count, p->q};
-            if (!(order == 4 && p->comm_ok))
+            LgCoef cf{p->controls.p, p->itab_idx.p, p->itab_w.p, p->KC, p->q, p->mapped ? p->nodecoef.p : nullptr};
+            if (!(order == 4 && p->comm_ok) && order != 6)
                 k_lg_assemble<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA1), L->arr(LA2N), L->G0.p, L->G.p, cf, jb, Bc, nn);
             k_lg_poly<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA2), L->arr(LA4), L->arr(LA6), L->arr(LW1), L->arr(LX1), L->arr(LT), L->arr(LVE), L->n, tot);
         } else {
@@ -818,10 +914,32 @@ int lg_backward_all(qocb_plan *p) {
         k_lg_unscale<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LAB), L->cur_sarr(), nn, tot);                // mbar
         double2 *AB = L->arr(LAB);
         if (order == 4 && p->comm_ok) {
-            if (p->pb.control_count > 0) {
-                LgCoef cf2{p->controls.p, p->itab_idx.p, p->itab_w.p, p->pb.control_count, p->q};
+            if (p->KC > 0) {
+                LgCoef cf2{p->controls.p, p->itab_idx.p, p->itab_w.p, p->KC, p->q, p->mapped ? p->nodecoef.p : nullptr};
                 k_lg_contract_comm<<<Bc, 256, 0, p->stream>>>(AB, L->G.p, L->C0.p, L->Cs.p, cf2, p->node_grad.p, jb, nn, dt);
             }
+            CU_TRY(p, cudaGetLastError());
+            continue;
+        }
+        if (order == 6) {
+            // oracle/adjoint_model.py:magnus_bwd; the forward pieces are rebuilt (the Pade reverse pass reused their arrays)
+            rc = lg_magnus6_pieces(p, jb, Bc); if (rc) return rc;
+            double2 *b1 = L->arr(LA1), *b2 = L->arr(LA2N), *e = L->arr(LTB), *pm = L->arr(LA6B), *qm = L->arr(LA4B);
+            double2 *pb = L->arr(LW1), *qb = L->arr(LX1), *db = L->arr(LVE), *t1 = L->arr(LUO), *eb = L->arr(LP);
+            double2 *b1b = L->arr(LRB), *b3b = L->arr(LQB), *c12b = L->arr(LUOB);
+            rc = lg_comm_bwd(p, pm, qm, AB, pb, qb, 1.0 / 240.0, 0., Bc); if (rc) return rc;              // pbar, qbar (= b2bar so far)
+            rc = lg_axpby(p, db, -1.0 / 60.0, qb, 0., nullptr, 0., nullptr, Bc); if (rc) return rc;       // dbar
+            rc = lg_comm_bwd(p, b1, e, db, t1, eb, 1., 0., Bc); if (rc) return rc;                        // t1, ebar
+            rc = lg_axpby(p, b1b, 1., AB, 1., t1, -20., pb, Bc); if (rc) return rc;
+            rc = lg_axpby(p, b3b, 0.5, AB, 2., eb, -1., pb, Bc); if (rc) return rc;
+            rc = lg_axpby(p, c12b, 1., eb, 1., pb, 0., nullptr, Bc); if (rc) return rc;
+            rc = lg_comm_bwd(p, b1, b2, c12b, b1b, qb, 1., 1., Bc); if (rc) return rc;                    // b1bar +=, b2bar +=
+            double2 *n0 = L->arr(LVEB), *n1 = L->arr(LYB), *n2 = L->arr(LT);
+            rc = lg_axpby(p, n0, -(QOCB_S15 / 3.0) * dt, qb, (10.0 / 3.0) * dt, b3b, 0., nullptr, Bc); if (rc) return rc;
+            rc = lg_axpby(p, n1, dt, b1b, -(20.0 / 3.0) * dt, b3b, 0., nullptr, Bc); if (rc) return rc;
+            rc = lg_axpby(p, n2, (QOCB_S15 / 3.0) * dt, qb, (10.0 / 3.0) * dt, b3b, 0., nullptr, Bc); if (rc) return rc;
+            if (p->KC > 0)
+                k_lg_contract<<<dim3(Bc, 3), 256, 0, p->stream>>>(n0, n1, n2, L->G.p, p->node_grad.p, jb, nn, p->KC, 3);
             CU_TRY(p, cudaGetLastError());
             continue;
         }
@@ -835,13 +953,15 @@ int lg_backward_all(qocb_plan *p) {
             rc = lg_gemm(p, false, true, AB, L->arr(LA2N), T, -1., 1., Bc); if (rc) return rc;
             rc = lg_axpby(p, L->arr(LA1B), 0.5 * dt, AB, f, T, 0., nullptr, Bc); if (rc) return rc;
         }
-        if (p->pb.control_count > 0)
-            k_lg_contract<<<dim3(Bc, p->q), 256, 0, p->stream>>>(L->arr(LA1B), L->arr(LA2NB), L->G.p, p->node_grad.p, jb, nn, p->pb.control_count, p->q);
+        if (p->KC > 0)
+            k_lg_contract<<<dim3(Bc, p->q), 256, 0, p->stream>>>(L->arr(LA1B), L->arr(LA2NB), nullptr, L->G.p, p->node_grad.p, jb, nn, p->KC, p->q);
         CU_TRY(p, cudaGetLastError());
     }
     const int totg = p->pb.control_eval_count * p->pb.control_count;
+    const double *ng = nullptr;
+    { int rc = node_grad_for_gather(p, &ng); if (rc) return rc; }
     if (totg > 0)
-        k_gather_grad<<<(totg + 127) / 128, 128, 0, p->stream>>>(p->csr_ptr.p, p->csr_idx.p, p->csr_w.p, p->node_grad.p, p->grad.p,
+        k_gather_grad<<<(totg + 127) / 128, 128, 0, p->stream>>>(p->csr_ptr.p, p->csr_idx.p, p->csr_w.p, ng, p->grad.p,
                                                                p->pb.control_eval_count, p->pb.control_count, p->q, p->Nloc - 1, 1);
     CU_TRY(p, cudaGetLastError());
     return 0;
@@ -907,7 +1027,8 @@ int reduce_level(qocb_plan *p, const double *in, double *out, int count) {
 int enqueue_expm_forward(qocb_plan *p, bool with_grad) {
     KArgs ka = make_kargs(p);
     if (!with_grad) ka.tape = nullptr;
-    int rc = dispatch(p->NP, [&] { return launch_forward<C8>(p, ka); }, [&] { return launch_forward<C16>(p, ka); },
+    int rc = enqueue_node_coefs(p); if (rc) return rc;
+    rc = dispatch(p->NP, [&] { return launch_forward<C8>(p, ka); }, [&] { return launch_forward<C16>(p, ka); },
                       [&] { return launch_forward<C32>(p, ka); }, [&] { return launch_forward<C64>(p, ka); });
     if (rc) return rc;
     // propagator tree up to the level the sweeps run on
@@ -975,8 +1096,10 @@ int enqueue_expm_backward(qocb_plan *p, cudaEvent_t mid) {
     if (rc) return rc;
     if (mid) cudaEventRecord(mid, p->stream);
     const int tot = p->pb.control_eval_count * p->pb.control_count;
+    const double *ng = nullptr;
+    rc = node_grad_for_gather(p, &ng); if (rc) return rc;
     if (tot > 0)
-        k_gather_grad<<<(tot + 127) / 128, 128, 0, p->stream>>>(p->csr_ptr.p, p->csr_idx.p, p->csr_w.p, p->node_grad.p,
+        k_gather_grad<<<(tot + 127) / 128, 128, 0, p->stream>>>(p->csr_ptr.p, p->csr_idx.p, p->csr_w.p, ng,
                                                               p->grad.p, p->pb.control_eval_count, p->pb.control_count,
                                                               p->q, p->Nloc - 1, p->pb.ensemble_count);
     CU_TRY(p, cudaGetLastError());
@@ -1050,12 +1173,12 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     const int NP = pad_dim(pb->hilbert_size);
     if (pb->hilbert_size < 1 || NP < 0) { set_error((qocb_plan *)nullptr, "hilbert_size must be in [1, 512]"); return -1; }
     const bool is_large = NP > 64;
-    if (is_large && pb->magnus_order == 6) { set_error((qocb_plan *)nullptr, "Magnus M6 is not implemented for hilbert_size > 64"); return -1; }
     if (is_large && pb->ensemble_count != 1) { set_error((qocb_plan *)nullptr, "ensembles are not implemented for hilbert_size > 64"); return -1; }
     if (pb->magnus_order != 2 && pb->magnus_order != 4 && pb->magnus_order != 6) { set_error((qocb_plan *)nullptr, "magnus_order must be 2, 4 or 6"); return -1; }
     if (pb->system_eval_count < 2) { set_error((qocb_plan *)nullptr, "system_eval_count must be >= 2"); return -1; }
     if (pb->control_count < 0 || pb->control_count > kMaxKR) { set_error((qocb_plan *)nullptr, "control_count (real channels) must be in [0, 16]"); return -1; }
     if (pb->control_count > 0 && pb->control_eval_count < 2) { set_error((qocb_plan *)nullptr, "control_eval_count must be >= 2"); return -1; }
+    if (pb->channel_count < 0 || pb->channel_count > kMaxKR) { set_error((qocb_plan *)nullptr, "channel_count must be in [0, 16]"); return -1; }
     if (pb->state_count < 1 || pb->cost_eval_step < 1 || pb->ensemble_count < 1) { set_error((qocb_plan *)nullptr, "state_count, cost_eval_step, ensemble_count must be >= 1"); return -1; }
     const bool sliced = !(pb->slice_begin == 0 && pb->slice_end == 0);
     if (sliced && (pb->slice_begin < 0 || pb->slice_end <= pb->slice_begin || pb->slice_end > pb->system_eval_count - 1)) { set_error((qocb_plan *)nullptr, "bad slice range: need 0 <= slice_begin < slice_end <= system_eval_count - 1"); return -1; }
@@ -1080,6 +1203,9 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     for (auto &e : p->ev) PTRY(cudaEventCreate(&e));
     const int N = p->Nloc, Nm1 = N - 1, E = pb->ensemble_count, M = pb->control_eval_count;   // LOCAL counts
     const int KR = pb->control_count, S = pb->state_count, q = p->q;
+    p->mapped = pb->channel_count > 0;
+    p->KC = p->mapped ? pb->channel_count : KR;
+    const int KC = p->KC;
     const size_t GM = 2 * (size_t)NP * NP;
     // ---- chunks -------------------------------------------------------------------------------------
     int occ = is_large ? 1 : dispatch(NP, [] { return occupancy_fwd<C8>(); }, [] { return occupancy_fwd<C16>(); },
@@ -1184,7 +1310,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     // ---- buffers -------------------------------------------------------------------------------------
     const size_t W = (size_t)E * Nm1;
     p->tape_mats = 8 + kStoredTapeR;
-    PTRY(p->G0.alloc((size_t)E * GM)); PTRY(p->G.alloc(std::max<size_t>(1, (size_t)KR) * GM));
+    PTRY(p->G0.alloc((size_t)E * GM)); PTRY(p->G.alloc(std::max<size_t>(1, (size_t)KC) * GM));
     PTRY(p->controls.alloc(std::max<size_t>(1, (size_t)M * KR)));
     PTRY(p->U.alloc(W * GM));
     PTRY(p->meta.alloc(W));
@@ -1199,7 +1325,12 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
         PTRY(p->redA.alloc((size_t)((p->nchunks + 1) / 2) * GM)); PTRY(p->redB.alloc((size_t)((p->nchunks + 3) / 4) * GM));
         PTRY(p->psi_in.alloc(VS)); PTRY(p->lam_in.alloc(VS));
     }
-    PTRY(p->node_grad.alloc(std::max<size_t>(1, W * q * KR))); PTRY(p->grad.alloc(std::max<size_t>(1, (size_t)M * KR)));
+    PTRY(p->node_grad.alloc(std::max<size_t>(1, W * q * KC)));
+    if (p->mapped) {
+        PTRY(p->nodecoef.alloc(std::max<size_t>(1, (size_t)Nm1 * q * KC))); PTRY(p->map_off.alloc(std::max<size_t>(1, (size_t)Nm1 * q * KC)));
+        PTRY(p->map_gain.alloc(std::max<size_t>(1, (size_t)Nm1 * q * KC * KR))); PTRY(p->node_grad_x.alloc(std::max<size_t>(1, W * q * KR)));
+    }
+    PTRY(p->grad.alloc(std::max<size_t>(1, (size_t)M * KR)));
     PTRY(p->cost.alloc(1)); PTRY(p->err_flag.alloc(1));
     PTRY(cudaMemset(p->err_flag.p, 0, sizeof(int)));
     PTRY(cudaMemset(p->controls.p, 0, sizeof(double) * p->controls.n));
@@ -1256,7 +1387,7 @@ int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
     if (!p || !h0) { set_error(p, "null argument"); return -1; }
     drop_graphs(p);
     CU_TRY(p, cudaSetDevice(p->pb.device));
-    const int n = p->pb.hilbert_size, NP = p->NP, E = p->pb.ensemble_count, KR = p->pb.control_count;
+    const int n = p->pb.hilbert_size, NP = p->NP, E = p->pb.ensemble_count, KR = p->KC;   // operator channels
     const size_t GM = 2 * (size_t)NP * NP;
     if (p->large) {                                    // interleaved generators G = -1j * H
         auto gen = [&](const double *src, double2 *dst_dev) -> cudaError_t {
@@ -1266,7 +1397,7 @@ int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
         };
         CU_TRY(p, gen(h0, p->large->G0.p));
         if (KR > 0) {
-            if (!a_ops) { set_error(p, "a_ops is null but control_count > 0"); return -1; }
+            if (!a_ops) { set_error(p, "a_ops is null but the operator channel count is > 0"); return -1; }
             for (int r = 0; r < KR; ++r) CU_TRY(p, gen(a_ops + (size_t)r * 2 * n * n, p->large->G.p + (size_t)r * n * n));
         }
         p->comm_ok = false;
@@ -1294,7 +1425,7 @@ int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
     for (int e = 0; e < E; ++e) to_planar(h0 + (size_t)e * 2 * n * n, buf.data() + (size_t)e * GM, n, NP, true);
     CU_TRY(p, cudaMemcpy(p->G0.p, buf.data(), sizeof(double) * E * GM, cudaMemcpyHostToDevice));
     if (KR > 0) {
-        if (!a_ops) { set_error(p, "a_ops is null but control_count > 0"); return -1; }
+        if (!a_ops) { set_error(p, "a_ops is null but the operator channel count is > 0"); return -1; }
         for (int r = 0; r < KR; ++r) to_planar(a_ops + (size_t)r * 2 * n * n, buf.data() + (size_t)r * GM, n, NP, true);
         CU_TRY(p, cudaMemcpy(p->G.p, buf.data(), sizeof(double) * KR * GM, cudaMemcpyHostToDevice));
     }
@@ -1340,6 +1471,21 @@ int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
             }
     }
     p->ops_set = true;
+    return 0;
+}
+
+int qocb_set_node_map(qocb_plan *p, const double *offset, const double *gain) {
+    if (!p || !offset) { set_error(p, "null argument"); return -1; }
+    if (!p->mapped) { set_error(p, "qocb_set_node_map needs a plan created with channel_count > 0"); return -1; }
+    const int KR = p->pb.control_count, KC = p->KC, q = p->q, Nm1 = p->Nloc - 1;
+    if (KR > 0 && !gain) { set_error(p, "gain is null but control_count > 0"); return -1; }
+    drop_graphs(p);
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const size_t o0 = (size_t)p->j0 * q * KC;                       // local slices [j0, j0 + Nloc - 1)
+    CU_TRY(p, cudaMemcpy(p->map_off.p, offset + o0, sizeof(double) * (size_t)Nm1 * q * KC, cudaMemcpyHostToDevice));
+    if (KR > 0)
+        CU_TRY(p, cudaMemcpy(p->map_gain.p, gain + o0 * KR, sizeof(double) * (size_t)Nm1 * q * KC * KR, cudaMemcpyHostToDevice));
+    p->map_set = true;
     return 0;
 }
 
@@ -1564,12 +1710,17 @@ int qocb_get_propagators(qocb_plan *p, double *props) {
     return 0;
 }
 
+static int launch_count_unmapped(qocb_plan *p, int32_t with_grad);
 int qocb_launch_count(qocb_plan *p, int32_t with_grad) {
     if (!p) return -1;
+    return launch_count_unmapped(p, with_grad) + (p->mapped ? (with_grad ? 2 : 1) : 0);   // k_node_coefs, k_node_grad_map
+}
+static int launch_count_unmapped(qocb_plan *p, int32_t with_grad) {
     if (p->large) {
         const int batches = (p->Nloc - 2 + p->large->B) / p->large->B;
-        const int fwd = p->pb.magnus_order == 4 ? 14 : 11;                   // own kernels + library calls per batch
-        return batches * (fwd + (with_grad ? fwd + (p->pb.magnus_order == 4 ? 38 : 30) : 0)) + (with_grad ? 3 : 1);
+        const int o = p->pb.magnus_order;
+        const int fwd = o == 6 ? 21 : o == 4 ? 14 : 11;                      // own kernels + library calls per batch
+        return batches * (fwd + (with_grad ? fwd + (o == 6 ? 60 : o == 4 ? 38 : 30) : 0)) + (with_grad ? 3 : 1);
     }
     if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->levels;
     int levels = 0;

@@ -62,6 +62,9 @@ struct GenArgs {
     // C0[r] = [G0, G_r] (per member) and Cs[(s<r)] = [G_s, G_r]; enabled for KR <= kMaxCommKR
     const double *C0, *Cs;
     int comm;
+    // time-dependent operators: channel coefficients of every local node, [slice][q][KR], precomputed by k_node_coefs
+    // (KR then counts operator channels); nullptr = interpolate the controls here
+    const double *nodecoef;
 };
 constexpr int kMaxCommKR = 6;
 __host__ __device__ inline int comm_pair(int s, int r, int KR) { return s * KR - s * (s + 1) / 2 + (r - s - 1); }   // s < r
@@ -71,6 +74,7 @@ template <class C>
 __device__ __forceinline__ void load_coefs(const Smem<C> &sm, const GenArgs &ga, int j) {
     for (int e = threadIdx.x; e < ga.q * ga.KR; e += C::NT) {
         const int i = e / ga.KR, r = e % ga.KR;
+        if (ga.nodecoef) { sm.coef[i * kMaxKR + r] = ga.nodecoef[(size_t)(j * ga.q + i) * ga.KR + r]; continue; }
         const int *id = ga.itab_idx + (j * ga.q + i) * 2;
         const double *w = ga.itab_w + (j * ga.q + i) * 2;
         sm.coef[i * kMaxKR + r] = ga.controls[id[0] * ga.KR + r] * w[0] + ga.controls[id[1] * ga.KR + r] * w[1];

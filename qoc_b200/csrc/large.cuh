@@ -12,7 +12,7 @@
 //     polynomial combinations, squaring selection, rank-S cotangent seeds, Magnus adjoint, contraction with the control
 //     operators, state / costate sweeps with the fused cost reductions - are kernels of this file.
 // The reverse pass recomputes the forward intermediates per batch (no tape across the evaluation), so memory stays
-// O(batch) + the propagators.  Magnus M2 and M4 only (M6 at n > 64: not implemented, fails loudly).
+// O(batch) + the propagators.  Magnus M2, M4 (product-free when KR <= 6) and M6 (batched commutator chain).
 // Matrices are interleaved complex128 (double2), row-major, dense n x n; state vectors stay planar ([s][2][n]) so the
 // cost reductions of sweep.cuh are shared.
 #pragma once
@@ -25,9 +25,11 @@ constexpr int kLgMaxSq = 6;                    // squarings kept per batch for t
 
 struct LgCoef {                                // interpolation of the controls at the Magnus nodes of the local slices
     const double *controls; const int *itab_idx; const double *itab_w; int KR, q;
+    const double *nodecoef;                    // precomputed channel coefficients [slice][q][KR] (time-dependent operators) or nullptr
 };
 
 __device__ __forceinline__ double lg_coef(const LgCoef &c, int j, int i, int r) {
+    if (c.nodecoef) return c.nodecoef[(size_t)(j * c.q + i) * c.KR + r];
     const int o = (j * c.q + i) * 2;
     return c.controls[c.itab_idx[o] * c.KR + r] * c.itab_w[o] + c.controls[c.itab_idx[o + 1] * c.KR + r] * c.itab_w[o + 1];
 }
@@ -47,6 +49,26 @@ __global__ void k_lg_assemble(double2 *a1, double2 *a2, const double2 *G0, const
         }
         a1[t] = v1;
         if (c.q > 1) a2[t] = v2;
+    }
+}
+
+// Magnus M6 combinations at the three Gauss-Legendre nodes (mathmethods.py:129-164): b1 = dt a2,
+// b2 = (sqrt15/3) dt (a3 - a1), b3 = (10/3) dt (a3 - 2 a2 + a1); the drift cancels in b2 and b3
+__global__ void k_lg_assemble6(double2 *b1, double2 *b2, double2 *b3, const double2 *G0, const double2 *G, LgCoef c,
+                               int j_begin, int B, int nn, double dt) {
+    const size_t tot = (size_t)B * nn;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / nn), e = (int)(t - (size_t)b * nn), j = j_begin + b;
+        double2 v1 = make_double2(dt * G0[e].x, dt * G0[e].y), v2 = make_double2(0., 0.), v3 = v2;
+        for (int r = 0; r < c.KR; ++r) {
+            const double2 g = G[(size_t)r * nn + e];
+            const double c1 = lg_coef(c, j, 0, r), c2 = lg_coef(c, j, 1, r), c3 = lg_coef(c, j, 2, r);
+            const double w1 = dt * c2, w2 = (QOCB_S15 / 3.0) * dt * (c3 - c1), w3 = (10.0 / 3.0) * dt * (c3 - 2.0 * c2 + c1);
+            v1.x += w1 * g.x; v1.y += w1 * g.y;
+            v2.x += w2 * g.x; v2.y += w2 * g.y;
+            v3.x += w3 * g.x; v3.y += w3 * g.y;
+        }
+        b1[t] = v1; b2[t] = v2; b3[t] = v3;
     }
 }
 
@@ -225,11 +247,11 @@ __global__ void k_lr_fill(const double2 *PSI, const double2 *LAM, const double2 
 }
 
 // node_grad[(j*q + i)*KR + r] = Re sum_e abar_i[b][e] G_r[e]; one CTA per (slice of the batch, node)
-__global__ void __launch_bounds__(256) k_lg_contract(const double2 *ab1, const double2 *ab2, const double2 *G, double *node_grad,
-                                                     int j_begin, int nn, int KR, int q) {
+__global__ void __launch_bounds__(256) k_lg_contract(const double2 *ab1, const double2 *ab2, const double2 *ab3, const double2 *G,
+                                                     double *node_grad, int j_begin, int nn, int KR, int q) {
     __shared__ double red[256];
     const int b = blockIdx.x, i = blockIdx.y;
-    const double2 *ab = (i == 0 ? ab1 : ab2) + (size_t)b * nn;
+    const double2 *ab = (i == 0 ? ab1 : i == 1 ? ab2 : ab3) + (size_t)b * nn;
     for (int r = 0; r < KR; ++r) {
         const double2 *g = G + (size_t)r * nn;
         double s = 0.;

@@ -80,6 +80,62 @@ class Problem(object):
             return h
         return hamiltonian
 
+    # time-dependent variant: rotating drives and a modulated drift,
+    #   H(u, t) = H0 + 0.3 cos(w0 t) D + sum_k [u_k e^{i w_k t} C_k + h.c.]           (complex controls)
+    #   H(u, t) = H0 + 0.3 cos(w0 t) D + sum_k u_k [cos(w_k t) A_k + sin(w_k t) B_k]  (real controls)
+    def _td_parts(self):
+        rng = np.random.default_rng(1000 + self.n)
+        d = rand_herm(rng, self.n)
+        d = d * (one_norm(self.h0) / one_norm(d))
+        b = []
+        for k in range(self.K):
+            x = rand_herm(rng, self.n)
+            b.append(x * (one_norm(self.drives[k] + self.drives[k].conj().T) / one_norm(x) / 2))
+        w = 2 * np.pi * (0.05 + 0.03 * np.arange(self.K + 1)) / 1.0
+        return d, np.array(b).reshape(self.K, self.n, self.n), w
+
+    def hamiltonian_td_numpy(self):
+        h0, dr, cc = self.h0, self.drives, self.complex_controls
+        d, b, w = self._td_parts()
+
+        def hamiltonian(controls, time):
+            h = h0 + 0.3 * np.cos(w[0] * time) * d
+            if controls is None:
+                return h
+            for k in range(dr.shape[0]):
+                if cc:
+                    ph = np.exp(1j * w[k + 1] * time)
+                    h = h + controls[k] * ph * dr[k] + np.conjugate(controls[k] * ph) * dr[k].conj().T
+                else:
+                    h = h + controls[k] * (np.cos(w[k + 1] * time) * dr[k] + np.sin(w[k + 1] * time) * b[k])
+            return h
+        return hamiltonian
+
+    def hamiltonian_td_torch(self):
+        import math
+        import torch
+        cdt = torch.complex128
+        h0 = torch.as_tensor(self.h0, dtype=cdt)
+        dr = torch.as_tensor(self.drives, dtype=cdt)
+        drd = dr.conj().transpose(-1, -2)
+        d0, b0, w = self._td_parts()
+        d, b = torch.as_tensor(d0, dtype=cdt), torch.as_tensor(b0, dtype=cdt)
+        cc = self.complex_controls
+
+        def hamiltonian(controls, time):
+            time = float(time)
+            h = h0 + 0.3 * math.cos(w[0] * time) * d
+            if controls is None:
+                return h
+            for k in range(dr.shape[0]):
+                if cc:
+                    ph = complex(math.cos(w[k + 1] * time), math.sin(w[k + 1] * time))
+                    h = h + controls[k] * ph * dr[k] + torch.conj(controls[k] * ph) * drd[k]
+                else:
+                    h = h + controls[k] * (math.cos(w[k + 1] * time) * dr[k] + math.sin(w[k + 1] * time) * b[k])
+            return h
+        return hamiltonian
+
     def costs(self, mod):
         """cost objects from `mod` (qoc_b200.standard or the oracle module - same constructor signatures)."""
         out = []

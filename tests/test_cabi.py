@@ -41,7 +41,7 @@ def test_no_gpu_fails_loudly():
     lib = _lib.load()
     pb = _lib.Problem(hilbert_size=4, state_count=1, control_count=1, control_eval_count=5, system_eval_count=5,
                       magnus_order=2, cost_eval_step=1, ensemble_count=1, device=0, store_tape=1,
-                      chunks_per_member=0, reserved=0, evolution_time=1.0)
+                      chunks_per_member=0, channel_count=0, evolution_time=1.0)
     handle = ctypes.c_void_p()
     rc = lib.qocb_plan_create(ctypes.byref(pb), ctypes.byref(handle))
     assert rc != 0 and not handle
@@ -61,7 +61,7 @@ def test_bad_arguments_rejected():
     handle = ctypes.c_void_p()
     pb = _lib.Problem(hilbert_size=4, state_count=1, control_count=1, control_eval_count=5, system_eval_count=5,
                       magnus_order=3, cost_eval_step=1, ensemble_count=1, device=0, store_tape=1,
-                      chunks_per_member=0, reserved=0, evolution_time=1.0)
+                      chunks_per_member=0, channel_count=0, evolution_time=1.0)
     assert lib.qocb_plan_create(ctypes.byref(pb), ctypes.byref(handle)) == -1
     assert b"magnus_order" in lib.qocb_last_error(None)
     pb.magnus_order = 2

@@ -21,6 +21,9 @@ CASES = [
     (96, 7, 1, 4, 4, False, 3, 8.0, 1, False),
     (130, 5, 2, 2, 4, True, 0, 30.0, 1, False),
     (68, 401, 2, 2, 2, False, 2, 1.0, 7, True),          # > 160 slices: sweeps run on a coarser level of the propagator tree
+    (66, 9, 2, 2, 6, False, 2, 1.0, 1, False),           # Magnus M6 through the batched commutator chain
+    (100, 6, 2, 3, 6, True, 0, 8.0, 2, True),
+    (72, 5, 1, 5, 6, False, 0, 30.0, 1, False),          # S > 4: dense reverse pass, squarings
 ]
 
 
@@ -30,7 +33,7 @@ def test_large_dim_vs_oracle(case):
     from oracle import qoc_oracle as orc
     from qoc_b200.core.plan import SchroedingerPlan
     from qoc_b200.models import MagnusPolicy
-    pol = {2: MagnusPolicy.M2, 4: MagnusPolicy.M4}
+    pol = {2: MagnusPolicy.M2, 4: MagnusPolicy.M4, 6: MagnusPolicy.M6}
     n, slices, K, S, order, cc, F, stiff, ces, step_target = case
     p = Problem(n, slices, K, S, order, complex_controls=cc, F=F, seed=n, stiff=stiff, cost_eval_step=ces, step_target=step_target)
     plan = SchroedingerPlan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M,
@@ -73,7 +76,7 @@ def test_large_dim_limits():
     import qoc_b200.standard as std
     from qoc_b200.core.plan import SchroedingerPlan
     from qoc_b200.models import MagnusPolicy
-    p = Problem(70, 3, 1, 1, 6)
+    p = Problem(520, 3, 1, 1, 2)
     with pytest.raises(RuntimeError):
         SchroedingerPlan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M,
-                         control_count=1, magnus_policy=MagnusPolicy.M6)
+                         control_count=1, magnus_policy=MagnusPolicy.M2)

@@ -6,7 +6,7 @@ import pytest
 import qoc_b200.standard as std
 from qoc_b200.core.common import (clip_control_norms, gen_controls_flat, initialize_controls, slap_controls,
                                   strip_controls)
-from qoc_b200.core.plan import extract_hamiltonian_structure
+from qoc_b200.core.plan import extract_hamiltonian_structure, extract_time_dependent_structure, _NODES
 from qoc_b200.models import MagnusPolicy, InterpolationPolicy, ProgramType
 from tests.problems import Problem, load_golden
 
@@ -156,6 +156,44 @@ def test_hamiltonian_structure_extraction():
         extract_hamiltonian_structure(lambda c, t: pr.h0 + t * c[0] * pr.drives[0], 3, False, pr.T)
     with pytest.raises(NotImplementedError):
         extract_hamiltonian_structure(lambda c, t: pr.h0 * np.cos(t), 0, False, pr.T)
+
+
+@pytest.mark.parametrize("cc,order", [(False, 2), (True, 4), (False, 6)])
+def test_time_dependent_structure_extraction(cc, order):
+    """a hamiltonian that uses its `time` argument is expanded over operator channels with per-node coefficients affine
+    in the controls; the expansion reproduces the callable at every Magnus node"""
+    p = Problem(6, 9, 2, 1, order, complex_controls=cc, seed=5)
+    ham = p.hamiltonian_td_numpy()
+    st = extract_hamiltonian_structure(ham, 2, cc, p.T, system_eval_count=p.N, magnus_order=order)
+    assert len(st) == 4
+    g0, ch, off, gain = st
+    q = order // 2
+    KR = 4 if cc else 2
+    assert off.shape == (p.N - 1, q, ch.shape[0]) and gain.shape == (p.N - 1, q, ch.shape[0], KR)
+    assert ch.shape[0] == 1 + 2 * 2                    # cos(w0 t) D, and a shared (cos, sin) pair per drive (real span)
+    rng = np.random.default_rng(0)
+    dt = p.T / (p.N - 1)
+    for j in (0, 3, p.N - 2):
+        for i, c in enumerate(_NODES[q]):
+            u = rng.standard_normal(2) + (1j * rng.standard_normal(2) if cc else 0)
+            x = np.concatenate([u.real, u.imag]) if cc else u
+            coef = off[j, i] + gain[j, i] @ x
+            model = g0 + np.tensordot(coef, ch, axes=(0, 0))
+            assert np.abs(model - ham(u, (j + c) * dt)).max() < 1e-12
+    # without the slice grid the callable cannot be expanded (Lindblad path): fails loudly
+    with pytest.raises(NotImplementedError):
+        extract_hamiltonian_structure(ham, 2, cc, p.T)
+    # non-linear in the controls: still refused
+    with pytest.raises(NotImplementedError):
+        extract_time_dependent_structure(lambda c, t: p.h0 * np.cos(t) + c[0] ** 2 * p.drives[0].real, 2, False, p.T, p.N, order)
+    # too many channels: refused
+    rng = np.random.default_rng(1)
+    mats = rng.standard_normal((40, 6, 6))
+    with pytest.raises(NotImplementedError):
+        extract_time_dependent_structure(lambda c, t: sum(np.cos((k + 1) * t) * mats[k] for k in range(40)), 0, False, p.T, 41, order)
+    # a time-dependent drift without controls
+    st0 = extract_hamiltonian_structure(lambda c, t: p.h0 * np.cos(0.1 * t), 0, False, p.T, system_eval_count=p.N, magnus_order=order)
+    assert len(st0) == 4 and st0[1].shape[0] == 1 and st0[3].shape[-1] == 0
 
 
 def test_constants_and_enums():
