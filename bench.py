@@ -336,6 +336,9 @@ def run_b200(args, name):
         achieved = dom_flops / (ms_per_step * 1e-3) / 1e12
         dom_name = "whole evaluation incl. NCCL exchange (per GPU)"
         stage_ms = {"total": ms_per_step}
+        if os.environ.get("QOCB_STAGE_TIMING") == "1":          # diagnostics run (rank 0's clock, extra events on the stream)
+            sn = ["forward_local", "gather_P", "forward_finish", "backward_particular", "gather_b", "backward_finish", "pack_reduce"]
+            stage_ms.update({k: float(v) / args.steps for k, v in zip(sn, stages[1:])})
     out = {"metric": "grape_cost_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",

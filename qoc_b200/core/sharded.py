@@ -19,6 +19,7 @@ engine-agnostic: `CudaShardEngine` runs the phases on a B200, tests plug a NumPy
 protocol at world_size 2 on CPU.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -129,17 +130,26 @@ class TorchDistComm(object):
         self.dist.all_reduce(t, group=self.group)
 
 
-def sharded_evaluate(engine, comm, all_p, all_b, with_grad):
-    """the protocol of the module docstring for one rank; returns the all-reduced result tensor (device)."""
+def sharded_evaluate(engine, comm, all_p, all_b, with_grad, mark=None):
+    """the protocol of the module docstring for one rank; returns the all-reduced result tensor (device).
+    mark: optional callable invoked after every phase (stage timing)."""
+    mark = mark or (lambda: None)
     p_loc = engine.forward_local(with_grad)
+    mark()
     comm.all_gather(all_p, p_loc)
+    mark()
     engine.forward_finish(all_p)
+    mark()
     if with_grad:
         b_loc = engine.backward_particular()
+        mark()
         comm.all_gather(all_b, b_loc)
+        mark()
         engine.backward_finish(all_p, all_b)
+        mark()
     res = engine.pack_result(with_grad)
     comm.all_reduce_sum(res)
+    mark()
     return res
 
 
@@ -203,17 +213,28 @@ class ShardedSchroedingerPlan(object):
             self._run(with_grad)
         e.stream.synchronize()
         total = 0.0
+        stages = np.zeros(8)
+        stage_timing = os.environ.get("QOCB_STAGE_TIMING") == "1"      # extra events: diagnostics, not for bench numbers
         for _ in range(iters):
             if flush_l2:
                 e.flush_l2()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            evs = []
+
+            def mark():
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                evs.append(ev)
             with torch.cuda.stream(e.stream):
                 t0.record()
-                sharded_evaluate(e, self.comm, self.all_p, self.all_b, with_grad)
+                sharded_evaluate(e, self.comm, self.all_p, self.all_b, with_grad, mark if stage_timing else None)
                 t1.record()
             e.stream.synchronize()
             total += t0.elapsed_time(t1)
-        stages = np.zeros(8)
+            prev = t0
+            for i, ev in enumerate(evs):         # forward_local, gather P, forward_finish, particular, gather b, finish, pack+reduce
+                stages[1 + i] += prev.elapsed_time(ev)
+                prev = ev
         stages[0] = total
         return total, stages
 

@@ -276,6 +276,35 @@ __global__ void __launch_bounds__(C::NT) k_reduce_props(const double *in, double
     for_owned<C>([&](int ii, int jj, int row, int col) { stg2<C>(dst, row, col, accv<C>(acc, ii, jj)); });
 }
 
+// radix-R version for the tail of the tree (shard propagator): out[i] = in[R i + R - 1] ... in[R i + 1] in[R i], the
+// products chained inside one CTA - fewer dependent launches than the pairwise tree when only the root is wanted
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_reduce_props_radix(const double *in, double *out, int count, int R) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<C> sm(smem_raw);
+    const int first = blockIdx.x * R, last = min(count, first + R);
+    double *dst = out + (size_t)blockIdx.x * C::GMAT;
+    if (last - first == 1) {
+        const double *lo = in + (size_t)first * C::GMAT;
+        for (int idx = threadIdx.x; idx < C::GMAT / 2; idx += C::NT)
+            reinterpret_cast<double2 *>(dst)[idx] = reinterpret_cast<const double2 *>(lo)[idx];
+        return;
+    }
+    g2s<C>(sm.X0, in + (size_t)first * C::GMAT);
+    for (int k = first + 1; k < last; ++k) {
+        g2s<C>(sm.X1, in + (size_t)k * C::GMAT);
+        __syncthreads();
+        Acc<C> acc; acc.zero();
+        mma_smem<C, false, false, false>(acc, sm.X1, sm.X0);
+        if (k + 1 == last) {
+            for_owned<C>([&](int ii, int jj, int row, int col) { stg2<C>(dst, row, col, accv<C>(acc, ii, jj)); });
+        } else {
+            __syncthreads();
+            for_owned<C>([&](int ii, int jj, int row, int col) { sts2<C>(sm.X0, row, col, accv<C>(acc, ii, jj)); });
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 int pad_dim(int n) {
     if (n <= 8) return 8;
@@ -367,6 +396,7 @@ struct qocb_plan {
     // controls and gradients crossing the ABI keep pb.control_count real channels
     int KC = 0;
     bool mapped = false, map_set = false;
+    bool particular_fresh = false;      // sharded: the boundary costates of this evaluation's particular pass are in `lam`
     // sweep coarsening: the state / costate sweeps run on chunks merged pairwise `levels` times (propagator tree);
     // lvl_count[l] chunks at level l, their propagators at lvlP + lvl_off[l] matrices, boundaries at cb_lvl + cb_off[l]
     int levels = 0, lvl_count[16] = {}, lvl_off[16] = {}, cb_off[16] = {};
@@ -400,7 +430,6 @@ void set_error(qocb_plan *plan, const char *msg) {
     if (plan) plan->err = msg;
     g_last_error = msg;
 }
-void set_error(const qocb_plan *plan, const char *msg) { set_error(const_cast<qocb_plan *>(plan), msg); }
 
 template <class C> int launch_forward(qocb_plan *p, const KArgs &a) {
     CU_TRY(p, cudaFuncSetAttribute(k_forward<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
@@ -513,6 +542,13 @@ int upload_costs(qocb_plan *p) {
 template <class C> int launch_reduce(qocb_plan *p, const double *in, double *out, int count) {
     CU_TRY(p, cudaFuncSetAttribute(k_reduce_props<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
     k_reduce_props<C><<<(count + 1) / 2, C::NT, Smem<C>::bytes(), p->stream>>>(in, out, count);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+template <class C> int launch_reduce_radix(qocb_plan *p, const double *in, double *out, int count, int R) {
+    CU_TRY(p, cudaFuncSetAttribute(k_reduce_props_radix<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
+    k_reduce_props_radix<C><<<(count + R - 1) / R, C::NT, Smem<C>::bytes(), p->stream>>>(in, out, count, R);
     CU_TRY(p, cudaGetLastError());
     return 0;
 }
@@ -978,12 +1014,12 @@ int lg_states_forward(qocb_plan *p, const double *psi_in_dev) {
     return 0;
 }
 
-int lg_costates(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, bool do_particular, bool do_sweeps) {
+int lg_costates(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, bool do_particular, bool do_sweeps, bool do_boundary = true) {
     LgSweep g = lg_sweep_args(p);
     g.a.lam_in = lam_in_dev; g.a.b_out = b_out_dev;
     const size_t sm = lg_sweep_smem(p);
     if (do_particular && p->have_step_costs) k_lg_sweep_bwd<true><<<g.nchunks, kLgThreads, sm, p->stream>>>(g);
-    k_lg_boundary_bwd<<<1, kLgThreads, sm, p->stream>>>(g, p->have_step_costs ? 1 : 0);
+    if (do_boundary) k_lg_boundary_bwd<<<1, kLgThreads, sm, p->stream>>>(g, p->have_step_costs ? 1 : 0);
     if (do_sweeps) k_lg_sweep_bwd<false><<<g.nchunks, kLgThreads, sm, p->stream>>>(g);
     CU_TRY(p, cudaGetLastError());
     return 0;
@@ -1054,11 +1090,13 @@ int enqueue_shard_propagator(qocb_plan *p, double *out_dev) {
         CU_TRY(p, cudaMemcpyAsync(out_dev, in, sizeof(double) * GM, cudaMemcpyDeviceToDevice, p->stream));
         return 0;
     }
+    const int R = 4;                                                 // 148 chunks: 148 -> 37 -> 10 -> 3 -> 1
     while (count > 1) {
-        double *out = (count <= 2) ? out_dev : bufs[which];
-        int rc = reduce_level(p, in, out, count);
+        double *out = (count <= R) ? out_dev : bufs[which];
+        int rc = dispatch(p->NP, [&] { return launch_reduce_radix<C8>(p, in, out, count, R); }, [&] { return launch_reduce_radix<C16>(p, in, out, count, R); },
+                          [&] { return launch_reduce_radix<C32>(p, in, out, count, R); }, [&] { return launch_reduce_radix<C64>(p, in, out, count, R); });
         if (rc) return rc;
-        in = out; count = (count + 1) / 2; which ^= 1;
+        in = out; count = (count + R - 1) / R; which ^= 1;
     }
     return 0;
 }
@@ -1077,13 +1115,13 @@ int enqueue_state_forward(qocb_plan *p, const double *psi_in_dev, cudaEvent_t mi
 
 // costate pass.  particular_only: chunk particular parts (if step costs) + boundary pass with `lam_in_dev`
 // (nullptr = zero) writing the costate at the first local state to b_out_dev; otherwise also the local sweeps.
-int enqueue_costate(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, bool do_particular, bool do_sweeps) {
+int enqueue_costate(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, bool do_particular, bool do_sweeps, bool do_boundary = true) {
     SweepArgs sa = make_sargs(p);
     sa.lam_in = lam_in_dev; sa.b_out = b_out_dev;
     const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
     if (do_particular && p->have_step_costs) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, true><<<p->lvl_count[p->levels], kSweepThreads, sw_smem, p->stream>>>(sa)));
     const dim3 bgrid(sa.E, boundary_state_groups(p));
-    SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<bgrid, kSweepThreads, sw_smem, p->stream>>>(sa, p->have_step_costs ? 1 : 0)));
+    if (do_boundary) SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<bgrid, kSweepThreads, sw_smem, p->stream>>>(sa, p->have_step_costs ? 1 : 0)));
     if (do_sweeps) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, false><<<p->lvl_count[p->levels], kSweepThreads, sw_smem, p->stream>>>(sa)));
     CU_TRY(p, cudaGetLastError());
     return 0;
@@ -1723,10 +1761,12 @@ static int launch_count_unmapped(qocb_plan *p, int32_t with_grad) {
         return batches * (fwd + (with_grad ? fwd + (o == 6 ? 60 : o == 4 ? 38 : 30) : 0)) + (with_grad ? 3 : 1);
     }
     if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->levels;
-    int levels = 0;
-    for (int c = p->nchunks; c > 1; c = (c + 1) / 2) ++levels;
-    // forward: expm, tree, prefix, boundary, sweep; backward: [particular], boundary, suffix, boundary, sweep, expm, gather, finalize, pack
-    return with_grad ? 1 + levels + 3 + (p->have_step_costs ? 1 : 0) + 8 : 1 + levels + 3 + 2;
+    int levels = p->levels;                                          // pairwise levels for the sweeps, then radix 4 to the root
+    for (int c = p->lvl_count[p->levels]; c > 1; c = (c + 3) / 4) ++levels;
+    // forward: expm, tree, prefix, boundary, sweep; backward: [particular sweeps], boundary (twice only with step costs on a
+    // shard that is not the last), suffix, sweep, expm, gather, finalize, pack
+    const int nb = (p->have_step_costs && !p->owns_final) ? 2 : 1;
+    return with_grad ? 1 + levels + 3 + (p->have_step_costs ? 1 : 0) + nb + 6 : 1 + levels + 3 + 2;
 }
 
 int qocb_time_resident(qocb_plan *p, int32_t with_grad, int32_t warmup, int32_t iters, int32_t flush_l2,
@@ -1772,6 +1812,7 @@ int qocb_shard_forward_local(qocb_plan *p, int32_t with_grad, double *shardP_dev
     if (!p->sharded) { set_error(p, "plan has no slice range"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
     int rc = ready(p); if (rc) return rc;
+    p->particular_fresh = false;
     if (p->large) {
         rc = lg_expm_all(p); if (rc) return rc;
         return lg_shard_propagator(p, reinterpret_cast<double2 *>(shardP_dev));
@@ -1789,7 +1830,7 @@ int qocb_shard_forward_finish(qocb_plan *p, const double *allP_dev, int32_t rank
         CU_TRY(p, cudaGetLastError());
         return lg_states_forward(p, p->psi_in.p);
     }
-    const size_t sm = sweep_smem_bytes(p->NP, p->pb.state_count, p->ip_total);
+    const size_t sm = prefix_smem_bytes(p->NP, p->pb.state_count);
     SWEEP_NP(p->NP, (k_prefix_states<NPc><<<1, kSweepThreads, sm, p->stream>>>(allP_dev, p->psi0.p, p->psi_in.p, rank, p->pb.state_count)));
     CU_TRY(p, cudaGetLastError());
     int rc = enqueue_state_forward(p, p->psi_in.p, nullptr); if (rc) return rc;
@@ -1799,6 +1840,12 @@ int qocb_shard_forward_finish(qocb_plan *p, const double *allP_dev, int32_t rank
 int qocb_shard_backward_particular(qocb_plan *p, double *b_dev) {
     if (!p || !b_dev) { set_error(p, "null argument"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
+    // without step costs a shard that does not hold the final state has no particular part: b = 0, nothing to run
+    if (!p->have_step_costs && !p->owns_final) {
+        CU_TRY(p, cudaMemsetAsync(b_dev, 0, sizeof(double) * (size_t)qocb_shard_vector_doubles(p), p->stream));
+        return 0;
+    }
+    p->particular_fresh = true;
     if (p->large) return lg_costates(p, nullptr, b_dev, true, false);
     return enqueue_costate(p, nullptr, b_dev, true, false);
 }
@@ -1806,19 +1853,22 @@ int qocb_shard_backward_particular(qocb_plan *p, double *b_dev) {
 int qocb_shard_backward_finish(qocb_plan *p, const double *allP_dev, const double *allb_dev, int32_t rank, int32_t world) {
     if (!p || !allP_dev || !allb_dev || rank < 0 || rank >= world) { set_error(p, "bad argument"); return -1; }
     CU_TRY(p, cudaSetDevice(p->pb.device));
+    // the last shard receives a zero costate: its boundary costates are those of the particular pass already in `lam`
+    const bool reuse = rank == world - 1 && p->owns_final && p->particular_fresh;
+    p->particular_fresh = false;
     if (p->large) {
         LargeImpl *L = p->large;
         if (L->allPT.n < (size_t)world * L->nn) CU_TRY(p, L->allPT.alloc((size_t)world * L->nn));
         k_lg_transpose<<<world * 64, dim3(16, 16), 0, p->stream>>>(L->allPT.p, reinterpret_cast<const double2 *>(allP_dev), L->n, world);
         k_lg_suffix<<<1, kLgThreads, lg_sweep_smem(p), p->stream>>>(L->allPT.p, allb_dev, p->lam_in.p, rank, world, L->n, p->pb.state_count);
         CU_TRY(p, cudaGetLastError());
-        int rc = lg_costates(p, p->lam_in.p, nullptr, false, true); if (rc) return rc;
+        int rc = lg_costates(p, p->lam_in.p, nullptr, false, true, !reuse); if (rc) return rc;
         return lg_backward_all(p);
     }
-    const size_t sm = sweep_smem_bytes(p->NP, p->pb.state_count, p->ip_total);
+    const size_t sm = prefix_smem_bytes(p->NP, p->pb.state_count);
     SWEEP_NP(p->NP, (k_suffix_costates<NPc><<<1, kSweepThreads, sm, p->stream>>>(allP_dev, allb_dev, p->lam_in.p, rank, world, p->pb.state_count)));
     CU_TRY(p, cudaGetLastError());
-    int rc = enqueue_costate(p, p->lam_in.p, nullptr, false, true); if (rc) return rc;
+    int rc = enqueue_costate(p, p->lam_in.p, nullptr, false, true, !reuse); if (rc) return rc;
     return enqueue_expm_backward(p, nullptr);
 }
 

@@ -77,7 +77,93 @@ __device__ __forceinline__ void prefetch_mat(double *sU, const double *gU) {
     }
 }
 
-// out[s][a] = sum_b U[a][b] in[s][b]   (TRANS: sum_b U[b][a] in[s][b]); vectors planar [s][2][NP] in shared memory
+// ---- mat-vec of the sweeps ---------------------------------------------------------------------------------------------
+// out[s][a] = sum_b U[a][b] in[s][b]   (TRANS: sum_b U[b][a] in[s][b]); vectors planar [s][2][NP] in shared memory.
+// Every element of a propagator is used exactly once per state, so the matrix is NOT staged through shared memory:
+// each thread loads the KPT elements it owns straight from global memory (L2) into registers - for the NEXT step while
+// the current one computes (`MatRegs` double buffer in the kernels) - and uses them for up to four states at a time.
+// Staging cost per 64 x 64 step measured before: 0.55 us of LDGSTS issue (or 1.0 us of per-row bulk copies) plus a
+// shared-memory-bandwidth-bound 0.95 us mat-vec; the sequential boundary passes are chains of exactly these steps.
+//   U v  : thread -> (row a = t / KS, k-part ks = t % KS), columns b = ks + KS i: KS consecutive lanes read KS
+//          consecutive doubles (full 32-byte sectors) and combine their partial sums by shuffles;
+//   U^T v: thread -> (column a = t % NP, k-part ks = t / NP), rows b = ks + KS i: a warp reads consecutive doubles of
+//          one row; the KS partial sums of a column live in different warps and are combined through `red`
+//          (shared scratch, kMvGroup * KS * 2 * NP doubles).
+template <int NP> struct MvMap {
+    static constexpr int KS0 = kSweepThreads / NP;
+    static constexpr int KS = KS0 > 32 ? (NP < 32 ? NP : 32) : (KS0 > NP ? NP : KS0);
+    static constexpr int KPT = NP / KS, ACTIVE = NP * KS;
+};
+constexpr int kMvGroup = 4;                      // states per pass over the registers
+
+template <int NP> struct MatRegs { double r[MvMap<NP>::KPT], i[MvMap<NP>::KPT]; };
+
+template <int NP, bool TRANS>
+__device__ __forceinline__ void load_mat_regs(MatRegs<NP> &m, const double *__restrict__ g) {
+    constexpr int KS = MvMap<NP>::KS, KPT = MvMap<NP>::KPT;
+    const int t = threadIdx.x;
+    if (t >= MvMap<NP>::ACTIVE) return;
+    const int a = TRANS ? t % NP : t / KS, ks = TRANS ? t / NP : t % KS;
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        const int b = ks + KS * i;
+        const int idx = TRANS ? b * NP + a : a * NP + b;
+        m.r[i] = __ldg(g + idx);
+        m.i[i] = __ldg(g + NP * NP + idx);
+    }
+}
+
+// all threads call (TRANS contains a barrier); `in` must be complete and `out` free before the call
+template <int NP, bool TRANS>
+__device__ __forceinline__ void matvec_regs(double *out, const double *in, const MatRegs<NP> &m, int S, double *red) {
+    constexpr int KS = MvMap<NP>::KS, KPT = MvMap<NP>::KPT;
+    const int t = threadIdx.x;
+    const bool active = t < MvMap<NP>::ACTIVE;
+    const int a = TRANS ? t % NP : t / KS, ks = TRANS ? t / NP : t % KS;
+    for (int s0 = 0; s0 < S; s0 += kMvGroup) {
+        const int sc = min(kMvGroup, S - s0);
+        if (active) {
+#pragma unroll
+            for (int g = 0; g < kMvGroup; ++g) {
+                if (g < sc) {
+                    const double *vr = in + (s0 + g) * 2 * NP, *vi = vr + NP;
+                    double re = 0., im = 0.;
+#pragma unroll
+                    for (int i = 0; i < KPT; ++i) {
+                        const double br = vr[ks + KS * i], bi = vi[ks + KS * i];
+                        re = fma(m.r[i], br, re); re = fma(-m.i[i], bi, re);
+                        im = fma(m.r[i], bi, im); im = fma(m.i[i], br, im);
+                    }
+                    if (TRANS) {
+                        red[(g * KS + ks) * 2 * NP + a] = re;
+                        red[(g * KS + ks) * 2 * NP + NP + a] = im;
+                    } else {
+#pragma unroll
+                        for (int o = KS / 2; o > 0; o >>= 1) {
+                            re += __shfl_xor_sync(0xffffffffu, re, o);
+                            im += __shfl_xor_sync(0xffffffffu, im, o);
+                        }
+                        if (ks == 0) { out[(s0 + g) * 2 * NP + a] = re; out[(s0 + g) * 2 * NP + NP + a] = im; }
+                    }
+                }
+            }
+        }
+        if (TRANS) {
+            __syncthreads();
+            for (int o = t; o < sc * 2 * NP; o += kSweepThreads) {
+                const int g = o / (2 * NP), x = o % (2 * NP);
+                double v = 0.;
+#pragma unroll
+                for (int k = 0; k < KS; ++k) v += red[(g * KS + k) * 2 * NP + x];
+                out[(s0 + g) * 2 * NP + x] = v;
+            }
+            if (s0 + kMvGroup < S) __syncthreads();             // `red` is reused by the next group
+        }
+    }
+}
+
+// shared-memory variant (matrix staged by prefetch_mat, row stride NP + 2): used by the short prefix / suffix kernels of
+// the time-sharded path.  Two lanes per output split the dot product.
 template <int NP, bool TRANS>
 __device__ __forceinline__ void matvec_smem(double *out, const double *in, const double *sU, int S) {
     constexpr int LDS = SwL<NP>::LDS, PL = SwL<NP>::PL;
@@ -202,16 +288,26 @@ __device__ void cost_add_seed(const SweepArgs &a, const double *ip, double *lam,
     __syncthreads();
 }
 
-// dynamic smem layout of the sweep kernels: U x 2 (double buffer) | v0 (S*2*NP) | v1 (S*2*NP) | ip (2*ip_total)
+// dynamic smem layout of the sweep kernels: red (U^T v partial sums) | v0 (S*2*NP) | v1 (S*2*NP) | ip (2*ip_total)
+__host__ __device__ inline size_t sweep_red_doubles(int NP) {
+    const int ks0 = kSweepThreads / NP;
+    const int ks = ks0 > 32 ? (NP < 32 ? NP : 32) : (ks0 > NP ? NP : ks0);       // MvMap<NP>::KS
+    return (size_t)kMvGroup * ks * 2 * NP;
+}
 __host__ __device__ inline size_t sweep_smem_bytes(int NP, int S, int ip_total) {
-    return sizeof(double) * ((size_t)4 * NP * (NP + 2) + (size_t)4 * S * NP + (size_t)2 * (ip_total > 0 ? ip_total : 1));
+    return sizeof(double) * (sweep_red_doubles(NP) + (size_t)4 * S * NP + (size_t)2 * (ip_total > 0 ? ip_total : 1));
+}
+// prefix / suffix kernels of the time-sharded path: U (padded) | v0 | v1
+__host__ __device__ inline size_t prefix_smem_bytes(int NP, int S) {
+    return sizeof(double) * ((size_t)2 * NP * (NP + 2) + (size_t)4 * S * NP);
 }
 
 template <int NP> struct SweepSmem {
-    double *U[2], *v0, *v1, *ip;
+    double *red, *v0, *v1, *ip;
+    // S: states held by this CTA
     __device__ __forceinline__ SweepSmem(double *sm, int S) {
-        U[0] = sm; U[1] = sm + SwL<NP>::MAT;
-        v0 = sm + 2 * SwL<NP>::MAT; v1 = v0 + S * 2 * NP; ip = v1 + S * 2 * NP;
+        red = sm;
+        v0 = sm + kMvGroup * MvMap<NP>::KS * 2 * NP; v1 = v0 + S * 2 * NP; ip = v1 + S * 2 * NP;
     }
     __device__ __forceinline__ void swap() { double *t = v0; v0 = v1; v1 = t; }
 };
@@ -219,6 +315,14 @@ template <int NP> struct SweepSmem {
 // (1) boundary states: psi[b_{c+1}] = P_c psi[b_c], sequential over the chunks of one member; grid = (E, state groups):
 // the pass is a chain of dependent mat-vecs whose per-step time is bound by reading the 32 n^2-byte propagator once per
 // state from shared memory, so the states are spread over CTAs (no coupling between states in this pass)
+#ifdef QOCB_PROFILE
+#define BPROF_DECL long long bpt__ = clock64();
+#define BPROF(id) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { const long long t__ = clock64(); g_prof[id] += t__ - bpt__; bpt__ = t__; } } while (0)
+#else
+#define BPROF_DECL
+#define BPROF(id) do { } while (0)
+#endif
+
 template <int NP>
 __global__ void __launch_bounds__(kSweepThreads) k_boundary_fwd(SweepArgs a) {
     extern __shared__ __align__(16) double sm_raw[];
@@ -228,24 +332,29 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_fwd(SweepArgs a) {
     SweepSmem<NP> sm(sm_raw, S);
     const int e = blockIdx.x;
     const int c0 = a.member_chunk0[e], c1 = a.member_chunk0[e + 1];
-    prefetch_mat<NP>(sm.U[0], a.chunkP + (size_t)c0 * 2 * NP * NP);
-    cp_async_commit();
+    MatRegs<NP> cur = {}, nxt = {};
+    load_mat_regs<NP, false>(cur, a.chunkP + (size_t)c0 * 2 * NP * NP);
     for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = a.psi_in[off + i];
     double *psi_e = a.psi + (size_t)e * a.N * VSA + off;
     for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[i] = a.psi_in[off + i];
+    BPROF_DECL
     for (int c = c0; c < c1; ++c) {
-        const int buf = (c - c0) & 1;
-        if (c + 1 < c1) prefetch_mat<NP>(sm.U[buf ^ 1], a.chunkP + (size_t)(c + 1) * 2 * NP * NP);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        matvec_smem<NP, false>(sm.v1, sm.v0, sm.U[buf], S);
-        __syncthreads();
+        if (c + 1 < c1) load_mat_regs<NP, false>(nxt, a.chunkP + (size_t)(c + 1) * 2 * NP * NP);
         const int kend = a.chunk_begin[c + 1] - e * (a.N - 1);      // state index at the end of chunk c
+        BPROF(20);
+        __syncthreads();                                            // v0 is complete
+        BPROF(21);
+        matvec_regs<NP, false>(sm.v1, sm.v0, cur, S, sm.red);
+        __syncthreads();
+        BPROF(22);
         for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[(size_t)kend * VSA + i] = sm.v1[i];
         sm.swap();
+        cur = nxt;
+        BPROF(23);
+#ifdef QOCB_PROFILE
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_prof[24] += 1;
+#endif
     }
-    cp_async_wait<0>();
 }
 
 // (2) local forward sweeps + cost values; grid = nchunks
@@ -259,20 +368,16 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_fwd(SweepArgs a) {
     const int e = wb / (a.N - 1), jb = wb - e * (a.N - 1), je = we - e * (a.N - 1);
     const double *gU = a.U + (size_t)(e * (a.N - 1)) * 2 * NP * NP;
     double *psi_e = a.psi + (size_t)e * a.N * VS;
-    if (jb + 1 < je) prefetch_mat<NP>(sm.U[0], gU + (size_t)jb * 2 * NP * NP);
-    cp_async_commit();
+    MatRegs<NP> cur = {}, nxt = {};
+    load_mat_regs<NP, false>(cur, gU + (size_t)jb * 2 * NP * NP);
     for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = psi_e[(size_t)jb * VS + i];
     __syncthreads();
     double cost = 0.;
     for (int j = jb; j < je; ++j) {
         const int k = j + 1;                                          // state produced by slice j
-        const int buf = (j - jb) & 1;
         if (k < je) {
-            if (k + 1 < je) prefetch_mat<NP>(sm.U[buf ^ 1], gU + (size_t)k * 2 * NP * NP);
-            cp_async_commit();
-            cp_async_wait<1>();
-            __syncthreads();
-            matvec_smem<NP, false>(sm.v1, sm.v0, sm.U[buf], S);
+            if (k + 1 < je) load_mat_regs<NP, false>(nxt, gU + (size_t)k * 2 * NP * NP);
+            matvec_regs<NP, false>(sm.v1, sm.v0, cur, S, sm.red);
             __syncthreads();
             for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[(size_t)k * VS + i] = sm.v1[i];
         } else {
@@ -285,9 +390,9 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_fwd(SweepArgs a) {
             cost += cost_value(a, sm.ip, st, fin);
         }
         sm.swap();
+        cur = nxt;
         __syncthreads();
     }
-    cp_async_wait<0>();
     if (threadIdx.x == 0) a.cost_part[c] = cost;
 }
 
@@ -305,17 +410,13 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_bwd(SweepArgs a) {
     const double *psi_e = a.psi + (size_t)e * a.N * VS;
     double *lam_e = a.lam + (size_t)e * a.N * VS;
     const int jstop = PARTICULAR ? jb : jb + 1;
-    if (je - 1 >= jstop) prefetch_mat<NP>(sm.U[0], gU + (size_t)(je - 1) * 2 * NP * NP);
-    cp_async_commit();
+    MatRegs<NP> cur = {}, nxt = {};
+    load_mat_regs<NP, true>(cur, gU + (size_t)(je - 1) * 2 * NP * NP);
     for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = PARTICULAR ? 0. : lam_e[(size_t)je * VS + i];
     __syncthreads();
     for (int j = je - 1; j >= jstop; --j) {
-        const int buf = (je - 1 - j) & 1;
-        if (j - 1 >= jstop) prefetch_mat<NP>(sm.U[buf ^ 1], gU + (size_t)(j - 1) * 2 * NP * NP);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        matvec_smem<NP, true>(sm.v1, sm.v0, sm.U[buf], S);            // lam_j = U_j^T lam_{j+1}
+        if (j - 1 >= jstop) load_mat_regs<NP, true>(nxt, gU + (size_t)(j - 1) * 2 * NP * NP);
+        matvec_regs<NP, true>(sm.v1, sm.v0, cur, S, sm.red);          // lam_j = U_j^T lam_{j+1}
         __syncthreads();
         const bool st = is_step_cost_state(j + a.j_off, a.ces);
         if (a.nterms > 0 && st) {                                     // + seed_j (state j < N-1: step costs only)
@@ -325,9 +426,9 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_bwd(SweepArgs a) {
         if (!PARTICULAR)
             for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)j * VS + i] = sm.v1[i];
         sm.swap();
+        cur = nxt;
         __syncthreads();
     }
-    cp_async_wait<0>();
     if (PARTICULAR)
         for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.part[(size_t)c * VS + i] = sm.v0[i];
 }
@@ -345,8 +446,8 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_bwd(SweepArgs a, int
     const int c0 = a.member_chunk0[e], c1 = a.member_chunk0[e + 1];
     const double *psi_e = a.psi + (size_t)e * a.N * VSA;
     double *lam_e = a.lam + (size_t)e * a.N * VSA + off;
-    prefetch_mat<NP>(sm.U[0], a.chunkP + (size_t)(c1 - 1) * 2 * NP * NP);
-    cp_async_commit();
+    MatRegs<NP> cur = {}, nxt = {};
+    load_mat_regs<NP, true>(cur, a.chunkP + (size_t)(c1 - 1) * 2 * NP * NP);
     for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = a.lam_in ? a.lam_in[off + i] : 0.;
     __syncthreads();
     if (a.nterms > 0 && a.add_final_seed) {                         // inner products of ALL states (coherent sums)
@@ -356,25 +457,29 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_bwd(SweepArgs a, int
     }
     for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)(a.N - 1) * VSA + i] = sm.v0[i];
     for (int c = c1 - 1; c >= c0; --c) {
-        const int buf = (c1 - 1 - c) & 1;
-        if (c - 1 >= c0) prefetch_mat<NP>(sm.U[buf ^ 1], a.chunkP + (size_t)(c - 1) * 2 * NP * NP);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        matvec_smem<NP, true>(sm.v1, sm.v0, sm.U[buf], S);
-        __syncthreads();
-        if (have_part)
-            for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v1[i] += a.part[(size_t)c * VSA + off + i];
+        if (c - 1 >= c0) load_mat_regs<NP, true>(nxt, a.chunkP + (size_t)(c - 1) * 2 * NP * NP);
         const int kbeg = a.chunk_begin[c] - e * (a.N - 1);
         __syncthreads();
+        matvec_regs<NP, true>(sm.v1, sm.v0, cur, S, sm.red);
+        __syncthreads();
+        if (have_part) {
+            for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v1[i] += a.part[(size_t)c * VSA + off + i];
+            __syncthreads();
+        }
         for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)kbeg * VSA + i] = sm.v1[i];
         sm.swap();
+        cur = nxt;
     }
-    cp_async_wait<0>();
     __syncthreads();
     if (a.b_out && e == 0)
         for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.b_out[off + i] = sm.v0[i];
 }
+
+template <int NP> struct PrefixSmem {
+    double *U[1], *v0, *v1;
+    __device__ __forceinline__ PrefixSmem(double *sm, int S) { U[0] = sm; v0 = sm + SwL<NP>::MAT; v1 = v0 + S * 2 * NP; }
+    __device__ __forceinline__ void swap() { double *t = v0; v0 = v1; v1 = t; }
+};
 
 // time sharding: state entering shard `rank` = P_{rank-1} ... P_0 psi0 (allP: [world][2*NP*NP]); grid = 1
 template <int NP>
@@ -382,7 +487,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_prefix_states(const double *a
                                                                  int rank, int S) {
     extern __shared__ __align__(16) double sm_raw[];
     const int VS = S * 2 * NP;
-    SweepSmem<NP> sm(sm_raw, S);
+    PrefixSmem<NP> sm(sm_raw, S);
     for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = psi0[i];
     __syncthreads();
     for (int r = 0; r < rank; ++r) {
@@ -404,7 +509,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_suffix_costates(const double 
                                                                    int rank, int world, int S) {
     extern __shared__ __align__(16) double sm_raw[];
     const int VS = S * 2 * NP;
-    SweepSmem<NP> sm(sm_raw, S);
+    PrefixSmem<NP> sm(sm_raw, S);
     for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = 0.;
     __syncthreads();
     for (int r = world - 1; r > rank; --r) {

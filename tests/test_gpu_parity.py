@@ -284,8 +284,8 @@ def test_errors_are_loud():
         Plan(lambda c, t: p.h0 + c[0] ** 2 * p.drives[0], p.initial_states, [], p.T, p.N, control_eval_count=p.M,
              control_count=1, magnus_policy=pol[2])
     with pytest.raises(NotImplementedError):
-        Plan(lambda c, t: p.h0 * (1 + t) + c[0] * p.drives[0], p.initial_states, [], p.T, p.N, control_eval_count=p.M,
-             control_count=1, magnus_policy=pol[2])
+        Plan(lambda c, t: p.h0 * (1 + t) + np.sin(c[0] * t) * p.drives[0], p.initial_states, [], p.T, p.N, control_eval_count=p.M,
+             control_count=1, magnus_policy=pol[2])          # time-dependent AND non-linear in the controls
 
 
 EDGE = [

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-phase clock64 breakdown of the expm kernels (CTA 0) on a B200.  Builds a -DQOCB_PROFILE variant of the
-library into gpurun_out/ (never the shipped .so), runs a workload and prints microseconds per slice and phase.
+library into build/ (never the shipped .so; `--build-only` compiles it ahead of a GPU call), runs a workload and prints microseconds per slice and phase.
 Usage (on the GPU box): python tools/phase_profile.py [workload]"""
 import ctypes
 import os
@@ -9,12 +9,16 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-out = os.path.join(ROOT, "gpurun_out", "libqocb200_prof.so")
+out = os.path.join(ROOT, "build", "libqocb200_prof.so")      # git-ignored, travels with gpurun: build it before the GPU call
 os.makedirs(os.path.dirname(out), exist_ok=True)
 csrc = os.path.join(ROOT, "qoc_b200", "csrc")
-subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DQOCB_PROFILE",
-                "-shared", "-Xcompiler", "-fPIC", "-lcublas", "-o", out, os.path.join(csrc, "capi.cu"), os.path.join(csrc, "lindblad.cu")],
-               check=True)
+srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)]
+if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in srcs):
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DQOCB_PROFILE",
+                    "-shared", "-Xcompiler", "-fPIC", "-lcublas", "-o", out, os.path.join(csrc, "capi.cu"),
+                    os.path.join(csrc, "lindblad.cu")], check=True)
+if "--build-only" in sys.argv:
+    sys.exit(0)
 os.environ["QOCB200_LIB"] = out
 import numpy as np  # noqa: E402
 import bench  # noqa: E402
@@ -23,7 +27,8 @@ from qoc_b200 import _lib  # noqa: E402
 from qoc_b200.core.plan import SchroedingerPlan  # noqa: E402
 from qoc_b200.models import MagnusPolicy  # noqa: E402
 
-name = sys.argv[1] if len(sys.argv) > 1 else "n64_2000_M4"
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+name = args[0] if args else "n64_2000_M4"
 p = bench.make_problem(name)
 pol = {2: MagnusPolicy.M2, 4: MagnusPolicy.M4, 6: MagnusPolicy.M6}
 plan = SchroedingerPlan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M,
@@ -47,3 +52,8 @@ names = {1: "fwd coefs+magnus", 2: "fwd one-norm/scale", 3: "fwd pade polynomial
 print("workload", name, "slices sampled by CTA 0:", int(slices))
 for k in sorted(names):
     print("  %-45s %8.2f us/slice" % (names[k], us[k]))
+
+steps = max(v[24], 1.0)
+print("boundary forward pass (CTA 0,0), per chunk step over %d steps:" % int(steps))
+for k, nm in ((20, "issue prefetch of next propagator"), (21, "wait for current propagator + barrier"), (22, "mat-vec + barrier"), (23, "store boundary state")):
+    print("  %-45s %8.3f us/step" % (nm, v[k] / steps / (ghz * 1e3)))
