@@ -268,25 +268,30 @@ __device__ void lu_panel_warp(double *Q, int *perm, int *piv8, int j0) {
     const bool va = ra < C::NP, vb = TWO && rb < C::NP;
     cplx pa[8], pb[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        pa[c] = va ? cplx{Qr[ra * C::LD + j0 + c], Qi[ra * C::LD + j0 + c]} : cplx{0., 0.};
-        pb[c] = vb ? cplx{Qr[rb * C::LD + j0 + c], Qi[rb * C::LD + j0 + c]} : cplx{0., 0.};
+    for (int c = 0; c < 8; c += 2) {                                // 16-byte accesses: a row's 8 panel entries are contiguous
+        double2 r = make_double2(0., 0.), i = r;
+        if (va) { r = *reinterpret_cast<const double2 *>(Qr + ra * C::LD + j0 + c); i = *reinterpret_cast<const double2 *>(Qi + ra * C::LD + j0 + c); }
+        pa[c] = {r.x, i.x}; pa[c + 1] = {r.y, i.y};
+        r = make_double2(0., 0.); i = r;
+        if (vb) { r = *reinterpret_cast<const double2 *>(Qr + rb * C::LD + j0 + c); i = *reinterpret_cast<const double2 *>(Qi + rb * C::LD + j0 + c); }
+        pb[c] = {r.x, i.x}; pb[c + 1] = {r.y, i.y};
     }
     int posa = ra, posb = rb;
     bool useda = !va, usedb = !vb;
     cplx dinv[8];                                                   // reciprocals of the U diagonal
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int ka = useda ? -1 : __double2hiint(fabs(pa[j].r) + fabs(pa[j].i));
-        const int kb = usedb ? -1 : __double2hiint(fabs(pb[j].r) + fabs(pb[j].i));
-        // smallest POSITION among the maxima, to follow izamax on the swapped matrix
+        // one REDUX finds the pivot and its owner: key = high word of |re| + |im| with its low 6 bits replaced by
+        // 63 - (32 * half + lane).  Magnitudes within 2^-14 of the maximum count as ties (any of them is an admissible
+        // pivot) and go to the smallest row id.
+        const int ka = useda ? -1 : ((__double2hiint(fabs(pa[j].r) + fabs(pa[j].i)) & ~63) | (63 - lane));
+        const int kb = usedb ? -1 : ((__double2hiint(fabs(pb[j].r) + fabs(pb[j].i)) & ~63) | (31 - lane));
         const int kmax = __reduce_max_sync(FULL, max(ka, kb));
-        const int ca = (ka == kmax) ? posa : 0x7fffffff, cb = (kb == kmax) ? posb : 0x7fffffff;
-        const int q = __reduce_min_sync(FULL, min(ca, cb));                 // position of the pivot row
-        const bool mine_a = (!useda && posa == q), mine_b = (!usedb && posb == q);
-        const unsigned ba = __ballot_sync(FULL, mine_a), bb = __ballot_sync(FULL, mine_b);
-        const bool from_a = ba != 0u;
-        const int owner = __ffs(from_a ? ba : bb) - 1;
+        const int id = 63 - (kmax & 63);
+        const bool from_a = id < 32;
+        const int owner = id & 31;
+        const bool mine_a = from_a && lane == owner, mine_b = !from_a && lane == owner;
+        const int q = __shfl_sync(FULL, from_a ? posa : posb, owner);          // position of the pivot row
         cplx u[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -302,7 +307,13 @@ __device__ void lu_panel_warp(double *Q, int *perm, int *piv8, int j0) {
         if (mine_a) { posa = tgt; useda = true; }
         if (mine_b) { posb = tgt; usedb = true; }
         if (lane == 0) { piv8[j] = q; const int tp = perm[tgt]; perm[tgt] = perm[q]; perm[q] = tp; }
-        const double dn = 1.0 / (u[j].r * u[j].r + u[j].i * u[j].i);
+        // 1 / u_jj: hardware reciprocal seed + two Newton steps (the IEEE division sequence is ~3x as many instructions,
+        // and the panel is bound by the instruction issue of this one warp)
+        const double nn = u[j].r * u[j].r + u[j].i * u[j].i;
+        double dn;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(dn) : "d"(nn));
+        dn = fma(dn, fma(-nn, dn, 1.0), dn);
+        dn = fma(dn, fma(-nn, dn, 1.0), dn);
         const cplx inv = {u[j].r * dn, -u[j].i * dn};
         dinv[j] = inv;
         if (!useda) {
@@ -323,41 +334,48 @@ __device__ void lu_panel_warp(double *Q, int *perm, int *piv8, int j0) {
 #endif
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        if (va) { Qr[posa * C::LD + j0 + c] = pa[c].r; Qi[posa * C::LD + j0 + c] = pa[c].i; }
-        if (vb) { Qr[posb * C::LD + j0 + c] = pb[c].r; Qi[posb * C::LD + j0 + c] = pb[c].i; }
+    for (int c = 0; c < 8; c += 2) {
+        if (va) {
+            *reinterpret_cast<double2 *>(Qr + posa * C::LD + j0 + c) = make_double2(pa[c].r, pa[c + 1].r);
+            *reinterpret_cast<double2 *>(Qi + posa * C::LD + j0 + c) = make_double2(pa[c].i, pa[c + 1].i);
+        }
+        if (vb) {
+            *reinterpret_cast<double2 *>(Qr + posb * C::LD + j0 + c) = make_double2(pb[c].r, pb[c + 1].r);
+            *reinterpret_cast<double2 *>(Qi + posb * C::LD + j0 + c) = make_double2(pb[c].i, pb[c + 1].i);
+        }
     }
     __syncwarp();
     // invert the diagonal block's factors: lanes 0-7 one column of inv(L_kk), lanes 8-15 one column of inv(U_kk).
     // Column c of the inverse = substitution applied to e_c; entries above (L) / below (U) the diagonal come out as
     // exact zeros, so the loops are branch-free and fully unrolled (x stays in registers).  Block entries are
     // warp-uniform shared-memory broadcasts.
+    // Right-looking substitution: as soon as x[r] is known every later partial sum is updated with it, so the dependent
+    // chain is one complex multiply-add per row (the row-oriented form chains all terms of a row behind x[r-1]).
     cplx x[8];
     const int c = lane & 7;
     const double *Br = Qr + j0 * C::LD + j0, *Bi = Qi + j0 * C::LD + j0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) x[r] = {(r == c) ? 1.0 : 0.0, 0.0};
     if (lane < 8) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            double sr = (r == c) ? 1.0 : 0.0, si = 0.;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (k < r) {
-                    const double lr = Br[r * C::LD + k], li = Bi[r * C::LD + k];
-                    sr -= lr * x[k].r - li * x[k].i; si -= lr * x[k].i + li * x[k].r;
+            for (int r2 = 0; r2 < 8; ++r2)
+                if (r2 > r) {
+                    const double lr = Br[r2 * C::LD + r], li = Bi[r2 * C::LD + r];
+                    x[r2].r -= lr * x[r].r - li * x[r].i; x[r2].i -= lr * x[r].i + li * x[r].r;
                 }
-            x[r] = {sr, si};
         }
     } else if (lane < 16) {
 #pragma unroll
         for (int r = 7; r >= 0; --r) {
-            double sr = (r == c) ? 1.0 : 0.0, si = 0.;
+            x[r] = cmul(x[r], dinv[r]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (k > r) {
-                    const double ur = Br[r * C::LD + k], ui = Bi[r * C::LD + k];
-                    sr -= ur * x[k].r - ui * x[k].i; si -= ur * x[k].i + ui * x[k].r;
+            for (int r2 = 0; r2 < 8; ++r2)
+                if (r2 < r) {
+                    const double ur = Br[r2 * C::LD + r], ui = Bi[r2 * C::LD + r];
+                    x[r2].r -= ur * x[r].r - ui * x[r].i; x[r2].i -= ur * x[r].i + ui * x[r].r;
                 }
-            x[r] = cmul({sr, si}, dinv[r]);
         }
     }
     __syncwarp();
