@@ -346,45 +346,39 @@ __device__ void lu_panel_warp(double *Q, int *perm, int *piv8, int j0) {
     }
     __syncwarp();
     // invert the diagonal block's factors: lanes 0-7 one column of inv(L_kk), lanes 8-15 one column of inv(U_kk).
-    // Column c of the inverse = substitution applied to e_c; entries above (L) / below (U) the diagonal come out as
-    // exact zeros, so the loops are branch-free and fully unrolled (x stays in registers).  Block entries are
-    // warp-uniform shared-memory broadcasts.
-    // Right-looking substitution: as soon as x[r] is known every later partial sum is updated with it, so the dependent
-    // chain is one complex multiply-add per row (the row-oriented form chains all terms of a row behind x[r-1]).
+    // Column c of the inverse = substitution applied to e_c, fully unrolled with x in registers; block entries are
+    // shared-memory broadcasts.  Right-looking form: as soon as x[r] is known every later partial sum is updated with it,
+    // so the dependent chain is one complex multiply-add per row.
     cplx x[8];
     const int c = lane & 7;
     const double *Br = Qr + j0 * C::LD + j0, *Bi = Qi + j0 * C::LD + j0;
+    // One instruction stream for both triangles (separate branches would run one after the other in this warp): lanes
+    // 8-15 walk U backwards by mirroring the indices, rr = 7 - r, and scale by the reciprocal diagonal; lanes 0-7 walk L
+    // forwards with a unit diagonal.
+    const bool isU = lane >= 8;
+    if (lane < 16) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) x[r] = {(r == c) ? 1.0 : 0.0, 0.0};
-    if (lane < 8) {
+        for (int r = 0; r < 8; ++r) x[r] = {((isU ? 7 - r : r) == c) ? 1.0 : 0.0, 0.0};
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
+            const cplx d = dinv[7 - r];
+            if (isU) x[r] = cmul(x[r], d);
 #pragma unroll
             for (int r2 = 0; r2 < 8; ++r2)
                 if (r2 > r) {
-                    const double lr = Br[r2 * C::LD + r], li = Bi[r2 * C::LD + r];
-                    x[r2].r -= lr * x[r].r - li * x[r].i; x[r2].i -= lr * x[r].i + li * x[r].r;
-                }
-        }
-    } else if (lane < 16) {
-#pragma unroll
-        for (int r = 7; r >= 0; --r) {
-            x[r] = cmul(x[r], dinv[r]);
-#pragma unroll
-            for (int r2 = 0; r2 < 8; ++r2)
-                if (r2 < r) {
-                    const double ur = Br[r2 * C::LD + r], ui = Bi[r2 * C::LD + r];
-                    x[r2].r -= ur * x[r].r - ui * x[r].i; x[r2].i -= ur * x[r].i + ui * x[r].r;
+                    const int off = isU ? (7 - r2) * C::LD + (7 - r) : r2 * C::LD + r;
+                    const double er = Br[off], ei = Bi[off];
+                    x[r2].r -= er * x[r].r - ei * x[r].i; x[r2].i -= er * x[r].i + ei * x[r].r;
                 }
         }
     }
     __syncwarp();
-    if (lane < 8) {
+    if (lane < 16) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) if (r > c) { Qr[(j0 + r) * C::LD + j0 + c] = x[r].r; Qi[(j0 + r) * C::LD + j0 + c] = x[r].i; }
-    } else if (lane < 16) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) if (r <= c) { Qr[(j0 + r) * C::LD + j0 + c] = x[r].r; Qi[(j0 + r) * C::LD + j0 + c] = x[r].i; }
+        for (int r = 0; r < 8; ++r) {
+            const int rr = isU ? 7 - r : r;
+            if (isU ? rr <= c : rr > c) { Qr[(j0 + rr) * C::LD + j0 + c] = x[r].r; Qi[(j0 + rr) * C::LD + j0 + c] = x[r].i; }
+        }
     }
     __syncwarp();
 #ifdef QOCB_PROFILE
