@@ -397,6 +397,7 @@ struct qocb_plan {
     int KC = 0;
     bool mapped = false, map_set = false;
     bool particular_fresh = false;      // sharded: the boundary costates of this evaluation's particular pass are in `lam`
+    const double *shardP_last = nullptr; // sharded: device buffer that received this shard's propagator in forward_local
     // sweep coarsening: the state / costate sweeps run on chunks merged pairwise `levels` times (propagator tree);
     // lvl_count[l] chunks at level l, their propagators at lvlP + lvl_off[l] matrices, boundaries at cb_lvl + cb_off[l]
     int levels = 0, lvl_count[16] = {}, lvl_off[16] = {}, cb_off[16] = {};
@@ -406,7 +407,7 @@ struct qocb_plan {
     cudaEvent_t ev[16] = {};
     DevBuf<double> C0, Cs, G0, G, controls, itab_w, U, tape, scratch, cta_tape, chunkP, psi, lam, part, cost_part, psi0,
         node_grad, grad, cost, csr_w, vecs, flush, redA, redB, psi_in, lam_in, lvlP, nodecoef, map_off, map_gain, node_grad_x;
-    DevBuf<int> itab_idx, tape_piv, meta, cta_piv, chunk_begin, member_chunk0, csr_ptr, csr_idx, counts, err_flag, cb_lvl, mc0_lvl;
+    DevBuf<int> itab_idx, tape_piv, meta, cta_piv, chunk_begin, member_chunk0, csr_ptr, csr_idx, counts, err_flag, cb_lvl, mc0_lvl, one_chunk;
     DevBuf<CostTerm> terms;
     std::vector<CostTerm> h_terms;
     std::vector<double> h_vecs;
@@ -1362,6 +1363,9 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     if (sliced) {
         PTRY(p->redA.alloc((size_t)((p->nchunks + 1) / 2) * GM)); PTRY(p->redB.alloc((size_t)((p->nchunks + 3) / 4) * GM));
         PTRY(p->psi_in.alloc(VS)); PTRY(p->lam_in.alloc(VS));
+        const int oc[4] = {0, Nm1, 0, 1};                           // the whole shard as one chunk: chunk_begin | member_chunk0
+        PTRY(p->one_chunk.alloc(4));
+        PTRY(cudaMemcpy(p->one_chunk.p, oc, sizeof(oc), cudaMemcpyHostToDevice));
     }
     PTRY(p->node_grad.alloc(std::max<size_t>(1, W * q * KC)));
     if (p->mapped) {
@@ -1818,6 +1822,7 @@ int qocb_shard_forward_local(qocb_plan *p, int32_t with_grad, double *shardP_dev
         return lg_shard_propagator(p, reinterpret_cast<double2 *>(shardP_dev));
     }
     rc = enqueue_expm_forward(p, with_grad != 0); if (rc) return rc;
+    p->shardP_last = shardP_dev;
     return enqueue_shard_propagator(p, shardP_dev);
 }
 
@@ -1844,6 +1849,18 @@ int qocb_shard_backward_particular(qocb_plan *p, double *b_dev) {
     if (!p->have_step_costs && !p->owns_final) {
         CU_TRY(p, cudaMemsetAsync(b_dev, 0, sizeof(double) * (size_t)qocb_shard_vector_doubles(p), p->stream));
         return 0;
+    }
+    if (!p->have_step_costs && !p->large && p->shardP_last) {
+        // last shard, final-step costs only: b = P_shard^T seed.  One mat-vec with the shard propagator (already built
+        // for the exchange) instead of the pass over all chunk boundaries - the other ranks wait for this value
+        SweepArgs sa = make_sargs(p);
+        sa.chunkP = p->shardP_last; sa.chunk_begin = p->one_chunk.p; sa.member_chunk0 = p->one_chunk.p + 2;
+        sa.lam_in = nullptr; sa.b_out = b_dev;
+        const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
+        const dim3 bgrid(1, boundary_state_groups(p));
+        SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<bgrid, kSweepThreads, sw_smem, p->stream>>>(sa, 0)));
+        CU_TRY(p, cudaGetLastError());
+        return 0;                                                   // particular_fresh stays false: the finish phase runs the full pass
     }
     p->particular_fresh = true;
     if (p->large) return lg_costates(p, nullptr, b_dev, true, false);
