@@ -24,6 +24,7 @@ CASES = [
     (66, 9, 2, 2, 6, False, 2, 1.0, 1, False),           # Magnus M6 through the batched commutator chain
     (100, 6, 2, 3, 6, True, 0, 8.0, 2, True),
     (72, 5, 1, 5, 6, False, 0, 30.0, 1, False),          # S > 4: dense reverse pass, squarings
+    (66, 5, 4, 2, 4, True, 1, 1.0, 1, False),            # KR = 8 > 6: Magnus M4 with explicit commutator products
 ]
 
 
