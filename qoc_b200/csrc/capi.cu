@@ -67,14 +67,28 @@ __global__ void __launch_bounds__(C::NT) k_forward(KArgs a) {
     const int wb = a.chunk_begin[c], we = a.chunk_begin[c + 1];
     double *scratch = a.scratch + (size_t)c * S_COUNT * C::GMAT;
     double *gP = a.chunkP + (size_t)c * C::GMAT;
+    bool parked = false;
     for (int w = wb; w < we; ++w) {
         const int e = w / (a.N - 1), j = w - e * (a.N - 1);
         GenArgs ga = a.ga;
         ga.G0 += (size_t)e * C::GMAT;
         ga.C0 += (size_t)e * ga.KR * C::GMAT;
         PROF_DECL
-        load_coefs<C>(sm, ga, j);
-        magnus_forward<C>(sm, ga, scratch);
+        double *gMnext = scratch + (size_t)S_E * C::GMAT;            // parked Magnus matrix (slot unused by the forward of M2 / M4)
+        if (parked) {                                                // assembled together with the previous slice's
+            g2s<C>(sm.X2, gMnext);
+            __syncthreads();
+            parked = false;
+        } else {
+            load_coefs<C>(sm, ga, j);
+            if (magnus_pair_ok<C>(ga) && w + 1 < we) {
+                load_coefs_to<C>(sm.red, ga, j + 1);
+                magnus_forward_pair<C>(sm, ga, sm.coef, sm.red, gMnext);
+                parked = true;
+            } else {
+                magnus_forward<C>(sm, ga, scratch);
+            }
+        }
         PROF_MARK(1);
         double *tape = a.tape ? a.tape + (size_t)w * a.tape_mats * C::GMAT : nullptr;
         int *piv = a.tape ? a.tape_piv + (size_t)w * C::NP : nullptr;

@@ -71,16 +71,18 @@ __host__ __device__ inline int comm_pair(int s, int r, int KR) { return s * KR -
 
 // interpolated control coefficients of slice j at the Magnus nodes -> sm.coef[i*kMaxKR + r]
 template <class C>
-__device__ __forceinline__ void load_coefs(const Smem<C> &sm, const GenArgs &ga, int j) {
+__device__ __forceinline__ void load_coefs_to(double *dst, const GenArgs &ga, int j) {
     for (int e = threadIdx.x; e < ga.q * ga.KR; e += C::NT) {
         const int i = e / ga.KR, r = e % ga.KR;
-        if (ga.nodecoef) { sm.coef[i * kMaxKR + r] = ga.nodecoef[(size_t)(j * ga.q + i) * ga.KR + r]; continue; }
+        if (ga.nodecoef) { dst[i * kMaxKR + r] = ga.nodecoef[(size_t)(j * ga.q + i) * ga.KR + r]; continue; }
         const int *id = ga.itab_idx + (j * ga.q + i) * 2;
         const double *w = ga.itab_w + (j * ga.q + i) * 2;
-        sm.coef[i * kMaxKR + r] = ga.controls[id[0] * ga.KR + r] * w[0] + ga.controls[id[1] * ga.KR + r] * w[1];
+        dst[i * kMaxKR + r] = ga.controls[id[0] * ga.KR + r] * w[0] + ga.controls[id[1] * ga.KR + r] * w[1];
     }
     __syncthreads();
 }
+template <class C>
+__device__ __forceinline__ void load_coefs(const Smem<C> &sm, const GenArgs &ga, int j) { load_coefs_to<C>(sm.coef, ga, j); }
 
 // owned pair of  alpha0 * G0 + sum_r cf[r] * G_r
 template <class C>
@@ -216,6 +218,46 @@ __device__ void magnus_forward(const Smem<C> &sm, const GenArgs &ga, double *scr
     for_owned<C>([&](int i, int j, int row, int col) {
         const c2 m = lds2<C>(sm.X0, row, col) + 0.5 * ldg2<C>(gB3, row, col) + (1.0 / 240.0) * accv<C>(acc, i, j);
         sts2<C>(sm.X2, row, col, m);
+    });
+    __syncthreads();
+}
+
+// Magnus matrices of TWO consecutive slices in one pass over the operators (orders without products: M2 and the
+// product-free M4).  The assembly streams 1 + KR (M2) or 1 + 2 KR + KR (KR - 1) / 2 (M4) operator matrices from L2
+// (0.94 MB per n = 64 slice at KR = 4); sharing the operator loads between two slices and parking the second matrix in
+// global memory (one 32 n^2-byte store and load) nearly halves that traffic: measured -1.7 us per slice.  (The same
+// pairing of the adjoint's inner products was measured to LOSE 8 % of k_backward and is not used.)
+// cfa / cfb: node coefficients of the two slices ([q][kMaxKR]).  Out: M_a in X2, M_b in gMb (global).
+template <class C>
+__device__ __forceinline__ bool magnus_pair_ok(const GenArgs &ga) { return ga.order == 2 || (ga.order == 4 && ga.comm); }
+
+template <class C>
+__device__ void magnus_forward_pair(const Smem<C> &sm, const GenArgs &ga, const double *cfa, const double *cfb, double *gMb) {
+    const double dt = ga.dt;
+    c2 va[C::TM][C::TN], vb[C::TM][C::TN];
+    for_owned<C>([&](int i, int j, int row, int col) { va[i][j] = dt * ldg2<C>(ga.G0, row, col); vb[i][j] = va[i][j]; });
+    auto axpy = [&](double wa, double wb, const double *g) {
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 x = ldg2<C>(g, row, col);
+            va[i][j] = va[i][j] + wa * x;
+            vb[i][j] = vb[i][j] + wb * x;
+        });
+    };
+    if (ga.order == 2) {
+        for (int r = 0; r < ga.KR; ++r) axpy(dt * cfa[r], dt * cfb[r], ga.G + (size_t)r * C::GMAT);
+    } else {
+        const double f = (QOCB_S3 / 12.0) * dt * dt;
+        const double *a1 = cfa, *a2 = cfa + kMaxKR, *b1 = cfb, *b2 = cfb + kMaxKR;
+        for (int r = 0; r < ga.KR; ++r) axpy(0.5 * dt * (a1[r] + a2[r]), 0.5 * dt * (b1[r] + b2[r]), ga.G + (size_t)r * C::GMAT);
+        for (int r = 0; r < ga.KR; ++r) axpy(f * (a1[r] - a2[r]), f * (b1[r] - b2[r]), ga.C0 + (size_t)r * C::GMAT);
+        for (int s_ = 0; s_ < ga.KR; ++s_)
+            for (int r = s_ + 1; r < ga.KR; ++r)
+                axpy(f * (a2[s_] * a1[r] - a2[r] * a1[s_]), f * (b2[s_] * b1[r] - b2[r] * b1[s_]),
+                     ga.Cs + (size_t)comm_pair(s_, r, ga.KR) * C::GMAT);
+    }
+    for_owned<C>([&](int i, int j, int row, int col) {
+        sts2<C>(sm.X2, row, col, va[i][j]);
+        stg2<C>(gMb, row, col, vb[i][j]);
     });
     __syncthreads();
 }
