@@ -18,7 +18,10 @@ def _mat(v, n):
 
 
 class NumpyShardEngine(object):
-    def __init__(self, rank, world, x_shape, h0, a_ops, psi0, terms, T, N, order, cost_eval_step=1):
+    def __init__(self, rank, world, x_shape, h0, a_ops, psi0, terms, T, N, order, cost_eval_step=1, node_map=None):
+        """node_map = (offset [N-1, q, KC], gain [N-1, q, KC, KR]): a_ops are operator channels of a time-dependent
+        hamiltonian with per-node coefficients offset + gain @ x(t) (qoc_b200/core/plan.py:extract_time_dependent_structure)"""
+        self.node_map = node_map
         self.rank, self.world = rank, world
         self.h0, self.a_ops, self.psi0, self.terms = h0, a_ops, psi0, terms
         self.T, self.N, self.order, self.ces = T, N, order, cost_eval_step
@@ -43,6 +46,8 @@ class NumpyShardEngine(object):
             a = []
             for i in range(self.idx.shape[1]):
                 c = self.x[self.idx[j, i, 0]] * self.w[j, i, 0] + self.x[self.idx[j, i, 1]] * self.w[j, i, 1]
+                if self.node_map is not None:
+                    c = self.node_map[0][j, i] + self.node_map[1][j, i] @ c
                 a.append(g0 + np.tensordot(c, g, axes=(0, 0)))
             u, tape = am.pade_fwd(am.magnus_fwd(a, self.dt, self.order))
             self.gens.append(a); self.tapes.append(tape); self.us.append(u)
@@ -101,6 +106,8 @@ class NumpyShardEngine(object):
             abar = am.magnus_bwd(self.gens[jl], self.dt, self.order, am.pade_bwd(self.tapes[jl], ubar))
             for i in range(self.idx.shape[1]):
                 cbar = np.real(np.einsum("ab,rab->r", abar[i], g))
+                if self.node_map is not None:
+                    cbar = self.node_map[1][j, i].T @ cbar
                 self.grad[self.idx[j, i, 0]] += self.w[j, i, 0] * cbar
                 self.grad[self.idx[j, i, 1]] += self.w[j, i, 1] * cbar
 

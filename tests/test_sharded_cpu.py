@@ -83,3 +83,58 @@ def test_sharded_protocol_gloo(world):
         assert np.abs(finals[:, :, 0] - f1).max() < 1e-13 and np.abs(finals0[:, :, 0] - f1).max() < 1e-13
         assert abs(cost - o_err) < 1e-12
         assert np.linalg.norm(grad[:, :2] + 1j * grad[:, 2:] - o_grad) / np.linalg.norm(o_grad) < 1e-11
+
+
+def _td_problem():
+    from oracle import adjoint_model as am
+    from qoc_b200.core.plan import extract_hamiltonian_structure
+    p = Problem(4, 9, 2, 2, 4, complex_controls=True, seed=5)
+    x = np.concatenate([p.controls.real, p.controls.imag], axis=1)
+    g0, channels, offset, gain = extract_hamiltonian_structure(p.hamiltonian_td_numpy(), 2, True, p.T, system_eval_count=p.N,
+                                                               magnus_order=4)
+    terms = [am.CostTerm(0, [p.target_states[s, :, 0][None] for s in range(2)], 1.0, 1, False)]
+    return p, x, g0, channels, (offset, gain), terms
+
+
+def _td_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.numpy_shard_engine import NumpyShardEngine
+        p, x, g0, channels, node_map, terms = _td_problem()
+        eng = NumpyShardEngine(rank, world, x.shape, g0, channels, p.initial_states[:, :, 0], terms, p.T, p.N, 4, node_map=node_map)
+        eng.upload(x)
+        all_p = torch.zeros(world * eng.GM, dtype=torch.float64)
+        all_b = torch.zeros(world * eng.VS, dtype=torch.float64)
+        res = sharded_evaluate(eng, TorchDistComm(), all_p, all_b, True)
+        q.put((rank,) + eng.unpack(res.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_time_dependent_gloo():
+    """world-size 2: the operator-channel expansion of a time-dependent hamiltonian (host logic of qocb_set_node_map) through the
+    sharding protocol, against the oracle calling the torch version of the same callable at every Magnus node"""
+    from oracle import qoc_oracle as orc
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_td_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    p = _td_problem()[0]
+    o_err, o_grad, o_fin = orc.schroedinger_cost_and_grad(p.controls, p.hamiltonian_td_torch(), p.initial_states,
+                                                          [orc.TargetStateInfidelity(p.target_states)], p.T, p.N, order=4)
+    for rank, cost, grad, finals in outs:
+        assert abs(cost - o_err) < 1e-12
+        assert np.linalg.norm(grad[:, :2] + 1j * grad[:, 2:] - o_grad) / np.linalg.norm(o_grad) < 1e-10
+        assert np.abs(finals - o_fin).max() < 1e-12
