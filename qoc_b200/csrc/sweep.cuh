@@ -51,7 +51,8 @@ struct SweepArgs {
 
 constexpr int kSweepThreads = 512;
 
-// ---- matrix pipeline: U_j staged global -> shared with 16-byte cp.async (LDGSTS), double buffered ---------------
+// ---- shared-memory staging of one propagator (16-byte cp.async), used only by the short prefix / suffix kernels of the
+// time-sharded path; the sweep and boundary kernels feed their mat-vecs from registers (see below) ------------------
 // Shared layout: planar, row stride LDS = NP + 2 doubles (rows stay 16-byte aligned).  With two lanes per output
 // (k-split) both access patterns are bank-conflict free for 64-bit loads:
 //   U   v : lane -> (a = lane / 2,  ks = lane % 2), b = 2 i + ks : bank = (2 a + ks) mod 16
@@ -313,8 +314,8 @@ template <int NP> struct SweepSmem {
 };
 
 // (1) boundary states: psi[b_{c+1}] = P_c psi[b_c], sequential over the chunks of one member; grid = (E, state groups):
-// the pass is a chain of dependent mat-vecs whose per-step time is bound by reading the 32 n^2-byte propagator once per
-// state from shared memory, so the states are spread over CTAs (no coupling between states in this pass)
+// the pass is a chain of dependent mat-vecs (per step: the next propagator's register prefetch, one k-split mat-vec, a
+// barrier, the store of the boundary state), so the states are spread over CTAs (no coupling between states in this pass)
 #ifdef QOCB_PROFILE
 #define BPROF_DECL long long bpt__ = clock64();
 #define BPROF(id) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { const long long t__ = clock64(); g_prof[id] += t__ - bpt__; bpt__ = t__; } } while (0)
