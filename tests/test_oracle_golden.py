@@ -230,3 +230,51 @@ def test_lindblad_adjoint_model_vs_oracle(path):
         band = max(band, rel(g_p, g_full))
     assert band > 1e-7                                   # the full gradient is not reproducible at 1e-10
     assert rel(g2c, g_full) < max(10 * band, 1e-4)
+
+
+class _LocalComm(object):
+    """single-process stand-in for the collectives of the sharding protocol"""
+
+    def all_gather(self, out, inp):
+        out.copy_(inp.repeat(out.numel() // inp.numel()))
+
+    def all_reduce_sum(self, t):
+        pass
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "schroedinger_timedep_*.npz"))))
+def test_time_dependent_hamiltonian_golden(path):
+    """hamiltonians that use their `time` argument: (1) the oracle against the reference forward (golden error / final
+    states, finite-difference gradient of the reference forward); (2) the product's host-side operator-channel expansion
+    (qoc_b200/core/plan.py:extract_time_dependent_structure, the tables behind qocb_set_node_map) evaluated by the NumPy
+    model, against the same reference outputs"""
+    import torch
+    from qoc_b200.core.plan import extract_hamiltonian_structure
+    from qoc_b200.core.sharded import sharded_evaluate
+    from oracle import adjoint_model as am
+    from tests.numpy_shard_engine import NumpyShardEngine
+    from tests.problems import Problem
+    g = np.load(path)
+    n, slices, K, S, order, cc, seed = (int(g["n"]), int(g["slices"]), int(g["K"]), int(g["S"]), int(g["order"]),
+                                        bool(g["complex_controls"]), int(g["seed"]))
+    p = Problem(n, slices, K, S, order, complex_controls=cc, seed=seed)
+    assert np.array_equal(p.controls, g["controls"])
+    err, grad, fin = orc.schroedinger_cost_and_grad(p.controls, p.hamiltonian_td_torch(), p.initial_states,
+                                                    [orc.TargetStateInfidelity(p.target_states, cost_multiplier=0.8)], p.T, p.N,
+                                                    order=order)
+    assert abs(err - float(g["error"])) < 1e-12
+    assert np.abs(fin - g["final_states"]).max() < 1e-12
+    assert np.linalg.norm(grad - g["fd_grad"]) / np.linalg.norm(g["fd_grad"]) < 2e-6
+    # the product's channel expansion
+    g0, channels, offset, gain = extract_hamiltonian_structure(p.hamiltonian_td_numpy(), K, cc, p.T, system_eval_count=p.N,
+                                                               magnus_order=order)
+    x = np.concatenate([p.controls.real, p.controls.imag], axis=1) if cc else p.controls
+    terms = [am.CostTerm(0, [p.target_states[s, :, 0][None] for s in range(S)], 0.8, 1, False)]
+    eng = NumpyShardEngine(0, 1, x.shape, g0, channels, p.initial_states[:, :, 0], terms, p.T, p.N, order, node_map=(offset, gain))
+    eng.upload(x)
+    res = sharded_evaluate(eng, _LocalComm(), torch.zeros(eng.GM, dtype=torch.float64), torch.zeros(eng.VS, dtype=torch.float64), True)
+    cost, gx, finals = eng.unpack(res.numpy())
+    gm = gx[:, :K] + 1j * gx[:, K:] if cc else gx
+    assert abs(cost - float(g["error"])) < 1e-12
+    assert np.abs(finals - g["final_states"]).max() < 1e-12
+    assert np.linalg.norm(gm - grad) / np.linalg.norm(grad) < 1e-10
