@@ -84,6 +84,9 @@ int qocb_cost_and_grad(qocb_plan *plan, const double *controls, double *cost, do
 /* all states of the last evaluation: [E][N][S][n] complex (the reference's save_intermediate_states payload,
    qoc/core/schroedingerdiscrete.py:395-402) */
 int qocb_get_states(qocb_plan *plan, double *states);
+/* final states of the last evaluation: [E][S][n] complex (reporter.final_states, qoc/core/schroedingerdiscrete.py:436);
+   waits for the plan stream, so it also serves evaluations enqueued with qocb_run_resident */
+int qocb_get_final_states(qocb_plan *plan, double *final_states);
 /* slice propagators U_j of the last evaluation: [E][N-1][n][n] complex */
 int qocb_get_propagators(qocb_plan *plan, double *props);
 
@@ -146,7 +149,19 @@ int qocb_expm_batched_time(int32_t n, int64_t batch, double norm_scale, int32_t 
 /* ---- Lindblad path: _evaluate_lindblad_discrete (qoc/core/lindbladdiscrete.py:357-441) and its jacobian (:322) -------
    Densities are [D][n][n] complex128, interleaved (NumPy C order).  H(x) = H0 + sum_r x_r A_r as above; the dissipator is
    sum_l gamma_l (L_l rho L_l^dag - 1/2 {L_l^dag L_l, rho}) with time-independent (gamma_l, L_l).  Each of the N-1
-   intervals is a fresh adaptive Dormand-Prince 5(4) integration (qoc/core/mathmethods.py:352-480). */
+   intervals is a fresh adaptive Dormand-Prince 5(4) integration (qoc/core/mathmethods.py:352-480).
+
+   CONTRACT OF THE LINDBLAD RESULTS (tolerances are asserted in tests/test_gpu_lindblad.py):
+     - cost and final densities: the reference's adaptive integration at atol = 1e-12, rtol = 0.  A rounding-level change of
+       one error norm near the accept threshold moves the whole step sequence, so two correct implementations agree to the
+       integrator's own tolerance, not to rounding: |cost - reference| and the final densities within 1e-9.
+     - gradient: the DISCRETE ADJOINT OF THE DORMAND-PRINCE MAP ON THE REALISED STEP GRID - every accepted step (x, h) of the
+       forward pass is held fixed and the Runge-Kutta stages, the 4th-order dense output at the interval end and the FSAL
+       coupling are differentiated exactly.  The reference's autograd tape additionally differentiates the step-size
+       controller (qoc/core/mathmethods.py:436-462), whose inputs are error norms taken at the rounding floor; those terms are
+       noise (perturbing the controls by 1e-13 moves the reference-equivalent full gradient by 1e-5 .. 1e-4).  The gradient
+       returned here matches the reference-equivalent gradient with the step grid frozen within 1e-7 relative, and the full
+       one within its own reproducibility band.  It is NOT claimed at the 1e-10 of the Schroedinger path. */
 typedef struct qocb_lplan qocb_lplan;
 
 typedef struct {

@@ -11,6 +11,7 @@ from qoc_b200.core.plan import LindbladPlan
 from qoc_b200.models import (Dummy, EvolveLindbladDiscreteState, EvolveLindbladResult, GrapeLindbladDiscreteState,
                              GrapeLindbladResult, InterpolationPolicy, ProgramType)
 from qoc_b200.standard.optimizers import Adam
+from qoc_b200.standard.utils import autograd_available
 
 
 def _plan_for(pstate, control_count, complex_controls, device=0):
@@ -126,6 +127,7 @@ def _evaluate_lindblad_discrete(controls, pstate, reporter):
     control_count, complex_controls = _program_controls_meta(pstate)
     plan = _plan_for(pstate, control_count, complex_controls)
     error, final_densities = plan.cost(controls)
+    _maybe_save_densities(pstate, reporter, plan)
     reporter.error = error
     reporter.final_densities = final_densities
     return error
@@ -136,7 +138,20 @@ def _value_and_jacobian_lindblad_discrete(controls, pstate, reporter):
     controls (lindbladdiscrete.py:322-328): grads = dE/dRe(u) + i dE/dIm(u)."""
     control_count, complex_controls = _program_controls_meta(pstate)
     plan = _plan_for(pstate, control_count, complex_controls)
-    error, grads, final_densities = plan.cost_and_grad(controls)
+    # with HIPS autograd installed the GPU evaluation runs as an autograd primitive (defvjp) under the reference's own
+    # ans_jacobian; without it the C ABI's value-and-gradient entry point is called directly (same numbers)
+    evaluate = plan.cost_and_grad_autograd if (autograd_available() and plan.KR > 0) else plan.cost_and_grad
+    error, grads, final_densities = evaluate(controls)
+    _maybe_save_densities(pstate, reporter, plan)
     reporter.error = error
     reporter.final_densities = final_densities
     return error, grads
+
+
+def _maybe_save_densities(pstate, reporter, plan):
+    """the reference writes the densities of every system step from inside its interval loop
+    (qoc/core/lindbladdiscrete.py:398-405, qoc/models/lindbladmodels.py:92-99, :315-334); the device keeps them all, so
+    one D2H after the evaluation fills the same dataset."""
+    if pstate.save_intermediate_densities_:
+        iteration = reporter.iteration if pstate.program_type == ProgramType.GRAPE else 0
+        pstate.save_all_intermediate_densities(iteration, plan.intermediate_densities())

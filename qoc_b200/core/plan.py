@@ -45,8 +45,28 @@ def _unit_controls(control_count, complex_controls):
     return zero, units
 
 
-def _is_time_dependent(hamiltonian, zero, units, evolution_time):
-    times = (0.0, 0.37 * evolution_time, 0.731 * evolution_time)
+def _probe_times(evolution_time, system_eval_count=None, magnus_order=None, dense=64, seed=4321):
+    """times at which a callable is checked for time dependence: the end points, `dense` evenly spread times, a few random
+    ones and - when the slice grid is known - Magnus node times the reference evaluates the callable at
+    (qoc/core/schroedingerdiscrete.py:483-497), including the first and last slices, so that windows, steps and envelopes
+    that vanish at a handful of fixed probe times are still seen."""
+    rng = np.random.default_rng(seed)
+    T = float(evolution_time)
+    times = [0.0, T, 0.37 * T, 0.731 * T]
+    times += list(np.linspace(0.0, T, dense + 2)[1:-1])
+    times += list(rng.uniform(0.0, T, 8))
+    if system_eval_count is not None and magnus_order is not None and system_eval_count > 1:
+        nsl = system_eval_count - 1
+        dt = T / nsl
+        picks = sorted(set([0, 1, nsl // 2, nsl - 2, nsl - 1] + [int(x) for x in rng.integers(0, nsl, 16)]))
+        for j in picks:
+            if 0 <= j < nsl:
+                times += [(j + c) * dt for c in _NODES[magnus_order // 2]]
+    return times
+
+
+def _is_time_dependent(hamiltonian, zero, units, evolution_time, system_eval_count=None, magnus_order=None):
+    times = _probe_times(evolution_time, system_eval_count, magnus_order)
     for u in [zero] + units:
         ref = np.asarray(hamiltonian(u, times[0]), dtype=np.complex128)
         tol = _PROBE_RTOL * max(1.0, np.abs(ref).max())
@@ -152,7 +172,7 @@ def extract_hamiltonian_structure(hamiltonian, control_count, complex_controls, 
     rng = np.random.default_rng(seed)
     t0, t1 = 0.0, 0.37 * evolution_time
     zero, units = _unit_controls(control_count, complex_controls) if control_count else (None, [])
-    if _is_time_dependent(hamiltonian, zero, units, evolution_time):
+    if _is_time_dependent(hamiltonian, zero, units, evolution_time, system_eval_count, magnus_order):
         if system_eval_count is None or magnus_order is None:
             raise NotImplementedError("time-dependent hamiltonian callables are not supported by this CUDA path yet "
                                       "(no CPU fallback)")
@@ -173,7 +193,7 @@ def extract_hamiltonian_structure(hamiltonian, control_count, complex_controls, 
             u = u + 1j * rng.standard_normal(control_count) * (1.0 + trial)
         x = np.concatenate([u.real, u.imag]) if complex_controls else u
         model = h0 + np.tensordot(x, a_ops, axes=(0, 0))
-        for t in (t0, t1):
+        for t in (t0, t1, float(rng.uniform(0.0, evolution_time)), float(evolution_time)):
             got = np.asarray(hamiltonian(u.astype(dtype), t), dtype=np.complex128)
             if not np.allclose(got, model, rtol=0, atol=_PROBE_RTOL * scale * (1 + np.abs(x).sum())):
                 raise NotImplementedError(
@@ -242,9 +262,13 @@ class SchroedingerPlan(object):
         psi0 = np.ascontiguousarray(initial_states.reshape(self.S, self.n), dtype=np.complex128)
         _lib.check(self.lib.qocb_set_states(handle, _lib.ptr(psi0)), handle)
         self.control_costs = []
+        from qoc_b200.models.cost import Cost
         for c in self.costs:
             terms = c.device_terms(self.S, self.n)
             if not terms:
+                if getattr(type(c), "control_value_and_grad", Cost.control_value_and_grad) is Cost.control_value_and_grad:
+                    raise NotImplementedError("The cost {} has neither device terms nor an analytic control gradient "
+                                              "(no CPU fallback).".format(c))
                 self.control_costs.append(c)
             for kind, step, weight, vecs, counts in terms:
                 vecs = np.ascontiguousarray(vecs, dtype=np.complex128)
@@ -301,6 +325,30 @@ class SchroedingerPlan(object):
         if extra_grad is not None:
             grads = grads + extra_grad
         return float(out[0]) + extra, grads, self._final_states(fs)
+
+    def cost_and_grad_autograd(self, controls):
+        """the same (error, grads, finals) through HIPS autograd: the GPU evaluation is registered as an autograd primitive
+        with defvjp (`make_autograd_primitive`) and differentiated with the reference's own operator
+        (`ans_jacobian`, qoc/core/schroedingerdiscrete.py:318, followed by the conjugate for complex controls, :323-324).
+        Used by the `_value_and_jacobian_*` seams whenever `autograd` is importable."""
+        from qoc_b200.standard.utils import ans_jacobian, make_autograd_primitive
+        prim = getattr(self, "_autograd_primitive", None)
+        if prim is None:
+            def value_and_grad(c):
+                err, g, fin = self.cost_and_grad(c)
+                self._autograd_finals = fin
+                return err, (np.conjugate(g) if np.iscomplexobj(g) else g)      # autograd convention: d/dx - i d/dy
+            prim = self._autograd_primitive = make_autograd_primitive(value_and_grad)
+        controls = np.asarray(controls)
+        error, jac = ans_jacobian(prim, 0)(controls)
+        grads = np.conjugate(jac) if np.iscomplexobj(controls) else jac
+        return float(error), grads, self._autograd_finals
+
+    def final_states(self):
+        """final states of the last evaluation (also of one enqueued through the device-resident hooks)."""
+        fs = np.empty((self.E, self.S, self.n), dtype=np.complex128)
+        _lib.check(self.lib.qocb_get_final_states(self.handle, _lib.ptr(fs)), self.handle)
+        return self._final_states(fs)
 
     def intermediate_states(self):
         """[N][S][n][1] states of the last evaluation (member 0 unless E > 1: then [E][N][S][n][1])."""
@@ -404,11 +452,17 @@ class LindbladPlan(object):
         self._check(self.lib.qocb_lindblad_set_operators(handle, _lib.ptr(h0c), _lib.ptr(aoc), _lib.ptr(gammas), _lib.ptr(lops)))
         self._check(self.lib.qocb_lindblad_set_densities(handle, _lib.ptr(rho0)))
         self.control_costs = []
+        from qoc_b200.models.cost import Cost
         for c in self.costs:
-            terms = c.device_terms_density(self.D, self.n) if hasattr(c, "device_terms_density") else []
+            terms = c.device_terms_density(self.D, self.n) if hasattr(c, "device_terms_density") else None
             if not terms:
-                if not hasattr(c, "control_value_and_grad"):
-                    raise NotImplementedError("cost {} has no CUDA descriptor for the Lindblad path".format(c))
+                # only genuine control-only costs (classes that override the analytic hook) may skip the device: a state
+                # cost passed by mistake or a user-defined density cost must not be dropped silently
+                hook = getattr(type(c), "control_value_and_grad", None)
+                if terms is None or hook is None or hook is Cost.control_value_and_grad:
+                    raise NotImplementedError("The cost {} has no B200 device descriptor for the Lindblad path (no CPU "
+                                              "fallback): density costs need `device_terms_density`, control-only costs "
+                                              "`control_value_and_grad`.".format(c))
                 self.control_costs.append(c)
             for kind, step, weight, mats, counts in terms:
                 mats = np.ascontiguousarray(mats, dtype=np.complex128)
@@ -424,6 +478,7 @@ class LindbladPlan(object):
 
     _real_channels = SchroedingerPlan._real_channels
     _control_costs = SchroedingerPlan._control_costs
+    cost_and_grad_autograd = SchroedingerPlan.cost_and_grad_autograd
 
     def cost(self, controls):
         x = self._real_channels(controls) if controls is not None else None

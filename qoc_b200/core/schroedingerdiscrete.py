@@ -14,6 +14,7 @@ from qoc_b200.models import (Dummy, EvolveSchroedingerDiscreteState, EvolveSchro
                              GrapeSchroedingerDiscreteState, GrapeSchroedingerResult, InterpolationPolicy,
                              MagnusPolicy, ProgramType)
 from qoc_b200.standard.optimizers import Adam
+from qoc_b200.standard.utils import autograd_available
 
 
 def _plan_for(pstate, control_count, complex_controls, device=0, store_tape=True):
@@ -141,7 +142,9 @@ def _evaluate_schroedinger_discrete(controls, pstate, reporter):
     """total cost of one evolution on the GPU; fills reporter.error / reporter.final_states
     (qoc/core/schroedingerdiscrete.py:356-438)."""
     control_count, complex_controls = _program_controls_meta(pstate)
-    plan = _plan_for(pstate, control_count, complex_controls, store_tape=False)
+    # the plan is cached on pstate: a GRAPE run whose optimiser calls `function` before `jacobian` (L-BFGS-B) must not end up
+    # with a recompute-mode plan for all its gradient evaluations
+    plan = _plan_for(pstate, control_count, complex_controls, store_tape=pstate.program_type == ProgramType.GRAPE)
     error, final_states = plan.cost(controls)
     _maybe_save_states(pstate, reporter, plan)
     reporter.error = error
@@ -154,7 +157,10 @@ def _value_and_jacobian_schroedinger_discrete(controls, pstate, reporter):
     complex controls (schroedingerdiscrete.py:318-324): grads = dE/dRe(u) + i dE/dIm(u)."""
     control_count, complex_controls = _program_controls_meta(pstate)
     plan = _plan_for(pstate, control_count, complex_controls)
-    error, grads, final_states = plan.cost_and_grad(controls)
+    # with HIPS autograd installed the GPU evaluation runs as an autograd primitive (defvjp) under the reference's own
+    # ans_jacobian; without it the C ABI's value-and-gradient entry point is called directly (same numbers)
+    evaluate = plan.cost_and_grad_autograd if (autograd_available() and plan.KR > 0) else plan.cost_and_grad
+    error, grads, final_states = evaluate(controls)
     _maybe_save_states(pstate, reporter, plan)
     reporter.error = error
     reporter.final_states = final_states

@@ -251,10 +251,62 @@ class ShardedSchroedingerPlan(object):
         self.engine = None
 
 
+def units_evaluate(engine, comm, with_grad):
+    """sharding of INDEPENDENT units - ensemble members, initial states - across ranks: every rank
+    runs the whole time loop for its units; there is no data-path exchange except
+      * the coherent overlap sums sum_s <t_s|psi_s> of `TargetStateInfidelity` when STATES are sharded (the cost couples the
+        states through |sum_s ip_s|^2, targetstateinfidelity.py:53-55): one all-reduce of a few complex numbers between the
+        forward and the backward pass (`engine.forward` returns them, empty when nothing couples);
+      * one all-reduce of [gradient | cost] at the end (each rank's contribution already weighted).
+    Engine interface: forward(with_grad) -> coherent partial sums (tensor, may be empty); backward(coherent_totals);
+    pack(with_grad) -> result tensor.  `CudaUnitEngine` runs it on a B200, tests/numpy_unit_engine.py on CPU (gloo)."""
+    coh = engine.forward(with_grad)
+    if coh is not None and coh.numel() > 0:
+        comm.all_reduce_sum(coh)
+    if with_grad:
+        engine.backward(coh)
+    res = engine.pack(with_grad)
+    comm.all_reduce_sum(res)
+    return res
+
+
+class CudaUnitEngine(object):
+    """one rank's share of an ensemble (members differ in the drift) on its GPU: the unsharded device pipeline over the
+    local members, the result [gradient | cost] packed on the device and weighted by members_local / members_total (the
+    cost of an ensemble is the mean over its members)."""
+
+    def __init__(self, plan, weight, device):
+        import torch
+        self.torch, self.plan, self.lib, self.h = torch, plan, plan.lib, plan.handle
+        self.dev = torch.device("cuda", device)
+        self.stream = torch.cuda.ExternalStream(self.lib.qocb_stream(self.h), device=self.dev)
+        self.count = plan.M * plan.KR
+        self.weight = float(weight)
+        self.result = torch.zeros(self.lib.qocb_shard_result_doubles(self.h), dtype=torch.float64, device=self.dev)
+        self.out = self.result[:self.count + 1]                     # [gradient | cost]; the tail (final states) stays local
+
+    def forward(self, with_grad):
+        _lib.check(self.lib.qocb_run_resident(self.h, int(with_grad)), self.h)      # whole pipeline: members are independent
+        return None
+
+    def backward(self, coh):
+        pass
+
+    def pack(self, with_grad):
+        _lib.check(self.lib.qocb_shard_pack_result(self.h, int(with_grad), ctypes.c_void_p(self.result.data_ptr())), self.h)
+        self.out.mul_(self.weight)                                  # enqueued on the plan stream (the caller made it current)
+        return self.out
+
+    def close(self):
+        self.stream.synchronize()
+        self.result = self.out = None
+        self.torch.cuda.synchronize(self.dev)
+
+
 class EnsembleShardedPlan(object):
-    """robust-control ensembles (build-side extension): members that differ in the drift are
-    independent units, so they are block-partitioned across the ranks with no data-path exchange; one all-reduce of
-    [cost, gradient] (weighted by the members each rank holds) ends the evaluation.  Cost = mean over members."""
+    """robust-control ensembles (cfg5): members that differ in the drift are independent units, block-partitioned across the
+    ranks; one NCCL all-reduce of [gradient | cost] on the plan stream ends the evaluation - inside the device-timed region,
+    no host bounce.  Cost = mean over members.  `cost_and_grad` returns the final states of the LOCAL members."""
 
     def __init__(self, hamiltonian, initial_states, costs, evolution_time, system_eval_count, ensemble_drifts, device=0,
                  group=None, **kw):
@@ -262,6 +314,7 @@ class EnsembleShardedPlan(object):
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.comm = TorchDistComm(group)
         drifts = np.asarray(ensemble_drifts)
         self.E_total = drifts.shape[0]
         b = slice_bounds(self.E_total, self.world)
@@ -271,33 +324,64 @@ class EnsembleShardedPlan(object):
         p = self.plan
         self.KR, self.K, self.M, self.S, self.n, self.E = p.KR, p.K, p.M, p.S, p.n, p.E
         self.complex_controls = p.complex_controls
-        self.weight = float(p.E) / self.E_total
-        self.dev = torch.device("cuda", device)
-        self.buf = torch.zeros(p.M * p.KR + 1, dtype=torch.float64, device=self.dev)
+        self.engine = CudaUnitEngine(p, float(p.E) / self.E_total, device)
+        self.host = torch.zeros(p.M * p.KR + 1, dtype=torch.float64).pin_memory()
 
     def upload(self, controls):
         self.plan.upload(controls)
 
+    def _evaluate(self, controls, with_grad):
+        e = self.engine
+        self.plan.upload(controls)
+        with self.torch.cuda.stream(e.stream):
+            res = units_evaluate(e, self.comm, with_grad)
+            self.host.copy_(res, non_blocking=True)
+        e.stream.synchronize()
+        out = self.host.numpy()
+        extra, extra_grad = self.plan._control_costs(np.asarray(controls), with_grad)
+        g = out[:-1].reshape(self.M, self.KR).copy()
+        grads = g[:, :self.K] + 1j * g[:, self.K:] if self.complex_controls else g
+        if with_grad and extra_grad is not None:
+            grads = grads + extra_grad
+        return float(out[-1]) + extra, grads, self.plan.final_states()
+
+    def cost(self, controls):
+        err, _, finals = self._evaluate(controls, False)
+        return err, finals
+
     def cost_and_grad(self, controls):
         """(mean cost, gradient of the mean cost, final states of the LOCAL members)."""
-        err, grads, finals = self.plan.cost_and_grad(controls)
-        g = np.concatenate([grads.real, grads.imag], axis=1) if self.complex_controls else np.asarray(grads)
-        host = np.concatenate([g.ravel(), [err]]) * self.weight
-        self.buf.copy_(self.torch.from_numpy(host))
-        self.dist.all_reduce(self.buf, group=self.group)
-        out = self.buf.cpu().numpy()
-        g = out[:-1].reshape(self.M, self.KR)
-        grads = g[:, :self.K] + 1j * g[:, self.K:] if self.complex_controls else g
-        return float(out[-1]), grads, finals
+        return self._evaluate(controls, True)
 
     def time_resident(self, with_grad=True, warmup=3, iters=10, flush_l2=True):
-        """device time of the local members (no exchange inside the device-resident pipeline: the members are independent;
-        the caller takes the max over ranks)."""
-        return self.plan.time_resident(with_grad, warmup, iters, flush_l2)
+        """device time of `iters` resident evaluations INCLUDING the closing all-reduce (CUDA events on the plan stream, this
+        rank's clock; the caller takes the max over ranks).  stages: per-kernel split of the local pipeline from one extra
+        evaluation timed by the C ABI, scaled to `iters`."""
+        torch, e = self.torch, self.engine
+        for _ in range(warmup):
+            with torch.cuda.stream(e.stream):
+                units_evaluate(e, self.comm, with_grad)
+        e.stream.synchronize()
+        total = 0.0
+        for _ in range(iters):
+            if flush_l2:
+                _lib.check(self.plan.lib.qocb_flush_l2(self.plan.handle), self.plan.handle)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(e.stream):
+                t0.record()
+                units_evaluate(e, self.comm, with_grad)
+                t1.record()
+            e.stream.synchronize()
+            total += t0.elapsed_time(t1)
+        _, stages = self.plan.time_resident(with_grad, 0, 1, flush_l2)
+        return total, np.asarray(stages) * iters
 
     def launch_count(self, with_grad=True):
-        return self.plan.launch_count(with_grad)
+        return self.plan.launch_count(with_grad) + 2                # + pack, scale
 
     def close(self):
-        self.buf = None
-        self.plan.close()
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+            self.host = None
+            self.plan.close()

@@ -1040,13 +1040,21 @@ int lg_costates(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, bool 
     return 0;
 }
 
-int lg_eval(qocb_plan *p, bool with_grad) {
+// ev != nullptr: stage boundaries as in enqueue_eval (1 expm forward incl. the propagator tree, 2-3 state sweeps,
+// 4 costate sweeps, 5-6 expm reverse + gather)
+int lg_eval(qocb_plan *p, bool with_grad, cudaEvent_t *ev) {
+    auto rec = [&](int i) { if (ev) cudaEventRecord(ev[i], p->stream); };
     int rc = lg_expm_all(p); if (rc) return rc;
+    rec(1); rec(2);
     rc = lg_states_forward(p, p->psi0.p); if (rc) return rc;
+    rec(3);
     if (with_grad) {
         rc = lg_costates(p, nullptr, nullptr, true, true); if (rc) return rc;
+        rec(4);
         rc = lg_backward_all(p); if (rc) return rc;
-    }
+        rec(5);
+    } else { rec(4); rec(5); }
+    rec(6); rec(7);
     return 0;
 }
 
@@ -1172,9 +1180,7 @@ int enqueue_eval(qocb_plan *p, bool with_grad, cudaEvent_t *ev) {
     auto rec = [&](int i) { if (ev) cudaEventRecord(ev[i], p->stream); };
     rec(0);
     if (p->large) {
-        rc = lg_eval(p, with_grad); if (rc) return rc;
-        for (int i = 1; i < 8; ++i) rec(i);
-        return 0;
+        return lg_eval(p, with_grad, ev);
     }
     rc = enqueue_expm_forward(p, with_grad); if (rc) return rc;
     rec(1);
@@ -1746,6 +1752,13 @@ int qocb_get_states(qocb_plan *p, double *states) {
                 states[2 * ((en * S + s) * n + a) + 1] = buf[en * VS + (size_t)s * 2 * NP + NP + a];
             }
     return 0;
+}
+
+int qocb_get_final_states(qocb_plan *p, double *final_states) {
+    if (!p || !final_states) { set_error(p, "null argument"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    return fetch_final_states(p, final_states);
 }
 
 int qocb_get_propagators(qocb_plan *p, double *props) {

@@ -34,5 +34,6 @@ class Cost(object):
                                   "supported by the CUDA path yet.".format(self))
 
     def control_value_and_grad(self, controls):
-        """control-only contribution (value, d/dx + i d/dy); state costs return (0, None)."""
+        """control-only costs override this with their analytic (value, d/dx + i d/dy).  The base implementation marks
+        "not a control-only cost": the plans accept a cost without device terms only if its class overrides this hook."""
         return 0.0, None

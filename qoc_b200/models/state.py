@@ -276,6 +276,16 @@ class EvolveLindbladDiscreteState(ProgramState):
         self._write("w", writer, "initial save")
 
 
+    def save_all_intermediate_densities(self, iteration, all_densities):
+        """one write of the whole [N][D][n][n] trajectory (qoc/models/lindbladmodels.py:92-99 writes it step by step)."""
+        if self.save_file_path is None:
+            return
+
+        def writer(f):
+            f["intermediate_densities"][...] = all_densities.astype(np.complex128)
+        self._write("a", writer, "intermediate densities")
+
+
 class EvolveLindbladResult(object):
     def __init__(self, error=None, final_densities=None):
         self.error = error
@@ -315,6 +325,19 @@ class GrapeLindbladDiscreteState(GrapeState):
                                                            + self.initial_densities.shape, dtype=np.complex128)
             self._write("w", writer, "initial save")
         self._print_header()
+
+
+    def save_all_intermediate_densities(self, iteration, all_densities):
+        """row `iteration // save_iteration_step` of the [save_count][N][D][n][n] dataset
+        (qoc/models/lindbladmodels.py:315-334)."""
+        if iteration > self.final_iteration or not self.should_save:
+            return
+        if self._due(iteration, self.save_iteration_step):
+            row = iteration // self.save_iteration_step
+
+            def writer(f):
+                f["intermediate_densities"][row] = all_densities.astype(np.complex128)
+            self._write("a", writer, "intermediate densities of iteration {}".format(iteration))
 
 
 class GrapeLindbladResult(object):

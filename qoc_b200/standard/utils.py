@@ -36,25 +36,65 @@ class CustomJSONEncoder(json.JSONEncoder):
 
 
 def make_autograd_primitive(value_and_grad):
-    """Wrap `value_and_grad(controls) -> (value, grad_autograd_convention)` as a HIPS-autograd primitive.
-    grad_autograd_convention is dE/dx - i dE/dy for complex controls (what autograd's make_vjp returns,
-    qoc/core/schroedingerdiscrete.py:320-322) and the plain real gradient for real controls."""
+    """Wrap `value_and_grad(controls) -> (value, grad_autograd_convention)` as a HIPS-autograd primitive with a VJP
+    (`autograd.extend.primitive` + `defvjp`), the contract BASELINE.json's north_star names.  grad_autograd_convention is
+    dE/dx - i dE/dy for complex controls (what autograd's make_vjp returns, qoc/core/schroedingerdiscrete.py:320-322) and
+    the plain real gradient for real controls.
+
+    The gradient is captured PER CALL: autograd invokes the vjp-maker right after the forward evaluation of the same call,
+    so the maker takes the gradient that evaluation produced (matched by the controls' bytes; re-evaluated if something else
+    ran in between) and closes over it.  Several forward calls followed by one backward pass therefore each keep their own
+    gradient."""
     from autograd.extend import defvjp, primitive        # raises ImportError when autograd is absent
-    cache = {}
+    pending = {}
+
+    def _key(controls):
+        a = np.ascontiguousarray(np.asarray(controls))
+        return (a.shape, a.dtype.str, a.tobytes())
 
     @primitive
     def gpu_cost(controls):
-        value, grad = value_and_grad(np.asarray(controls))
-        cache["grad"] = grad
+        controls = np.asarray(controls)
+        value, grad = value_and_grad(controls)
+        pending[_key(controls)] = np.array(grad, copy=True)
+        while len(pending) > 8:                          # forward-only calls never collect their entry
+            pending.pop(next(iter(pending)))
         return value
 
-    defvjp(gpu_cost, lambda ans, controls: (lambda g: g * cache["grad"]))
+    def vjp_maker(ans, controls):
+        grad = pending.pop(_key(controls), None)
+        if grad is None:
+            grad = np.array(value_and_grad(np.asarray(controls))[1], copy=True)
+        return lambda g: g * grad
+
+    defvjp(gpu_cost, vjp_maker)
     return gpu_cost
 
 
-def ans_jacobian(value_and_grad, argnum=0):
-    """drop-in for qoc.standard.utils.autogradutil.ans_jacobian on a GPU-backed evaluation: returns a function
-    giving (value, jacobian) with the jacobian in autograd's convention."""
-    def wrapped(*args):
-        return value_and_grad(*args)
-    return wrapped
+def ans_jacobian(function, argnum=0):
+    """drop-in for `qoc.standard.utils.autogradutil.ans_jacobian` (:10-31): returns a function giving
+    (ans, jacobian of ans with respect to positional argument `argnum`) through HIPS autograd's `make_vjp`, one pull-back
+    per basis vector of the output space (one for the scalar cost).  `function` may contain GPU-backed primitives made by
+    `make_autograd_primitive`.  Needs `autograd` (ImportError otherwise); the product's own evaluation path calls the C
+    ABI's value-and-gradient entry point directly and does not depend on it."""
+    from autograd.core import make_vjp
+    from autograd.extend import vspace
+
+    def value_and_jacobian(*args, **kwargs):
+        def of_one_argument(x):
+            full = list(args)
+            full[argnum] = x
+            return function(*full, **kwargs)
+        pullback, ans = make_vjp(of_one_argument, args[argnum])
+        out_space = vspace(ans)
+        rows = [pullback(basis_vector) for basis_vector in out_space.standard_basis()]
+        return ans, np.stack(rows).reshape(out_space.shape + vspace(args[argnum]).shape)
+    return value_and_jacobian
+
+
+def autograd_available():
+    try:
+        import autograd.extend  # noqa: F401
+        return True
+    except ImportError:
+        return False

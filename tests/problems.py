@@ -18,10 +18,18 @@ def one_norm(a):
 
 
 def haar_columns(rng, n, count):
-    z = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
-    q, r = np.linalg.qr(z)
-    q = q * (np.diag(r) / np.abs(np.diag(r)))
-    return q[:, :count]
+    """`count` columns of Haar unitaries: one frame when count <= n, otherwise several independent frames side by side
+    (cfg5 has S = 64 states in a 32-dimensional space; the reference places no constraint on the state list)."""
+    blocks = []
+    while True:
+        z = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        q, r = np.linalg.qr(z)
+        q = q * (np.diag(r) / np.abs(np.diag(r)))
+        blocks.append(q[:, :min(n, count)])
+        count -= n
+        if count <= 0:
+            break
+    return blocks[0] if len(blocks) == 1 else np.concatenate(blocks, axis=1)
 
 
 class Problem(object):
@@ -52,7 +60,7 @@ class Problem(object):
             self.controls = (rng.standard_normal((self.M, K)) + 1j * rng.standard_normal((self.M, K))) * (0.5 / np.sqrt(2))
         else:
             self.controls = rng.standard_normal((self.M, K)) * 0.5
-        cols = haar_columns(rng, n, min(n, S * (1 + F)))
+        cols = haar_columns(rng, n, min(n, S * (1 + F)) if S <= n else S)
         self.initial_states = np.ascontiguousarray(haar_columns(rng, n, S).T)[:, :, None]
         self.target_states = np.ascontiguousarray(cols[:, :S].T)[:, :, None]
         self.F = F

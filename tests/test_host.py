@@ -251,3 +251,36 @@ def test_autograd_primitive_registration_with_stub(monkeypatch):
     (vjp_maker,) = registry[f]
     vjp = vjp_maker(3.5, np.zeros((2, 1), dtype=complex))
     assert np.array_equal(vjp(2.0), 2.0 * grad)            # cotangent of the scalar cost times the stored gradient
+    # gradients are captured per call: two forward evaluations (autograd runs the vjp-maker right after each), then the
+    # backward passes in reverse order must each see their own gradient
+    g = make_autograd_primitive(lambda controls: (float(np.sum(controls.real)), 3.0 * controls))
+    (maker,) = registry[g] if g in registry else (None,)
+    c1, c2 = np.full((2, 1), 1.0 + 0j), np.full((2, 1), 5.0 + 0j)
+    a1 = g(c1); v1 = maker(a1, c1)
+    a2 = g(c2); v2 = maker(a2, c2)
+    assert np.array_equal(v2(1.0), 3.0 * c2) and np.array_equal(v1(1.0), 3.0 * c1)
+    # a vjp-maker that missed its forward evaluation (entry evicted) re-evaluates instead of returning a stale gradient
+    v3 = maker(0.0, np.full((2, 1), 7.0 + 0j))
+    assert np.array_equal(v3(1.0), 21.0 * np.ones((2, 1)))
+
+
+def test_ans_jacobian_over_gpu_style_primitive(monkeypatch):
+    """`ans_jacobian(primitive, 0)(controls)` - the reference's differentiation operator over a defvjp-registered value and
+    gradient function (tests/fake_autograd.py stands in for HIPS autograd)."""
+    from tests import fake_autograd
+    fake_autograd.install(monkeypatch)
+    from qoc_b200.standard.utils import ans_jacobian, autograd_available, make_autograd_primitive
+    assert autograd_available()
+    calls = []
+
+    def value_and_grad(c):
+        calls.append(c.copy())
+        return float(np.sum(np.abs(c) ** 2)), 2 * np.conjugate(c)        # autograd convention d/dx - i d/dy of |c|^2
+    f = make_autograd_primitive(value_and_grad)
+    c = np.array([[1.0 + 2.0j], [0.5 - 1.0j]])
+    val, jac = ans_jacobian(f, 0)(c)
+    assert val == float(np.sum(np.abs(c) ** 2)) and np.array_equal(jac, 2 * np.conjugate(c))
+    assert len(calls) == 1                                              # one evaluation serves value and gradient
+    g = ans_jacobian(lambda a, b: f(b), 1)                              # argnum selects the differentiated argument
+    val2, jac2 = g("unused", 2 * c)
+    assert np.array_equal(jac2, 4 * np.conjugate(c))
