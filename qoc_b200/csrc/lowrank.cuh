@@ -28,6 +28,7 @@ constexpr int LR_LD = 52, LR_PL = 64 * LR_LD, LR_TLD = 12, LR_TPL = 64 * LR_TLD;
 template <class C, bool T, int MASK, bool NEG, int LDB, int PLB>
 __device__ __forceinline__ void tile_mma_thin(c2 &acc, const double *A, int ar0, int ak0, const double *B, int bk0, int bc0) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double p1a = 0., p1b = 0., p2a = 0., p2b = 0., p3a = 0., p3b = 0.;   // 3M partial products (tile.cuh: Acc)
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
         double ar, ai;
@@ -35,11 +36,12 @@ __device__ __forceinline__ void tile_mma_thin(c2 &acc, const double *A, int ar0,
         if (NEG) { ar = -ar; ai = -ai; }
         const int bidx = (bk0 + 4 * ks + t) * LDB + bc0 + g;
         const double br = B[bidx], bi = B[PLB + bidx];
-        dmma884(acc.r0, acc.r1, ar, br);
-        dmma884(acc.i0, acc.i1, ar, bi);
-        dmma884(acc.r0, acc.r1, -ai, bi);
-        dmma884(acc.i0, acc.i1, ai, br);
+        dmma884(p1a, p1b, ar, br);
+        dmma884(p2a, p2b, ai, bi);
+        dmma884(p3a, p3b, ar + ai, br + bi);
     }
+    acc.r0 += p1a - p2a; acc.r1 += p1b - p2b;
+    acc.i0 += p3a - p1a - p2a; acc.i1 += p3b - p1b - p2b;
 }
 template <int LD, int PL> __device__ __forceinline__ c2 ld_thin(const double *M, int r0, int c0) {
     const int lane = threadIdx.x & 31, row = r0 + (lane >> 2), col = c0 + (lane & 3) * 2;
@@ -78,9 +80,8 @@ __device__ __forceinline__ void mma_lowrank(Acc<C> &acc, const double *L, int lc
 #pragma unroll
             for (int j = 0; j < C::TN; ++j) {
                 dmma884(acc.v[i][j][0], acc.v[i][j][1], ar[i], br[j]);
-                dmma884(acc.v[i][j][2], acc.v[i][j][3], ar[i], bi[j]);
-                dmma884(acc.v[i][j][0], acc.v[i][j][1], -ai[i], bi[j]);
-                dmma884(acc.v[i][j][2], acc.v[i][j][3], ai[i], br[j]);
+                dmma884(acc.v[i][j][2], acc.v[i][j][3], ai[i], bi[j]);
+                dmma884(acc.v[i][j][4], acc.v[i][j][5], ar[i] + ai[i], br[j] + bi[j]);
             }
     }
 }

@@ -40,16 +40,22 @@ struct Cfg {
     static_assert(NT % NP == 0 && PARTS >= 1 && PARTS <= 32 && (32 % PARTS) == 0, "bad PARTS");
 };
 
+// Complex products use the 3M scheme: with A = Ar + i Ai, B = Br + i Bi,
+//     P1 = Ar Br,  P2 = Ai Bi,  P3 = (Ar + Ai)(Br + Bi)   =>   Re(AB) = P1 - P2,  Im(AB) = P3 - P1 - P2,
+// three real DMMA products per k-step instead of four (the operand sums are one DADD per fragment element and k-step).
+// The accumulator keeps the three partial products apart - they are independent chains for the tensor pipe - and they are
+// combined once, when the result is read (accv).  Normwise the rounding error is that of the four-product form (both are
+// sums of products of the same magnitudes); everything downstream is tested against the oracle at 1e-10 / 1e-12.
 template <class C>
 struct Acc {
-    double v[C::TM][C::TN][4];   // [0..1] real (col, col+1), [2..3] imaginary
+    double v[C::TM][C::TN][6];   // [0..1] P1 (col, col+1), [2..3] P2, [4..5] P3
     __device__ __forceinline__ void zero() {
 #pragma unroll
         for (int i = 0; i < C::TM; ++i)
 #pragma unroll
             for (int j = 0; j < C::TN; ++j)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[i][j][e] = 0.0;
+                for (int e = 0; e < 6; ++e) v[i][j][e] = 0.0;
     }
 };
 
@@ -68,20 +74,20 @@ __device__ __forceinline__ void mma_smem(Acc<C> &acc, const double *__restrict__
 #pragma unroll 2
     for (int kk = 0; kk < C::NP / 4; ++kk) {
         const int k = kk * 4 + t;
-        double ar[C::TM], ai[C::TM], nai[C::TM], br[C::TN], bi[C::TN];
+        double ar[C::TM], ai[C::TM], sa[C::TM], br[C::TN], bi[C::TN], sb[C::TN];
 #pragma unroll
         for (int i = 0; i < C::TM; ++i) {
             const int r = row0 + i * 8;
             const int idx = TA ? (k * C::LD + r) : (r * C::LD + k);
             double xr = A[idx], xi = A[C::PLANE + idx];
             if (NEG) { xr = -xr; xi = -xi; }
-            ar[i] = xr; ai[i] = xi; nai[i] = -xi;
+            ar[i] = xr; ai[i] = xi; sa[i] = xr + xi;
         }
 #pragma unroll
         for (int j = 0; j < C::TN; ++j) {
             const int c = col0 + j * 8;
             const int idx = TB ? (c * C::LD + k) : (k * C::LD + c);
-            br[j] = B[idx]; bi[j] = B[C::PLANE + idx];
+            br[j] = B[idx]; bi[j] = B[C::PLANE + idx]; sb[j] = br[j] + bi[j];
         }
 #pragma unroll
         for (int i = 0; i < C::TM; ++i)
@@ -90,15 +96,11 @@ __device__ __forceinline__ void mma_smem(Acc<C> &acc, const double *__restrict__
 #pragma unroll
         for (int i = 0; i < C::TM; ++i)
 #pragma unroll
-            for (int j = 0; j < C::TN; ++j) dmma884(acc.v[i][j][2], acc.v[i][j][3], ar[i], bi[j]);
+            for (int j = 0; j < C::TN; ++j) dmma884(acc.v[i][j][2], acc.v[i][j][3], ai[i], bi[j]);
 #pragma unroll
         for (int i = 0; i < C::TM; ++i)
 #pragma unroll
-            for (int j = 0; j < C::TN; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], nai[i], bi[j]);
-#pragma unroll
-        for (int i = 0; i < C::TM; ++i)
-#pragma unroll
-            for (int j = 0; j < C::TN; ++j) dmma884(acc.v[i][j][2], acc.v[i][j][3], ai[i], br[j]);
+            for (int j = 0; j < C::TN; ++j) dmma884(acc.v[i][j][4], acc.v[i][j][5], sa[i], sb[j]);
     }
 }
 
@@ -135,7 +137,8 @@ template <class C> __device__ __forceinline__ void sts2(double *s, int row, int 
     *reinterpret_cast<double2 *>(s + C::PLANE + row * C::LD + col) = make_double2(v.i0, v.i1);
 }
 template <class C> __device__ __forceinline__ c2 accv(const Acc<C> &a, int i, int j) {
-    return {a.v[i][j][0], a.v[i][j][1], a.v[i][j][2], a.v[i][j][3]};
+    const double *p = a.v[i][j];                                   // 3M recombination
+    return {p[0] - p[2], p[1] - p[3], p[4] - p[0] - p[2], p[5] - p[1] - p[3]};
 }
 __device__ __forceinline__ c2 operator+(const c2 &a, const c2 &b) { return {a.r0 + b.r0, a.r1 + b.r1, a.i0 + b.i0, a.i1 + b.i1}; }
 __device__ __forceinline__ c2 operator-(const c2 &a, const c2 &b) { return {a.r0 - b.r0, a.r1 - b.r1, a.i0 - b.i0, a.i1 - b.i1}; }
@@ -210,6 +213,7 @@ __device__ __forceinline__ void ld_afrag(const double *M, int r0, int k0, int g,
 template <class C, bool T, int MASK, bool NEG>
 __device__ __forceinline__ void tile_mma(c2 &acc, const double *A, int ar0, int ak0, const double *B, int bk0, int bc0) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double p1a = 0., p1b = 0., p2a = 0., p2b = 0., p3a = 0., p3b = 0.;   // 3M partial products (see Acc)
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
         double ar, ai;
@@ -217,11 +221,12 @@ __device__ __forceinline__ void tile_mma(c2 &acc, const double *A, int ar0, int 
         if (NEG) { ar = -ar; ai = -ai; }
         const int bidx = (bk0 + 4 * ks + t) * C::LD + bc0 + g;
         const double br = B[bidx], bi = B[C::PLANE + bidx];
-        dmma884(acc.r0, acc.r1, ar, br);
-        dmma884(acc.i0, acc.i1, ar, bi);
-        dmma884(acc.r0, acc.r1, -ai, bi);
-        dmma884(acc.i0, acc.i1, ai, br);
+        dmma884(p1a, p1b, ar, br);
+        dmma884(p2a, p2b, ai, bi);
+        dmma884(p3a, p3b, ar + ai, br + bi);
     }
+    acc.r0 += p1a - p2a; acc.r1 += p1b - p2b;
+    acc.i0 += p3a - p1a - p2a; acc.i1 += p3b - p1b - p2b;
 }
 template <class C> __device__ __forceinline__ c2 ld_ctile(const double *M, int r0, int c0) {
     const int lane = threadIdx.x & 31;

@@ -115,11 +115,12 @@ def test_grape_programs_write_their_results(monkeypatch):
     files = fake_h5py.install(monkeypatch)
     import qoc_b200 as qoc
     import qoc_b200.standard as std
+    from qoc_b200.models import MagnusPolicy
     from tests.problems import Problem
     p = Problem(4, 12, 1, 2, 4, complex_controls=True, seed=3)
     res = qoc.grape_schroedinger_discrete(1, p.M, p.costs(std), p.T, p.hamiltonian_numpy(), p.initial_states, p.N,
                                           complex_controls=True, initial_controls=p.controls, iteration_count=4,
-                                          log_iteration_step=0, magnus_policy=qoc.MagnusPolicy.M4, save_file_path="/m/s.h5",
+                                          log_iteration_step=0, magnus_policy=MagnusPolicy.M4, save_file_path="/m/s.h5",
                                           save_intermediate_states=True, save_iteration_step=1)
     f = files["/m/s.h5"]
     best = int(np.argmin(f["error"]))
@@ -131,7 +132,7 @@ def test_grape_programs_write_their_results(monkeypatch):
         assert np.allclose(traj[it, 0], p.initial_states) and np.array_equal(traj[it, -1], f["final_states"][it])
         assert np.abs(np.linalg.norm(traj[it, :, :, :, 0], axis=-1) - 1).max() < 1e-12
     ev = qoc.evolve_schroedinger_discrete(p.T, p.hamiltonian_numpy(), p.initial_states, p.N, controls=f["controls"][2],
-                                          costs=p.costs(std), magnus_policy=qoc.MagnusPolicy.M4, save_file_path="/m/e.h5",
+                                          costs=p.costs(std), magnus_policy=MagnusPolicy.M4, save_file_path="/m/e.h5",
                                           save_intermediate_states=True)
     assert abs(ev.error - f["error"][2]) < 1e-14 and np.array_equal(files["/m/e.h5"]["intermediate_states"], traj[2])
     # Lindblad twin
