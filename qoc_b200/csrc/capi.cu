@@ -9,6 +9,7 @@
 
 #include "../../include/qocb200.h"
 #include "expm_slice.cuh"
+#include "magnus.cuh"
 #include "sweep.cuh"
 #include "large.cuh"
 #include "zgemm.cuh"
@@ -56,17 +57,35 @@ struct KArgs {
     double *node_grad;          // [E*(N-1)][q][KR]
     int S;
     int lowrank;                // 1: use the rank-S reverse pass where it applies (QOCB_NO_LOWRANK=1 disables it)
+    int herm;                   // 1: every operator is Hermitian => anti-Hermitian Magnus matrices (pivot-free LU where safe)
     int *err_flag;
 };
 
+// TMA feed of k_forward (tma.cuh): tensor maps of the propagator buffer U (whose slot j holds the Magnus matrix M_j, written
+// by k_magnus, until slice j has consumed it) and of the chunk-propagator buffer.  Passed as a __grid_constant__ parameter:
+// the maps must live in parameter / constant space for cp.async.bulk.tensor.
+struct FeedMaps {
+    CUtensorMap mapU, mapP;
+    int tma;            // 1: both maps are valid, fetch asynchronously; 0: plain 16-byte loads at the point of use
+    int premagnus;      // 1: U[w] holds M_w (magnus.cuh); 0: assemble the Magnus matrix in this kernel
+};
+
 template <class C>
-__global__ void __launch_bounds__(C::NT) k_forward(KArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(C::NT) k_forward(KArgs a, const __grid_constant__ FeedMaps fm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<C> sm(smem_raw);
     const int c = blockIdx.x;
     const int wb = a.chunk_begin[c], we = a.chunk_begin[c + 1];
     double *scratch = a.scratch + (size_t)c * S_COUNT * C::GMAT;
     double *gP = a.chunkP + (size_t)c * C::GMAT;
+    const bool tma = fm.tma != 0, premag = fm.premagnus != 0;
+    uint64_t *barM = sm.bar, *barP = sm.bar + 1;
+    uint32_t phM = 0, phP = 0;
+    if (tma) {
+        if (threadIdx.x == 0) { mbar_init(barM, 1); mbar_init(barP, 1); mbar_init_fence(); }
+        __syncthreads();
+        if (premag && wb < we && threadIdx.x == 0) tma_fetch_matrix<C::NP>(sm.X2, &fm.mapU, wb, barM);
+    }
     bool parked = false;
     for (int w = wb; w < we; ++w) {
         const int e = w / (a.N - 1), j = w - e * (a.N - 1);
@@ -74,8 +93,12 @@ __global__ void __launch_bounds__(C::NT) k_forward(KArgs a) {
         ga.G0 += (size_t)e * C::GMAT;
         ga.C0 += (size_t)e * ga.KR * C::GMAT;
         PROF_DECL
+        double *gU = a.U + (size_t)w * C::GMAT;
         double *gMnext = scratch + (size_t)S_E * C::GMAT;            // parked Magnus matrix (slot unused by the forward of M2 / M4)
-        if (parked) {                                                // assembled together with the previous slice's
+        if (premag) {                                                // M_w was written into U[w] by k_magnus
+            if (tma) { mbar_wait(barM, phM); phM ^= 1; }
+            else { g2s<C>(sm.X2, gU); __syncthreads(); }
+        } else if (parked) {                                         // assembled together with the previous slice's
             g2s<C>(sm.X2, gMnext);
             __syncthreads();
             parked = false;
@@ -92,23 +115,31 @@ __global__ void __launch_bounds__(C::NT) k_forward(KArgs a) {
         PROF_MARK(1);
         double *tape = a.tape ? a.tape + (size_t)w * a.tape_mats * C::GMAT : nullptr;
         int *piv = a.tape ? a.tape_piv + (size_t)w * C::NP : nullptr;
-        const int s = pade_forward<C>(sm, tape, piv, scratch + (size_t)S_T0 * C::GMAT, scratch + (size_t)S_T1 * C::GMAT, a.s_cap);
+        Feed feed;
+        feed.mapM = &fm.mapU; feed.mapP = &fm.mapP; feed.barM = barM; feed.barP = barP; feed.fetchedP = false;
+        feed.idxM = (tma && premag && w + 1 < we) ? (long long)w + 1 : -1;
+        feed.idxP = (tma && w > wb) ? (long long)c : -1;
+        const double *Ubuf = sm.X1;
+        const int s = pade_forward<C>(sm, tape, piv, scratch + (size_t)S_T0 * C::GMAT, scratch + (size_t)S_T1 * C::GMAT, a.s_cap,
+                                      &feed, &Ubuf, a.herm);
         if (threadIdx.x == 0) a.meta[w] = s;
-        double *gU = a.U + (size_t)w * C::GMAT;
         if (w == wb) {
             for_owned<C>([&](int, int, int row, int col) {
-                const c2 u = lds2<C>(sm.X1, row, col);
+                const c2 u = lds2<C>(Ubuf, row, col);
                 stg2<C>(gU, row, col, u);
                 stg2<C>(gP, row, col, u);
             });
+            __syncthreads();                                         // X2 (LU -> tape) is rewritten by the next slice's Magnus matrix
         } else {
-            for_owned<C>([&](int, int, int row, int col) { stg2<C>(gU, row, col, lds2<C>(sm.X1, row, col)); });
-            g2s<C>(sm.X0, gP);
-            __syncthreads();
+            double *Pbuf = Ubuf == sm.X0 ? sm.X1 : sm.X0;
+            for_owned<C>([&](int, int, int row, int col) { stg2<C>(gU, row, col, lds2<C>(Ubuf, row, col)); });
+            if (feed.fetchedP) { mbar_wait(barP, phP); phP ^= 1; }
+            else { g2s<C>(Pbuf, gP); __syncthreads(); }
             Acc<C> acc; acc.zero();
-            mma_smem<C, false, false, false>(acc, sm.X1, sm.X0);      // P <- U_j P
+            mma_smem<C, false, false, false>(acc, Ubuf, Pbuf);        // P <- U_j P
             for_owned<C>([&](int i, int jj, int row, int col) { stg2<C>(gP, row, col, accv<C>(acc, i, jj)); });
         }
+        if (tma) fence_proxy_async_all();                            // the chunk propagator just written is fetched by TMA next slice
 #ifdef QOCB_PROFILE
         { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { g_prof[7] += clock64() - prof_t0__; g_prof[0] += 1; } }
 #endif
@@ -117,7 +148,7 @@ __global__ void __launch_bounds__(C::NT) k_forward(KArgs a) {
 
 template <class C>
 __global__ void __launch_bounds__(C::NT) k_backward(KArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<C> sm(smem_raw);
     const int c = blockIdx.x;
     const int wb = a.chunk_begin[c], we = a.chunk_begin[c + 1];
@@ -139,7 +170,8 @@ __global__ void __launch_bounds__(C::NT) k_backward(KArgs a) {
             s = a.meta[w];
         } else {
             magnus_forward<C>(sm, ga, scratch);
-            s = pade_forward<C>(sm, ctape, cpiv, scratch + (size_t)S_T0 * C::GMAT, scratch + (size_t)S_T1 * C::GMAT, kCtaTapeR);
+            s = pade_forward<C>(sm, ctape, cpiv, scratch + (size_t)S_T0 * C::GMAT, scratch + (size_t)S_T1 * C::GMAT, kCtaTapeR,
+                                nullptr, nullptr, a.herm);
             if (s > kCtaTapeR && threadIdx.x == 0) *a.err_flag = 1;
             tape = ctape; piv = cpiv;
             __syncthreads();
@@ -227,7 +259,7 @@ __global__ void k_finalize_cost(const double *cost_part, int nchunks, int E, dou
 
 template <class C>
 __global__ void __launch_bounds__(C::NT) k_expm(const double *in, double *out, double *scratch, long long batch) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<C> sm(smem_raw);
     double *sc = scratch + (size_t)blockIdx.x * 3 * C::GMAT;
     for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
@@ -242,7 +274,7 @@ __global__ void __launch_bounds__(C::NT) k_expm(const double *in, double *out, d
 template <class C>
 __global__ void __launch_bounds__(C::NT) k_expm_vjp(const double *in, const double *ubar, double *out, double *abar,
                                                     double *scratch, double *cta_tape, int *cta_piv, long long batch) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<C> sm(smem_raw);
     double *sc = scratch + (size_t)blockIdx.x * S_COUNT * C::GMAT;
     double *tape = cta_tape + (size_t)blockIdx.x * (8 + kCtaTapeR) * C::GMAT;
@@ -272,7 +304,7 @@ __global__ void k_pack_result(const double *grad, const double *cost, const doub
 // pairwise product tree over propagators: out[i] = in[2i+1] * in[2i] (later slices on the left); an odd tail is copied
 template <class C>
 __global__ void __launch_bounds__(C::NT) k_reduce_props(const double *in, double *out, int count) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<C> sm(smem_raw);
     const int i = blockIdx.x;
     const double *lo = in + (size_t)(2 * i) * C::GMAT;
@@ -294,7 +326,7 @@ __global__ void __launch_bounds__(C::NT) k_reduce_props(const double *in, double
 // products chained inside one CTA - fewer dependent launches than the pairwise tree when only the root is wanted
 template <class C>
 __global__ void __launch_bounds__(C::NT) k_reduce_props_radix(const double *in, double *out, int count, int R) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<C> sm(smem_raw);
     const int first = blockIdx.x * R, last = min(count, first + R);
     double *dst = out + (size_t)blockIdx.x * C::GMAT;
@@ -427,6 +459,9 @@ struct qocb_plan {
     std::vector<double> h_vecs;
     std::vector<int> h_counts;
     int ip_total = 0;
+    FeedMaps fm;                        // TMA tensor maps of U and chunkP (k_forward); fm.tma = 0 when TMA is unavailable
+    bool premagnus_ok = true;           // QOCB_NO_PREMAGNUS=1: assemble the Magnus matrices inside k_forward (A/B comparison)
+    bool hermitian = false;             // H0 (every member) and every operator channel are Hermitian (QOCB_NO_NOPIV=1 clears it)
     double *h_pinned = nullptr;         // [M*KR controls | M*KR grad | 1 cost]
     // CUDA graph of one whole host-facing evaluation (H2D controls, all kernels, D2H of gradient, cost, final states and the
     // error flag): replayed by qocb_cost / qocb_cost_and_grad from the third call on - launch-bound small problems gain 2x
@@ -447,8 +482,22 @@ void set_error(qocb_plan *plan, const char *msg) {
 }
 
 template <class C> int launch_forward(qocb_plan *p, const KArgs &a) {
+    FeedMaps fm = p->fm;
+    fm.premagnus = 0;
+    // Magnus matrices of all slices in one streaming pass (magnus.cuh) whenever the order needs no matrix products
+    if (p->premagnus_ok && (a.ga.order == 2 || (a.ga.order == 4 && a.ga.comm))) {
+        const long long W = (long long)a.E * (a.N - 1);
+        const int slabs = (C::GMAT + kMagSlab - 1) / kMagSlab;
+        const long long groups = std::max<long long>(1, std::min<long long>((W + 7) / 8, (3LL * p->num_sms + slabs - 1) / slabs));
+        const long long per_block = (W + groups - 1) / groups;
+        const size_t smem = magnus_smem_bytes(a.ga.order, a.ga.KR);
+        CU_TRY(p, cudaFuncSetAttribute(k_magnus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_magnus<<<dim3(slabs, (unsigned)((W + per_block - 1) / per_block)), kMagThreads, smem, p->stream>>>(a.ga, C::GMAT, a.N - 1, W, per_block, a.U);
+        CU_TRY(p, cudaGetLastError());
+        fm.premagnus = 1;
+    }
     CU_TRY(p, cudaFuncSetAttribute(k_forward<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
-    k_forward<C><<<p->nchunks, C::NT, Smem<C>::bytes(), p->stream>>>(a);
+    k_forward<C><<<p->nchunks, C::NT, Smem<C>::bytes(), p->stream>>>(a, fm);
     CU_TRY(p, cudaGetLastError());
     return 0;
 }
@@ -521,6 +570,7 @@ KArgs make_kargs(qocb_plan *p) {
     a.psi = p->psi.p; a.lam = p->lam.p; a.node_grad = p->node_grad.p; a.S = p->pb.state_count;
     a.err_flag = p->err_flag.p;
     { const char *nl = getenv("QOCB_NO_LOWRANK"); a.lowrank = (nl && nl[0] == '1') ? 0 : 1; }
+    a.herm = p->hermitian ? 1 : 0;
     return a;
 }
 
@@ -1387,6 +1437,14 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
         PTRY(p->one_chunk.alloc(4));
         PTRY(cudaMemcpy(p->one_chunk.p, oc, sizeof(oc), cudaMemcpyHostToDevice));
     }
+    if (!is_large) {
+        std::memset(&p->fm, 0, sizeof(p->fm));
+        const char *nt = getenv("QOCB_NO_TMA"), *npm = getenv("QOCB_NO_PREMAGNUS");
+        if (!(nt && nt[0] == '1'))
+            p->fm.tma = (qocb_host::make_matrix_map(&p->fm.mapU, p->U.p, (long long)W, NP) &&
+                         qocb_host::make_matrix_map(&p->fm.mapP, p->chunkP.p, p->nchunks, NP)) ? 1 : 0;
+        p->premagnus_ok = !(npm && npm[0] == '1');
+    }
     PTRY(p->node_grad.alloc(std::max<size_t>(1, W * q * KC)));
     if (p->mapped) {
         PTRY(p->nodecoef.alloc(std::max<size_t>(1, (size_t)Nm1 * q * KC))); PTRY(p->map_off.alloc(std::max<size_t>(1, (size_t)Nm1 * q * KC)));
@@ -1482,6 +1540,24 @@ int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
         }
         p->ops_set = true;
         return 0;
+    }
+    {   // Hermitian operators => anti-Hermitian generators: selects the pivot-free LU where it is safe (tile.cuh)
+        auto is_herm = [&](const double *h) {
+            double mx = 0., dev = 0.;
+            for (int r = 0; r < n; ++r)
+                for (int c = 0; c <= r; ++c) {
+                    const double ar = h[2 * ((size_t)r * n + c)], ai = h[2 * ((size_t)r * n + c) + 1];
+                    const double br = h[2 * ((size_t)c * n + r)], bi = h[2 * ((size_t)c * n + r) + 1];
+                    mx = std::max(mx, std::max(std::fabs(ar) + std::fabs(ai), std::fabs(br) + std::fabs(bi)));
+                    dev = std::max(dev, std::fabs(ar - br) + std::fabs(ai + bi));
+                }
+            return dev <= 1e-13 * mx;
+        };
+        bool herm = true;
+        for (int e = 0; e < E && herm; ++e) herm = is_herm(h0 + (size_t)e * 2 * n * n);
+        for (int r = 0; r < KR && herm && a_ops; ++r) herm = is_herm(a_ops + (size_t)r * 2 * n * n);
+        const char *np_ = getenv("QOCB_NO_NOPIV");
+        p->hermitian = herm && !(np_ && np_[0] == '1');
     }
     std::vector<double> buf((size_t)std::max(E, KR) * GM);
     for (int e = 0; e < E; ++e) to_planar(h0 + (size_t)e * 2 * n * n, buf.data() + (size_t)e * GM, n, NP, true);
@@ -1791,8 +1867,9 @@ static int launch_count_unmapped(qocb_plan *p, int32_t with_grad) {
         const int fwd = o == 6 ? 21 : o == 4 ? 14 : 11;                      // own kernels + library calls per batch
         return batches * (fwd + (with_grad ? fwd + (o == 6 ? 60 : o == 4 ? 38 : 30) : 0)) + (with_grad ? 3 : 1);
     }
-    if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->levels;
-    int levels = p->levels;                                          // pairwise levels for the sweeps, then radix 4 to the root
+    const int pm = (p->premagnus_ok && (p->pb.magnus_order == 2 || (p->pb.magnus_order == 4 && p->comm_ok))) ? 1 : 0;   // k_magnus
+    if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->levels + pm;
+    int levels = p->levels + pm;                                          // pairwise levels for the sweeps, then radix 4 to the root
     for (int c = p->lvl_count[p->levels]; c > 1; c = (c + 3) / 4) ++levels;
     // forward: expm, tree, prefix, boundary, sweep; backward: [particular sweeps], boundary (twice only with step costs on a
     // shard that is not the last), suffix, sweep, expm, gather, finalize, pack

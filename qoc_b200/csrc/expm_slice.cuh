@@ -13,6 +13,7 @@
 #pragma once
 #include "tile.cuh"
 #include "lowrank.cuh"
+#include "tma.cuh"
 
 namespace qocb {
 
@@ -38,15 +39,17 @@ struct Smem {
     double *red;                // 64 + kMaxQ*kMaxKR*NWARP doubles of reduction scratch
     double *coef;               // [kMaxQ][kMaxKR]
     int *piv;                   // [NP] row permutation of the LU, then [8] pivots of the current panel
+    uint64_t *bar;              // [2] mbarriers of the TMA feed (k_forward): next Magnus matrix, chunk propagator
     __device__ __forceinline__ Smem(unsigned char *base) {
-        double *d = reinterpret_cast<double *>(base);
+        double *d = reinterpret_cast<double *>(base);   // base is 128-byte aligned; SMAT * 8 is a multiple of 128 (TMA destinations)
         X0 = d; X1 = d + C::SMAT; X2 = d + 2 * C::SMAT;
         red = d + 3 * C::SMAT;
         coef = red + 64 + kMaxQ * kMaxKR * C::NWARP;
         piv = reinterpret_cast<int *>(coef + kMaxQ * kMaxKR);
+        bar = reinterpret_cast<uint64_t *>(piv + C::NP + 8);
     }
     static constexpr size_t bytes() {
-        return sizeof(double) * (3 * C::SMAT + 64 + kMaxQ * kMaxKR * C::NWARP + kMaxQ * kMaxKR) + sizeof(int) * (C::NP + 8);
+        return sizeof(double) * (3 * C::SMAT + 64 + kMaxQ * kMaxKR * C::NWARP + kMaxQ * kMaxKR) + sizeof(int) * (C::NP + 8) + 2 * sizeof(uint64_t);
     }
 };
 
@@ -265,8 +268,25 @@ __device__ void magnus_forward_pair(const Smem<C> &sm, const GenArgs &ga, const 
 // ---------------------------------------------------------------------------------------------------------
 // Pade-13 forward.  In: M in X2.  Out: U = expm(M) in X1 (all threads past a barrier); returns s.
 // tape: 8 + s matrices are written when tape != nullptr (T_R + i holds R_i for i < s); piv_out: int[NP].
+// Asynchronous feed of k_forward (tma.cuh).  While the substitutions and squarings of this slice run, pade_forward starts
+//   * the chunk propagator (matrix idxP of mapP) into X1 as soon as the solve has consumed its right-hand side - only when
+//     the slice needs no squarings, because then U stays in X0 and X1 is free until the chunk product;
+//   * the next slice's Magnus matrix (matrix idxM of mapM) into X2 once the LU factors have gone to the tape.
+// Negative indices skip a fetch.  fetchedP reports whether the propagator fetch was issued.
+struct Feed {
+    const CUtensorMap *mapM, *mapP;
+    long long idxM, idxP;
+    uint64_t *barM, *barP;
+    bool fetchedP;
+};
+
+// u_out != nullptr: the caller accepts U in X0 when no squarings are needed (*u_out = X0 or X1); otherwise U is in X1.
+// herm != 0: the argument is anti-Hermitian (Hermitian operators): slices with ||A||_1 < QOCB_NOPIV_NORM factor the Pade
+// denominator without pivoting (tile.cuh: lu_factor_blocked_nopiv).
+#define QOCB_NOPIV_NORM 2.5
 template <class C>
-__device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, double *tmpY, double *tmpV, int s_cap) {
+__device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, double *tmpY, double *tmpV, int s_cap,
+                            Feed *feed = nullptr, const double **u_out = nullptr, int herm = 0) {
     PROF_DECL
     // one-norm: max column sum of |m_ij|   (expm.py:103-116)
     {
@@ -371,13 +391,25 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
     });
     __syncthreads();
     PROF_MARK(3);
-    lu_factor_blocked<C>(sm.X2, sm.piv, sm.piv + C::NP);
+    if (herm && s == 0 && norm < QOCB_NOPIV_NORM) lu_factor_blocked_nopiv<C>(sm.X2, sm.piv);
+    else lu_factor_blocked<C>(sm.X2, sm.piv, sm.piv + C::NP);
     PROF_MARK(4);
-    lu_solve_blocked<C, false>(sm.X2, sm.piv, sm.X1, sm.X0);            // R0 = Q^-1 P in X0 (Y is dead)
+    {
+        const bool feedP = feed != nullptr && feed->idxP >= 0 && s == 0;
+        if (feed) feed->fetchedP = feedP;
+        auto b_free = [&]() {
+            if (feedP && threadIdx.x == 0) tma_fetch_matrix<C::NP>(sm.X1, feed->mapP, feed->idxP, feed->barP);
+        };
+        lu_solve_blocked<C, false>(sm.X2, sm.piv, sm.X1, sm.X0, b_free);   // R0 = Q^-1 P in X0 (Y is dead)
+    }
     PROF_MARK(5);
     if (keep) {
         s2g<C>(tape + (size_t)T_LU * C::GMAT, sm.X2);                   // LUi format (tile.cuh) + row permutation
         for (int c = threadIdx.x; c < C::NP; c += C::NT) piv_out[c] = sm.piv[c];
+    }
+    if (feed != nullptr && feed->idxM >= 0) {                           // X2 is dead from here on
+        __syncthreads();
+        if (threadIdx.x == 0) tma_fetch_matrix<C::NP>(sm.X2, feed->mapM, feed->idxM, feed->barM);
     }
     const double *cur = sm.X0;
     for (int i = 0; i < s; ++i) {                                        // expm.py:249-250
@@ -388,7 +420,8 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
         __syncthreads();
         cur = sm.X1;
     }
-    if (s == 0) {
+    if (u_out) *u_out = s == 0 ? sm.X0 : sm.X1;
+    if (s == 0 && !u_out) {
         for_owned<C>([&](int, int, int row, int col) { sts2<C>(sm.X1, row, col, lds2<C>(sm.X0, row, col)); });
         __syncthreads();
     }

@@ -1,0 +1,105 @@
+// magnus.cuh - Magnus matrices of ALL slices in one streaming pass (orders without matrix products: M2 and the
+// product-free M4; qoc/core/mathmethods.py:72-122).
+//
+// For those orders the Magnus matrix of a slice is a linear combination of a few fixed operators,
+//     M_j = sum_c w_c(j) Op_c,     Op = [G0 | G_r | [G0, G_r] | [G_s, G_r] (s < r)],
+// with weights that depend on the interpolated controls only (expm_slice.cuh: magnus_forward).  Assembling it inside the
+// expm kernel streams 1 + 2 KR + KR (KR - 1) / 2 operator matrices from L2 per slice - latency-bound with one 8-warp CTA
+// per SM (12 - 14 us of a 148 us slice at n = 64, KR = 4).  Here the work is turned around: a CTA keeps a 512-element slab
+// of every operator in shared memory and walks over the slices, so each operator element is read once per CTA and the
+// kernel is bound by its output stream (32 n^2 bytes per slice, written once, coalesced 16-byte stores).  The matrices go
+// into the slice-propagator buffer U - slot j holds M_j until the expm kernel has consumed it (it prefetches it by TMA
+// during the previous slice) and overwrites it with U_j - so the pass needs no memory of its own.
+#pragma once
+#include "expm_slice.cuh"
+
+namespace qocb {
+
+constexpr int kMagThreads = 256, kMagSlab = 2 * kMagThreads, kMagTile = 32, kMagGroup = 8;
+constexpr int kMagMaxOps = 1 + 2 * kMaxCommKR + kMaxCommKR * (kMaxCommKR - 1) / 2 > 1 + kMaxKR ? 1 + 2 * kMaxCommKR + kMaxCommKR * (kMaxCommKR - 1) / 2 : 1 + kMaxKR;
+
+__host__ __device__ inline int magnus_op_count(int order, int KR) { return order == 4 ? 1 + 2 * KR + KR * (KR - 1) / 2 : 1 + KR; }
+__host__ inline size_t magnus_smem_bytes(int order, int KR) {
+    return sizeof(double) * ((size_t)magnus_op_count(order, KR) * (kMagSlab + kMagTile));
+}
+
+// out[w][GMAT] = Magnus matrix of work item w = member * Nm1 + slice, for w in the block's range; grid = (slabs, groups)
+__global__ void __launch_bounds__(kMagThreads) k_magnus(GenArgs ga, int GMAT, int Nm1, long long W, long long per_block, double *out) {
+    extern __shared__ __align__(16) double mg_sm[];
+    const int KR = ga.KR, q = ga.q, tid = threadIdx.x;
+    const bool m4 = ga.order == 4;
+    const int nops = magnus_op_count(ga.order, KR);
+    double *ops = mg_sm;                                   // [nops][kMagSlab]
+    double *wts = mg_sm + (size_t)nops * kMagSlab;         // [nops][kMagTile]
+    const int e0 = blockIdx.x * kMagSlab + 2 * tid;        // first of the two matrix elements (doubles) of this thread
+    const bool live = e0 < GMAT;
+    const long long wbeg = (long long)blockIdx.y * per_block, wend = min(W, wbeg + per_block);
+    const double dt = ga.dt, f = (QOCB_S3 / 12.0) * dt * dt;
+    long long member = -1;
+    auto load_slab = [&](int c, const double *src) {
+        double2 v = make_double2(0., 0.);
+        if (live) v = *reinterpret_cast<const double2 *>(src + e0);
+        *reinterpret_cast<double2 *>(ops + (size_t)c * kMagSlab + 2 * tid) = v;
+    };
+    for (long long w0 = wbeg; w0 < wend;) {
+        const long long e = w0 / Nm1;
+        const int j0 = (int)(w0 - e * Nm1);
+        const int cnt = (int)min((long long)kMagTile, min(wend - w0, (long long)(Nm1 - j0)));
+        __syncthreads();                                    // the previous tile is done with ops / wts
+        if (e != member) {                                  // operator slabs: drift-dependent ones per member, the rest once
+            load_slab(0, ga.G0 + (size_t)e * GMAT);
+            if (m4) for (int r = 0; r < KR; ++r) load_slab(1 + KR + r, ga.C0 + ((size_t)e * KR + r) * GMAT);
+            if (member < 0) {
+                for (int r = 0; r < KR; ++r) load_slab(1 + r, ga.G + (size_t)r * GMAT);
+                if (m4) for (int pr = 0; pr < KR * (KR - 1) / 2; ++pr) load_slab(1 + 2 * KR + pr, ga.Cs + (size_t)pr * GMAT);
+            }
+            member = e;
+        }
+        // weights of the tile: wts[c][jj]
+        for (int idx = tid; idx < cnt * nops; idx += kMagThreads) {
+            const int jj = idx / nops, c = idx - jj * nops, j = j0 + jj;
+            auto coef = [&](int node, int r) -> double {
+                if (ga.nodecoef) return ga.nodecoef[(size_t)(j * q + node) * KR + r];
+                const int *id = ga.itab_idx + (j * q + node) * 2;
+                const double *iw = ga.itab_w + (j * q + node) * 2;
+                return ga.controls[id[0] * KR + r] * iw[0] + ga.controls[id[1] * KR + r] * iw[1];
+            };
+            double wv;
+            if (c == 0) wv = dt;
+            else if (!m4) wv = dt * coef(0, c - 1);
+            else if (c <= KR) wv = 0.5 * dt * (coef(0, c - 1) + coef(1, c - 1));
+            else if (c <= 2 * KR) wv = f * (coef(0, c - 1 - KR) - coef(1, c - 1 - KR));
+            else {
+                int pr = c - 1 - 2 * KR, s_ = 0;
+                while (pr >= KR - 1 - s_) { pr -= KR - 1 - s_; ++s_; }
+                const int r = s_ + 1 + pr;                  // comm_pair(s_, r, KR) == c - 1 - 2 KR
+                wv = f * (coef(1, s_) * coef(0, r) - coef(1, r) * coef(0, s_));
+            }
+            wts[c * kMagTile + jj] = wv;
+        }
+        __syncthreads();
+        for (int jj = 0; jj < cnt; jj += kMagGroup) {
+            double2 acc[kMagGroup];
+#pragma unroll
+            for (int u = 0; u < kMagGroup; ++u) acc[u] = make_double2(0., 0.);
+            for (int c = 0; c < nops; ++c) {
+                const double2 o = *reinterpret_cast<const double2 *>(ops + (size_t)c * kMagSlab + 2 * tid);
+                const double *wr = wts + c * kMagTile + jj;
+#pragma unroll
+                for (int u = 0; u < kMagGroup; u += 2) {
+                    const double2 ww = *reinterpret_cast<const double2 *>(wr + u);   // jj and u are even: 16-byte aligned
+                    acc[u].x = fma(ww.x, o.x, acc[u].x); acc[u].y = fma(ww.x, o.y, acc[u].y);
+                    acc[u + 1].x = fma(ww.y, o.x, acc[u + 1].x); acc[u + 1].y = fma(ww.y, o.y, acc[u + 1].y);
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int u = 0; u < kMagGroup; ++u)
+                    if (jj + u < cnt) *reinterpret_cast<double2 *>(out + (size_t)(w0 + jj + u) * GMAT + e0) = acc[u];
+            }
+        }
+        w0 += cnt;
+    }
+}
+
+}  // namespace qocb

@@ -429,10 +429,160 @@ __device__ void lu_factor_blocked(double *Q, int *perm, int *piv8) {
     }
 }
 
+// ---- blocked LU WITHOUT pivoting -------------------------------------------------------------------------------------
+// For an anti-Hermitian argument A = -i H dt (every physical GRAPE problem: H0 and the control operators are Hermitian)
+// the Pade denominator Q = V - U is a polynomial of A with real coefficients: it is a normal matrix with eigenvalues
+// q(i lam) = b0 e^{-i lam / 2} (1 + O(1e-10)) for the eigenvalues i lam of A, so its Hermitian part is b0 cos(lam / 2) > 0
+// as long as |lam| <= ||A||_1 < pi.  A matrix with a positive definite Hermitian part has an LU factorisation without
+// pivoting whose growth is bounded (Golub & Van Loan, sec. 4.2.2: || |L||U| || <= n (||T|| + ||S T^-1 S||), T, S the
+// Hermitian / skew parts), i.e. it is backward stable, and zgesv's row exchanges buy nothing.  pade_forward takes this path
+// when the plan's operators are Hermitian and ||A||_1 < 2.5 (cos(1.25) = 0.32: growth below ~4); everything else goes
+// through the pivoted factorisation above.  Same LUi storage, identity permutation - the solves and the reverse pass
+// do not know the difference.
+// What it removes: the single-warp pivot search over the whole panel column (REDUX + broadcasts on 64 rows, the row
+// position bookkeeping, the row swaps of every column tile).  Per panel only the 8 x 8 diagonal block is factored by one
+// warp; L21 = A21 inv(U11) and U12 = inv(L11) A12 are DMMA tile products spread over all warps.
+
+// acc (8 x 8 tile) += A[ar0:+8, ak0:+8] * maskU(B[bk0:+8, bc0:+8]); maskU keeps the upper triangle incl. the diagonal of the
+// STORED block (the inv(U_kk) half of an LUi diagonal block)
+template <class C>
+__device__ __forceinline__ void tile_mma_bupper(c2 &acc, const double *A, int ar0, int ak0, const double *B, int bk0, int bc0) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double p1a = 0., p1b = 0., p2a = 0., p2b = 0., p3a = 0., p3b = 0.;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const int aidx = (ar0 + g) * C::LD + ak0 + 4 * ks + t;
+        const double ar = A[aidx], ai = A[C::PLANE + aidx];
+        const int bidx = (bk0 + 4 * ks + t) * C::LD + bc0 + g;
+        double br = B[bidx], bi = B[C::PLANE + bidx];
+        if (4 * ks + t > g) { br = 0.; bi = 0.; }                  // stored row > stored column: the inv(L) half
+        dmma884(p1a, p1b, ar, br);
+        dmma884(p2a, p2b, ai, bi);
+        dmma884(p3a, p3b, ar + ai, br + bi);
+    }
+    acc.r0 += p1a - p2a; acc.r1 += p1b - p2b;
+    acc.i0 += p3a - p1a - p2a; acc.i1 += p3b - p1b - p2b;
+}
+
+// warp 0: unpivoted LU of the 8 x 8 diagonal block at (j0, j0), then the in-place inversion of its factors (LUi format)
+template <class C>
+__device__ void lu_diag_warp(double *Q, int j0) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    double *Qr = Q, *Qi = Q + C::PLANE;
+    const bool va = lane < 8;
+    const int ra = j0 + (lane & 7);
+    cplx pa[8];
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+        const double2 r = *reinterpret_cast<const double2 *>(Qr + ra * C::LD + j0 + c);
+        const double2 i = *reinterpret_cast<const double2 *>(Qi + ra * C::LD + j0 + c);
+        pa[c] = {r.x, i.x}; pa[c + 1] = {r.y, i.y};
+    }
+    cplx dinv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        cplx u[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c >= j) { u[c].r = __shfl_sync(FULL, pa[c].r, j); u[c].i = __shfl_sync(FULL, pa[c].i, j); }
+        const double nn = u[j].r * u[j].r + u[j].i * u[j].i;
+        double dn;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(dn) : "d"(nn));
+        dn = fma(dn, fma(-nn, dn, 1.0), dn);
+        dn = fma(dn, fma(-nn, dn, 1.0), dn);
+        const cplx inv = {u[j].r * dn, -u[j].i * dn};
+        dinv[j] = inv;
+        if ((lane & 7) > j) {
+            const cplx l = cmul(pa[j], inv);
+            pa[j] = l;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) if (c > j) { pa[c].r -= l.r * u[c].r - l.i * u[c].i; pa[c].i -= l.r * u[c].i + l.i * u[c].r; }
+        }
+    }
+    __syncwarp();
+    if (va) {
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            *reinterpret_cast<double2 *>(Qr + ra * C::LD + j0 + c) = make_double2(pa[c].r, pa[c + 1].r);
+            *reinterpret_cast<double2 *>(Qi + ra * C::LD + j0 + c) = make_double2(pa[c].i, pa[c + 1].i);
+        }
+    }
+    __syncwarp();
+    // inversion of the factors, as in lu_panel_warp: lanes 0-7 one column of inv(L_kk), lanes 8-15 one column of inv(U_kk)
+    cplx x[8];
+    const int c = lane & 7;
+    const double *Br = Qr + j0 * C::LD + j0, *Bi = Qi + j0 * C::LD + j0;
+    const bool isU = lane >= 8;
+    if (lane < 16) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[r] = {((isU ? 7 - r : r) == c) ? 1.0 : 0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const cplx d = dinv[7 - r];
+            if (isU) x[r] = cmul(x[r], d);
+#pragma unroll
+            for (int r2 = 0; r2 < 8; ++r2)
+                if (r2 > r) {
+                    const int off = isU ? (7 - r2) * C::LD + (7 - r) : r2 * C::LD + r;
+                    const double er = Br[off], ei = Bi[off];
+                    x[r2].r -= er * x[r].r - ei * x[r].i; x[r2].i -= er * x[r].i + ei * x[r].r;
+                }
+        }
+    }
+    __syncwarp();
+    if (lane < 16) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int rr = isU ? 7 - r : r;
+            if (isU ? rr <= c : rr > c) { Qr[(j0 + rr) * C::LD + j0 + c] = x[r].r; Qi[(j0 + rr) * C::LD + j0 + c] = x[r].i; }
+        }
+    }
+    __syncwarp();
+}
+
+// In-place blocked LU of Q without pivoting (LUi format, perm = identity).  Ends with a barrier.
+template <class C>
+__device__ void lu_factor_blocked_nopiv(double *Q, int *perm) {
+    constexpr int NB = C::NP / 8;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < C::NP; i += C::NT) perm[i] = i;
+    PROF_DECL
+    for (int kb = 0; kb < NB; ++kb) {
+        const int j0 = kb * 8, nt = NB - kb - 1;
+        __syncthreads();
+        if (warp == 0) lu_diag_warp<C>(Q, j0);
+        __syncthreads();
+        PROF_MARK(14);
+        for (int x = warp; x < 2 * nt; x += C::NWARP) {
+            c2 v = czero();
+            if (x < nt) {                                          // U12 = inv(L11) A12
+                const int c0 = (kb + 1 + x) * 8;
+                tile_mma<C, false, MASK_LINV, false>(v, Q, j0, j0, Q, j0, c0);
+                __syncwarp();
+                st_ctile<C>(Q, j0, c0, v);
+            } else {                                               // L21 = A21 inv(U11)
+                const int r0 = (kb + 1 + x - nt) * 8;
+                tile_mma_bupper<C>(v, Q, r0, j0, Q, j0, j0);
+                __syncwarp();
+                st_ctile<C>(Q, r0, j0, v);
+            }
+        }
+        __syncthreads();
+        for (int ct = kb + 1 + warp; ct < NB; ct += C::NWARP) tile_update_rows<C, false>(Q, Q, kb, ct * 8, kb + 1, NB, 1);   // A22 -= L21 U12
+        PROF_MARK(15);
+    }
+    __syncthreads();
+}
+
 // X <- Q^{-1} B (TRANS = false) or Q^{-T} B (TRANS = true); LU in LUi format.  B is read from `B`, the result is
 // written to `X` (B != X: the row permutation is applied out of place).  Both end with a barrier.
-template <class C, bool TRANS>
-__device__ void lu_solve_blocked(const double *LU, const int *perm, double *B, double *X) {
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `b_free` is called by every thread once B is no longer read (TRANS = false: right after the row permutation has been
+// applied out of place) - k_forward uses it to start an asynchronous fetch into that buffer
+template <class C, bool TRANS, class Hook = NoHook>
+__device__ void lu_solve_blocked(const double *LU, const int *perm, double *B, double *X, Hook b_free = Hook()) {
     constexpr int NB = C::NP / 8;
     const int warp = threadIdx.x >> 5;
     double *W = TRANS ? B : X;                                     // the substitutions run in place on W
@@ -444,6 +594,7 @@ __device__ void lu_solve_blocked(const double *LU, const int *perm, double *B, d
                 *reinterpret_cast<const double2 *>(B + plane * C::PLANE + perm[row] * C::LD + 2 * cc);
         }
         __syncthreads();
+        b_free();
     }
     for (int ct = warp; ct < NB; ct += C::NWARP) {
         const int c0 = ct * 8;
