@@ -464,96 +464,88 @@ __device__ __forceinline__ void tile_mma_bupper(c2 &acc, const double *A, int ar
     acc.i0 += p3a - p1a - p2a; acc.i1 += p3b - p1b - p2b;
 }
 
-// warp 0: unpivoted LU of the 8 x 8 diagonal block at (j0, j0), then the in-place inversion of its factors (LUi format)
+// One warp: unpivoted LU of the 8 x 8 diagonal block at (j0, j0) and the inverses of its factors, in place (LUi format).
+// The block lives in registers in the DMMA accumulator layout - lane (g, t) holds row g, columns 2t and 2t + 1 - so all
+// 32 lanes work on every elimination step (8 shuffles + 8 DFMA per lane and step for the block; the dependent chain per
+// step is one pivot broadcast, the reciprocal (hardware seed + two Newton steps) and one complex multiply-add).
+//   * forward elimination runs on [A | Z], Z = I: afterwards A holds U (upper) and the multipliers (lower), Z = inv(L);
+//   * a backward (Jordan) sweep on Y = I with the rows scaled by 1 / u_jj gives Y = inv(U).
+// No pivoting: see the note above for when that is safe.
+__device__ __forceinline__ c2 shfl_c2(const c2 &v, int src) {
+    constexpr unsigned FULL = 0xffffffffu;
+    return {__shfl_sync(FULL, v.r0, src), __shfl_sync(FULL, v.r1, src), __shfl_sync(FULL, v.i0, src), __shfl_sync(FULL, v.i1, src)};
+}
 template <class C>
 __device__ void lu_diag_warp(double *Q, int j0) {
     constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    double *Qr = Q, *Qi = Q + C::PLANE;
-    const bool va = lane < 8;
-    const int ra = j0 + (lane & 7);
-    cplx pa[8];
-#pragma unroll
-    for (int c = 0; c < 8; c += 2) {
-        const double2 r = *reinterpret_cast<const double2 *>(Qr + ra * C::LD + j0 + c);
-        const double2 i = *reinterpret_cast<const double2 *>(Qi + ra * C::LD + j0 + c);
-        pa[c] = {r.x, i.x}; pa[c + 1] = {r.y, i.y};
-    }
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    c2 a = ld_ctile<C>(Q, j0, j0);
+    c2 z = {g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0, 0., 0.};
+    c2 y = z;
     cplx dinv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        cplx u[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            if (c >= j) { u[c].r = __shfl_sync(FULL, pa[c].r, j); u[c].i = __shfl_sync(FULL, pa[c].i, j); }
-        const double nn = u[j].r * u[j].r + u[j].i * u[j].i;
+        const int tj = j >> 1;
+        const bool odd = (j & 1) != 0;
+        const double sr = odd ? a.r1 : a.r0, si = odd ? a.i1 : a.i0;     // this lane's entry of column j (if it owns one)
+        const double pr = __shfl_sync(FULL, sr, 4 * j + tj), pi = __shfl_sync(FULL, si, 4 * j + tj);      // u_jj
+        const double er = __shfl_sync(FULL, sr, 4 * g + tj), ei = __shfl_sync(FULL, si, 4 * g + tj);      // a_gj
+        const c2 u = shfl_c2(a, 4 * j + t), w = shfl_c2(z, 4 * j + t);                                      // row j of A and Z
+        const double nn = pr * pr + pi * pi;
         double dn;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(dn) : "d"(nn));
         dn = fma(dn, fma(-nn, dn, 1.0), dn);
         dn = fma(dn, fma(-nn, dn, 1.0), dn);
-        const cplx inv = {u[j].r * dn, -u[j].i * dn};
+        const cplx inv = {pr * dn, -pi * dn};
         dinv[j] = inv;
-        if ((lane & 7) > j) {
-            const cplx l = cmul(pa[j], inv);
-            pa[j] = l;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) if (c > j) { pa[c].r -= l.r * u[c].r - l.i * u[c].i; pa[c].i -= l.r * u[c].i + l.i * u[c].r; }
+        if (g > j) {
+            const cplx l = cmul({er, ei}, inv);
+            if (2 * t > j) { a.r0 -= l.r * u.r0 - l.i * u.i0; a.i0 -= l.r * u.i0 + l.i * u.r0; }
+            else if (2 * t == j) { a.r0 = l.r; a.i0 = l.i; }
+            if (2 * t + 1 > j) { a.r1 -= l.r * u.r1 - l.i * u.i1; a.i1 -= l.r * u.i1 + l.i * u.r1; }
+            else if (2 * t + 1 == j) { a.r1 = l.r; a.i1 = l.i; }
+            z.r0 -= l.r * w.r0 - l.i * w.i0; z.i0 -= l.r * w.i0 + l.i * w.r0;
+            z.r1 -= l.r * w.r1 - l.i * w.i1; z.i1 -= l.r * w.i1 + l.i * w.r1;
         }
     }
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+        const int tj = j >> 1;
+        const bool odd = (j & 1) != 0;
+        if (g == j) {
+            const cplx d = dinv[j];
+            const cplx y0 = cmul({y.r0, y.i0}, d), y1 = cmul({y.r1, y.i1}, d);
+            y = {y0.r, y1.r, y0.i, y1.i};
+        }
+        const c2 w = shfl_c2(y, 4 * j + t);                                                                 // row j of inv(U)
+        const double er = __shfl_sync(FULL, odd ? a.r1 : a.r0, 4 * g + tj), ei = __shfl_sync(FULL, odd ? a.i1 : a.i0, 4 * g + tj);   // u_gj
+        if (g < j) {
+            y.r0 -= er * w.r0 - ei * w.i0; y.i0 -= er * w.i0 + ei * w.r0;
+            y.r1 -= er * w.r1 - ei * w.i1; y.i1 -= er * w.i1 + ei * w.r1;
+        }
+    }
+    const c2 out = {g > 2 * t ? z.r0 : y.r0, g > 2 * t + 1 ? z.r1 : y.r1, g > 2 * t ? z.i0 : y.i0, g > 2 * t + 1 ? z.i1 : y.i1};
     __syncwarp();
-    if (va) {
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-            *reinterpret_cast<double2 *>(Qr + ra * C::LD + j0 + c) = make_double2(pa[c].r, pa[c + 1].r);
-            *reinterpret_cast<double2 *>(Qi + ra * C::LD + j0 + c) = make_double2(pa[c].i, pa[c + 1].i);
-        }
-    }
-    __syncwarp();
-    // inversion of the factors, as in lu_panel_warp: lanes 0-7 one column of inv(L_kk), lanes 8-15 one column of inv(U_kk)
-    cplx x[8];
-    const int c = lane & 7;
-    const double *Br = Qr + j0 * C::LD + j0, *Bi = Qi + j0 * C::LD + j0;
-    const bool isU = lane >= 8;
-    if (lane < 16) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) x[r] = {((isU ? 7 - r : r) == c) ? 1.0 : 0.0, 0.0};
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const cplx d = dinv[7 - r];
-            if (isU) x[r] = cmul(x[r], d);
-#pragma unroll
-            for (int r2 = 0; r2 < 8; ++r2)
-                if (r2 > r) {
-                    const int off = isU ? (7 - r2) * C::LD + (7 - r) : r2 * C::LD + r;
-                    const double er = Br[off], ei = Bi[off];
-                    x[r2].r -= er * x[r].r - ei * x[r].i; x[r2].i -= er * x[r].i + ei * x[r].r;
-                }
-        }
-    }
-    __syncwarp();
-    if (lane < 16) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int rr = isU ? 7 - r : r;
-            if (isU ? rr <= c : rr > c) { Qr[(j0 + rr) * C::LD + j0 + c] = x[r].r; Qi[(j0 + rr) * C::LD + j0 + c] = x[r].i; }
-        }
-    }
+    st_ctile<C>(Q, j0, j0, out);
     __syncwarp();
 }
 
-// In-place blocked LU of Q without pivoting (LUi format, perm = identity).  Ends with a barrier.
+// In-place blocked LU of Q without pivoting (LUi format, perm = identity).  Ends with a barrier.  Look-ahead: during the
+// trailing update of panel kb, warp 0 updates only the next diagonal tile and factors it straight away, the other warps
+// share the rest of the trailing matrix - the single-warp diagonal factorisation runs in the shadow of the update.
 template <class C>
 __device__ void lu_factor_blocked_nopiv(double *Q, int *perm) {
     constexpr int NB = C::NP / 8;
+    constexpr int HELP = C::NWARP > 1 ? C::NWARP - 1 : 1;          // warps sharing the trailing update beside warp 0
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < C::NP; i += C::NT) perm[i] = i;
+    __syncthreads();
     PROF_DECL
-    for (int kb = 0; kb < NB; ++kb) {
+    if (warp == 0) lu_diag_warp<C>(Q, 0);
+    __syncthreads();
+    PROF_MARK(14);
+    for (int kb = 0; kb < NB - 1; ++kb) {
         const int j0 = kb * 8, nt = NB - kb - 1;
-        __syncthreads();
-        if (warp == 0) lu_diag_warp<C>(Q, j0);
-        __syncthreads();
-        PROF_MARK(14);
         for (int x = warp; x < 2 * nt; x += C::NWARP) {
             c2 v = czero();
             if (x < nt) {                                          // U12 = inv(L11) A12
@@ -569,10 +561,22 @@ __device__ void lu_factor_blocked_nopiv(double *Q, int *perm) {
             }
         }
         __syncthreads();
-        for (int ct = kb + 1 + warp; ct < NB; ct += C::NWARP) tile_update_rows<C, false>(Q, Q, kb, ct * 8, kb + 1, NB, 1);   // A22 -= L21 U12
+        // A22 -= L21 U12
+        if (C::NWARP == 1) {
+            for (int ct = kb + 1; ct < NB; ++ct) tile_update_rows<C, false>(Q, Q, kb, ct * 8, kb + 1, NB, 1);
+            lu_diag_warp<C>(Q, j0 + 8);
+        } else if (warp == 0) {
+            tile_update_rows<C, false>(Q, Q, kb, j0 + 8, kb + 1, kb + 2, 1);   // the next diagonal tile first ...
+            __syncwarp();
+            lu_diag_warp<C>(Q, j0 + 8);                                       // ... and its factorisation
+        } else {
+            // column tiles kb+1 .. NB-1 over the helper warps; in column kb+1 the diagonal tile belongs to warp 0
+            for (int ct = kb + 1 + (warp - 1); ct < NB; ct += HELP)
+                tile_update_rows<C, false>(Q, Q, kb, ct * 8, ct == kb + 1 ? kb + 2 : kb + 1, NB, 1);
+        }
+        __syncthreads();
         PROF_MARK(15);
     }
-    __syncthreads();
 }
 
 // X <- Q^{-1} B (TRANS = false) or Q^{-T} B (TRANS = true); LU in LUi format.  B is read from `B`, the result is

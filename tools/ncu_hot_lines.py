@@ -10,7 +10,7 @@ hdr = None
 fname = None
 data = []
 for r in rows:
-    if len(r) == 2 and r[0] == "File Name":
+    if len(r) == 2 and r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]
         continue
     if len(r) > 6 and r[0] == "Line No":
