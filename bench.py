@@ -539,19 +539,140 @@ def run_lindblad(args, name):
     plan.close()
 
 
+# ---- batched matrix exponential (BASELINE.json metric 2: "batched expm GFLOP/s"; SURVEY.md section 8d shapes) --------------------
+EXPM_WORKLOADS = {
+    # name: (n, batch): working sets (32 n^2 bytes per matrix) well above the 126 MB L2 for the HBM-bound sizes
+    "expm_batched_n2": (2, 1 << 22), "expm_batched_n4": (4, 1 << 20), "expm_batched_n8": (8, 1 << 18),
+    "expm_batched_n16": (16, 1 << 15), "expm_batched_n32": (32, 1 << 13), "expm_batched_n64": (64, 1 << 12),
+}
+
+
+def expm_flops(n, s=0):
+    """W (6 + 4/3 + s), W = 8 n^3 (6 products, LU + two n-RHS triangular solves, s squarings)."""
+    return 8.0 * n ** 3 * (6 + 4.0 / 3 + s)
+
+
+def expm_sample(n, count, norm=1.5, seed=0):
+    """anti-hermitian matrices -i H dt with ||.||_1 = norm (s = 0), as the GRAPE slices produce them"""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((count, n, n)) + 1j * rng.standard_normal((count, n, n))
+    h = (x + x.conj().transpose(0, 2, 1)) / 2
+    h *= (norm / np.abs(h).sum(axis=1).max(axis=1))[:, None, None]
+    return np.ascontiguousarray(-1j * h)
+
+
+def oracle_expm_rate(n, seconds=10.0, threads=1):
+    """matrices/s of the oracle's expm_pade (torch complex128 restatement of expm.py:210-252) on the host, ~`seconds` of work"""
+    import torch
+    from oracle import qoc_oracle as orc
+    torch.set_num_threads(threads)
+    a = torch.as_tensor(expm_sample(n, 64))
+    for k in range(4):
+        orc.expm_pade(a[k])
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for k in range(64):
+            orc.expm_pade(a[k])
+        done += 64
+    return done / (time.perf_counter() - t0)
+
+
+def run_expm(args, name):
+    import ctypes
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, batch = EXPM_WORKLOADS[name]
+    fl = expm_flops(n)
+    cfg = {"workload": name, "hilbert_dim": n, "batch": batch, "norm": 1.5, "squarings": 0,
+           "l2": "a 256 MiB flush write between launches (n <= 4); working set %.0f MB" % (32.0 * n * n * batch / 1e6)}
+    if args.impl == "reference":
+        t0 = time.perf_counter()
+        rates = [oracle_expm_rate(n, seconds=max(2.0, 20.0 / max(1, args.steps)), threads=1) for _ in range(max(1, args.steps))]
+        rate = float(np.mean(rates))
+        val = rate * fl / 1e9
+        print(json.dumps({"impl": "reference", "metric": "batched_expm_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * batch / rate, "higher_is_better": True,
+                          "scaling": "replicas only", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": 1, "kind": "port", "matrices_per_s": rate,
+                                           "sample": "oracle expm_pade (torch complex128 restatement of expm.py:210-252) looped over 64 "
+                                                     "matrices for a bounded time per step; ms_per_step is scaled to the batch"},
+                          "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "wall_s": time.perf_counter() - t0}))
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the expm kernels have no CPU fallback")
+    from qoc_b200 import _lib
+    from qoc_b200.standard.functions import expm
+    lib = _lib.load()
+    tot, best = ctypes.c_double(), ctypes.c_double()
+    sampler = ClockSampler(0)
+    sampler.start()
+    _lib.check(lib.qocb_expm_batched_bench(n, batch, 1.5, max(3, args.warmup), args.steps, ctypes.byref(tot), ctypes.byref(best), 0))
+    ms = tot.value / args.steps
+    # end to end through the public call with host buffers (H2D of the batch, D2H of the result inside the timed region)
+    eb = min(batch, 1 << 16 if n <= 8 else 1 << 12)
+    a = expm_sample(n, eb)
+    for _ in range(3):
+        got = expm(a)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        got = expm(a)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    rate = batch / (ms * 1e-3)
+    gbs = 32.0 * n * n * rate / 1e9
+    tfl = fl * rate / 1e12
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hsrc = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        hbm, hsrc = 6529.7, "fallback (round-1 MEASURED_PEAKS.json)"
+    if n <= 4:
+        roof = {"bound": "hbm", "kernel": "k_expm_thread" if n <= 2 else "k_expm_rows", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                "frac": gbs / hbm, "traffic": None, "peak_source": hsrc, "algorithmic_bytes_per_launch": 32.0 * n * n * batch,
+                "fp64_tflops": tfl, "fp64_frac": tfl / FP64_TENSOR_PEAK_TFLOPS}
+    else:
+        roof = {"bound": "tensor", "kernel": "k_expm", "achieved": tfl, "peak": FP64_TENSOR_PEAK_TFLOPS,
+                "unit": "TFLOP/s", "frac": tfl / FP64_TENSOR_PEAK_TFLOPS, "traffic": None, "algorithmic_flops_per_launch": fl * batch,
+                "peak_source": "FP64 pipe measured on this pool (profiles/r01_microbench_fp64.jsonl; tensor = vector peak on B200)",
+                "hbm_gbs": gbs}
+    out = {"metric": "batched_expm_gflops", "value": tfl * 1e3, "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None,
+           "dtype": "c128 (f64)", "data": "synthetic", "config": cfg, "matrices_per_s": rate,
+           "e2e": {"value": fl * eb / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 16 * n * n * eb,
+                   "d2h_bytes_per_step": 16 * n * n * eb, "batch": eb, "matrices_per_s": eb / e2e_s},
+           "gpu_launches": args.steps, "roofline": roof, "clocks": clocks}
+    if not args.no_cpu_baseline:
+        crate = oracle_expm_rate(n, seconds=10.0, threads=1)
+        out["cpu_baseline"] = {"value": crate * fl / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": "port", "matrices_per_s": crate,
+                               "sample": "oracle expm_pade looped over 64 matrices for 10 s; published reference figure: 2.18 ms per "
+                                         "n = 64 matrix on 8 CPU cores (report.tex:250)"}
+    import torch as _t
+    from oracle import qoc_oracle as orc
+    k = min(16, eb)
+    want = np.stack([orc.expm_pade(_t.as_tensor(a[i])).numpy() for i in range(k)])
+    out["parity"] = {"matrices": k, "rel_err": float(np.linalg.norm(got[:k] - want) / np.linalg.norm(want)), "tolerance": 1e-12}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="n64_2000_M4", choices=sorted(WORKLOADS) + sorted(LINDBLAD_WORKLOADS))
+    ap.add_argument("--workload", default="n64_2000_M4", choices=sorted(WORKLOADS) + sorted(LINDBLAD_WORKLOADS) + sorted(EXPM_WORKLOADS))
     ap.add_argument("--cpu-slices", type=int, default=400, help="slices of the bounded CPU-baseline sample")
     ap.add_argument("--ref-slices", type=int, default=100, help="slices per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check", action="store_true", help="kept for compatibility: every N > 1 line now carries its parity block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload in EXPM_WORKLOADS:
+        run_expm(args, args.workload)
+        return
     if args.workload in LINDBLAD_WORKLOADS:
         if int(os.environ.get("RANK", "0")) == 0:
             run_lindblad(args, args.workload)

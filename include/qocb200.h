@@ -146,6 +146,12 @@ int qocb_expm_vjp_batched(int32_t n, int64_t batch, const double *a, const doubl
 /* device-resident timing of the batched expm: returns ms per launch (best of `iters`) */
 int qocb_expm_batched_time(int32_t n, int64_t batch, double norm_scale, int32_t iters, double *ms_best, int32_t device);
 
+/* the same with `warmup` untimed launches and the total over exactly `iters` timed ones (bench.py --workload expm_batched_n*):
+   ms_total / ms_best may be NULL.  n <= 4 runs the register-resident kernels (one matrix per thread for n <= 2, per 4-lane
+   group for n = 3, 4) on [batch][n][n] interleaved complex128 with a 256 MiB L2 flush between launches. */
+int qocb_expm_batched_bench(int32_t n, int64_t batch, double norm_scale, int32_t warmup, int32_t iters, double *ms_total,
+                            double *ms_best, int32_t device);
+
 /* ---- Lindblad path: _evaluate_lindblad_discrete (qoc/core/lindbladdiscrete.py:357-441) and its jacobian (:322) -------
    Densities are [D][n][n] complex128, interleaved (NumPy C order).  H(x) = H0 + sum_r x_r A_r as above; the dissipator is
    sum_l gamma_l (L_l rho L_l^dag - 1/2 {L_l^dag L_l, rho}) with time-independent (gamma_l, L_l).  Each of the N-1

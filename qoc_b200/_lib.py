@@ -23,7 +23,7 @@ EXPORTS = [
     "qocb_add_cost", "qocb_clear_costs", "qocb_cost", "qocb_cost_and_grad", "qocb_get_states", "qocb_get_final_states",
     "qocb_get_propagators", "qocb_upload_controls", "qocb_run_resident", "qocb_sync", "qocb_download_result",
     "qocb_time_resident", "qocb_launch_count", "qocb_stream", "qocb_expm_batched", "qocb_expm_vjp_batched",
-    "qocb_expm_batched_time", "qocb_version", "qocb_flush_l2", "qocb_shard_matrix_doubles",
+    "qocb_expm_batched_time", "qocb_expm_batched_bench", "qocb_version", "qocb_flush_l2", "qocb_shard_matrix_doubles",
     "qocb_shard_vector_doubles", "qocb_shard_forward_local", "qocb_shard_forward_finish",
     "qocb_shard_backward_particular", "qocb_shard_backward_finish", "qocb_shard_result_doubles",
     "qocb_shard_pack_result", "qocb_lindblad_create", "qocb_lindblad_destroy", "qocb_lindblad_last_error",
@@ -129,6 +129,7 @@ def load():
     lib.qocb_expm_batched.argtypes = [i32, i64, vp, vp, i32]
     lib.qocb_expm_vjp_batched.argtypes = [i32, i64, vp, vp, vp, vp, i32]
     lib.qocb_expm_batched_time.argtypes = [i32, i64, dbl, i32, vp, i32]
+    lib.qocb_expm_batched_bench.argtypes = [i32, i64, dbl, i32, i32, vp, vp, i32]
     lib.qocb_version.restype = C.c_char_p
     lib.qocb_lindblad_create.argtypes = [C.POINTER(LindbladProblem), C.POINTER(vp)]
     lib.qocb_lindblad_destroy.argtypes = [vp]

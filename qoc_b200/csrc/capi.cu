@@ -13,6 +13,7 @@
 #include "sweep.cuh"
 #include "large.cuh"
 #include "zgemm.cuh"
+#include "small.cuh"
 
 using namespace qocb;
 
@@ -2011,6 +2012,54 @@ int qocb_shard_pack_result(qocb_plan *p, int32_t with_grad, double *result_dev) 
 // ---- standalone batched expm --------------------------------------------------------------------------
 }  // extern "C"
 
+// n <= 4: register-resident kernels of small.cuh on the caller's layout ([batch][n][n] interleaved complex128, device).
+// (The lane-per-row kernel also instantiates for n = 5 .. 8 with 8-lane groups, but there it needs 250+ registers per thread and
+// measured 3.8 TFLOP/s at n = 8 against 4.9 for the one-warp DMMA tile path of k_expm<Cfg<8,1,1>>, so 5 <= n <= 8 stays there.)
+constexpr int kSmallMaxDim = 4;
+static cudaError_t expm_small_launch(int n, long long batch, const double2 *din, double2 *dout, cudaStream_t st) {
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int threads = 128;
+    const int T = n <= 2 ? 1 : 4;
+    const long long units = (batch * T + threads - 1) / threads;          // blocks needed for one matrix per thread / group
+    const int grid = (int)std::max<long long>(1, std::min<long long>(units, (long long)sms * 32));
+    switch (n) {
+        case 1: k_expm_thread<1><<<grid, threads, 0, st>>>(din, dout, batch); break;
+        case 2: k_expm_thread<2><<<grid, threads, 0, st>>>(din, dout, batch); break;
+        case 3: k_expm_rows<3, 4><<<grid, threads, 0, st>>>(din, dout, batch); break;
+        case 4: k_expm_rows<4, 4><<<grid, threads, 0, st>>>(din, dout, batch); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+static int expm_small_impl(int n, long long batch, const double *a, double *out) {
+    qocb_plan *np = nullptr;
+    DevBuf<double2> din, dout;
+    const size_t cnt = (size_t)batch * n * n;
+    CU_TRY(np, din.alloc(cnt)); CU_TRY(np, dout.alloc(cnt));
+    CU_TRY(np, cudaMemcpy(din.p, a, sizeof(double2) * cnt, cudaMemcpyHostToDevice));
+    CU_TRY(np, expm_small_launch(n, batch, din.p, dout.p, 0));
+    CU_TRY(np, cudaDeviceSynchronize());
+    CU_TRY(np, cudaMemcpy(out, dout.p, sizeof(double2) * cnt, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// persistent grid of the standalone expm kernels: every CTA slot the SM can hold (small dimensions are latency-bound: one
+// 8 x 8 problem per warp needs many warps in flight)
+template <class C>
+static int expm_grid(long long batch, int sms, bool vjp) {
+    int occ = 0;
+    if (vjp) {
+        cudaFuncSetAttribute(k_expm_vjp<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expm_vjp<C>, C::NT, Smem<C>::bytes());
+    } else {
+        cudaFuncSetAttribute(k_expm<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expm<C>, C::NT, Smem<C>::bytes());
+    }
+    occ = std::max(1, std::min(occ, 32));
+    return (int)std::min<long long>(batch, (long long)sms * occ);
+}
+
 template <class C>
 static int expm_batched_impl(int n, long long batch, const double *a, const double *ubar, double *out, double *abar) {
     const size_t GM = C::GMAT;
@@ -2021,7 +2070,7 @@ static int expm_batched_impl(int n, long long batch, const double *a, const doub
     CU_TRY(np, din.alloc((size_t)batch * GM)); CU_TRY(np, dout.alloc((size_t)batch * GM));
     for (long long b = 0; b < batch; ++b) to_planar(a + (size_t)b * 2 * n * n, h.data() + (size_t)b * GM, n, C::NP, false);
     CU_TRY(np, cudaMemcpy(din.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
-    const int grid = (int)std::min<long long>(batch, (long long)sms * 8);
+    const int grid = expm_grid<C>(batch, sms, ubar != nullptr);
     CU_TRY(np, scratch.alloc((size_t)grid * S_COUNT * GM));
     if (ubar) {
         CU_TRY(np, dub.alloc((size_t)batch * GM)); CU_TRY(np, dab.alloc((size_t)batch * GM));
@@ -2052,6 +2101,7 @@ int qocb_expm_batched(int32_t n, int64_t batch, const double *a, double *out, in
     const int NP = pad_dim(n);
     if (NP < 0 || NP > 64) { set_error((qocb_plan *)nullptr, "the standalone batched expm hooks cover n in [1, 64]"); return -1; }
     if (cudaSetDevice(device) != cudaSuccess) { set_error((qocb_plan *)nullptr, "cudaSetDevice failed (no CPU path)"); return -2; }
+    { const char *ns = getenv("QOCB_NO_SMALL"); if (n <= kSmallMaxDim && !(ns && ns[0] == '1')) return expm_small_impl(n, batch, a, out); }
     return dispatch(NP, [&] { return expm_batched_impl<C8>(n, batch, a, nullptr, out, nullptr); },
                     [&] { return expm_batched_impl<C16>(n, batch, a, nullptr, out, nullptr); },
                     [&] { return expm_batched_impl<C32>(n, batch, a, nullptr, out, nullptr); },
@@ -2072,8 +2122,55 @@ int qocb_expm_vjp_batched(int32_t n, int64_t batch, const double *a, const doubl
 
 }  // extern "C"
 
+// device-resident timing of the small-dimension kernels: `distinct` anti-hermitian matrices -i H of one-norm norm_scale tiled
+// over the batch in the caller's interleaved layout; a 256 MiB write between launches evicts the L2
+static int expm_small_time(int n, long long batch, double norm_scale, int iters, double *ms_best, int warmup = 2, double *ms_total = nullptr) {
+    qocb_plan *np = nullptr;
+    DevBuf<double2> din, dout; DevBuf<double> flush;
+    const size_t nn = (size_t)n * n, cnt = (size_t)batch * nn;
+    CU_TRY(np, din.alloc(cnt)); CU_TRY(np, dout.alloc(cnt));
+    const size_t flush_bytes = 256ull << 20;
+    CU_TRY(np, flush.alloc(flush_bytes / sizeof(double)));
+    const int distinct = 4096;
+    std::vector<double> h((size_t)distinct * nn * 2, 0.0);
+    unsigned long long st = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return ((st >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0; };
+    for (int d = 0; d < distinct; ++d) {
+        std::vector<double> hr(nn), hi(nn);
+        for (int r = 0; r < n; ++r)
+            for (int c = r; c < n; ++c) {
+                const double x = rnd(), y = (r == c) ? 0.0 : rnd();
+                hr[(size_t)r * n + c] = x; hi[(size_t)r * n + c] = y; hr[(size_t)c * n + r] = x; hi[(size_t)c * n + r] = -y;
+            }
+        double nrm = 0;
+        for (int c = 0; c < n; ++c) { double s_ = 0; for (int r = 0; r < n; ++r) s_ += std::hypot(hr[(size_t)r * n + c], hi[(size_t)r * n + c]); nrm = std::max(nrm, s_); }
+        const double f = norm_scale / std::max(nrm, 1e-300);
+        for (size_t e = 0; e < nn; ++e) { h[2 * (d * nn + e)] = f * hi[e]; h[2 * (d * nn + e) + 1] = -f * hr[e]; }   // -i H
+    }
+    for (long long b = 0; b < batch; b += distinct) {
+        const long long c_ = std::min<long long>(distinct, batch - b);
+        CU_TRY(np, cudaMemcpy(din.p + (size_t)b * nn, h.data(), sizeof(double2) * c_ * nn, cudaMemcpyHostToDevice));
+    }
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 1e30;
+    double total = 0.;
+    for (int i = 0; i < iters + warmup; ++i) {
+        CU_TRY(np, cudaMemsetAsync(flush.p, i & 0xff, flush_bytes, 0));
+        cudaEventRecord(e0);
+        CU_TRY(np, expm_small_launch(n, batch, din.p, dout.p, 0));
+        cudaEventRecord(e1);
+        CU_TRY(np, cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= warmup) { total += ms; if (ms < best) best = ms; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_best) *ms_best = best;
+    if (ms_total) *ms_total = total;
+    return 0;
+}
+
 template <class C>
-static int expm_time_impl(int n, long long batch, double norm_scale, int iters, double *ms_best) {
+static int expm_time_impl(int n, long long batch, double norm_scale, int iters, double *ms_best, int warmup = 2, double *ms_total = nullptr) {
     const size_t GM = C::GMAT;
     qocb_plan *np = nullptr;
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -2105,32 +2202,48 @@ static int expm_time_impl(int n, long long batch, double norm_scale, int iters, 
         const long long cnt = std::min<long long>(distinct, batch - b);
         CU_TRY(np, cudaMemcpy(din.p + (size_t)b * GM, h.data(), sizeof(double) * cnt * GM, cudaMemcpyHostToDevice));
     }
-    const int grid = (int)std::min<long long>(batch, (long long)sms * 8);
+    const int grid = expm_grid<C>(batch, sms, false);
     CU_TRY(np, scratch.alloc((size_t)grid * 3 * GM));
     CU_TRY(np, cudaFuncSetAttribute(k_expm<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     double best = 1e30;
-    for (int i = 0; i < iters + 2; ++i) {
+    double total = 0.;
+    for (int i = 0; i < iters + warmup; ++i) {
         cudaEventRecord(e0);
         k_expm<C><<<grid, C::NT, Smem<C>::bytes()>>>(din.p, dout.p, scratch.p, batch);
         cudaEventRecord(e1);
         CU_TRY(np, cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1);
-        if (i >= 2 && ms < best) best = ms;
+        if (i >= warmup) { total += ms; if (ms < best) best = ms; }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     CU_TRY(np, cudaGetLastError());
-    *ms_best = best;
+    if (ms_best) *ms_best = best;
+    if (ms_total) *ms_total = total;
     return 0;
 }
 
 extern "C" {
+
+int qocb_expm_batched_bench(int32_t n, int64_t batch, double norm_scale, int32_t warmup, int32_t iters, double *ms_total, double *ms_best,
+                            int32_t device) {
+    if (batch < 1 || iters < 1 || warmup < 0) return -1;
+    const int NP = pad_dim(n);
+    if (NP < 0 || NP > 64) { set_error((qocb_plan *)nullptr, "the standalone batched expm hooks cover n in [1, 64]"); return -1; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error((qocb_plan *)nullptr, "cudaSetDevice failed (no CPU path)"); return -2; }
+    { const char *ns = getenv("QOCB_NO_SMALL"); if (n <= kSmallMaxDim && !(ns && ns[0] == '1')) return expm_small_time(n, batch, norm_scale, iters, ms_best, warmup, ms_total); }
+    return dispatch(NP, [&] { return expm_time_impl<C8>(n, batch, norm_scale, iters, ms_best, warmup, ms_total); },
+                    [&] { return expm_time_impl<C16>(n, batch, norm_scale, iters, ms_best, warmup, ms_total); },
+                    [&] { return expm_time_impl<C32>(n, batch, norm_scale, iters, ms_best, warmup, ms_total); },
+                    [&] { return expm_time_impl<C64>(n, batch, norm_scale, iters, ms_best, warmup, ms_total); });
+}
 
 int qocb_expm_batched_time(int32_t n, int64_t batch, double norm_scale, int32_t iters, double *ms_best, int32_t device) {
     if (!ms_best || batch < 1) return -1;
     const int NP = pad_dim(n);
     if (NP < 0 || NP > 64) { set_error((qocb_plan *)nullptr, "the standalone batched expm hooks cover n in [1, 64]"); return -1; }
     if (cudaSetDevice(device) != cudaSuccess) { set_error((qocb_plan *)nullptr, "cudaSetDevice failed (no CPU path)"); return -2; }
+    { const char *ns = getenv("QOCB_NO_SMALL"); if (n <= kSmallMaxDim && !(ns && ns[0] == '1')) return expm_small_time(n, batch, norm_scale, iters, ms_best); }
     return dispatch(NP, [&] { return expm_time_impl<C8>(n, batch, norm_scale, iters, ms_best); },
                     [&] { return expm_time_impl<C16>(n, batch, norm_scale, iters, ms_best); },
                     [&] { return expm_time_impl<C32>(n, batch, norm_scale, iters, ms_best); },

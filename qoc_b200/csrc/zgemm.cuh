@@ -67,13 +67,14 @@ __global__ void __launch_bounds__(ZG_NT) k_zgemm(const double2 *__restrict__ A, 
         }
     };
 
-    double acc[Z::TM][Z::TN][4];
+    // 3M complex products (tile.cuh: Acc): P1 = Ar Br, P2 = Ai Bi, P3 = (Ar + Ai)(Br + Bi); three DMMA per tile and k-step
+    double acc[Z::TM][Z::TN][6];
 #pragma unroll
     for (int i = 0; i < Z::TM; ++i)
 #pragma unroll
         for (int j = 0; j < Z::TN; ++j)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.0;
+            for (int q = 0; q < 6; ++q) acc[i][j][q] = 0.0;
 
     const int panels = (k + ZG_BK - 1) / ZG_BK;
     load_panel(0, 0);
@@ -93,13 +94,18 @@ __global__ void __launch_bounds__(ZG_NT) k_zgemm(const double2 *__restrict__ A, 
 #pragma unroll
             for (int j = 0; j < Z::TN; ++j) b[j] = bs[(kk * 4 + t) * Z::LDB + col0 + j * 8 + g];
 #pragma unroll
+            double sa[Z::TM], sb[Z::TN];
+#pragma unroll
+            for (int i = 0; i < Z::TM; ++i) sa[i] = a[i].x + a[i].y;
+#pragma unroll
+            for (int j = 0; j < Z::TN; ++j) sb[j] = b[j].x + b[j].y;
+#pragma unroll
             for (int i = 0; i < Z::TM; ++i)
 #pragma unroll
                 for (int j = 0; j < Z::TN; ++j) {
                     dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
-                    dmma884(acc[i][j][2], acc[i][j][3], a[i].x, b[j].y);
-                    dmma884(acc[i][j][0], acc[i][j][1], -a[i].y, b[j].y);
-                    dmma884(acc[i][j][2], acc[i][j][3], a[i].y, b[j].x);
+                    dmma884(acc[i][j][2], acc[i][j][3], a[i].y, b[j].y);
+                    dmma884(acc[i][j][4], acc[i][j][5], sa[i], sb[j]);
                 }
         }
         __syncthreads();
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(ZG_NT) k_zgemm(const double2 *__restrict__ A, 
                 for (int q = 0; q < 2; ++q)
                     if (c + q < nc) {
                         double2 *dst = C + (size_t)r * ldc + c + q;
-                        double2 v = make_double2(alpha * acc[i][j][q], alpha * acc[i][j][2 + q]);
+                        double2 v = make_double2(alpha * (acc[i][j][q] - acc[i][j][2 + q]), alpha * (acc[i][j][4 + q] - acc[i][j][q] - acc[i][j][2 + q]));
                         if (beta != 0.0) { const double2 o = *dst; v.x += beta * o.x; v.y += beta * o.y; }
                         *dst = v;
                     }
