@@ -225,7 +225,9 @@ def run_reference(args, name):
     p = make_problem(name)
     slices = p.N - 1
     threads, t1, ta = pick_threads(p)
-    sample = cpu_sample(p, int(args.ref_slices))
+    # the whole pulse whenever one evaluation of the oracle costs seconds (n <= 64: ~4 s for 2000 slices on 16 cores), a bounded
+    # sample scaled linearly otherwise (cfg4: n = 256 x 10^4 slices would take hours)
+    sample = slices if (p.n <= 64 and args.ref_slices <= 0) else cpu_sample(p, int(args.ref_slices) if args.ref_slices > 0 else 100)
     for _ in range(args.warmup):
         oracle_time(p, min(sample, 8), 0 + 1, threads)
     t0 = time.perf_counter()
@@ -240,7 +242,7 @@ def run_reference(args, name):
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64)",
            "data": "synthetic", "config": workload_config(name, p),
            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
-                            "sample": "%d of %d slices (of one ensemble member) per step (fwd+bwd), scaled linearly; oracle = torch complex128 "
+                            "sample": "%d of %d slices (of one ensemble member) per step (fwd+bwd; scaled linearly when fewer than all); oracle = torch complex128 "
                                       "restatement of the reference (autograd absent in this image); 1 thread %.3fs vs %d "
                                       "threads %.3fs on an 8-slice calibration" % (sample, slices, t1, os.cpu_count() or 1, ta)},
            "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -483,7 +485,35 @@ def lindblad_problem(name):
                 lops=a[None], rho0=rho0, targ=targ)
 
 
+def run_lindblad_reference(args, name):
+    """reference arm of the Lindblad workloads: the oracle (torch restatement of lindbladdiscrete.py:357-495 with the adaptive
+    RKDP5 of mathmethods.py:352-480, gradient by torch.autograd through the step-size controller as the reference's tape does)
+    on the host, one full cost+gradient evaluation per step."""
+    import torch
+    from oracle import qoc_oracle as orc
+    q = lindblad_problem(name)
+    torch.set_num_threads(1)
+    ocosts = [orc.TargetDensityInfidelity(q["targ"])]
+    oh, old = orc.make_hamiltonian(q["h0"], q["drive"], True), orc.make_lindblad_data(q["gam"], q["lops"])
+    for _ in range(args.warmup):
+        orc.lindblad_cost_and_grad(q["controls"], oh, old, q["rho0"], ocosts, q["T"], q["N"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.lindblad_cost_and_grad(q["controls"], oh, old, q["rho0"], ocosts, q["T"], q["N"])
+    sec = (time.perf_counter() - t0) / args.steps
+    val = 1.0 / sec
+    print(json.dumps({"impl": "reference", "metric": "grape_cost_grad_evals_per_sec", "value": val, "unit": "evals/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                      "scaling": "replicas only", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+                      "config": {"workload": name, "hilbert_dim": q["n"], "densities": q["D"], "intervals": q["N"] - 1},
+                      "cpu_baseline": {"value": val, "unit": "evals/s", "cores": 1, "kind": "port",
+                                       "sample": "full cost+gradient evaluations of the oracle (every adaptive step, no truncation)"},
+                      "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
 def run_lindblad(args, name):
+    if args.impl == "reference":
+        return run_lindblad_reference(args, name)
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the GRAPE hot path has no CPU fallback")
@@ -506,8 +536,6 @@ def run_lindblad(args, name):
     sec = (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop()
     st = plan.stats()
-    if args.impl == "reference":
-        return
     torch.set_num_threads(1)
     ocosts = [orc.TargetDensityInfidelity(q["targ"])]
     oh, old = orc.make_hamiltonian(q["h0"], q["drive"], True), orc.make_lindblad_data(q["gam"], q["lops"])
@@ -665,7 +693,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="n64_2000_M4", choices=sorted(WORKLOADS) + sorted(LINDBLAD_WORKLOADS) + sorted(EXPM_WORKLOADS))
     ap.add_argument("--cpu-slices", type=int, default=400, help="slices of the bounded CPU-baseline sample")
-    ap.add_argument("--ref-slices", type=int, default=100, help="slices per step of the --impl reference arm")
+    ap.add_argument("--ref-slices", type=int, default=0, help="slices per step of the --impl reference arm (0 = the whole pulse for n <= 64, "
+                                                               "100 scaled linearly above)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check", action="store_true", help="kept for compatibility: every N > 1 line now carries its parity block")
     args = ap.parse_args()

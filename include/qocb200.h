@@ -48,6 +48,8 @@ typedef struct {
     int32_t slice_end;           /* (both 0 = the whole pulse, unsharded).  See the qocb_shard_* calls below */
     int32_t channel_count;       /* KC: operator channels of a time-dependent hamiltonian (qocb_set_node_map);
                                     0 = control_count (time-independent operators, one per real control channel) */
+    int32_t state_total;         /* state sharding (qocb_state_shard_*): total number of initial states over all ranks; */
+    int32_t state_first;         /* index of this plan's first state among them.  0 / 0 = all states are here */
     double evolution_time;       /* T */
 } qocb_problem;
 
@@ -135,6 +137,21 @@ int qocb_shard_backward_finish(qocb_plan *plan, const double *allP_dev, const do
                                int32_t world);
 int qocb_shard_result_doubles(qocb_plan *plan);
 int qocb_shard_pack_result(qocb_plan *plan, int32_t with_grad, double *result_dev);
+
+/* ---- sharding of the initial STATES (independent units; one plan per rank, created with state_count = the local
+   states, state_total / state_first set, and the cost vectors of the local states only).  Every rank computes every slice
+   propagator - they depend on the controls alone - and sweeps its own states; cost normalisations use state_total.  The only
+   coupling is the coherent target infidelity 1 - |sum_s <t_s|psi_s>|^2 / S^2 (targetstateinfidelity.py:53-55):
+     1. qocb_state_shard_forward(plan, with_grad, coh_dev)   expm + state sweeps; coh_dev[qocb_state_shard_coherent_doubles] =
+        this rank's partial overlap sums (re, im per coherent term and cost step); the cost so far excludes those terms
+        -- all-reduce(sum) coh_dev (skip when the count is 0)
+     2. qocb_state_shard_finish(plan, with_grad, coh_dev)    coherent values from the totals (added once, by the rank with
+        state_first = 0), then - with_grad - costate sweeps seeded from the totals, expm / Magnus adjoints, gradient
+     3. qocb_shard_pack_result(plan, with_grad, result_dev)  [gradient | cost | ...] -- all-reduce(sum) the first M*KR + 1 doubles.
+   The calls only enqueue on the plan stream.  Not combinable with time-slice sharding or ensembles. */
+int qocb_state_shard_coherent_doubles(qocb_plan *plan);
+int qocb_state_shard_forward(qocb_plan *plan, int32_t with_grad, double *coh_dev);
+int qocb_state_shard_finish(qocb_plan *plan, int32_t with_grad, const double *coh_dev);
 
 /* standalone batched matrix exponential (qoc/standard/functions/expm.py:210-252), bench / test hook.
    a, out: [batch][n][n] complex on the host. */

@@ -26,7 +26,8 @@ EXPORTS = [
     "qocb_expm_batched_time", "qocb_expm_batched_bench", "qocb_version", "qocb_flush_l2", "qocb_shard_matrix_doubles",
     "qocb_shard_vector_doubles", "qocb_shard_forward_local", "qocb_shard_forward_finish",
     "qocb_shard_backward_particular", "qocb_shard_backward_finish", "qocb_shard_result_doubles",
-    "qocb_shard_pack_result", "qocb_lindblad_create", "qocb_lindblad_destroy", "qocb_lindblad_last_error",
+    "qocb_shard_pack_result", "qocb_state_shard_coherent_doubles", "qocb_state_shard_forward", "qocb_state_shard_finish",
+    "qocb_lindblad_create", "qocb_lindblad_destroy", "qocb_lindblad_last_error",
     "qocb_lindblad_set_operators", "qocb_lindblad_set_densities", "qocb_lindblad_add_cost", "qocb_lindblad_cost",
     "qocb_lindblad_cost_and_grad", "qocb_lindblad_stats", "qocb_lindblad_get_densities",
 ]
@@ -38,7 +39,7 @@ class Problem(C.Structure):
                 ("control_eval_count", C.c_int32), ("system_eval_count", C.c_int32), ("magnus_order", C.c_int32),
                 ("cost_eval_step", C.c_int32), ("ensemble_count", C.c_int32), ("device", C.c_int32),
                 ("store_tape", C.c_int32), ("chunks_per_member", C.c_int32), ("slice_begin", C.c_int32),
-                ("slice_end", C.c_int32), ("channel_count", C.c_int32),
+                ("slice_end", C.c_int32), ("channel_count", C.c_int32), ("state_total", C.c_int32), ("state_first", C.c_int32),
                 ("evolution_time", C.c_double)]
 
 
@@ -151,6 +152,9 @@ def load():
     lib.qocb_shard_backward_finish.argtypes = [vp, vp, vp, i32, i32]
     lib.qocb_shard_result_doubles.argtypes = [vp]
     lib.qocb_shard_pack_result.argtypes = [vp, i32, vp]
+    lib.qocb_state_shard_coherent_doubles.argtypes = [vp]
+    lib.qocb_state_shard_forward.argtypes = [vp, i32, vp]
+    lib.qocb_state_shard_finish.argtypes = [vp, i32, vp]
     _lib = lib
     return lib
 

@@ -211,7 +211,7 @@ class SchroedingerPlan(object):
                  control_eval_count=0, control_count=0, complex_controls=False,
                  magnus_policy=MagnusPolicy.M2, cost_eval_step=1,
                  interpolation_policy=InterpolationPolicy.LINEAR, device=0, store_tape=True,
-                 chunks_per_member=0, ensemble_drifts=None, structure=None, slice_range=None):
+                 chunks_per_member=0, ensemble_drifts=None, structure=None, slice_range=None, state_slice=None):
         if interpolation_policy != InterpolationPolicy.LINEAR:
             raise NotImplementedError("The interpolation policy {} is not yet supported for this method."
                                       "".format(interpolation_policy))
@@ -219,6 +219,17 @@ class SchroedingerPlan(object):
             raise ValueError("Unrecognized magnus policy {}.".format(magnus_policy))
         self.lib = _lib.load()
         initial_states = np.asarray(initial_states)
+        # state sharding (qoc_b200/core/sharded.py): this plan holds states [s0, s1) of S_total; normalisations use S_total
+        self.S_total = initial_states.shape[0]
+        self.state_first = 0
+        if state_slice is not None:
+            s0, s1 = int(state_slice[0]), int(state_slice[1])
+            if not 0 <= s0 < s1 <= self.S_total:
+                raise ValueError("bad state slice {} of {} states".format(state_slice, self.S_total))
+            if ensemble_drifts is not None or slice_range is not None:
+                raise NotImplementedError("state sharding cannot be combined with ensembles or time-slice sharding")
+            initial_states = initial_states[s0:s1]
+            self.state_first = s0
         self.S, self.n = initial_states.shape[0], initial_states.shape[1]
         self.K = int(control_count)
         self.M = int(control_eval_count)
@@ -249,6 +260,7 @@ class SchroedingerPlan(object):
                           slice_begin=0 if slice_range is None else int(slice_range[0]),
                           slice_end=0 if slice_range is None else int(slice_range[1]),
                           channel_count=0 if node_map is None else int(a_ops.shape[0]),
+                          state_total=self.S_total if state_slice is not None else 0, state_first=self.state_first,
                           evolution_time=float(evolution_time))
         handle = ctypes.c_void_p()
         _lib.check(self.lib.qocb_plan_create(ctypes.byref(pb), ctypes.byref(handle)))
@@ -264,7 +276,11 @@ class SchroedingerPlan(object):
         self.control_costs = []
         from qoc_b200.models.cost import Cost
         for c in self.costs:
-            terms = c.device_terms(self.S, self.n)
+            terms = c.device_terms(self.S_total, self.n)
+            if state_slice is not None:                  # the vectors (and counts) of the local states only
+                terms = [(kind, step, weight, np.asarray(vecs)[self.state_first:self.state_first + self.S],
+                          None if counts is None else np.asarray(counts)[self.state_first:self.state_first + self.S])
+                         for kind, step, weight, vecs, counts in terms]
             if not terms:
                 if getattr(type(c), "control_value_and_grad", Cost.control_value_and_grad) is Cost.control_value_and_grad:
                     raise NotImplementedError("The cost {} has neither device terms nor an analytic control gradient "

@@ -303,6 +303,136 @@ class CudaUnitEngine(object):
         self.torch.cuda.synchronize(self.dev)
 
 
+class CudaStateEngine(object):
+    """one rank's share of the initial STATES on its GPU (`units_evaluate` interface): every rank computes every slice
+    propagator and sweeps its own states; the coherent overlap sums of TargetStateInfidelity are the only coupling."""
+
+    def __init__(self, plan, device):
+        import torch
+        self.torch, self.plan, self.lib, self.h = torch, plan, plan.lib, plan.handle
+        self.dev = torch.device("cuda", device)
+        self.stream = torch.cuda.ExternalStream(self.lib.qocb_stream(self.h), device=self.dev)
+        self.count = plan.M * plan.KR
+        ncoh = self.lib.qocb_state_shard_coherent_doubles(self.h)
+        self.coh = torch.zeros(max(ncoh, 0), dtype=torch.float64, device=self.dev)
+        self.result = torch.zeros(self.lib.qocb_shard_result_doubles(self.h), dtype=torch.float64, device=self.dev)
+        self.out = self.result[:self.count + 1]
+
+    def _coh_ptr(self):
+        return ctypes.c_void_p(self.coh.data_ptr()) if self.coh.numel() else None
+
+    def forward(self, with_grad):
+        self.with_grad = with_grad
+        _lib.check(self.lib.qocb_state_shard_forward(self.h, int(with_grad), self._coh_ptr()), self.h)
+        return self.coh
+
+    def backward(self, coh):
+        _lib.check(self.lib.qocb_state_shard_finish(self.h, 1, self._coh_ptr()), self.h)
+
+    def pack(self, with_grad):
+        if not with_grad:                                           # forward only: the coherent values still need the totals
+            _lib.check(self.lib.qocb_state_shard_finish(self.h, 0, self._coh_ptr()), self.h)
+        _lib.check(self.lib.qocb_shard_pack_result(self.h, int(with_grad), ctypes.c_void_p(self.result.data_ptr())), self.h)
+        return self.out
+
+    def close(self):
+        self.stream.synchronize()
+        self.coh = self.result = self.out = None
+        self.torch.cuda.synchronize(self.dev)
+
+
+class StateShardedPlan(object):
+    """independent initial states sharded across the ranks of the default group (BASELINE north star:
+    "independent initial states and ensemble members are also sharded").  Pays off when the state sweeps and the rank-S / dense
+    reverse pass weigh against the (replicated) expm work, i.e. many states on a small Hilbert space (cfg5: S = 64, n = 32).
+    `cost_and_grad` returns the final states of ALL states (all-gathered)."""
+
+    def __init__(self, hamiltonian, initial_states, costs, evolution_time, system_eval_count, device=0, group=None, **kw):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.comm = TorchDistComm(group)
+        initial_states = np.asarray(initial_states)
+        self.S_total = initial_states.shape[0]
+        self.bounds = slice_bounds(self.S_total, self.world)
+        sl = (self.bounds[self.rank], self.bounds[self.rank + 1])
+        self.plan = SchroedingerPlan(hamiltonian, initial_states, costs, evolution_time, system_eval_count, device=device,
+                                     state_slice=sl, **kw)
+        p = self.plan
+        self.KR, self.K, self.M, self.S, self.n, self.E = p.KR, p.K, p.M, self.S_total, p.n, 1
+        self.complex_controls = p.complex_controls
+        self.engine = CudaStateEngine(p, device)
+        self.host = torch.zeros(p.M * p.KR + 1, dtype=torch.float64).pin_memory()
+        self.smax = max(self.bounds[g + 1] - self.bounds[g] for g in range(self.world))
+        kwt = dict(dtype=torch.complex128, device=self.engine.dev)
+        self.fin_local = torch.zeros(self.smax * p.n, **kwt)
+        self.fin_all = torch.zeros(self.world * self.smax * p.n, **kwt)
+
+    def upload(self, controls):
+        self.plan.upload(controls)
+
+    def _evaluate(self, controls, with_grad):
+        e, p = self.engine, self.plan
+        p.upload(controls)
+        with self.torch.cuda.stream(e.stream):
+            res = units_evaluate(e, self.comm, with_grad)
+            self.host.copy_(res, non_blocking=True)
+        e.stream.synchronize()
+        out = self.host.numpy()
+        local = p.final_states()                                    # (S_local, n, 1)
+        self.fin_local.zero_()
+        self.fin_local[:local.size] = self.torch.from_numpy(np.ascontiguousarray(local).ravel()).to(self.engine.dev)
+        self.dist.all_gather_into_tensor(self.fin_all, self.fin_local, group=self.group)
+        allf = self.fin_all.cpu().numpy().reshape(self.world, self.smax, p.n)
+        finals = np.concatenate([allf[g, :self.bounds[g + 1] - self.bounds[g]] for g in range(self.world)])[:, :, None]
+        extra, extra_grad = p._control_costs(np.asarray(controls), with_grad)
+        g = out[:-1].reshape(self.M, self.KR).copy()
+        grads = g[:, :self.K] + 1j * g[:, self.K:] if self.complex_controls else g
+        if with_grad and extra_grad is not None:
+            grads = grads + extra_grad
+        return float(out[-1]) + extra, grads, finals
+
+    def cost(self, controls):
+        err, _, finals = self._evaluate(controls, False)
+        return err, finals
+
+    def cost_and_grad(self, controls):
+        return self._evaluate(controls, True)
+
+    def time_resident(self, with_grad=True, warmup=3, iters=10, flush_l2=True):
+        """device time of `iters` resident evaluations including both all-reduces (this rank's clock)."""
+        torch, e = self.torch, self.engine
+        for _ in range(warmup):
+            with torch.cuda.stream(e.stream):
+                units_evaluate(e, self.comm, with_grad)
+        e.stream.synchronize()
+        total = 0.0
+        for _ in range(iters):
+            if flush_l2:
+                _lib.check(self.plan.lib.qocb_flush_l2(self.plan.handle), self.plan.handle)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(e.stream):
+                t0.record()
+                units_evaluate(e, self.comm, with_grad)
+                t1.record()
+            e.stream.synchronize()
+            total += t0.elapsed_time(t1)
+        stages = np.zeros(8)
+        stages[0] = total
+        return total, stages
+
+    def launch_count(self, with_grad=True):
+        return self.plan.launch_count(with_grad) + 2
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+            self.host = self.fin_local = self.fin_all = None
+            self.plan.close()
+
+
 class EnsembleShardedPlan(object):
     """robust-control ensembles (cfg5): members that differ in the drift are independent units, block-partitioned across the
     ranks; one NCCL all-reduce of [gradient | cost] on the plan stream ends the evaluation - inside the device-timed region,

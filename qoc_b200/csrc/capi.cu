@@ -460,6 +460,10 @@ struct qocb_plan {
     std::vector<double> h_vecs;
     std::vector<int> h_counts;
     int ip_total = 0;
+    int coh_total = 0;                  // overlap-sum slots of the coherent target terms (state sharding)
+    bool state_sharded = false;
+    double *coh_out = nullptr;          // state sharding: device buffers of the current evaluation (caller-owned)
+    const double *coh_in = nullptr;
     FeedMaps fm;                        // TMA tensor maps of U and chunkP (k_forward); fm.tma = 0 when TMA is unavailable
     bool premagnus_ok = true;           // QOCB_NO_PREMAGNUS=1: assemble the Magnus matrices inside k_forward (A/B comparison)
     bool hermitian = false;             // H0 (every member) and every operator channel are Hermitian (QOCB_NO_NOPIV=1 clears it)
@@ -589,6 +593,10 @@ SweepArgs make_sargs(qocb_plan *p) {
         s.member_chunk0 = p->mc0_lvl.p + 2 * p->levels;
     }
     s.psi = p->psi.p; s.lam = p->lam.p; s.part = p->part.p; s.cost_part = p->cost_part.p; s.psi_in = p->psi0.p;
+    s.S_norm = p->state_sharded ? p->pb.state_total : p->pb.state_count;
+    s.const_on = (!p->state_sharded || p->pb.state_first == 0) ? 1 : 0;
+    s.coh_out = p->state_sharded ? p->coh_out : nullptr;
+    s.coh_in = p->state_sharded ? p->coh_in : nullptr;
     return s;
 }
 
@@ -1227,6 +1235,7 @@ int enqueue_finalize(qocb_plan *p) {
 // enqueue one (unsharded) evaluation on the plan stream; ev != nullptr records stage boundaries (8 events)
 int enqueue_eval(qocb_plan *p, bool with_grad, cudaEvent_t *ev) {
     if (p->sharded) { set_error(p, "this plan covers a slice range: use the qocb_shard_* phase calls"); return -1; }
+    if (p->state_sharded) { set_error(p, "this plan holds a share of the states: use the qocb_state_shard_* phase calls"); return -1; }
     int rc = ready(p); if (rc) return rc;
     auto rec = [&](int i) { if (ev) cudaEventRecord(ev[i], p->stream); };
     rec(0);
@@ -1292,6 +1301,9 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     if (pb->state_count < 1 || pb->cost_eval_step < 1 || pb->ensemble_count < 1) { set_error((qocb_plan *)nullptr, "state_count, cost_eval_step, ensemble_count must be >= 1"); return -1; }
     const bool sliced = !(pb->slice_begin == 0 && pb->slice_end == 0);
     if (sliced && (pb->slice_begin < 0 || pb->slice_end <= pb->slice_begin || pb->slice_end > pb->system_eval_count - 1)) { set_error((qocb_plan *)nullptr, "bad slice range: need 0 <= slice_begin < slice_end <= system_eval_count - 1"); return -1; }
+    const bool st_sharded = pb->state_total > 0;                    // also a single-rank "shard" of all states goes through the phase calls
+    if (pb->state_total < 0 || pb->state_first < 0 || (pb->state_total > 0 && pb->state_first + pb->state_count > pb->state_total)) { set_error((qocb_plan *)nullptr, "bad state range: need state_first + state_count <= state_total"); return -1; }
+    if (st_sharded && (sliced || pb->ensemble_count != 1)) { set_error((qocb_plan *)nullptr, "state sharding cannot be combined with time-slice sharding or ensembles"); return -1; }
     if (sliced && pb->ensemble_count != 1) { set_error((qocb_plan *)nullptr, "time-slice sharding and ensembles are mutually exclusive (shard the members instead)"); return -1; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error((qocb_plan *)nullptr, "no CUDA device available (this library has no CPU path)"); return -2; }
@@ -1300,6 +1312,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     p->NP = NP;
     p->q = pb->magnus_order / 2;
     p->sharded = sliced;
+    p->state_sharded = st_sharded;
     p->j0 = sliced ? pb->slice_begin : 0;
     p->Nloc = (sliced ? pb->slice_end - pb->slice_begin : pb->system_eval_count - 1) + 1;
     p->owns_final = !sliced || pb->slice_end == pb->system_eval_count - 1;
@@ -1460,7 +1473,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     PTRY(cudaMallocHost(&p->h_pinned, sizeof(double) * (2 * std::max<size_t>(1, (size_t)M * KR) + 8)));
     PTRY(cudaMallocHost(&p->h_fin, sizeof(double) * (size_t)E * S * 2 * NP));
     PTRY(cudaMallocHost(&p->h_flag, sizeof(int)));
-    { const char *ng = getenv("QOCB_NO_GRAPH"); p->use_graph = !(ng && ng[0] == '1') && !is_large && !sliced; }
+    { const char *ng = getenv("QOCB_NO_GRAPH"); p->use_graph = !(ng && ng[0] == '1') && !is_large && !sliced && !st_sharded; }
     // sweep kernels may need > 48 KB of dynamic shared memory
     {
         const int big = 200 * 1024;
@@ -1646,7 +1659,7 @@ int qocb_set_states(qocb_plan *p, const double *psi0) {
 int qocb_clear_costs(qocb_plan *p) {
     if (!p) return -1;
     drop_graphs(p);
-    p->h_terms.clear(); p->h_vecs.clear(); p->h_counts.clear(); p->ip_total = 0; p->have_step_costs = false;
+    p->h_terms.clear(); p->h_vecs.clear(); p->h_counts.clear(); p->ip_total = 0; p->coh_total = 0; p->have_step_costs = false;
     p->terms.release();
     return 0;
 }
@@ -1663,6 +1676,8 @@ int qocb_add_cost(qocb_plan *p, int32_t kind, int32_t step_cost, double weight, 
     t.cnt_off = (int)p->h_counts.size();
     t.ip_off = p->ip_total;
     p->ip_total += S * fmax;
+    t.coh_off = p->coh_total;
+    if (kind == QOCB_COST_TARGET_COHERENT) p->coh_total += t.step ? (p->pb.system_eval_count - 1) / p->pb.cost_eval_step : 1;
     const size_t base = p->h_vecs.size();
     p->h_vecs.resize(base + (size_t)S * fmax * 2 * NP, 0.0);
     for (int s = 0; s < S; ++s) {
@@ -1991,6 +2006,44 @@ int qocb_shard_backward_finish(qocb_plan *p, const double *allP_dev, const doubl
     SWEEP_NP(p->NP, (k_suffix_costates<NPc><<<1, kSweepThreads, sm, p->stream>>>(allP_dev, allb_dev, p->lam_in.p, rank, world, p->pb.state_count)));
     CU_TRY(p, cudaGetLastError());
     int rc = enqueue_costate(p, p->lam_in.p, nullptr, false, true, !reuse); if (rc) return rc;
+    return enqueue_expm_backward(p, nullptr);
+}
+
+// ---- state sharding phases -------------------------------------------------------------------------------------
+int qocb_state_shard_coherent_doubles(qocb_plan *p) { return p ? 2 * p->coh_total : -1; }
+
+int qocb_state_shard_forward(qocb_plan *p, int32_t with_grad, double *coh_dev) {
+    if (!p || (p->coh_total > 0 && !coh_dev)) { set_error(p, "null argument"); return -1; }
+    if (!p->state_sharded) { set_error(p, "plan was not created with a state range (state_total / state_first)"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    int rc = ready(p); if (rc) return rc;
+    p->coh_out = coh_dev; p->coh_in = nullptr;
+    if (p->coh_total > 0) CU_TRY(p, cudaMemsetAsync(coh_dev, 0, sizeof(double) * 2 * p->coh_total, p->stream));
+    if (p->large) {
+        rc = lg_expm_all(p); if (rc) return rc;
+        return lg_states_forward(p, p->psi0.p);                    // includes the sum of the chunk costs
+    }
+    rc = enqueue_expm_forward(p, with_grad != 0); if (rc) return rc;
+    rc = enqueue_state_forward(p, p->psi0.p, nullptr); if (rc) return rc;
+    return enqueue_finalize(p);
+}
+
+int qocb_state_shard_finish(qocb_plan *p, int32_t with_grad, const double *coh_dev) {
+    if (!p || (p->coh_total > 0 && !coh_dev)) { set_error(p, "null argument"); return -1; }
+    if (!p->state_sharded) { set_error(p, "plan was not created with a state range (state_total / state_first)"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    p->coh_out = nullptr; p->coh_in = p->coh_total > 0 ? coh_dev : nullptr;
+    if (p->coh_total > 0 && p->pb.state_first == 0) {
+        k_coherent_value<<<1, 32, 0, p->stream>>>(p->terms.p, (int)p->h_terms.size(), coh_dev, p->pb.cost_eval_step, p->pb.system_eval_count,
+                                                 p->pb.state_total, 1, p->cost.p);
+        CU_TRY(p, cudaGetLastError());
+    }
+    if (!with_grad) return 0;
+    if (p->large) {
+        int rc = lg_costates(p, nullptr, nullptr, true, true); if (rc) return rc;
+        return lg_backward_all(p);
+    }
+    int rc = enqueue_costate(p, nullptr, nullptr, true, true); if (rc) return rc;
     return enqueue_expm_backward(p, nullptr);
 }
 

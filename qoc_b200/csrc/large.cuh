@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(kLgThreads) k_lg_sweep_fwd(LgSweep g) {
         const bool st = is_step_cost_state(k + a.j_off, a.ces), fin = (k + a.j_off == a.Nglob - 1);
         if (a.nterms > 0 && (st || fin)) {
             cost_inner_products(a, v1, ip, st, fin);
-            cost += cost_value(a, ip, st, fin);
+            cost += cost_value(a, ip, st, fin, k + a.j_off);
         }
         double *t = v0; v0 = v1; v1 = t;
         __syncthreads();
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kLgThreads) k_lg_sweep_bwd(LgSweep g) {
         lg_matvec(v1, v0, g.UT + (size_t)j * n * n, n, S);
         if (a.nterms > 0 && is_step_cost_state(j + a.j_off, a.ces)) {
             cost_inner_products(a, a.psi + (size_t)j * VS, ip, true, false);
-            cost_add_seed(a, ip, v1, true, false);
+            cost_add_seed(a, ip, v1, true, false, j + a.j_off);
         }
         if (!PARTICULAR) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.lam[(size_t)j * VS + i] = v1[i];
         double *t = v0; v0 = v1; v1 = t;
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kLgThreads) k_lg_boundary_bwd(LgSweep g, int h
     if (a.nterms > 0 && a.add_final_seed) {
         const bool st = is_step_cost_state(a.N - 1 + a.j_off, a.ces);
         cost_inner_products(a, a.psi + (size_t)(a.N - 1) * VS, ip, st, true);
-        cost_add_seed(a, ip, v0, st, true);
+        cost_add_seed(a, ip, v0, st, true, a.N - 1 + a.j_off);
     }
     for (int i = threadIdx.x; i < VS; i += kLgThreads) a.lam[(size_t)(a.N - 1) * VS + i] = v0[i];
     for (int c = g.nchunks - 1; c >= 0; --c) {

@@ -24,6 +24,7 @@ struct CostTerm {
     int vec_off;       // offset (in vectors) into the plan's vector pool: index (s * fmax + f)
     int cnt_off;       // offset into the counts pool: F_s per state
     int ip_off;        // offset into the shared inner-product scratch
+    int coh_off;       // coherent target terms: first slot of this term in the overlap-sum buffer of a state-sharded plan
     double w;          // cost_multiplier / normalisation
 };
 
@@ -47,7 +48,18 @@ struct SweepArgs {
     int j_off, Nglob;              // time sharding: global index of local slice 0; global system_eval_count.
                                    // N above is the LOCAL state count (local slices + 1)
     int add_final_seed;            // this shard owns the final state (seed of the final-step costs)
+    // sharding of the initial STATES across ranks (qocb_state_shard_*): S above is the local count, normalisations use the
+    // total; the coherent target cost couples all states through T = sum_s <t_s|psi_s>: the forward pass writes the local
+    // partial sums (one complex slot per coherent term and cost step) to coh_out and leaves the value to
+    // k_coherent_value, the backward pass seeds from the all-reduced totals in coh_in.  Unsharded: S_norm = S, const_on = 1,
+    // both pointers null.
+    int S_norm, const_on;
+    double *coh_out;
+    const double *coh_in;
 };
+
+// slot of the overlap sum of coherent term `tm` at global state index k (step terms: cost steps k = ces, 2 ces, ...)
+__device__ __forceinline__ int coh_slot(const CostTerm &tm, int k, int ces) { return tm.coh_off + (tm.step ? k / ces - 1 : 0); }
 
 constexpr int kSweepThreads = 512;
 
@@ -223,7 +235,7 @@ __device__ void cost_inner_products(const SweepArgs &a, const double *psi, doubl
 }
 
 // value of the active cost terms at one state set (thread 0 returns it; other threads return 0)
-__device__ double cost_value(const SweepArgs &a, const double *ip, bool step_state, bool final_state) {
+__device__ double cost_value(const SweepArgs &a, const double *ip, bool step_state, bool final_state, int kglob) {
     double val = 0.;
     if (threadIdx.x == 0) {
         for (int t = 0; t < a.nterms; ++t) {
@@ -232,14 +244,19 @@ __device__ double cost_value(const SweepArgs &a, const double *ip, bool step_sta
             if (tm.kind == 0) {
                 double tr = 0., ti = 0.;
                 for (int s = 0; s < a.S; ++s) { tr += ip[2 * (tm.ip_off + s * tm.fmax)]; ti += ip[2 * (tm.ip_off + s * tm.fmax) + 1]; }
-                val += tm.w * (1.0 - (tr * tr + ti * ti) / ((double)a.S * a.S));
+                if (a.coh_out) {                                   // states sharded: the value needs the sum over ALL ranks
+                    const int sl = coh_slot(tm, kglob, a.ces);
+                    a.coh_out[2 * sl] = tr; a.coh_out[2 * sl + 1] = ti;
+                } else {
+                    val += tm.w * (1.0 - (tr * tr + ti * ti) / ((double)a.S_norm * a.S_norm));
+                }
             } else if (tm.kind == 1) {
                 double acc = 0.;
                 for (int s = 0; s < a.S; ++s) {
                     const double r = ip[2 * (tm.ip_off + s * tm.fmax)], i = ip[2 * (tm.ip_off + s * tm.fmax) + 1];
                     acc += r * r + i * i;
                 }
-                val += tm.w * (1.0 - acc / a.S);
+                val += tm.w * ((a.const_on ? 1.0 : 0.0) - acc / a.S_norm);
             } else {
                 double acc = 0.;
                 for (int s = 0; s < a.S; ++s) {
@@ -259,15 +276,17 @@ __device__ double cost_value(const SweepArgs &a, const double *ip, bool step_sta
 }
 
 // lam[s][a] += d cost / d psi_s[a] in autograd's convention (d/dx - i d/dy):  sum coef * conj(v[a])
-__device__ void cost_add_seed(const SweepArgs &a, const double *ip, double *lam, bool step_state, bool final_state,
+__device__ void cost_add_seed(const SweepArgs &a, const double *ip, double *lam, bool step_state, bool final_state, int kglob,
                               int sb = 0, int sc = -1) {
     if (sc < 0) sc = a.S;                                  // lam holds states [sb, sb + sc) only
     for (int t = 0; t < a.nterms; ++t) {
         const CostTerm tm = a.terms[t];
         if (!((tm.step && step_state) || (!tm.step && final_state))) continue;
         double tr = 0., ti = 0.;
-        if (tm.kind == 0)
-            for (int s = 0; s < a.S; ++s) { tr += ip[2 * (tm.ip_off + s * tm.fmax)]; ti += ip[2 * (tm.ip_off + s * tm.fmax) + 1]; }
+        if (tm.kind == 0) {
+            if (a.coh_in) { const int sl = coh_slot(tm, kglob, a.ces); tr = a.coh_in[2 * sl]; ti = a.coh_in[2 * sl + 1]; }
+            else for (int s = 0; s < a.S; ++s) { tr += ip[2 * (tm.ip_off + s * tm.fmax)]; ti += ip[2 * (tm.ip_off + s * tm.fmax) + 1]; }
+        }
         for (int o = threadIdx.x; o < sc * a.NP; o += kSweepThreads) {
             const int sl = o / a.NP, s = sb + sl, b = o % a.NP;
             const int F = a.counts[tm.cnt_off + s];
@@ -275,8 +294,8 @@ __device__ void cost_add_seed(const SweepArgs &a, const double *ip, double *lam,
             for (int f = 0; f < F; ++f) {
                 const double *v = a.vecs + (size_t)(tm.vec_off + s * tm.fmax + f) * 2 * a.NP;
                 double cr, ci;         // coefficient = scale * conj(ip or total)
-                if (tm.kind == 0) { const double k = -2.0 * tm.w / ((double)a.S * a.S); cr = k * tr; ci = -k * ti; }
-                else if (tm.kind == 1) { const double k = -2.0 * tm.w / a.S; cr = k * ip[2 * (tm.ip_off + s * tm.fmax)]; ci = -k * ip[2 * (tm.ip_off + s * tm.fmax) + 1]; }
+                if (tm.kind == 0) { const double k = -2.0 * tm.w / ((double)a.S_norm * a.S_norm); cr = k * tr; ci = -k * ti; }
+                else if (tm.kind == 1) { const double k = -2.0 * tm.w / a.S_norm; cr = k * ip[2 * (tm.ip_off + s * tm.fmax)]; ci = -k * ip[2 * (tm.ip_off + s * tm.fmax) + 1]; }
                 else { const double k = 2.0 * tm.w / F; cr = k * ip[2 * (tm.ip_off + s * tm.fmax + f)]; ci = -k * ip[2 * (tm.ip_off + s * tm.fmax + f) + 1]; }
                 const double vr = v[b], vi = -v[a.NP + b];              // conj(v)
                 sr += cr * vr - ci * vi;
@@ -287,6 +306,23 @@ __device__ void cost_add_seed(const SweepArgs &a, const double *ip, double *lam,
         }
     }
     __syncthreads();
+}
+
+// state-sharded plans: value of the coherent target terms from the all-reduced overlap sums, added to *cost by the one
+// rank that counts constants.  nslots[t] slots per term (cost steps of a step term, 1 otherwise).
+__global__ void k_coherent_value(const CostTerm *terms, int nterms, const double *coh, int ces, int Nglob, int S_norm, int E, double *cost) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double val = 0.;
+    for (int t = 0; t < nterms; ++t) {
+        const CostTerm tm = terms[t];
+        if (tm.kind != 0) continue;
+        const int cnt = tm.step ? (Nglob - 1) / ces : 1;
+        for (int q = 0; q < cnt; ++q) {
+            const double tr = coh[2 * (tm.coh_off + q)], ti = coh[2 * (tm.coh_off + q) + 1];
+            val += tm.w * (1.0 - (tr * tr + ti * ti) / ((double)S_norm * S_norm));
+        }
+    }
+    *cost += val / E;
 }
 
 // dynamic smem layout of the sweep kernels: red (U^T v partial sums) | v0 (S*2*NP) | v1 (S*2*NP) | ip (2*ip_total)
@@ -388,7 +424,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_fwd(SweepArgs a) {
         const bool st = is_step_cost_state(k + a.j_off, a.ces), fin = (k + a.j_off == a.Nglob - 1);
         if (a.nterms > 0 && (st || fin)) {
             cost_inner_products(a, sm.v1, sm.ip, st, fin);
-            cost += cost_value(a, sm.ip, st, fin);
+            cost += cost_value(a, sm.ip, st, fin, k + a.j_off);
         }
         sm.swap();
         cur = nxt;
@@ -422,7 +458,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_bwd(SweepArgs a) {
         const bool st = is_step_cost_state(j + a.j_off, a.ces);
         if (a.nterms > 0 && st) {                                     // + seed_j (state j < N-1: step costs only)
             cost_inner_products(a, psi_e + (size_t)j * VS, sm.ip, true, false);
-            cost_add_seed(a, sm.ip, sm.v1, true, false);
+            cost_add_seed(a, sm.ip, sm.v1, true, false, j + a.j_off);
         }
         if (!PARTICULAR)
             for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)j * VS + i] = sm.v1[i];
@@ -454,7 +490,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_bwd(SweepArgs a, int
     if (a.nterms > 0 && a.add_final_seed) {                         // inner products of ALL states (coherent sums)
         const bool st = is_step_cost_state(a.N - 1 + a.j_off, a.ces);
         cost_inner_products(a, psi_e + (size_t)(a.N - 1) * VSA, sm.ip, st, true);
-        cost_add_seed(a, sm.ip, sm.v0, st, true, sb, S);
+        cost_add_seed(a, sm.ip, sm.v0, st, true, a.N - 1 + a.j_off, sb, S);
     }
     for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)(a.N - 1) * VSA + i] = sm.v0[i];
     for (int c = c1 - 1; c >= c0; --c) {
