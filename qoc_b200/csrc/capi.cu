@@ -408,9 +408,11 @@ struct LargeImpl {
     DevBuf<double2 *> ptrQ, ptrP, ptrRB, ptrPSI;
     bool lowrank = false;
     DevBuf<int> piv, info, sarr, cb;
-    std::vector<int> h_s;
+    std::vector<int> h_smax;            // largest squaring count per batch, read back ONCE per evaluation (after the forward)
+    DevBuf<int> smax_dev;               // [batches + 1]: per batch of the forward pass; last slot: scratch of recomputed batches
     int lstar = 0, nchunks = 0, lvl_count[24] = {}, lvl_off[24] = {};   // pairwise propagator tree levels 0..lstar
     bool use_cublas_gemm = false;       // QOCB_LARGE_CUBLAS=1: library ZGEMM instead of zgemm.cuh (A/B comparison)
+    bool cluster_boundary = true;       // boundary passes on an 8-CTA cluster (QOCB_NO_CLUSTER=1: the single-CTA kernels)
     // reverse-pass tape (stored when it fits): M, A2, A4, A6, Y, LU(Q), R0 of every local slice + pivots + squaring counts.
     // tj >= 0 redirects those work arrays (and pivots / counts / LU pointers) to the tape entries of slices tj, tj+1, ...
     DevBuf<double2> tape;
@@ -671,11 +673,12 @@ inline int lg_blocks(size_t tot) { return (int)std::min<size_t>((tot + 255) / 25
 
 // own DMMA GEMM, general shapes: C (m x nc, ldc) = alpha op(A) (m x k) op(B) (k x nc) + beta C over `batch` matrices
 int lg_gemm_rect(qocb_plan *p, bool ta, bool tb, const double2 *A, const double2 *B, double2 *C, int m, int nc, int k, int lda, int ldb,
-                 int ldc, double alpha, double beta, int batch, long long sA, long long sB, long long sC) {
+                 int ldc, double alpha, double beta, int batch, long long sA, long long sB, long long sC, const int *gate = nullptr,
+                 int gate_level = 0) {
     const bool thin = nc <= 16;
     const int bn = thin ? 16 : 64;
     const dim3 grid(((m + 63) / 64) * ((nc + bn - 1) / bn), batch);
-#define ZG_LAUNCH(TA_, TB_, BN_) k_zgemm<TA_, TB_, BN_><<<grid, ZG_NT, ZgTile<BN_>::smem, p->stream>>>(A, B, C, m, nc, k, lda, ldb, ldc, alpha, beta, sA, sB, sC)
+#define ZG_LAUNCH(TA_, TB_, BN_) k_zgemm<TA_, TB_, BN_><<<grid, ZG_NT, ZgTile<BN_>::smem, p->stream>>>(A, B, C, m, nc, k, lda, ldb, ldc, alpha, beta, sA, sB, sC, gate, gate_level)
     if (thin) {
         if (!ta && !tb) ZG_LAUNCH(false, false, 16); else if (ta && !tb) ZG_LAUNCH(true, false, 16);
         else if (!ta && tb) ZG_LAUNCH(false, true, 16); else ZG_LAUNCH(true, true, 16);
@@ -690,12 +693,12 @@ int lg_gemm_rect(qocb_plan *p, bool ta, bool tb, const double2 *A, const double2
 
 // row-major C = alpha op(A) op(B) + beta C over `batch` matrices (strides in elements)
 int lg_gemm(qocb_plan *p, bool ta, bool tb, const double2 *A, const double2 *B, double2 *C, double alpha, double beta, int batch,
-            long long sA = -1, long long sB = -1, long long sC = -1) {
+            long long sA = -1, long long sB = -1, long long sC = -1, const int *gate = nullptr, int gate_level = 0) {
     LargeImpl *L = p->large;
     const int n = L->n;
     if (sA < 0) sA = L->nn; if (sB < 0) sB = L->nn; if (sC < 0) sC = L->nn;
-    if (!L->use_cublas_gemm) {                         // own DMMA tile kernel (zgemm.cuh)
-        return lg_gemm_rect(p, ta, tb, A, B, C, n, n, n, n, n, n, alpha, beta, batch, sA, sB, sC);
+    if (!L->use_cublas_gemm || gate) {                 // own DMMA tile kernel (zgemm.cuh); gated launches exist only there
+        return lg_gemm_rect(p, ta, tb, A, B, C, n, n, n, n, n, n, alpha, beta, batch, sA, sB, sC, gate, gate_level);
     }
     const cuDoubleComplex a = make_cuDoubleComplex(alpha, 0.), b = make_cuDoubleComplex(beta, 0.);
     BL_TRY(p, cublasZgemmStridedBatched(L->blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, n, n, n, &a,
@@ -808,7 +811,9 @@ int large_init(qocb_plan *p) {
         for (int b = 0; b < L->B; ++b) hp2[b] = L->lr.p + (size_t)b * 4 * n;
         CU_TRY(p, cudaMemcpy(L->ptrPSI.p, hp2.data(), sizeof(double2 *) * L->B, cudaMemcpyHostToDevice));
     }
-    L->h_s.resize(L->B);
+    L->h_smax.assign((Lsl + L->B - 1) / L->B + 1, 0);
+    CU_TRY(p, L->smax_dev.alloc(L->h_smax.size()));
+    CU_TRY(p, cudaMemset(L->smax_dev.p, 0, sizeof(int) * L->h_smax.size()));
     L->Lsl = Lsl;
     L->batch_taped.assign((Lsl + L->B - 1) / L->B, 0);
     if (p->pb.store_tape) {
@@ -830,14 +835,19 @@ int large_init(qocb_plan *p) {
     CU_TRY(p, cudaFuncSetAttribute(k_lg_sweep_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(p, cudaFuncSetAttribute(k_lg_boundary_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(p, cudaFuncSetAttribute(k_lg_boundary_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_boundary_fwd_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_boundary_bwd_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    { const char *nc = getenv("QOCB_NO_CLUSTER"); L->cluster_boundary = !(nc && nc[0] == '1'); }
     CU_TRY(p, cudaFuncSetAttribute(k_lg_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU_TRY(p, cudaFuncSetAttribute(k_lg_suffix, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     return 0;
 }
 
 // forward intermediates of slices [jb, jb + Bc); keep: also R0 and the squaring inputs for the reverse pass.
-// smax_out: largest squaring count of the batch.  Leaves U_j in arr(LP).
-int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_out) {
+// Leaves U_j in arr(LP).  No host synchronisation: the squaring loop enqueues a fixed number of GATED launches that return at
+// once beyond the largest squaring count of the batch (smax_slot, device).  keep: the capacity is that of the reverse pass.
+constexpr int kLgFwdMaxSq = 10;          // forward-only capacity: ||M||_1 up to 5.37 * 2^10; beyond it the device error flag is raised
+int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_slot) {
     LargeImpl *L = p->large;
     const int nn = L->nn, order = p->pb.magnus_order;
     const size_t tot = (size_t)Bc * nn;
@@ -860,7 +870,8 @@ int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_out) {
     }
     }
     k_lg_norm_scale<<<Bc, 256, 0, p->stream>>>(L->arr(LM), L->cur_sarr(), L->n);
-    CU_TRY(p, cudaMemcpyAsync(L->h_s.data(), L->cur_sarr(), sizeof(int) * Bc, cudaMemcpyDeviceToHost, p->stream));
+    const int cap = keep ? kLgMaxSq : kLgFwdMaxSq;
+    k_lg_batch_max<<<1, 256, 0, p->stream>>>(L->cur_sarr(), Bc, smax_slot, cap, p->err_flag.p);
     rc = lg_gemm(p, false, false, L->arr(LM), L->arr(LM), L->arr(LA2), 1., 0., Bc); if (rc) return rc;
     rc = lg_gemm(p, false, false, L->arr(LA2), L->arr(LA2), L->arr(LA4), 1., 0., Bc); if (rc) return rc;
     rc = lg_gemm(p, false, false, L->arr(LA2), L->arr(LA4), L->arr(LA6), 1., 0., Bc); if (rc) return rc;
@@ -875,17 +886,12 @@ int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_out) {
     BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_N, L->n, L->n, reinterpret_cast<const cuDoubleComplex *const *>(L->cur_ptrQ()), L->n, L->cur_piv(),
                                   reinterpret_cast<cuDoubleComplex **>(L->ptrP.p), L->n, &hinfo, Bc));   // R0 = P Q^-1 (row-major)
     if (keep || L->tj >= 0) { rc = lg_copy(p, L->arr(LR0), L->arr(LP), Bc); if (rc) return rc; }
-    CU_TRY(p, cudaStreamSynchronize(p->stream));                    // squaring counts of the batch
-    int smax = 0;
-    for (int b = 0; b < Bc; ++b) smax = std::max(smax, L->h_s[b]);
-    if (keep && smax > kLgMaxSq) { set_error(p, "scaling count exceeds the reverse-pass capacity of the large-dimension path"); return -4; }
-    for (int i = 0; i < smax; ++i) {
-        if (keep) { rc = lg_copy(p, L->arr(LRS0 + i), L->arr(LP), Bc); if (rc) return rc; }
-        rc = lg_gemm(p, false, false, L->arr(LP), L->arr(LP), L->arr(LT), 1., 0., Bc); if (rc) return rc;
-        k_lg_select<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LP), L->arr(LT), L->cur_sarr(), i, nn, tot);
+    for (int i = 0; i < cap; ++i) {                                 // expm.py:249-250, gated on the device
+        if (keep) k_lg_copy_gated<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LRS0 + i), L->arr(LP), tot, smax_slot, i);
+        rc = lg_gemm(p, false, false, L->arr(LP), L->arr(LP), L->arr(LT), 1., 0., Bc, -1, -1, -1, smax_slot, i); if (rc) return rc;
+        k_lg_select<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LP), L->arr(LT), L->cur_sarr(), i, nn, tot, smax_slot);
     }
     CU_TRY(p, cudaGetLastError());
-    *smax_out = smax;
     return 0;
 }
 
@@ -895,12 +901,10 @@ int lg_expm_all(qocb_plan *p) {
     { int rc = enqueue_node_coefs(p); if (rc) return rc; }
     for (int jb = 0; jb < Lsl; jb += L->B) {
         const int Bc = std::min(L->B, Lsl - jb);
-        int smax = 0;
         L->tj = L->taped ? jb : -1;                                 // forward intermediates go straight to the tape
-        int rc = lg_forward_batch(p, jb, Bc, false, &smax);
+        int rc = lg_forward_batch(p, jb, Bc, false, L->smax_dev.p + jb / L->B);
         L->tj = -1;
         if (rc) return rc;
-        L->batch_taped[jb / L->B] = (L->taped && smax == 0) ? 1 : 0;   // batches with squarings are recomputed
         rc = lg_copy(p, reinterpret_cast<double2 *>(p->U.p) + (size_t)jb * L->nn, L->arr(LP), Bc); if (rc) return rc;
     }
     // transposed copies for the costate sweeps; pairwise product tree up to the chunk level of the sweeps
@@ -940,10 +944,18 @@ int lg_backward_all(qocb_plan *p) {
     LargeImpl *L = p->large;
     const int Lsl = p->Nloc - 1, nn = L->nn, order = p->pb.magnus_order, n = L->n;
     const double dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
+    // the one host synchronisation of an evaluation on this path: squaring counts of the forward batches (taped batches
+    // without squarings are replayed from the tape, the others recompute their forward pass)
+    CU_TRY(p, cudaMemcpyAsync(L->h_smax.data(), L->smax_dev.p, sizeof(int) * L->h_smax.size(), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    for (size_t bi = 0; bi + 1 < L->h_smax.size(); ++bi) {
+        if (L->h_smax[bi] > kLgMaxSq) { set_error(p, "scaling count exceeds the reverse-pass capacity of the large-dimension path"); return -4; }
+        L->batch_taped[bi] = (L->taped && L->h_smax[bi] == 0) ? 1 : 0;
+    }
     for (int jb = 0; jb < Lsl; jb += L->B) {
         const int Bc = std::min(L->B, Lsl - jb);
         const size_t tot = (size_t)Bc * nn;
-        int smax = 0, rc = 0;
+        int smax = L->h_smax[jb / L->B], rc = 0;                    // same controls as the forward pass => same counts
         if (L->batch_taped[jb / L->B]) {
             // taped batch: only the cheap elementwise pieces are rebuilt (node generators for the Magnus adjoint, W1, X1)
             L->tj = jb;
@@ -953,7 +965,7 @@ int lg_backward_all(qocb_plan *p) {
             k_lg_poly<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LA2), L->arr(LA4), L->arr(LA6), L->arr(LW1), L->arr(LX1), L->arr(LT), L->arr(LVE), L->n, tot);
         } else {
             L->tj = -1;
-            rc = lg_forward_batch(p, jb, Bc, true, &smax); if (rc) return rc;
+            rc = lg_forward_batch(p, jb, Bc, true, L->smax_dev.p + (L->h_smax.size() - 1)); if (rc) return rc;
         }
         struct TjReset { LargeImpl *l; ~TjReset() { l->tj = -1; } } tj_reset{L};
         double2 *RB = L->arr(LRB), *T = L->arr(LT), *M = L->arr(LM);
@@ -1081,7 +1093,8 @@ int lg_states_forward(qocb_plan *p, const double *psi_in_dev) {
     LgSweep g = lg_sweep_args(p);
     g.a.psi_in = psi_in_dev;
     const size_t sm = lg_sweep_smem(p);
-    k_lg_boundary_fwd<<<1, kLgThreads, sm, p->stream>>>(g);
+    if (p->large->cluster_boundary) k_lg_boundary_fwd_cl<<<kLgCluster, kLgThreads, sm, p->stream>>>(g);
+    else k_lg_boundary_fwd<<<1, kLgThreads, sm, p->stream>>>(g);
     k_lg_sweep_fwd<<<g.nchunks, kLgThreads, sm, p->stream>>>(g);
     k_finalize_cost<<<1, 32, 0, p->stream>>>(p->cost_part.p, g.nchunks, 1, p->cost.p);
     CU_TRY(p, cudaGetLastError());
@@ -1093,7 +1106,10 @@ int lg_costates(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, bool 
     g.a.lam_in = lam_in_dev; g.a.b_out = b_out_dev;
     const size_t sm = lg_sweep_smem(p);
     if (do_particular && p->have_step_costs) k_lg_sweep_bwd<true><<<g.nchunks, kLgThreads, sm, p->stream>>>(g);
-    if (do_boundary) k_lg_boundary_bwd<<<1, kLgThreads, sm, p->stream>>>(g, p->have_step_costs ? 1 : 0);
+    if (do_boundary) {
+        if (p->large->cluster_boundary) k_lg_boundary_bwd_cl<<<kLgCluster, kLgThreads, sm, p->stream>>>(g, p->have_step_costs ? 1 : 0);
+        else k_lg_boundary_bwd<<<1, kLgThreads, sm, p->stream>>>(g, p->have_step_costs ? 1 : 0);
+    }
     if (do_sweeps) k_lg_sweep_bwd<false><<<g.nchunks, kLgThreads, sm, p->stream>>>(g);
     CU_TRY(p, cudaGetLastError());
     return 0;

@@ -16,6 +16,7 @@
 // Matrices are interleaved complex128 (double2), row-major, dense n x n; state vectors stay planar ([s][2][n]) so the
 // cost reductions of sweep.cuh are shared.
 #pragma once
+#include <cooperative_groups.h>
 #include <cublas_v2.h>
 
 namespace qocb {
@@ -181,10 +182,26 @@ __global__ void k_lg_pq(const double2 *Ve, const double2 *Uo, double2 *P, double
     }
 }
 
-// dst[b] = (level < s_b) ? src[b] : dst[b]   (squaring / reverse-squaring selection per slice)
-__global__ void k_lg_select(double2 *dst, const double2 *src, const int *sarr, int level, int nn, size_t tot) {
+// dst[b] = (level < s_b) ? src[b] : dst[b]   (squaring / reverse-squaring selection per slice); gate: see k_zgemm
+__global__ void k_lg_select(double2 *dst, const double2 *src, const int *sarr, int level, int nn, size_t tot, const int *gate = nullptr) {
+    if (gate != nullptr && level >= *gate) return;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x)
         if (level < sarr[t / nn]) dst[t] = src[t];
+}
+// gated copy (squaring inputs kept for the reverse pass)
+__global__ void k_lg_copy_gated(double2 *dst, const double2 *src, size_t tot, const int *gate, int level) {
+    if (level >= *gate) return;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) dst[t] = src[t];
+}
+// largest squaring count of a batch -> *smax (device); counts above `cap` raise the device error flag
+__global__ void k_lg_batch_max(const int *sarr, int B, int *smax, int cap, int *err_flag) {
+    __shared__ int red[256];
+    int m = 0;
+    for (int b = threadIdx.x; b < B; b += 256) m = max(m, sarr[b]);
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] = max(red[threadIdx.x], red[threadIdx.x + o]); __syncthreads(); }
+    if (threadIdx.x == 0) { *smax = red[0]; if (red[0] > cap) *err_flag = 1; }
 }
 
 // x[b] *= 2^-s_b
@@ -286,13 +303,15 @@ __global__ void k_lg_transpose(double2 *dst, const double2 *src, int n, int batc
 }
 
 // out[s][a] = sum_b U[a][b] in[s][b]; vectors planar [s][2][n] in shared memory; ends with a barrier
+// a_begin / a_end: output rows computed by this call (the cluster boundary passes split the rows over their CTAs)
 template <int NPL>          // double2 per lane per row: n <= 32 * NPL
-__device__ void lg_matvec_rows(double *out, const double *in, const double2 *U, int n, int S) {
+__device__ void lg_matvec_rows(double *out, const double *in, const double2 *U, int n, int S, int a_begin = 0, int a_end = -1) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = kLgThreads / 32, D = NPL <= 8 ? 4 : 2;
+    if (a_end < 0) a_end = n;
     for (int s0 = 0; s0 < S; s0 += 4) {
         const int sc = min(4, S - s0);
-        for (int a0 = warp; a0 < n; a0 += NW * D) {
+        for (int a0 = a_begin + warp; a0 < a_end; a0 += NW * D) {
             double2 u[D][NPL];
 #pragma unroll
             for (int d = 0; d < D; ++d) {
@@ -300,7 +319,7 @@ __device__ void lg_matvec_rows(double *out, const double *in, const double2 *U, 
 #pragma unroll
                 for (int k = 0; k < NPL; ++k) {
                     const int c = lane + 32 * k;
-                    u[d][k] = (a < n && c < n) ? U[(size_t)a * n + c] : make_double2(0., 0.);
+                    u[d][k] = (a < a_end && c < n) ? U[(size_t)a * n + c] : make_double2(0., 0.);
                 }
             }
 #pragma unroll
@@ -323,17 +342,17 @@ __device__ void lg_matvec_rows(double *out, const double *in, const double2 *U, 
                 for (int s = 0; s < 4; ++s) {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) { ar[s] += __shfl_xor_sync(0xffffffffu, ar[s], o); ai[s] += __shfl_xor_sync(0xffffffffu, ai[s], o); }
-                    if (lane == 0 && s < sc && a < n) { out[(s0 + s) * 2 * n + a] = ar[s]; out[(s0 + s) * 2 * n + n + a] = ai[s]; }
+                    if (lane == 0 && s < sc && a < a_end) { out[(s0 + s) * 2 * n + a] = ar[s]; out[(s0 + s) * 2 * n + n + a] = ai[s]; }
                 }
             }
         }
     }
     __syncthreads();
 }
-__device__ __forceinline__ void lg_matvec(double *out, const double *in, const double2 *U, int n, int S) {
-    if (n <= 128) lg_matvec_rows<4>(out, in, U, n, S);
-    else if (n <= 256) lg_matvec_rows<8>(out, in, U, n, S);
-    else lg_matvec_rows<16>(out, in, U, n, S);
+__device__ __forceinline__ void lg_matvec(double *out, const double *in, const double2 *U, int n, int S, int a_begin = 0, int a_end = -1) {
+    if (n <= 128) lg_matvec_rows<4>(out, in, U, n, S, a_begin, a_end);
+    else if (n <= 256) lg_matvec_rows<8>(out, in, U, n, S, a_begin, a_end);
+    else lg_matvec_rows<16>(out, in, U, n, S, a_begin, a_end);
 }
 
 struct LgSweep {
@@ -437,6 +456,84 @@ __global__ void __launch_bounds__(kLgThreads) k_lg_boundary_bwd(LgSweep g, int h
         __syncthreads();
     }
     if (a.b_out) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.b_out[i] = v0[i];
+}
+
+// ---- boundary passes on a thread-block cluster ------------------------------------------------------------------------
+// The passes over the chunk boundaries are chains of dependent mat-vecs with an n x n propagator (1 MB at n = 256): one CTA
+// pulls that through a single SM's L2 port (64 us per step at n = 256; 2 x 157 steps = 15 % of a cfg4 evaluation).  Here the
+// rows of each mat-vec are split over the kLgCluster CTAs of ONE cluster: every CTA keeps the whole vector in its shared
+// memory, computes its slice of the result, writes that slice into the next-vector buffer of every CTA of the cluster through
+// distributed shared memory, and the cluster barrier ends the step.
+constexpr int kLgCluster = 8;
+namespace cgx = cooperative_groups;
+
+// out-slice [a0, a1) of v1 (all states) -> the v1 buffer of every CTA of the cluster
+__device__ __forceinline__ void lg_cluster_share(cgx::cluster_group &cl, double *v1, int n, int S, int a0, int a1) {
+    const int len = a1 - a0;
+    for (unsigned r = 0; r < cl.num_blocks(); ++r) {
+        if (r == cl.block_rank()) continue;
+        double *dst = cl.map_shared_rank(v1, r);
+        for (int i = threadIdx.x; i < S * 2 * len; i += kLgThreads) {
+            const int sp = i / len, a = a0 + i - sp * len;           // sp = state * 2 + plane
+            dst[sp * n + a] = v1[sp * n + a];
+        }
+    }
+}
+
+__global__ void __cluster_dims__(kLgCluster, 1, 1) __launch_bounds__(kLgThreads) k_lg_boundary_fwd_cl(LgSweep g) {
+    extern __shared__ __align__(16) double sm_raw[];
+    cgx::cluster_group cl = cgx::this_cluster();
+    const SweepArgs &a = g.a;
+    const int n = a.NP, S = a.S, VS = S * 2 * n;
+    const int rank = (int)cl.block_rank(), per = (n + kLgCluster - 1) / kLgCluster;
+    const int a0 = min(n, rank * per), a1 = min(n, a0 + per);
+    double *v0 = sm_raw, *v1 = v0 + VS;
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) { v0[i] = a.psi_in[i]; if (rank == 0) a.psi[i] = a.psi_in[i]; }
+    cl.sync();
+    for (int c = 0; c < g.nchunks; ++c) {
+        lg_matvec(v1, v0, g.P + (size_t)c * n * n, n, S, a0, a1);   // ends with a block barrier
+        lg_cluster_share(cl, v1, n, S, a0, a1);
+        const int kend = a.chunk_begin[c + 1];
+        for (int i = threadIdx.x; i < S * 2 * (a1 - a0); i += kLgThreads) {      // this CTA's slice of the boundary state
+            const int sp = i / (a1 - a0), x = a0 + i - sp * (a1 - a0);
+            a.psi[(size_t)kend * VS + sp * n + x] = v1[sp * n + x];
+        }
+        cl.sync();                                                  // every slice of v1 has arrived everywhere; v0 is free
+        double *t = v0; v0 = v1; v1 = t;
+    }
+}
+
+__global__ void __cluster_dims__(kLgCluster, 1, 1) __launch_bounds__(kLgThreads) k_lg_boundary_bwd_cl(LgSweep g, int have_part) {
+    extern __shared__ __align__(16) double sm_raw[];
+    cgx::cluster_group cl = cgx::this_cluster();
+    const SweepArgs &a = g.a;
+    const int n = a.NP, S = a.S, VS = S * 2 * n;
+    const int rank = (int)cl.block_rank(), per = (n + kLgCluster - 1) / kLgCluster;
+    const int a0 = min(n, rank * per), a1 = min(n, a0 + per);
+    double *v0 = sm_raw, *v1 = v0 + VS, *ip = v1 + VS;
+    for (int i = threadIdx.x; i < VS; i += kLgThreads) v0[i] = a.lam_in ? a.lam_in[i] : 0.;
+    __syncthreads();
+    if (a.nterms > 0 && a.add_final_seed) {                         // every CTA seeds its own full copy (same arithmetic everywhere)
+        const bool st = is_step_cost_state(a.N - 1 + a.j_off, a.ces);
+        cost_inner_products(a, a.psi + (size_t)(a.N - 1) * VS, ip, st, true);
+        cost_add_seed(a, ip, v0, st, true, a.N - 1 + a.j_off);
+    }
+    if (rank == 0) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.lam[(size_t)(a.N - 1) * VS + i] = v0[i];
+    cl.sync();
+    for (int c = g.nchunks - 1; c >= 0; --c) {
+        lg_matvec(v1, v0, g.PT + (size_t)c * n * n, n, S, a0, a1);
+        const int kbeg = a.chunk_begin[c];
+        for (int i = threadIdx.x; i < S * 2 * (a1 - a0); i += kLgThreads) {
+            const int sp = i / (a1 - a0), x = a0 + i - sp * (a1 - a0);
+            if (have_part) v1[sp * n + x] += a.part[(size_t)c * VS + sp * n + x];
+            a.lam[(size_t)kbeg * VS + sp * n + x] = v1[sp * n + x];
+        }
+        __syncthreads();
+        lg_cluster_share(cl, v1, n, S, a0, a1);
+        cl.sync();
+        double *t = v0; v0 = v1; v1 = t;
+    }
+    if (a.b_out && rank == 0) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.b_out[i] = v0[i];
 }
 
 // time sharding: psi_in = P_{rank-1} .. P_0 psi0   /   lam_in from the later shards (allPT: transposed shard propagators)

@@ -31,7 +31,10 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, b
 template <bool TA, bool TB, int BN>
 __global__ void __launch_bounds__(ZG_NT) k_zgemm(const double2 *__restrict__ A, const double2 *__restrict__ B, double2 *C,
                                                  int m, int nc, int k, int lda, int ldb, int ldc, double alpha, double beta,
-                                                 long long sA, long long sB, long long sC) {
+                                                 long long sA, long long sB, long long sC, const int *gate = nullptr, int gate_level = 0) {
+    // gated launches (squarings of the scaling-and-squaring loop): the host enqueues a fixed number of them, the device skips
+    // those beyond the largest squaring count of the batch - no host synchronisation to learn the count
+    if (gate != nullptr && gate_level >= *gate) return;
     using Z = ZgTile<BN>;
     extern __shared__ __align__(16) unsigned char zg_raw[];
     double2 *As = reinterpret_cast<double2 *>(zg_raw);                       // [2][BM][LDA]

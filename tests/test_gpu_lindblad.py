@@ -152,3 +152,49 @@ def test_grape_lindblad_runs_and_descends():
                                          lindblad_data=lambda t: (np.array([1e-3]), np.stack([a])))
     assert res.best_error < first.error
     assert res.best_final_densities.shape == (1, 2, 2) and res.best_controls.shape == (11, 1)
+
+
+def test_grape_lindblad_trajectory_matches_oracle_driven_optimisation():
+    """cfg2-like problem (examples/1_transmon_pi_dechoerence.py:22-60: n = 2, one density, amplitude damping, complex control):
+    `grape_lindblad_discrete` with Adam for k iterations against the SAME host optimiser driven by the oracle's cost and
+    frozen-grid gradient (the contract of include/qocb200.h).  The errors along the trajectory and the final controls must
+    agree: gradient differences of 1e-7 move an Adam step by 1e-7 * learning rate, far below what the assertion allows."""
+    import qoc_b200 as qoc
+    import qoc_b200.standard as std
+    from oracle import qoc_oracle as orc
+    from qoc_b200.core.common import slap_controls, strip_controls
+    n, T, M, N, k = 2, 10.0, 11, 3, 6
+    a = np.diag(np.sqrt(np.arange(1, n)), 1).astype(complex)
+    h0 = np.diag(np.arange(n) - 0.5).astype(complex)
+    rho0 = np.zeros((1, n, n), dtype=complex); rho0[0, 0, 0] = 1
+    targ = np.zeros((1, n, n), dtype=complex); targ[0, 1, 1] = 1
+    gam = np.array([1e-3])
+    u0 = 0.1 * (1 - 1j) / np.sqrt(2) * np.ones((M, 1), dtype=complex)
+    errors = []
+
+    class Rec(std.Adam):
+        def run(self, function, iteration_count, initial_params, jacobian, args=()):
+            def jac(params, *a_):
+                g, term = jacobian(params, *a_)
+                errors.append(a_[1].error)                   # reporter.error of this iteration
+                return g, term
+            return super().run(function, iteration_count, initial_params, jac, args=args)
+    res = qoc.grape_lindblad_discrete(1, M, [std.TargetDensityInfidelity(targ)], T, rho0, N, complex_controls=True,
+                                      hamiltonian=numpy_hamiltonian(h0, a[None], True), lindblad_data=lambda t: (gam, a[None]),
+                                      initial_controls=u0.copy(), iteration_count=k, log_iteration_step=0, optimizer=Rec())
+    # the same Adam on the host, fed by the oracle
+    o_err = []
+    oh, old = orc.make_hamiltonian(h0, a[None], True), orc.make_lindblad_data(gam, a[None])
+
+    def o_fun(params, *a_):
+        return 0.0, False
+
+    def o_jac(params, *a_):
+        u = slap_controls(True, params, (M, 1))
+        e, g, _ = orc.lindblad_cost_and_grad(u, oh, old, rho0, [orc.TargetDensityInfidelity(targ)], T, N, freeze_steps=True)
+        o_err.append(e)
+        return strip_controls(True, g), False
+    std.Adam().run(o_fun, k, strip_controls(True, u0.copy()), o_jac)
+    assert len(errors) == k and len(o_err) == k
+    assert np.abs(np.array(errors) - np.array(o_err)).max() < 1e-8, (errors, o_err)
+    assert errors[-1] < errors[0] and res.best_error == min(errors)
