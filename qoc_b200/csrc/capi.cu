@@ -59,6 +59,7 @@ struct KArgs {
     int S;
     int lowrank;                // 1: use the rank-S reverse pass where it applies (QOCB_NO_LOWRANK=1 disables it)
     int herm;                   // 1: every operator is Hermitian => anti-Hermitian Magnus matrices (pivot-free LU where safe)
+    int tape_min;               // 1: slices without squarings keep {A, A2, LU} only (Krylov reverse pass, lowrank == 2)
     int *err_flag;
 };
 
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(C::NT) k_forward(KArgs a, const __grid_constan
         feed.idxP = (tma && w > wb) ? (long long)c : -1;
         const double *Ubuf = sm.X1;
         const int s = pade_forward<C>(sm, tape, piv, scratch + (size_t)S_T0 * C::GMAT, scratch + (size_t)S_T1 * C::GMAT, a.s_cap,
-                                      &feed, &Ubuf, a.herm);
+                                      &feed, &Ubuf, a.herm, a.tape_min);
         if (threadIdx.x == 0) a.meta[w] = s;
         if (w == wb) {
             for_owned<C>([&](int, int, int row, int col) {
@@ -147,8 +148,14 @@ __global__ void __launch_bounds__(C::NT) k_forward(KArgs a, const __grid_constan
     }
 }
 
+// tensor maps of the stored tape and of the per-CTA recompute tape for the Krylov reverse pass
+struct TapeMaps {
+    CUtensorMap mapT, mapC;
+    int tma;
+};
+
 template <class C>
-__global__ void __launch_bounds__(C::NT) k_backward(KArgs a) {
+__global__ void __launch_bounds__(C::NT) k_backward(KArgs a, const __grid_constant__ TapeMaps tmaps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<C> sm(smem_raw);
     const int c = blockIdx.x;
@@ -157,6 +164,11 @@ __global__ void __launch_bounds__(C::NT) k_backward(KArgs a) {
     double *ctape = a.cta_tape + (size_t)c * (8 + kCtaTapeR) * C::GMAT;
     int *cpiv = a.cta_piv + (size_t)c * C::NP;
     const int VS = a.S * 2 * C::NP;
+    uint32_t ph0 = 0, ph1 = 0;
+    if (tmaps.tma) {
+        if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_init(sm.bar + 1, 1); mbar_init_fence(); }
+        __syncthreads();
+    }
     for (int w = wb; w < we; ++w) {
         PROF_DECL
         const int e = w / (a.N - 1), j = w - e * (a.N - 1);
@@ -172,16 +184,26 @@ __global__ void __launch_bounds__(C::NT) k_backward(KArgs a) {
         } else {
             magnus_forward<C>(sm, ga, scratch);
             s = pade_forward<C>(sm, ctape, cpiv, scratch + (size_t)S_T0 * C::GMAT, scratch + (size_t)S_T1 * C::GMAT, kCtaTapeR,
-                                nullptr, nullptr, a.herm);
+                                nullptr, nullptr, a.herm, a.tape_min);
             if (s > kCtaTapeR && threadIdx.x == 0) *a.err_flag = 1;
             tape = ctape; piv = cpiv;
+            if (tmaps.tma) fence_proxy_async_all();                    // this CTA's tape stores are read back by TMA
             __syncthreads();
         }
         const double *psi = a.psi + ((size_t)e * a.N + j) * VS;
         const double *lam = a.lam + ((size_t)e * a.N + j + 1) * VS;
         bool done = false;
         if constexpr (C::NP == 64 && C::NWARP == 8) {
-            if (a.S <= 4 && s == 0 && a.lowrank) {                     // rank-S reverse pass (lowrank.cuh)
+            if (a.S <= 4 && s == 0 && a.lowrank == 2) {                // rank-S reverse pass on the Krylov basis of A2
+                PROF_MARK(9);
+                TapeFeed tf;
+                tf.tape = tape; tf.bar0 = sm.bar; tf.bar1 = sm.bar + 1; tf.ph0 = &ph0; tf.ph1 = &ph1;
+                const bool stored = tape != ctape;
+                tf.map = tmaps.tma ? (stored ? &tmaps.mapT : &tmaps.mapC) : nullptr;
+                tf.idx0 = stored ? (long long)w * a.tape_mats : (long long)c * (8 + kCtaTapeR);
+                pade_backward_krylov<C>(sm, tf, piv, psi, psi + VS, lam, a.S);
+                done = true;
+            } else if (a.S <= 4 && s == 0 && a.lowrank == 1) {         // rank-S reverse pass, re-associated form (lowrank.cuh)
                 PROF_MARK(9);
                 pade_backward_lowrank<C>(sm, tape, piv, psi, psi + VS, lam, a.S);
                 done = true;
@@ -467,6 +489,8 @@ struct qocb_plan {
     double *coh_out = nullptr;          // state sharding: device buffers of the current evaluation (caller-owned)
     const double *coh_in = nullptr;
     FeedMaps fm;                        // TMA tensor maps of U and chunkP (k_forward); fm.tma = 0 when TMA is unavailable
+    TapeMaps tmaps;                     // ... of the stored tape and the per-CTA recompute tape (k_backward)
+    int lowrank_mode = 2;               // 0 dense reverse pass, 1 re-associated rank-S form, 2 Krylov basis of A2 (QOCB_LOWRANK=0/1/2)
     bool premagnus_ok = true;           // QOCB_NO_PREMAGNUS=1: assemble the Magnus matrices inside k_forward (A/B comparison)
     bool hermitian = false;             // H0 (every member) and every operator channel are Hermitian (QOCB_NO_NOPIV=1 clears it)
     double *h_pinned = nullptr;         // [M*KR controls | M*KR grad | 1 cost]
@@ -510,7 +534,7 @@ template <class C> int launch_forward(qocb_plan *p, const KArgs &a) {
 }
 template <class C> int launch_backward(qocb_plan *p, const KArgs &a) {
     CU_TRY(p, cudaFuncSetAttribute(k_backward<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
-    k_backward<C><<<p->nchunks, C::NT, Smem<C>::bytes(), p->stream>>>(a);
+    k_backward<C><<<p->nchunks, C::NT, Smem<C>::bytes(), p->stream>>>(a, p->tmaps);
     CU_TRY(p, cudaGetLastError());
     return 0;
 }
@@ -576,8 +600,9 @@ KArgs make_kargs(qocb_plan *p) {
     a.scratch = p->scratch.p; a.cta_tape = p->cta_tape.p; a.cta_piv = p->cta_piv.p; a.chunkP = p->chunkP.p;
     a.psi = p->psi.p; a.lam = p->lam.p; a.node_grad = p->node_grad.p; a.S = p->pb.state_count;
     a.err_flag = p->err_flag.p;
-    { const char *nl = getenv("QOCB_NO_LOWRANK"); a.lowrank = (nl && nl[0] == '1') ? 0 : 1; }
+    a.lowrank = p->lowrank_mode;
     a.herm = p->hermitian ? 1 : 0;
+    a.tape_min = (p->lowrank_mode == 2 && p->NP == 64 && p->pb.state_count <= 4) ? 1 : 0;
     return a;
 }
 
@@ -1509,6 +1534,18 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
             if (e != cudaSuccess) { cudaGetLastError(); p->tape.release(); }
             else PTRY(p->tape_piv.alloc(W * NP));
         }
+    }
+    // Krylov reverse pass: tensor maps of the tapes; reverse-pass variant (QOCB_NO_LOWRANK=1: dense, QOCB_LOWRANK=1: the
+    // re-associated rank-S form of round 1, default: Krylov basis of A2)
+    std::memset(&p->tmaps, 0, sizeof(p->tmaps));
+    if (!is_large && p->fm.tma) {
+        bool ok = qocb_host::make_matrix_map(&p->tmaps.mapC, p->cta_tape.p, (long long)p->nchunks * (8 + kCtaTapeR), NP);
+        if (p->tape.p) ok = ok && qocb_host::make_matrix_map(&p->tmaps.mapT, p->tape.p, (long long)W * p->tape_mats, NP);
+        p->tmaps.tma = ok ? 1 : 0;
+    }
+    {
+        const char *nl = getenv("QOCB_NO_LOWRANK"), *lm = getenv("QOCB_LOWRANK");
+        p->lowrank_mode = (nl && nl[0] == '1') ? 0 : ((lm && lm[0] >= '0' && lm[0] <= '2') ? lm[0] - '0' : 2);
     }
 #undef PTRY
     *out = p;

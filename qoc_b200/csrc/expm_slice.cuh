@@ -286,7 +286,7 @@ struct Feed {
 #define QOCB_NOPIV_NORM 2.5
 template <class C>
 __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, double *tmpY, double *tmpV, int s_cap,
-                            Feed *feed = nullptr, const double **u_out = nullptr, int herm = 0) {
+                            Feed *feed = nullptr, const double **u_out = nullptr, int herm = 0, int tape_min = 0) {
     PROF_DECL
     // one-norm: max column sum of |m_ij|   (expm.py:103-116)
     {
@@ -323,6 +323,8 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
     const double scale = ldexp(1.0, -s);
     PROF_MARK(2);
     const bool keep = tape != nullptr;
+    // tape_min: slices without squarings are differentiated by the Krylov reverse pass, which reads A, A2 and the LU factors only
+    const bool full = keep && !(tape_min && s == 0);
     double *tA = keep ? tape + (size_t)T_A * C::GMAT : tmpV;        // A is always needed once more (for Uo)
     // A = M * 2^-s   -> X2 and tape
     for_owned<C>([&](int, int, int row, int col) {
@@ -343,7 +345,7 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
     for_owned<C>([&](int i, int j, int row, int col) {
         const c2 v = accv<C>(acc, i, j);
         sts2<C>(sm.X1, row, col, v);
-        if (keep) stg2<C>(tape + (size_t)T_A4 * C::GMAT, row, col, v);
+        if (full) stg2<C>(tape + (size_t)T_A4 * C::GMAT, row, col, v);
     });
     __syncthreads();
     acc.zero(); mma_smem<C, false, false, false>(acc, sm.X0, sm.X1);     // A6 -> X2 (A is on the tape)
@@ -360,7 +362,7 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
         sts2<C>(sm.X1, row, col, x1);          // over A4
         stg2<C>(tmpY, row, col, yu);
         stg2<C>(keep ? tape + (size_t)T_LU * C::GMAT : tmpV + C::GMAT, row, col, yv);   // parked until Ve is formed
-        if (keep) {
+        if (full) {
             stg2<C>(tape + (size_t)T_A6 * C::GMAT, row, col, a6);
             stg2<C>(tape + (size_t)T_W1 * C::GMAT, row, col, w1);
             stg2<C>(tape + (size_t)T_X1 * C::GMAT, row, col, x1);
@@ -373,7 +375,7 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
     for_owned<C>([&](int i, int j, int row, int col) {
         const c2 y = accv<C>(acc, i, j) + ldg2<C>(tmpY, row, col);
         sts2<C>(sm.X0, row, col, y);                                    // Y over W1
-        if (keep) stg2<C>(tape + (size_t)T_Y * C::GMAT, row, col, y);
+        if (full) stg2<C>(tape + (size_t)T_Y * C::GMAT, row, col, y);
     });
     acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X1);     // A6 X1   (X0 not an operand)
     __syncthreads();
@@ -722,6 +724,165 @@ __device__ void pade_backward_lowrank(const Smem<C> &sm, const double *tape, con
     mma_lowrank<C, TLD, TPL, TLD, TPL>(acc, EL, 0, EL, 4, 4);
     mma_smem<C, false, true, false>(acc, X0, sm.X1);
     mma_smem<C, true, false, false>(acc, sm.X1, X0);
+    __syncthreads();
+    for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(X0, row, col, accv<C>(acc, i, j)); });
+    __syncthreads();
+    PROF_MARK(12);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Rank-S reverse pass on a Krylov basis of A2 (NP = 64, S <= 4, s = 0) - the same graph as pade_backward_lowrank, with
+// every product by A4, A6, W1, X1 or Y replaced by repeated application of B = A2 (A4 = B^2, A6 = B^3, W1 / X1 / Y are
+// polynomials of B) to the thin blocks.  With Kp[k] = B^k p, Km[k] = B^k m, KL[k] = (B^T)^k [a | l]:
+//     X_c = R6            = [ sum_k b(7+2k) Kp[k] | sum_k b(6+2k) Km[k] | b13 Kp[0] | b12 Km[0] ]
+//     X_b = R4 + B R6     = [ sum_k b(5+2k) Kp[k] | sum_k b(4+2k) Km[k] | sum_k b(11+2k) Kp[k] | sum_k b(10+2k) Km[k] ]
+//     X_a = R2 + B^2 R6 + B R4 = [ sum_k b(3+2k) Kp[k] | sum_k b(2+2k) Km[k] | sum_k b(9+2k) Kp[k] | sum_k b(8+2k) Km[k] ]
+//     Y p = sum_k b(1+2k) Kp[k]                          (coefficients beyond b13 / b12 are zero)
+//     L_b = [KL[0] | KL[3]],  A2^T L_b = [KL[1] | KL[4]],  A2^T A2^T L_b = [KL[2] | KL[5]]
+//     a2bar = L_b X_a^T + (A2^T L_b) X_b^T + (A2^T A2^T L_b) X_c^T,     mbar = l (Y p)^T + a2bar A^T + A^T a2bar.
+// Two Krylov chains of six thin (n x 8) DMMA products with ONE resident matrix replace the nine tape matrices of the
+// re-associated form: the tape of such a slice is {A, A2, LU} (3 instead of 8 matrices written by the forward pass and
+// read here), and the loads are TMA boxes issued one stage ahead into the two matrix buffers.
+struct TapeFeed {
+    const double *tape;          // tape of the slice (slot s at tape + s * GMAT)
+    const CUtensorMap *map;      // tensor map of the buffer holding it, or nullptr: plain loads
+    long long idx0;              // matrix index of slot 0 in that buffer
+    uint64_t *bar0, *bar1;       // mbarriers of the two matrix buffers (X0, X1)
+    uint32_t *ph0, *ph1;
+};
+
+template <class C>
+__device__ __forceinline__ void tape_fetch(const TapeFeed &tf, double *dst, int slot, uint64_t *bar) {
+    if (tf.map) { if (threadIdx.x == 0) tma_fetch_matrix<C::NP>(dst, tf.map, tf.idx0 + slot, bar); }
+    else g2s<C>(dst, tf.tape + (size_t)slot * C::GMAT);
+}
+__device__ __forceinline__ void tape_wait(const TapeFeed &tf, uint64_t *bar, uint32_t *ph) {
+    if (tf.map) { mbar_wait(bar, *ph); *ph ^= 1; }
+    else __syncthreads();
+}
+
+template <class C>
+__device__ void pade_backward_krylov(const Smem<C> &sm, const TapeFeed &tf, const int *tperm, const double *psi, const double *psi1,
+                                     const double *lam1, int S) {
+    static_assert(C::NP == 64 && C::NWARP == 8, "the Krylov reverse pass is laid out for NP = 64 with 8 warps");
+    PROF_DECL
+    constexpr int NP = C::NP, LD = LR_LD, PL = LR_PL, TLD = LR_TLD, TPL = LR_TPL, ELD = 8, EPL = NP * ELD;
+    double *X0 = sm.X0, *X1 = sm.X1;
+    double *LEFT = sm.X1, *RIGHT = sm.X1 + 2 * PL, *PP0 = sm.X1 + 4 * PL, *PP1 = PP0 + 2 * TPL, *EL = PP1 + 2 * TPL;
+    static_assert(4 * PL + 4 * TPL + 2 * EPL <= 2 * C::SMAT, "thin buffers exceed the X1 / X2 region");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = lane & 3;
+    const int frow = warp * 8 + (lane >> 2);
+    // ---- stage 0: LU -> X0, A -> X1 (asynchronous); [0 | lam] -> PP1, [p | m] -> PP0
+    tape_fetch<C>(tf, X0, T_LU, tf.bar0);
+    tape_fetch<C>(tf, X1, T_A, tf.bar1);
+    for (int e = threadIdx.x; e < NP * 4; e += C::NT) {
+        const int row = e >> 2, c = e & 3;
+        const bool on = c < S;
+        const double lr = on ? lam1[c * 2 * NP + row] : 0., li = on ? lam1[c * 2 * NP + NP + row] : 0.;
+        const double pr = on ? psi[c * 2 * NP + row] : 0., pi = on ? psi[c * 2 * NP + NP + row] : 0.;
+        const double qr = on ? psi1[c * 2 * NP + row] : 0., qi = on ? psi1[c * 2 * NP + NP + row] : 0.;
+        PP1[row * TLD + c] = 0.; PP1[TPL + row * TLD + c] = 0.;
+        PP1[row * TLD + 4 + c] = lr; PP1[TPL + row * TLD + 4 + c] = li;
+        PP0[row * TLD + c] = pr + qr; PP0[TPL + row * TLD + c] = pi + qi;
+        PP0[row * TLD + 4 + c] = pr - qr; PP0[TPL + row * TLD + 4 + c] = pi - qi;
+    }
+    for (int c = threadIdx.x; c < NP; c += C::NT) sm.piv[c] = tperm[c];
+    __syncthreads();
+    tape_wait(tf, tf.bar0, tf.ph0);
+    // ---- stage 1: l = Q^-T lam (thin solve on PP1[:, 0:8]); the LU factors are dead afterwards: A2 -> X0
+    lu_solve_thin_T<C, TLD, TPL>(X0, PP1);
+    tape_fetch<C>(tf, X0, T_A2, tf.bar0);
+    for (int e = threadIdx.x; e < NP * 4; e += C::NT) {             // row un-permutation through EL
+        const int row = e >> 2, c = e & 3, pr = sm.piv[row];
+        EL[pr * ELD + c] = PP1[row * TLD + 4 + c]; EL[EPL + pr * ELD + c] = PP1[TPL + row * TLD + 4 + c];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < NP * 4; e += C::NT) {
+        const int row = e >> 2, c = e & 3;
+        PP1[row * TLD + 4 + c] = EL[row * ELD + c]; PP1[TPL + row * TLD + 4 + c] = EL[EPL + row * ELD + c];
+    }
+    __syncthreads();
+    tape_wait(tf, tf.bar1, tf.ph1);
+    // ---- stage 2: a = A^T l (A in X1) -> PP1[:, 0:4]
+    {
+        const c2 v = thin_tile<C, true, TLD, TPL>(X1, PP1, warp, 0);
+        __syncthreads();
+        if (t >= 2) {
+            *reinterpret_cast<double2 *>(PP1 + frow * TLD + 2 * (t - 2)) = make_double2(v.r0, v.r1);
+            *reinterpret_cast<double2 *>(PP1 + TPL + frow * TLD + 2 * (t - 2)) = make_double2(v.i0, v.i1);
+        }
+    }
+    __syncthreads();                                                // A is dead: the LEFT / RIGHT area (over X1) is free
+    // ---- stage 3: KL[0] = [a | l] -> LEFT[:, 0:8]; power-0 terms of RIGHT; EL = [l | b1 p]
+    for (int e = threadIdx.x; e < NP * 4; e += C::NT) {
+        const int row = e >> 2, c = e & 3;
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+            const double av = PP1[pl * TPL + row * TLD + c], lv = PP1[pl * TPL + row * TLD + 4 + c];
+            const double pv = PP0[pl * TPL + row * TLD + c], mv = PP0[pl * TPL + row * TLD + 4 + c];
+            double *L = LEFT + pl * PL + row * LD, *R = RIGHT + pl * PL + row * LD;
+            L[c] = av; L[4 + c] = lv;
+            R[0 + c] = kB[3] * pv; R[4 + c] = kB[2] * mv; R[8 + c] = kB[9] * pv; R[12 + c] = kB[8] * mv;       // X_a
+            R[16 + c] = kB[5] * pv; R[20 + c] = kB[4] * mv; R[24 + c] = kB[11] * pv; R[28 + c] = kB[10] * mv;   // X_b
+            R[32 + c] = kB[7] * pv; R[36 + c] = kB[6] * mv; R[40 + c] = kB[13] * pv; R[44 + c] = kB[12] * mv;   // X_c
+            EL[pl * EPL + row * ELD + c] = lv; EL[pl * EPL + row * ELD + 4 + c] = kB[1] * pv;
+        }
+    }
+    __syncthreads();
+    tape_wait(tf, tf.bar0, tf.ph0);
+    // ---- stage 4: the two Krylov chains with B = A2 in X0
+    {
+        double *cur = PP0, *nxt = PP1;
+        const bool ppart = t < 2;                                   // this lane's tile columns: p block (0:4) or m block (4:8)
+        const int cc = 2 * (t & 1);                                 // column pair inside the block
+#pragma unroll 1
+        for (int k = 0; k < 6; ++k) {
+            const int kk = k + 1;                                   // power produced in this step
+            const c2 v = thin_tile<C, false, TLD, TPL>(X0, cur, warp, 0);
+            st_thin<TLD, TPL>(nxt, warp * 8, 0, v);
+            // contributions of B^kk p / B^kk m to X_a, X_b, X_c (sub-blocks 0 / 1 and 2 / 3) and to Y p
+            double *Rr = RIGHT + frow * LD, *Ri = RIGHT + PL + frow * LD;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int i0 = (ppart ? 3 : 2) + 2 * q + 2 * kk, i1 = (ppart ? 9 : 8) + 2 * q + 2 * kk;
+                if (i0 <= (ppart ? 13 : 12)) {
+                    const double b = kB[i0];
+                    const int col = q * 16 + (ppart ? 0 : 4) + cc;
+                    Rr[col] += b * v.r0; Rr[col + 1] += b * v.r1; Ri[col] += b * v.i0; Ri[col + 1] += b * v.i1;
+                }
+                if (i1 <= (ppart ? 13 : 12)) {
+                    const double b = kB[i1];
+                    const int col = q * 16 + (ppart ? 8 : 12) + cc;
+                    Rr[col] += b * v.r0; Rr[col + 1] += b * v.r1; Ri[col] += b * v.i0; Ri[col + 1] += b * v.i1;
+                }
+            }
+            if (ppart) {
+                const double b = kB[1 + 2 * kk];
+                double *Er = EL + frow * ELD + 4 + cc, *Ei = EL + EPL + frow * ELD + 4 + cc;
+                Er[0] += b * v.r0; Er[1] += b * v.r1; Ei[0] += b * v.i0; Ei[1] += b * v.i1;
+            }
+            if (k < 5) {                                            // KL[kk] = B^T KL[k]
+                const int off0 = (k % 3) * 16 + (k / 3) * 8, off1 = (kk % 3) * 16 + (kk / 3) * 8;
+                st_thin<LD, PL>(LEFT, warp * 8, off1, thin_tile<C, true, LD, PL>(X0, LEFT, warp, off0));
+            }
+            __syncthreads();
+            double *tmp = cur; cur = nxt; nxt = tmp;
+        }
+    }
+    // ---- stage 5: A2 is dead: A -> X0 (asynchronous) while a2bar = [L_b A2^T L_b A2^T A2^T L_b] [X_a X_b X_c]^T is formed
+    tape_fetch<C>(tf, X0, T_A, tf.bar0);
+    Acc<C> acc;
+    acc.zero();
+    mma_lowrank<C, LD, PL, LD, PL>(acc, LEFT, 0, RIGHT, 0, 48);
+    __syncthreads();                                                // LEFT / RIGHT are dead
+    for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(X1, row, col, accv<C>(acc, i, j)); });
+    __syncthreads();
+    tape_wait(tf, tf.bar0, tf.ph0);
+    // ---- stage 6: mbar = l (Y p)^T + a2bar A^T + A^T a2bar
+    acc.zero();
+    mma_lowrank<C, ELD, EPL, ELD, EPL>(acc, EL, 0, EL, 4, 4);
+    mma_smem<C, false, true, false>(acc, X1, X0);
+    mma_smem<C, true, false, false>(acc, X0, X1);
     __syncthreads();
     for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(X0, row, col, accv<C>(acc, i, j)); });
     __syncthreads();

@@ -88,37 +88,37 @@ __device__ __forceinline__ void mma_lowrank(Acc<C> &acc, const double *L, int lc
 
 // W[:, 0:8] <- Q^-T W[:, 0:8] (LUi factors in LU, C layout; W thin with LR_LD / LR_PL); the row un-permutation is left
 // to the caller: result row i belongs to row perm[i].  Diagonal tiles by warp 0, the other row tiles spread over the warps.
-template <class C>
+template <class C, int LDW = LR_LD, int PLW = LR_PL>
 __device__ void lu_solve_thin_T(const double *LU, double *W) {
     constexpr int NB = C::NP / 8;
     const int warp = threadIdx.x >> 5;
     for (int kb = 0; kb < NB; ++kb) {                              // U^T y = b
         if (warp == 0) {
             c2 z = czero();
-            tile_mma_thin<C, true, MASK_UINV, false, LR_LD, LR_PL>(z, LU, kb * 8, kb * 8, W, kb * 8, 0);
+            tile_mma_thin<C, true, MASK_UINV, false, LDW, PLW>(z, LU, kb * 8, kb * 8, W, kb * 8, 0);
             __syncwarp();
-            st_thin<LR_LD, LR_PL>(W, kb * 8, 0, z);
+            st_thin<LDW, PLW>(W, kb * 8, 0, z);
         }
         __syncthreads();
         for (int rt = kb + 1 + warp; rt < NB; rt += C::NWARP) {
-            c2 a = ld_thin<LR_LD, LR_PL>(W, rt * 8, 0);
-            tile_mma_thin<C, true, MASK_NONE, true, LR_LD, LR_PL>(a, LU, rt * 8, kb * 8, W, kb * 8, 0);
-            st_thin<LR_LD, LR_PL>(W, rt * 8, 0, a);
+            c2 a = ld_thin<LDW, PLW>(W, rt * 8, 0);
+            tile_mma_thin<C, true, MASK_NONE, true, LDW, PLW>(a, LU, rt * 8, kb * 8, W, kb * 8, 0);
+            st_thin<LDW, PLW>(W, rt * 8, 0, a);
         }
         __syncthreads();
     }
     for (int kb = NB - 1; kb >= 0; --kb) {                         // L^T z = y
         if (warp == 0) {
             c2 z = czero();
-            tile_mma_thin<C, true, MASK_LINV, false, LR_LD, LR_PL>(z, LU, kb * 8, kb * 8, W, kb * 8, 0);
+            tile_mma_thin<C, true, MASK_LINV, false, LDW, PLW>(z, LU, kb * 8, kb * 8, W, kb * 8, 0);
             __syncwarp();
-            st_thin<LR_LD, LR_PL>(W, kb * 8, 0, z);
+            st_thin<LDW, PLW>(W, kb * 8, 0, z);
         }
         __syncthreads();
         for (int rt = warp; rt < kb; rt += C::NWARP) {
-            c2 a = ld_thin<LR_LD, LR_PL>(W, rt * 8, 0);
-            tile_mma_thin<C, true, MASK_NONE, true, LR_LD, LR_PL>(a, LU, rt * 8, kb * 8, W, kb * 8, 0);
-            st_thin<LR_LD, LR_PL>(W, rt * 8, 0, a);
+            c2 a = ld_thin<LDW, PLW>(W, rt * 8, 0);
+            tile_mma_thin<C, true, MASK_NONE, true, LDW, PLW>(a, LU, rt * 8, kb * 8, W, kb * 8, 0);
+            st_thin<LDW, PLW>(W, rt * 8, 0, a);
         }
         __syncthreads();
     }
