@@ -60,6 +60,7 @@ struct KArgs {
     int lowrank;                // 1: use the rank-S reverse pass where it applies (QOCB_NO_LOWRANK=1 disables it)
     int herm;                   // 1: every operator is Hermitian => anti-Hermitian Magnus matrices (pivot-free LU where safe)
     int tape_min;               // 1: slices without squarings keep {A, A2, LU} only (Krylov reverse pass, lowrank == 2)
+    int post_adj;               // 1: slices replayed from the stored tape leave mbar in their A slot; k_magnus_adj does the Magnus adjoint
     int *err_flag;
 };
 
@@ -226,7 +227,13 @@ __global__ void __launch_bounds__(C::NT) k_backward(KArgs a, const __grid_consta
             PROF_MARK(9);
             pade_backward<C>(sm, tape, piv, s, a.U + (size_t)w * C::GMAT, scratch);
         }
-        magnus_backward<C>(sm, ga, scratch, a.node_grad + (size_t)w * ga.q * ga.KR);
+        if (a.post_adj && tape != ctape) {                          // the slice's tape is dead: its A slot takes mbar (magnus.cuh)
+            double *gM = a.tape + ((size_t)w * a.tape_mats + T_A) * C::GMAT;
+            for_owned<C>([&](int, int, int row, int col) { stg2<C>(gM, row, col, lds2<C>(sm.X0, row, col)); });
+            __syncthreads();
+        } else {
+            magnus_backward<C>(sm, ga, scratch, a.node_grad + (size_t)w * ga.q * ga.KR);
+        }
         PROF_MARK(13);
     }
 }
@@ -490,6 +497,8 @@ struct qocb_plan {
     const double *coh_in = nullptr;
     FeedMaps fm;                        // TMA tensor maps of U and chunkP (k_forward); fm.tma = 0 when TMA is unavailable
     TapeMaps tmaps;                     // ... of the stored tape and the per-CTA recompute tape (k_backward)
+    bool post_adj_ok = false;           // Magnus adjoint as a streaming pass after k_backward (single member, stored tape)
+    DevBuf<double> adj_partial;         // [slabs][W][kAdjMaxOps] slab sums of k_magnus_adj
     int lowrank_mode = 2;               // 0 dense reverse pass, 1 re-associated rank-S form, 2 Krylov basis of A2 (QOCB_LOWRANK=0/1/2)
     bool premagnus_ok = true;           // QOCB_NO_PREMAGNUS=1: assemble the Magnus matrices inside k_forward (A/B comparison)
     bool hermitian = false;             // H0 (every member) and every operator channel are Hermitian (QOCB_NO_NOPIV=1 clears it)
@@ -536,6 +545,20 @@ template <class C> int launch_backward(qocb_plan *p, const KArgs &a) {
     CU_TRY(p, cudaFuncSetAttribute(k_backward<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::bytes()));
     k_backward<C><<<p->nchunks, C::NT, Smem<C>::bytes(), p->stream>>>(a, p->tmaps);
     CU_TRY(p, cudaGetLastError());
+    if (a.post_adj) {                                               // Magnus adjoint of all slices in one streaming pass
+        const long long W = (long long)a.E * (a.N - 1);
+        const int slabs = (C::GMAT + kAdjSlab - 1) / kAdjSlab;
+        const long long tiles = (W + 7) / 8;
+        const long long groups = std::max<long long>(1, std::min<long long>(tiles, (3LL * p->num_sms + slabs - 1) / slabs));
+        const long long per = (tiles + groups - 1) / groups;
+        const size_t smem = magnus_adj_smem_bytes(a.ga.order, a.ga.KR);
+        CU_TRY(p, cudaFuncSetAttribute(k_magnus_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_magnus_adj<<<dim3(slabs, (unsigned)((tiles + per - 1) / per)), kAdjThreads, smem, p->stream>>>(
+            a.ga, C::GMAT, C::GPLANE, W, per, a.tape + (size_t)T_A * C::GMAT, (long long)a.tape_mats * C::GMAT, p->adj_partial.p);
+        const long long tot = W * a.ga.q * a.ga.KR;
+        k_magnus_adj_final<<<(unsigned)((tot + 127) / 128), 128, 0, p->stream>>>(a.ga, p->adj_partial.p, slabs, W, a.meta, a.s_cap, a.node_grad);
+        CU_TRY(p, cudaGetLastError());
+    }
     return 0;
 }
 
@@ -603,6 +626,7 @@ KArgs make_kargs(qocb_plan *p) {
     a.lowrank = p->lowrank_mode;
     a.herm = p->hermitian ? 1 : 0;
     a.tape_min = (p->lowrank_mode == 2 && p->NP == 64 && p->pb.state_count <= 4) ? 1 : 0;
+    a.post_adj = (p->post_adj_ok && p->tape.p && (a.ga.order == 2 || (a.ga.order == 4 && a.ga.comm)) && a.ga.KR > 0) ? 1 : 0;
     return a;
 }
 
@@ -1543,6 +1567,11 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
         if (p->tape.p) ok = ok && qocb_host::make_matrix_map(&p->tmaps.mapT, p->tape.p, (long long)W * p->tape_mats, NP);
         p->tmaps.tma = ok ? 1 : 0;
     }
+    if (!is_large && E == 1 && p->tape.p && p->premagnus_ok && KC <= kMaxCommKR) {
+        const size_t slabs = (GM + kAdjSlab - 1) / kAdjSlab;
+        PTRY(p->adj_partial.alloc(slabs * W * kAdjMaxOps));
+        p->post_adj_ok = true;
+    }
     {
         const char *nl = getenv("QOCB_NO_LOWRANK"), *lm = getenv("QOCB_LOWRANK");
         p->lowrank_mode = (nl && nl[0] == '1') ? 0 : ((lm && lm[0] >= '0' && lm[0] <= '2') ? lm[0] - '0' : 2);
@@ -1937,13 +1966,14 @@ static int launch_count_unmapped(qocb_plan *p, int32_t with_grad) {
         return batches * (fwd + (with_grad ? fwd + (o == 6 ? 60 : o == 4 ? 38 : 30) : 0)) + (with_grad ? 3 : 1);
     }
     const int pm = (p->premagnus_ok && (p->pb.magnus_order == 2 || (p->pb.magnus_order == 4 && p->comm_ok))) ? 1 : 0;   // k_magnus
-    if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->levels + pm;
+    const int pa = (with_grad && pm && p->post_adj_ok && p->pb.control_count > 0) ? 2 : 0;                            // k_magnus_adj, k_magnus_adj_final
+    if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->levels + pm + pa;
     int levels = p->levels + pm;                                          // pairwise levels for the sweeps, then radix 4 to the root
     for (int c = p->lvl_count[p->levels]; c > 1; c = (c + 3) / 4) ++levels;
     // forward: expm, tree, prefix, boundary, sweep; backward: [particular sweeps], boundary (twice only with step costs on a
     // shard that is not the last), suffix, sweep, expm, gather, finalize, pack
     const int nb = (p->have_step_costs && !p->owns_final) ? 2 : 1;
-    return with_grad ? 1 + levels + 3 + (p->have_step_costs ? 1 : 0) + nb + 6 : 1 + levels + 3 + 2;
+    return with_grad ? 1 + levels + 3 + (p->have_step_costs ? 1 : 0) + nb + 6 + pa : 1 + levels + 3 + 2;
 }
 
 int qocb_time_resident(qocb_plan *p, int32_t with_grad, int32_t warmup, int32_t iters, int32_t flush_l2,

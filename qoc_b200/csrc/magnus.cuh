@@ -102,4 +102,99 @@ __global__ void __launch_bounds__(kMagThreads) k_magnus(GenArgs ga, int GMAT, in
     }
 }
 
+// ---- the adjoint of the same pass -------------------------------------------------------------------------------------
+// The Magnus adjoint of these orders needs the inner products <mbar_j, Op_c> = Re sum_ab mbar_j[ab] Op_c[ab] of the cotangent of
+// every slice's Magnus matrix with the control operators and their commutators (expm_slice.cuh: magnus_backward).  Inside
+// k_backward that streams 2 KR + KR (KR - 1) / 2 operator matrices from L2 per slice (13 us of a 60 us slice at n = 64).
+// Turned around it is one skinny GEMM  D[j][c] = sum_e mbar[j][e] Op'[c][e]  (Op' = Op with the imaginary plane negated):
+// k_backward leaves mbar_j in the (dead) A slot of the slice's tape, a CTA of k_magnus_adj keeps a 512-element slab of every
+// operator in shared memory and walks over tiles of 8 slices with DMMA (m = slices, n = operators, k = slab elements),
+// k_magnus_adj_final sums the slabs in a fixed order and applies the coefficient formulas.  HBM-bound: mbar is read once.
+constexpr int kAdjSlab = 512, kAdjLD = kAdjSlab + 4, kAdjMaxOps = 32, kAdjThreads = 256;
+
+__host__ __device__ inline int magnus_adj_op_count(int order, int KR) { return order == 4 ? 2 * KR + KR * (KR - 1) / 2 : KR; }
+__host__ inline size_t magnus_adj_smem_bytes(int order, int KR) {
+    const int nt = (magnus_adj_op_count(order, KR) + 7) / 8;
+    return sizeof(double) * ((size_t)nt * 8 * kAdjLD + (size_t)(kAdjThreads / 32) * nt * 64);
+}
+
+// partial[(slab * W + w) * kAdjMaxOps + c] = sum over the slab of mbar_w[e] Op'_c[e];  grid = (slabs, groups of slice tiles)
+__global__ void __launch_bounds__(kAdjThreads) k_magnus_adj(GenArgs ga, int GMAT, int GPLANE, long long W, long long tiles_per_block,
+                                                            const double *mbar0, long long stride, double *partial) {
+    extern __shared__ __align__(16) double ad_sm[];
+    const int KR = ga.KR, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int nops = magnus_adj_op_count(ga.order, KR), NTn = (nops + 7) / 8;
+    double *ops = ad_sm;                                    // [NTn * 8][kAdjLD]
+    double *red = ad_sm + (size_t)NTn * 8 * kAdjLD;         // [warps][NTn][64]
+    const int e_base = blockIdx.x * kAdjSlab;
+    for (int idx = tid; idx < NTn * 8 * kAdjSlab; idx += kAdjThreads) {
+        const int c = idx / kAdjSlab, i = idx - c * kAdjSlab, e = e_base + i;
+        double v = 0.;
+        if (c < nops && e < GMAT) {
+            const double *src = c < KR ? ga.G + (size_t)c * GMAT : (c < 2 * KR ? ga.C0 + (size_t)(c - KR) * GMAT : ga.Cs + (size_t)(c - 2 * KR) * GMAT);
+            v = e < GPLANE ? src[e] : -src[e];
+        }
+        ops[c * kAdjLD + i] = v;
+    }
+    __syncthreads();
+    const long long tiles = (W + 7) / 8;
+    const long long tl0 = (long long)blockIdx.y * tiles_per_block, tl1 = min(tiles, tl0 + tiles_per_block);
+    for (long long tl = tl0; tl < tl1; ++tl) {
+        const long long j = tl * 8 + g;
+        const double *row = mbar0 + (size_t)min(j, W - 1) * stride + e_base;
+        double acc[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = 0.; acc[nt][1] = 0.; }
+#pragma unroll 4
+        for (int ks = 0; ks < kAdjSlab / 32 / 4 * 4; ++ks) {         // 16 k-steps of 4 over this warp's 64 elements
+            const int k = warp * 64 + ks * 4 + t;
+            const double a = (j < W && e_base + k < GMAT) ? row[k] : 0.;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+                if (nt < NTn) dmma884(acc[nt][0], acc[nt][1], a, ops[(nt * 8 + g) * kAdjLD + k]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+            if (nt < NTn) { red[(warp * NTn + nt) * 64 + g * 8 + 2 * t] = acc[nt][0]; red[(warp * NTn + nt) * 64 + g * 8 + 2 * t + 1] = acc[nt][1]; }
+        __syncthreads();
+        for (int o = tid; o < NTn * 64; o += kAdjThreads) {
+            const int nt = o >> 6, r = (o >> 3) & 7, c = o & 7;
+            double v = 0.;
+#pragma unroll
+            for (int w_ = 0; w_ < kAdjThreads / 32; ++w_) v += red[(w_ * NTn + nt) * 64 + r * 8 + c];
+            const long long jj = tl * 8 + r;
+            if (jj < W) partial[((size_t)blockIdx.x * W + jj) * kAdjMaxOps + nt * 8 + c] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// node_grad[w][node][r] from the slab sums; only slices whose mbar went through the tape (meta[w] <= s_cap)
+__global__ void k_magnus_adj_final(GenArgs ga, const double *partial, int slabs, long long W, const int *meta, int s_cap, double *node_grad) {
+    const long long tix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int KR = ga.KR, q = ga.q;
+    if (tix >= W * q * KR) return;
+    const int r = (int)(tix % KR), node = (int)((tix / KR) % q);
+    const long long w = tix / ((long long)KR * q);
+    if (meta[w] > s_cap) return;
+    auto D = [&](int c) { double v = 0.; for (int sl = 0; sl < slabs; ++sl) v += partial[((size_t)sl * W + w) * kAdjMaxOps + c]; return v; };
+    const double dt = ga.dt;
+    if (ga.order == 2) { node_grad[tix] = dt * D(r); return; }
+    const int j = (int)w;                                   // single member: the slice index
+    auto coef = [&](int nd, int rr) -> double {
+        if (ga.nodecoef) return ga.nodecoef[(size_t)(j * q + nd) * KR + rr];
+        const int *id = ga.itab_idx + (j * q + nd) * 2;
+        const double *iw = ga.itab_w + (j * q + nd) * 2;
+        return ga.controls[id[0] * KR + rr] * iw[0] + ga.controls[id[1] * KR + rr] * iw[1];
+    };
+    const double f = (QOCB_S3 / 12.0) * dt * dt;
+    double acc = D(KR + r);
+    for (int s_ = 0; s_ < KR; ++s_) {
+        if (s_ == r) continue;
+        const double kk = s_ < r ? D(2 * KR + comm_pair(s_, r, KR)) : -D(2 * KR + comm_pair(r, s_, KR));
+        acc += coef(node == 0 ? 1 : 0, s_) * kk;             // node 0 pairs with the coefficients of node 1 and vice versa
+    }
+    node_grad[tix] = 0.5 * dt * D(r) + (node == 0 ? f : -f) * acc;
+}
+
 }  // namespace qocb
