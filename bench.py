@@ -325,7 +325,7 @@ def run_b200(args, name):
     if p.n > 64:
         stage_names_note = "n > 64: stages are not split (batched pipeline)"
     fwd_f, bwd_f = flops_per_slice(p.n, p.S, p.order)
-    names = ["expm_fwd", "boundary_fwd", "sweep_fwd", "sweep_bwd", "expm_bwd", "gather", "finalize", "spare"]
+    names = ["expm_fwd", "boundary_fwd", "sweep_fwd", "sweep_bwd", "expm_bwd", "gather", "finalize", "prop_tree"]
     stage_ms = {k: float(v) / args.steps for k, v in zip(names, stages)}
     total_flops = (fwd_f + bwd_f) * slices * p.E
     fwd_f, bwd_f = fwd_f * p.E, bwd_f * p.E
@@ -333,7 +333,7 @@ def run_b200(args, name):
         dom = max(("expm_fwd", "expm_bwd"), key=lambda k: stage_ms[k])
         dom_flops = (fwd_f if dom == "expm_fwd" else bwd_f) * slices / (world if p.E > 1 else 1)
         achieved = dom_flops / (stage_ms[dom] * 1e-3) / 1e12
-        dom_name = "k_backward" if dom == "expm_bwd" else "k_forward"
+        dom_name = "k_backward (+ k_magnus_adj)" if dom == "expm_bwd" else "k_forward (+ k_magnus: the Magnus assembly is part of the slice's algorithmic FLOPs)"
     else:       # no per-kernel split across the collectives: whole evaluation, per GPU
         dom_flops = total_flops / world
         achieved = dom_flops / (ms_per_step * 1e-3) / 1e12
@@ -358,7 +358,7 @@ def run_b200(args, name):
            "gpu_launches": plan.launch_count(True) * args.steps,
            "roofline": {"bound": "tensor", "kernel": dom_name,
                         "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                        "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": ncu_traffic(name, dom_name),
+                        "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": ncu_traffic(name, "k_backward" if dom_name.startswith("k_backward") else "k_forward"),
                         "peak_source": "FP64 DMMA pipe measured on this pool (profiles/r01_microbench_fp64.jsonl); "
                                        "MEASURED_PEAKS.json has HBM and bf16 only",
                         "algorithmic_flops_per_launch": dom_flops,

@@ -100,8 +100,9 @@ int qocb_run_resident(qocb_plan *plan, int32_t with_grad);
 int qocb_sync(qocb_plan *plan);
 int qocb_download_result(qocb_plan *plan, double *cost, double *grad);
 /* time `iters` resident evaluations with CUDA events on the plan stream after `warmup` untimed ones.
-   ms_total[0] = total ms; kernel_ms[8] = summed ms of each pipeline stage (expm forward, boundary fwd, sweep
-   fwd, sweep bwd (all three), expm reverse, gather, finalize, spare); flush_l2 != 0 writes a 256 MiB buffer
+   ms_total[0] = total ms; kernel_ms[8] = summed ms of each pipeline stage (expm forward = Magnus pass + k_forward, boundary
+   fwd, sweep fwd, sweep bwd (all three), expm reverse (k_backward + Magnus adjoint pass), gather, finalize, propagator tree
+   between the expm forward and the boundary pass); flush_l2 != 0 writes a 256 MiB buffer
    between evaluations (outside the stage timers, inside ms_total only if count_flush != 0). */
 int qocb_time_resident(qocb_plan *plan, int32_t with_grad, int32_t warmup, int32_t iters, int32_t flush_l2,
                        double *ms_total, double *stage_ms);
