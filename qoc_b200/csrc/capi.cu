@@ -442,6 +442,7 @@ struct LargeImpl {
     int lstar = 0, nchunks = 0, lvl_count[24] = {}, lvl_off[24] = {};   // pairwise propagator tree levels 0..lstar
     bool use_cublas_gemm = false;       // QOCB_LARGE_CUBLAS=1: library ZGEMM instead of zgemm.cuh (A/B comparison)
     bool cluster_boundary = true;       // boundary passes on an 8-CTA cluster (QOCB_NO_CLUSTER=1: the single-CTA kernels)
+    bool tma_gemm = true;               // operand panels by TMA (k_zgemm_tma); QOCB_NO_TMA=1: the cp.async kernel
     // reverse-pass tape (stored when it fits): M, A2, A4, A6, Y, LU(Q), R0 of every local slice + pivots + squaring counts.
     // tj >= 0 redirects those work arrays (and pivots / counts / LU pointers) to the tape entries of slices tj, tj+1, ...
     DevBuf<double2> tape;
@@ -727,6 +728,26 @@ int lg_gemm_rect(qocb_plan *p, bool ta, bool tb, const double2 *A, const double2
     const bool thin = nc <= 16;
     const int bn = thin ? 16 : 64;
     const dim3 grid(((m + 63) / 64) * ((nc + bn - 1) / bn), batch);
+    if (p->large && p->large->tma_gemm) {                          // TMA-fed variant (zgemm.cuh): operand tensor maps per call
+        ZgMaps maps;
+        const bool okA = ta ? qocb_host::make_zgemm_map(&maps.a, A, k, m, lda, sA, batch, ZG_LDT, ZG_BK)
+                            : qocb_host::make_zgemm_map(&maps.a, A, m, k, lda, sA, batch, ZG_LDA, ZG_BM);
+        const bool okB = tb ? qocb_host::make_zgemm_map(&maps.b, B, nc, k, ldb, sB, batch, ZG_LDA, bn)
+                            : qocb_host::make_zgemm_map(&maps.b, B, k, nc, ldb, sB, batch, bn + 2, ZG_BK);
+        if (okA && okB) {
+#define ZT_LAUNCH(TA_, TB_, BN_) k_zgemm_tma<TA_, TB_, BN_><<<grid, ZG_NT, ZgTmaTile<TA_, TB_, BN_>::smem, p->stream>>>(maps, C, m, nc, k, ldc, alpha, beta, sC, gate, gate_level)
+            if (thin) {
+                if (!ta && !tb) ZT_LAUNCH(false, false, 16); else if (ta && !tb) ZT_LAUNCH(true, false, 16);
+                else if (!ta && tb) ZT_LAUNCH(false, true, 16); else ZT_LAUNCH(true, true, 16);
+            } else {
+                if (!ta && !tb) ZT_LAUNCH(false, false, 64); else if (ta && !tb) ZT_LAUNCH(true, false, 64);
+                else if (!ta && tb) ZT_LAUNCH(false, true, 64); else ZT_LAUNCH(true, true, 64);
+            }
+#undef ZT_LAUNCH
+            CU_TRY(p, cudaGetLastError());
+            return 0;
+        }
+    }
 #define ZG_LAUNCH(TA_, TB_, BN_) k_zgemm<TA_, TB_, BN_><<<grid, ZG_NT, ZgTile<BN_>::smem, p->stream>>>(A, B, C, m, nc, k, lda, ldb, ldc, alpha, beta, sA, sB, sC, gate, gate_level)
     if (thin) {
         if (!ta && !tb) ZG_LAUNCH(false, false, 16); else if (ta && !tb) ZG_LAUNCH(true, false, 16);
@@ -818,6 +839,11 @@ int large_init(qocb_plan *p) {
     ZG_ATTR(false, false, 64); ZG_ATTR(true, false, 64); ZG_ATTR(false, true, 64); ZG_ATTR(true, true, 64);
     ZG_ATTR(false, false, 16); ZG_ATTR(true, false, 16); ZG_ATTR(false, true, 16); ZG_ATTR(true, true, 16);
 #undef ZG_ATTR
+#define ZT_ATTR(TA_, TB_, BN_) CU_TRY(p, cudaFuncSetAttribute(k_zgemm_tma<TA_, TB_, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZgTmaTile<TA_, TB_, BN_>::smem))
+    ZT_ATTR(false, false, 64); ZT_ATTR(true, false, 64); ZT_ATTR(false, true, 64); ZT_ATTR(true, true, 64);
+    ZT_ATTR(false, false, 16); ZT_ATTR(true, false, 16); ZT_ATTR(false, true, 16); ZT_ATTR(true, true, 16);
+#undef ZT_ATTR
+    { const char *nt = getenv("QOCB_NO_TMA"); L->tma_gemm = qocb_host::encode_tiled_fn() != nullptr && !(nt && nt[0] == '1'); }
     BL_TRY(p, cublasCreate(&L->blas));
     BL_TRY(p, cublasSetStream(L->blas, p->stream));
     CU_TRY(p, L->G0.alloc(L->nn)); CU_TRY(p, L->G.alloc((size_t)std::max(1, p->KC) * L->nn));
