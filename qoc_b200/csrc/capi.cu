@@ -443,6 +443,9 @@ struct LargeImpl {
     bool use_cublas_gemm = false;       // QOCB_LARGE_CUBLAS=1: library ZGEMM instead of zgemm.cuh (A/B comparison)
     bool cluster_boundary = true;       // boundary passes on an 8-CTA cluster (QOCB_NO_CLUSTER=1: the single-CTA kernels)
     bool tma_gemm = true;               // operand panels by TMA (k_zgemm_tma); QOCB_NO_TMA=1: the cp.async kernel
+    bool own_lu = false;                // block LU + block substitutions on the own GEMM (Hermitian operators, ||A||_1 < 2.5 checked on
+                                        // the device; QOCB_LARGE_CUBLAS_LU=1 or a raised lu_flag: cuBLAS getrf / getrs)
+    DevBuf<int> lu_flag;
     // reverse-pass tape (stored when it fits): M, A2, A4, A6, Y, LU(Q), R0 of every local slice + pivots + squaring counts.
     // tj >= 0 redirects those work arrays (and pivots / counts / LU pointers) to the tape entries of slices tj, tj+1, ...
     DevBuf<double2> tape;
@@ -826,6 +829,63 @@ int lg_magnus6_pieces(qocb_plan *p, int jb, int Bc) {
     return lg_axpby(p, L->arr(LA6B), -20., b1, -1., b3, 1., c12, Bc);
 }
 
+// ---- own LU and block substitutions of the large-dimension path (large.cuh: k_lg_blockinv) ---------------------------------
+constexpr int kLgBlk = 64;
+
+// in-place block LU of the Bc matrices at Q (row-major n x n, batch stride nn)
+int lg_block_lu(qocb_plan *p, double2 *Q, int Bc) {
+    LargeImpl *L = p->large;
+    const int n = L->n;
+    const long long nn = L->nn;
+    for (int k0 = 0; k0 < n; k0 += kLgBlk) {
+        const int bs = std::min(kLgBlk, n - k0), rest = n - k0 - bs;
+        k_lg_blockinv<C64><<<Bc, C64::NT, Smem<C64>::bytes(), p->stream>>>(Q, n, k0, bs, nn, L->lu_flag.p);
+        CU_TRY(p, cudaGetLastError());
+        if (rest <= 0) break;
+        double2 *D = Q + (size_t)k0 * n + k0, *Q12 = D + bs, *Q21 = Q + (size_t)(k0 + bs) * n + k0, *Q22 = Q21 + bs;
+        int rc = lg_gemm_rect(p, false, false, D, Q12, Q12, bs, rest, bs, n, n, n, 1., 0., Bc, nn, nn, nn); if (rc) return rc;      // U12 = D^-1 Q12 (in place)
+        rc = lg_gemm_rect(p, false, false, Q21, Q12, Q22, rest, rest, bs, n, n, n, -1., 1., Bc, nn, nn, nn); if (rc) return rc;     // Q22 -= Q21 U12
+    }
+    return 0;
+}
+
+// X <- X Q^-1 (transposed = false) or X Q^-T (true) for the block factors at Q; X: m x n with row stride ldx, batch stride sX.
+// T: scratch of Bc matrices (row stride n, batch stride nn, at least m rows each).
+int lg_solve_right(qocb_plan *p, const double2 *Q, double2 *X, int m, int ldx, long long sX, double2 *T, int Bc, bool transposed) {
+    LargeImpl *L = p->large;
+    const int n = L->n;
+    const long long nn = L->nn;
+    const int nb = (n + kLgBlk - 1) / kLgBlk;
+    int rc;
+    if (!transposed) {
+        // X L U = P:  Y = X L solves Y U = P (U unit block upper), then X L = Y (L block lower, inverted diagonal blocks stored)
+        for (int j = 1; j < nb; ++j) {
+            const int c0 = j * kLgBlk, bs = std::min(kLgBlk, n - c0);
+            rc = lg_gemm_rect(p, false, false, X, Q + c0, X + c0, m, bs, c0, ldx, n, ldx, -1., 1., Bc, sX, nn, sX); if (rc) return rc;
+        }
+        for (int j = nb - 1; j >= 0; --j) {
+            const int c0 = j * kLgBlk, bs = std::min(kLgBlk, n - c0), rest = n - c0 - bs;
+            if (rest > 0) { rc = lg_gemm_rect(p, false, false, T + c0 + bs, Q + (size_t)(c0 + bs) * n + c0, X + c0, m, bs, rest, n, n, ldx, -1., 1., Bc, nn, nn, sX); if (rc) return rc; }
+            rc = lg_gemm_rect(p, false, false, X + c0, Q + (size_t)c0 * n + c0, T + c0, m, bs, bs, ldx, n, n, 1., 0., Bc, sX, nn, nn); if (rc) return rc;
+        }
+    } else {
+        // X U^T L^T = R:  Z = X U^T solves Z L^T = R (forward over the column blocks), then X U^T = Z (backward)
+        for (int j = 0; j < nb; ++j) {
+            const int c0 = j * kLgBlk, bs = std::min(kLgBlk, n - c0);
+            if (j > 0) { rc = lg_gemm_rect(p, false, true, T, Q + (size_t)c0 * n, X + c0, m, bs, c0, n, n, ldx, -1., 1., Bc, nn, nn, sX); if (rc) return rc; }
+            rc = lg_gemm_rect(p, false, true, X + c0, Q + (size_t)c0 * n + c0, T + c0, m, bs, bs, ldx, n, n, 1., 0., Bc, sX, nn, nn); if (rc) return rc;
+        }
+        for (int j = nb - 2; j >= 0; --j) {
+            const int c0 = j * kLgBlk, bs = std::min(kLgBlk, n - c0), rest = n - c0 - bs;
+            rc = lg_gemm_rect(p, false, true, T + c0 + bs, Q + (size_t)c0 * n + c0 + bs, T + c0, m, bs, rest, n, n, n, -1., 1., Bc, nn, nn, nn); if (rc) return rc;
+        }
+    }
+    const size_t tot = (size_t)Bc * m * n;
+    k_lg_copy_rect<<<lg_blocks(tot), 256, 0, p->stream>>>(X, T, m, n, ldx, n, sX, nn, Bc);
+    CU_TRY(p, cudaGetLastError());
+    return 0;
+}
+
 int large_init(qocb_plan *p) {
     LargeImpl *L = new LargeImpl();
     p->large = L;
@@ -844,6 +904,9 @@ int large_init(qocb_plan *p) {
     ZT_ATTR(false, false, 16); ZT_ATTR(true, false, 16); ZT_ATTR(false, true, 16); ZT_ATTR(true, true, 16);
 #undef ZT_ATTR
     { const char *nt = getenv("QOCB_NO_TMA"); L->tma_gemm = qocb_host::encode_tiled_fn() != nullptr && !(nt && nt[0] == '1'); }
+    CU_TRY(p, cudaFuncSetAttribute(k_lg_blockinv<C64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C64>::bytes()));
+    CU_TRY(p, L->lu_flag.alloc(1));
+    CU_TRY(p, cudaMemset(L->lu_flag.p, 0, sizeof(int)));
     BL_TRY(p, cublasCreate(&L->blas));
     BL_TRY(p, cublasSetStream(L->blas, p->stream));
     CU_TRY(p, L->G0.alloc(L->nn)); CU_TRY(p, L->G.alloc((size_t)std::max(1, p->KC) * L->nn));
@@ -944,7 +1007,7 @@ int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_slot) {
         k_lg_axpby<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LM), 0.5 * dt, L->arr(LA1), 0.5 * dt, L->arr(LA2N), (QOCB_S3 / 12.0) * dt * dt, L->arr(LT), tot);
     }
     }
-    k_lg_norm_scale<<<Bc, 256, 0, p->stream>>>(L->arr(LM), L->cur_sarr(), L->n);
+    k_lg_norm_scale<<<Bc, 256, 0, p->stream>>>(L->arr(LM), L->cur_sarr(), L->n, L->own_lu ? L->lu_flag.p : nullptr);
     const int cap = keep ? kLgMaxSq : kLgFwdMaxSq;
     k_lg_batch_max<<<1, 256, 0, p->stream>>>(L->cur_sarr(), Bc, smax_slot, cap, p->err_flag.p);
     rc = lg_gemm(p, false, false, L->arr(LM), L->arr(LM), L->arr(LA2), 1., 0., Bc); if (rc) return rc;
@@ -956,10 +1019,15 @@ int lg_forward_batch(qocb_plan *p, int jb, int Bc, bool keep, int *smax_slot) {
     rc = lg_gemm(p, false, false, L->arr(LM), L->arr(LY), L->arr(LUO), 1., 0., Bc); if (rc) return rc;
     k_lg_pq<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LVE), L->arr(LUO), L->arr(LP), L->arr(LQ), tot);
     CU_TRY(p, cudaGetLastError());
-    BL_TRY(p, cublasZgetrfBatched(L->blas, L->n, reinterpret_cast<cuDoubleComplex **>(L->cur_ptrQ()), L->n, L->cur_piv(), L->info.p, Bc));
-    int hinfo = 0;
-    BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_N, L->n, L->n, reinterpret_cast<const cuDoubleComplex *const *>(L->cur_ptrQ()), L->n, L->cur_piv(),
-                                  reinterpret_cast<cuDoubleComplex **>(L->ptrP.p), L->n, &hinfo, Bc));   // R0 = P Q^-1 (row-major)
+    if (L->own_lu) {                                               // R0 = P Q^-1 by the block LU on the own GEMM
+        rc = lg_block_lu(p, L->arr(LQ), Bc); if (rc) return rc;
+        rc = lg_solve_right(p, L->arr(LQ), L->arr(LP), L->n, L->n, nn, L->arr(LT), Bc, false); if (rc) return rc;
+    } else {
+        BL_TRY(p, cublasZgetrfBatched(L->blas, L->n, reinterpret_cast<cuDoubleComplex **>(L->cur_ptrQ()), L->n, L->cur_piv(), L->info.p, Bc));
+        int hinfo = 0;
+        BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_N, L->n, L->n, reinterpret_cast<const cuDoubleComplex *const *>(L->cur_ptrQ()), L->n, L->cur_piv(),
+                                      reinterpret_cast<cuDoubleComplex **>(L->ptrP.p), L->n, &hinfo, Bc));   // R0 = P Q^-1 (row-major)
+    }
     if (keep || L->tj >= 0) { rc = lg_copy(p, L->arr(LR0), L->arr(LP), Bc); if (rc) return rc; }
     for (int i = 0; i < cap; ++i) {                                 // expm.py:249-250, gated on the device
         if (keep) k_lg_copy_gated<<<lg_blocks(tot), 256, 0, p->stream>>>(L->arr(LRS0 + i), L->arr(LP), tot, smax_slot, i);
@@ -974,13 +1042,26 @@ int lg_expm_all(qocb_plan *p) {
     LargeImpl *L = p->large;
     const int Lsl = p->Nloc - 1;
     { int rc = enqueue_node_coefs(p); if (rc) return rc; }
-    for (int jb = 0; jb < Lsl; jb += L->B) {
-        const int Bc = std::min(L->B, Lsl - jb);
-        L->tj = L->taped ? jb : -1;                                 // forward intermediates go straight to the tape
-        int rc = lg_forward_batch(p, jb, Bc, false, L->smax_dev.p + jb / L->B);
-        L->tj = -1;
-        if (rc) return rc;
-        rc = lg_copy(p, reinterpret_cast<double2 *>(p->U.p) + (size_t)jb * L->nn, L->arr(LP), Bc); if (rc) return rc;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        for (int jb = 0; jb < Lsl; jb += L->B) {
+            const int Bc = std::min(L->B, Lsl - jb);
+            L->tj = L->taped ? jb : -1;                             // forward intermediates go straight to the tape
+            int rc = lg_forward_batch(p, jb, Bc, false, L->smax_dev.p + jb / L->B);
+            L->tj = -1;
+            if (rc) return rc;
+            rc = lg_copy(p, reinterpret_cast<double2 *>(p->U.p) + (size_t)jb * L->nn, L->arr(LP), Bc); if (rc) return rc;
+        }
+        // the one host synchronisation of an evaluation on this path: squaring counts of the batches (the reverse pass
+        // replays taped batches without squarings and recomputes the others) and the verdict on the own LU
+        int lu_flag = 0;
+        CU_TRY(p, cudaMemcpyAsync(L->h_smax.data(), L->smax_dev.p, sizeof(int) * L->h_smax.size(), cudaMemcpyDeviceToHost, p->stream));
+        if (L->own_lu) CU_TRY(p, cudaMemcpyAsync(&lu_flag, L->lu_flag.p, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        CU_TRY(p, cudaStreamSynchronize(p->stream));
+        if (!(L->own_lu && lu_flag)) break;
+        // a slice left the regime in which the unpivoted block LU is safe (||A||_1 >= 2.5 or an ill-conditioned diagonal block):
+        // this plan factors with cuBLAS getrf / getrs from now on, and the forward pass is redone
+        L->own_lu = false;
+        CU_TRY(p, cudaMemsetAsync(L->lu_flag.p, 0, sizeof(int), p->stream));
     }
     // transposed copies for the costate sweeps; pairwise product tree up to the chunk level of the sweeps
     const double2 *U = reinterpret_cast<const double2 *>(p->U.p);
@@ -1019,10 +1100,8 @@ int lg_backward_all(qocb_plan *p) {
     LargeImpl *L = p->large;
     const int Lsl = p->Nloc - 1, nn = L->nn, order = p->pb.magnus_order, n = L->n;
     const double dt = p->pb.evolution_time / (p->pb.system_eval_count - 1);
-    // the one host synchronisation of an evaluation on this path: squaring counts of the forward batches (taped batches
-    // without squarings are replayed from the tape, the others recompute their forward pass)
-    CU_TRY(p, cudaMemcpyAsync(L->h_smax.data(), L->smax_dev.p, sizeof(int) * L->h_smax.size(), cudaMemcpyDeviceToHost, p->stream));
-    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    // squaring counts of the forward batches were read back at the end of lg_expm_all: taped batches without squarings are
+    // replayed from the tape, the others recompute their forward pass
     for (size_t bi = 0; bi + 1 < L->h_smax.size(); ++bi) {
         if (L->h_smax[bi] > kLgMaxSq) { set_error(p, "scaling count exceeds the reverse-pass capacity of the large-dimension path"); return -4; }
         L->batch_taped[bi] = (L->taped && L->h_smax[bi] == 0) ? 1 : 0;
@@ -1053,9 +1132,13 @@ int lg_backward_all(qocb_plan *p) {
             const size_t tot4 = (size_t)Bc * n * 4;
             k_lr_load<<<lg_blocks(tot4), 256, 0, p->stream>>>(PSI, LAM, p->psi.p, p->lam.p, jb, Bc, n, S);
             CU_TRY(p, cudaMemsetAsync(LEFT, 0, sizeof(double2) * (size_t)Bc * 48 * n, p->stream));
-            int hinfo2 = 0;                                        // psit = Q^-1 psi (columns = states)
-            BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_T, n, S, reinterpret_cast<const cuDoubleComplex *const *>(L->cur_ptrQ()), n, L->cur_piv(),
-                                          reinterpret_cast<cuDoubleComplex **>(L->ptrPSI.p), n, &hinfo2, Bc));
+            if (L->own_lu) {                                       // psit = Q^-1 psi: rows of PSI are the states, PSI <- PSI Q^-T
+                rc = lg_solve_right(p, L->arr(LQ), PSI, 4, n, 4LL * n, L->arr(LT), Bc, true); if (rc) return rc;
+            } else {
+                int hinfo2 = 0;                                    // psit = Q^-1 psi (columns = states)
+                BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_T, n, S, reinterpret_cast<const cuDoubleComplex *const *>(L->cur_ptrQ()), n, L->cur_piv(),
+                                              reinterpret_cast<cuDoubleComplex **>(L->ptrPSI.p), n, &hinfo2, Bc));
+            }
             auto G = [&](bool ta, bool tb, const double2 *A_, const double2 *B_, double2 *C_, int m_, int nc_, int k_, int lda_, int ldb_, int ldc_,
                          double be, long long sa, long long sb, long long sc) {
                 return lg_gemm_rect(p, ta, tb, A_, B_, C_, m_, nc_, k_, lda_, ldb_, ldc_, 1.0, be, Bc, sa, sb, sc);
@@ -1083,9 +1166,13 @@ int lg_backward_all(qocb_plan *p) {
             rc = lg_gemm(p, true, false, L->arr(LRS0 + i), RB, T, 1., 1., Bc); if (rc) return rc;
             k_lg_select<<<lg_blocks(tot), 256, 0, p->stream>>>(RB, T, L->cur_sarr(), i, nn, tot);
         }
-        int hinfo = 0;                                             // pbar = rbar Q^-T
-        BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_T, n, n, reinterpret_cast<const cuDoubleComplex *const *>(L->cur_ptrQ()), n, L->cur_piv(),
-                                      reinterpret_cast<cuDoubleComplex **>(L->ptrRB.p), n, &hinfo, Bc));
+        if (L->own_lu) {                                           // pbar = rbar Q^-T
+            rc = lg_solve_right(p, L->arr(LQ), RB, n, n, nn, T, Bc, true); if (rc) return rc;
+        } else {
+            int hinfo = 0;
+            BL_TRY(p, cublasZgetrsBatched(L->blas, CUBLAS_OP_T, n, n, reinterpret_cast<const cuDoubleComplex *const *>(L->cur_ptrQ()), n, L->cur_piv(),
+                                          reinterpret_cast<cuDoubleComplex **>(L->ptrRB.p), n, &hinfo, Bc));
+        }
         rc = lg_gemm(p, true, false, L->arr(LR0), RB, L->arr(LQB), -1., 0., Bc); if (rc) return rc;       // qbar = -R0^T pbar
         rc = lg_axpby(p, L->arr(LUOB), 1., RB, -1., L->arr(LQB), 0., nullptr, Bc); if (rc) return rc;
         rc = lg_axpby(p, L->arr(LVEB), 1., RB, 1., L->arr(LQB), 0., nullptr, Bc); if (rc) return rc;
@@ -1633,7 +1720,25 @@ int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
     CU_TRY(p, cudaSetDevice(p->pb.device));
     const int n = p->pb.hilbert_size, NP = p->NP, E = p->pb.ensemble_count, KR = p->KC;   // operator channels
     const size_t GM = 2 * (size_t)NP * NP;
+    auto is_hermitian = [&](const double *h) {
+        double mx = 0., dev = 0.;
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c <= r; ++c) {
+                const double ar = h[2 * ((size_t)r * n + c)], ai = h[2 * ((size_t)r * n + c) + 1];
+                const double br = h[2 * ((size_t)c * n + r)], bi = h[2 * ((size_t)c * n + r) + 1];
+                mx = std::max(mx, std::max(std::fabs(ar) + std::fabs(ai), std::fabs(br) + std::fabs(bi)));
+                dev = std::max(dev, std::fabs(ar - br) + std::fabs(ai + bi));
+            }
+        return dev <= 1e-13 * mx;
+    };
     if (p->large) {                                    // interleaved generators G = -1j * H
+        {   // Hermitian operators: the Pade denominator may be factored by the own block LU (large.cuh) while ||A||_1 < 2.5
+            bool herm = is_hermitian(h0);
+            for (int r = 0; r < KR && herm && a_ops; ++r) herm = is_hermitian(a_ops + (size_t)r * 2 * n * n);
+            const char *cl = getenv("QOCB_LARGE_CUBLAS_LU");
+            p->hermitian = herm;
+            p->large->own_lu = herm && !(cl && cl[0] == '1');
+        }
         auto gen = [&](const double *src, double2 *dst_dev) -> cudaError_t {
             std::vector<double> g(2 * (size_t)n * n);
             for (size_t e = 0; e < (size_t)n * n; ++e) { g[2 * e] = src[2 * e + 1]; g[2 * e + 1] = -src[2 * e]; }
@@ -1666,17 +1771,7 @@ int qocb_set_operators(qocb_plan *p, const double *h0, const double *a_ops) {
         return 0;
     }
     {   // Hermitian operators => anti-Hermitian generators: selects the pivot-free LU where it is safe (tile.cuh)
-        auto is_herm = [&](const double *h) {
-            double mx = 0., dev = 0.;
-            for (int r = 0; r < n; ++r)
-                for (int c = 0; c <= r; ++c) {
-                    const double ar = h[2 * ((size_t)r * n + c)], ai = h[2 * ((size_t)r * n + c) + 1];
-                    const double br = h[2 * ((size_t)c * n + r)], bi = h[2 * ((size_t)c * n + r) + 1];
-                    mx = std::max(mx, std::max(std::fabs(ar) + std::fabs(ai), std::fabs(br) + std::fabs(bi)));
-                    dev = std::max(dev, std::fabs(ar - br) + std::fabs(ai + bi));
-                }
-            return dev <= 1e-13 * mx;
-        };
+        auto is_herm = is_hermitian;
         bool herm = true;
         for (int e = 0; e < E && herm; ++e) herm = is_herm(h0 + (size_t)e * 2 * n * n);
         for (int r = 0; r < KR && herm && a_ops; ++r) herm = is_herm(a_ops + (size_t)r * 2 * n * n);

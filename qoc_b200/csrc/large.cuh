@@ -139,7 +139,9 @@ __global__ void k_lg_axpby(double2 *out, double alpha, const double2 *x, double 
 }
 
 // one-norm, squaring count and scaling per slice (expm.py:103-116, :229-241); one CTA per slice, in place
-__global__ void __launch_bounds__(256) k_lg_norm_scale(double2 *A, int *sarr, int n) {
+// lu_flag (optional): raised when a scaled matrix has ||A||_1 >= QOCB_NOPIV_NORM - the block LU without inter-block
+// pivoting (below) is only used under that bound
+__global__ void __launch_bounds__(256) k_lg_norm_scale(double2 *A, int *sarr, int n, int *lu_flag = nullptr) {
     __shared__ double red[256];
     double2 *a = A + (size_t)blockIdx.x * n * n;
     double best = 0.;
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(256) k_lg_norm_scale(double2 *A, int *sarr, in
     if (!(norm < QOCB_THETA13)) { s = (int)ceil(log2(norm / QOCB_THETA13)); if (s < 0) s = 0; }
     if (threadIdx.x == 0) sarr[blockIdx.x] = s;
     const double scale = ldexp(1.0, -s);
+    if (lu_flag != nullptr && threadIdx.x == 0 && !(norm * scale < QOCB_NOPIV_NORM)) *lu_flag = 1;
     for (int e = threadIdx.x; e < n * n; e += 256) { a[e].x *= scale; a[e].y *= scale; }
 }
 
@@ -456,6 +459,63 @@ __global__ void __launch_bounds__(kLgThreads) k_lg_boundary_bwd(LgSweep g, int h
         __syncthreads();
     }
     if (a.b_out) for (int i = threadIdx.x; i < VS; i += kLgThreads) a.b_out[i] = v0[i];
+}
+
+// ---- own batched LU of the Pade denominator for n > 64 -------------------------------------------------------------------
+// Block LU with 64 x 64 blocks and no pivoting BETWEEN blocks, for anti-Hermitian arguments with ||A||_1 < 2.5 (see tile.cuh:
+// the denominator then has a positive definite Hermitian part, so every leading principal block and every Schur
+// complement is safely invertible).  Right-looking, per block column k:
+//     D_k <- inverse of the current diagonal block         k_lg_blockinv: one CTA, the pivoted DMMA LU + solve of tile.cuh
+//     U[k, j>k] <- D_k^-1 Q[k, j>k]                        batched DMMA GEMM (zgemm.cuh), in place (one row tile per CTA)
+//     Q[i>k, j>k] -= Q[i>k, k] U[k, j>k]                   batched DMMA GEMM
+// which leaves Q = L U with L block lower triangular (inverted diagonal blocks stored) and U unit block upper triangular.
+// The solves X Q = P (forward pass) and X Q^T = R (reverse pass) are block substitutions made of the same GEMMs
+// (capi.cu: lg_block_lu, lg_solve_right).  Everything else (general matrices, larger norms) stays on cuBLAS getrf / getrs.
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_lg_blockinv(double2 *Q, int n, int k0, int bs, long long stride, int *lu_flag) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem<C> sm(smem_raw);
+    double2 *q = Q + (size_t)blockIdx.x * stride + (size_t)k0 * n + k0;
+    double mx = 0.;
+    for (int idx = threadIdx.x; idx < C::NP * C::NP; idx += C::NT) {
+        const int r = idx / C::NP, c = idx - r * C::NP;
+        double2 v = make_double2(r == c ? 1.0 : 0.0, 0.0);          // identity padding decouples the unused rows / columns
+        if (r < bs && c < bs) { v = q[(size_t)r * n + c]; mx = fmax(mx, fabs(v.x) + fabs(v.y)); }
+        sm.X2[r * C::LD + c] = v.x; sm.X2[C::PLANE + r * C::LD + c] = v.y;
+        sm.X1[r * C::LD + c] = r == c ? 1.0 : 0.0; sm.X1[C::PLANE + r * C::LD + c] = 0.0;
+    }
+    __syncthreads();
+    lu_factor_blocked<C>(sm.X2, sm.piv, sm.piv + C::NP);
+    lu_solve_blocked<C, false>(sm.X2, sm.piv, sm.X1, sm.X0);        // X0 = D^-1
+    double mi = 0.;
+    for (int idx = threadIdx.x; idx < C::NP * C::NP; idx += C::NT) {
+        const int r = idx / C::NP, c = idx - r * C::NP;
+        if (r < bs && c < bs) {
+            const double2 v = make_double2(sm.X0[r * C::LD + c], sm.X0[C::PLANE + r * C::LD + c]);
+            mi = fmax(mi, fabs(v.x) + fabs(v.y));
+            q[(size_t)r * n + c] = v;
+        }
+    }
+    // conditioning guard: max|D| * max|D^-1| * bs bounds the 1-norm condition number from above
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mi = fmax(mi, __shfl_xor_sync(0xffffffffu, mi, o)); }
+    __shared__ double gmx[32], gmi[32];
+    if ((threadIdx.x & 31) == 0) { gmx[threadIdx.x >> 5] = mx; gmi[threadIdx.x >> 5] = mi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < C::NWARP; ++w) { mx = fmax(mx, gmx[w]); mi = fmax(mi, gmi[w]); }
+        if (!(mx * mi * bs < 1e10)) *lu_flag = 1;
+    }
+}
+
+// dst[b][r][c] = src[b][r][c] for r < rows, c < cols (row strides ldd / lds, batch strides sd / ss)
+__global__ void k_lg_copy_rect(double2 *dst, const double2 *src, int rows, int cols, int ldd, int lds, long long sd, long long ss, int batch) {
+    const size_t per = (size_t)rows * cols, tot = per * batch;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = t / per, e = t - b * per;
+        const int r = (int)(e / cols), c = (int)(e - (size_t)r * cols);
+        dst[b * sd + (size_t)r * ldd + c] = src[b * ss + (size_t)r * lds + c];
+    }
 }
 
 // ---- boundary passes on a thread-block cluster ------------------------------------------------------------------------
