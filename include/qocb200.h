@@ -89,6 +89,11 @@ int qocb_get_states(qocb_plan *plan, double *states);
 /* final states of the last evaluation: [E][S][n] complex (reporter.final_states, qoc/core/schroedingerdiscrete.py:436);
    waits for the plan stream, so it also serves evaluations enqueued with qocb_run_resident */
 int qocb_get_final_states(qocb_plan *plan, double *final_states);
+/* per-node cotangents of the operator-channel coefficients of the last qocb_cost_and_grad: [E][N-1][q][KC], dE / d coef[j][i][c]
+   (KC = channel_count, or control_count when that is 0).  With control_count = 0 and the coefficients uploaded as the offset
+   table of qocb_set_node_map this is the device half of the chain rule through a hamiltonian(controls, time) callable that
+   is not affine in the controls (qoc_b200/core/plan.py: NonlinearSchroedingerPlan). */
+int qocb_get_node_grad(qocb_plan *plan, double *node_grad);
 /* slice propagators U_j of the last evaluation: [E][N-1][n][n] complex */
 int qocb_get_propagators(qocb_plan *plan, double *props);
 

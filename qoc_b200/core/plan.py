@@ -28,6 +28,10 @@ from qoc_b200.models.enums import InterpolationPolicy, MagnusPolicy
 _PROBE_RTOL = 1e-10
 
 
+class NonlinearHamiltonian(NotImplementedError):
+    """raised by the structure extraction when the callable is not affine in (Re u, Im u)."""
+
+
 _MAX_CHANNELS = 16          # kMaxKR of the CUDA kernels
 _NODES = {1: (0.5,), 2: (0.5 - np.sqrt(3.0) / 6, 0.5 + np.sqrt(3.0) / 6),
           3: (0.5 - np.sqrt(15.0) / 10, 0.5, 0.5 + np.sqrt(15.0) / 10)}          # mathmethods.py:88,113-114,148-150
@@ -157,9 +161,9 @@ def extract_time_dependent_structure(hamiltonian, control_count, complex_control
         model = g0 + np.tensordot(offset[k] + gain[k] @ x, channels, axes=(0, 0))
         got = np.asarray(hamiltonian(u.astype(zero.dtype), times[k]), dtype=np.complex128)
         if not np.allclose(got, model, rtol=0, atol=_PROBE_RTOL * scale * (1 + np.abs(x).sum())):
-            raise NotImplementedError(
-                "hamiltonian(controls, time) is not affine in (Re u, Im u); non-linear callables are not supported "
-                "by the CUDA path yet (no CPU fallback)")
+            raise NonlinearHamiltonian(
+                "hamiltonian(controls, time) is not affine in (Re u, Im u); a SchroedingerPlan needs that form - "
+                "`make_schroedinger_plan` handles non-linear callables (no CPU fallback)")
     return (g0, channels, np.ascontiguousarray(offset.reshape(nsl, q, KC)),
             np.ascontiguousarray(gain.reshape(nsl, q, KC, KR)))
 
@@ -196,9 +200,9 @@ def extract_hamiltonian_structure(hamiltonian, control_count, complex_controls, 
         for t in (t0, t1, float(rng.uniform(0.0, evolution_time)), float(evolution_time)):
             got = np.asarray(hamiltonian(u.astype(dtype), t), dtype=np.complex128)
             if not np.allclose(got, model, rtol=0, atol=_PROBE_RTOL * scale * (1 + np.abs(x).sum())):
-                raise NotImplementedError(
-                    "hamiltonian(controls, time) is not of the form H0 + sum_k Re(u_k) A_k + Im(u_k) B_k; non-linear "
-                    "callables are not supported by the CUDA path yet (no CPU fallback)")
+                raise NonlinearHamiltonian(
+                    "hamiltonian(controls, time) is not of the form H0 + sum_k Re(u_k) A_k + Im(u_k) B_k; a SchroedingerPlan "
+                    "needs that form - `make_schroedinger_plan` handles non-linear callables (no CPU fallback)")
     return h0, a_ops
 
 
@@ -218,6 +222,7 @@ class SchroedingerPlan(object):
         if not isinstance(magnus_policy, MagnusPolicy):
             raise ValueError("Unrecognized magnus policy {}.".format(magnus_policy))
         self.lib = _lib.load()
+        self._q = magnus_policy.order // 2
         initial_states = np.asarray(initial_states)
         # state sharding (qoc_b200/core/sharded.py): this plan holds states [s0, s1) of S_total; normalisations use S_total
         self.S_total = initial_states.shape[0]
@@ -366,6 +371,13 @@ class SchroedingerPlan(object):
         _lib.check(self.lib.qocb_get_final_states(self.handle, _lib.ptr(fs)), self.handle)
         return self._final_states(fs)
 
+    def node_grad(self):
+        """per-node cotangents of the operator-channel coefficients of the last cost_and_grad: [N-1][q][KC] (member 0)."""
+        KC = self.structure[1].shape[0]
+        buf = np.zeros((self.N - 1, self._q, KC))
+        _lib.check(self.lib.qocb_get_node_grad(self.handle, _lib.ptr(buf)), self.handle)
+        return buf
+
     def intermediate_states(self):
         """[N][S][n][1] states of the last evaluation (member 0 unless E > 1: then [E][N][S][n][1])."""
         buf = np.empty((self.E, self.N, self.S, self.n), dtype=np.complex128)
@@ -402,6 +414,174 @@ class SchroedingerPlan(object):
             self.close()
         except Exception:
             pass
+
+
+def _interp_pair(x, xs):
+    """the two control points and weights the reference's linear interpolation uses at time x, including its
+    extrapolation rule outside [xs[0], xs[-1]] (qoc/core/mathmethods.py:54-65)."""
+    M = len(xs)
+    if x <= xs[0]:
+        i0, i1 = 0, 1
+    elif x >= xs[M - 1]:
+        i0, i1 = M - 2, M - 1
+    else:
+        i1 = int(np.argmax(x <= xs))
+        i0 = i1 - 1
+    w1 = (x - xs[i0]) / (xs[i1] - xs[i0])
+    return i0, i1, 1.0 - w1, w1
+
+
+class NonlinearSchroedingerPlan(object):
+    """`hamiltonian(controls, time)` callables that are NOT affine in the controls, e.g.
+    H0 + u0^2 X + sin(u1 t) Y.  The reference differentiates through the callable with autograd; here
+
+      * once per plan, the callable is sampled at random controls and node times and H - G0 is expanded over a small real
+        operator basis {A_c}, c < 16 (anything that needs more channels raises NotImplementedError);
+      * per evaluation the HOST calls the callable at every Magnus node of every slice - exactly where the reference calls it
+        (qoc/core/schroedingerdiscrete.py:483-497) - with the linearly interpolated controls, projects H - G0 on the basis
+        (residual checked) and uploads the channel coefficients; the same CUDA kernels propagate and differentiate with
+        respect to those coefficients (`qocb_set_node_map` with control_count = 0, `qocb_get_node_grad`);
+      * the chain rule through the callable uses a NUMERIC Jacobian of the coefficients with respect to (Re u, Im u) at each
+        node: 4-point central differences (error O(h^4)), about 1e-11 relative for smooth callables.  Cost and final states
+        keep the 1e-10 parity of the affine path; the gradient is as accurate as that Jacobian (tests assert 1e-8).
+
+    The host work is O(nodes * control channels) Python calls per evaluation: a generality path, not a fast one."""
+
+    def __init__(self, hamiltonian, initial_states, costs, evolution_time, system_eval_count, control_eval_count=0,
+                 control_count=0, complex_controls=False, magnus_policy=MagnusPolicy.M2, cost_eval_step=1,
+                 interpolation_policy=InterpolationPolicy.LINEAR, device=0, store_tape=True, seed=1234, **unused):
+        from qoc_b200.models.cost import Cost
+        self.hamiltonian = hamiltonian
+        self.K, self.M, self.N = int(control_count), int(control_eval_count), int(system_eval_count)
+        self.complex_controls = bool(complex_controls)
+        self.KR = self.K * (2 if self.complex_controls else 1)
+        self.T = float(evolution_time)
+        self.q = magnus_policy.order // 2
+        nsl = self.N - 1
+        dt = self.T / nsl
+        self.times = np.array([[(j + c) * dt for c in _NODES[self.q]] for j in range(nsl)])         # [N-1][q]
+        xs = np.linspace(0, self.T, self.M)
+        self.pairs = [[_interp_pair(t, xs) for t in row] for row in self.times]
+        dtype = np.complex128 if self.complex_controls else np.float64
+        rng = np.random.default_rng(seed)
+        zero = np.zeros(self.K, dtype=dtype)
+        self.g0 = np.array(hamiltonian(zero, float(self.times[0, 0])), dtype=np.complex128)
+        n = self.g0.shape[0]
+        basis = _RealBasis(_MAX_CHANNELS)
+        probe_times = list(self.times.ravel()[np.linspace(0, self.times.size - 1, min(12, self.times.size)).astype(int)])
+        for t in probe_times:
+            basis.add(np.asarray(hamiltonian(zero, float(t)), dtype=np.complex128) - self.g0)
+            for trial in range(10):
+                u = rng.standard_normal(self.K) * (0.3 + 0.5 * trial)
+                if self.complex_controls:
+                    u = u + 1j * rng.standard_normal(self.K) * (0.3 + 0.5 * trial)
+                basis.add(np.asarray(hamiltonian(u.astype(dtype), float(t)), dtype=np.complex128) - self.g0)
+        self.KC = len(basis.vecs)
+        if self.KC == 0:
+            raise ValueError("the hamiltonian does not depend on controls or time: use a SchroedingerPlan")
+        self.basis = np.array(basis.vecs)                                    # [KC][2 n^2] orthonormal over the reals
+        self.scale = max(1.0, basis.scale)
+        channels = basis.matrices(self.g0.shape)
+        offset = np.zeros((nsl, self.q, self.KC))
+        gain = np.zeros((nsl, self.q, self.KC, 0))
+        self.state_costs = [c for c in costs if getattr(type(c), "control_value_and_grad", Cost.control_value_and_grad)
+                            is Cost.control_value_and_grad]
+        self.control_costs = [c for c in costs if c not in self.state_costs]
+        self.inner = SchroedingerPlan(None, initial_states, self.state_costs, evolution_time, system_eval_count,
+                                      control_eval_count=0, control_count=0, complex_controls=False, magnus_policy=magnus_policy,
+                                      cost_eval_step=cost_eval_step, interpolation_policy=interpolation_policy, device=device,
+                                      store_tape=store_tape, structure=(self.g0, channels, offset, gain))
+        self.S, self.n, self.E = self.inner.S, n, 1
+
+    # -- host side of one evaluation ---------------------------------------------------------------------
+    def _project(self, h):
+        d = h - self.g0
+        v = np.concatenate([d.real.ravel(), d.imag.ravel()])
+        c = self.basis @ v
+        if np.abs(v - c @ self.basis).max() > 1e-9 * self.scale:
+            raise RuntimeError("hamiltonian(controls, time) left the operator basis found at plan creation (a term that the "
+                               "probing did not excite): not representable on the CUDA path")
+        return c
+
+    def _coefficients(self, controls, want_jacobian):
+        controls = np.asarray(controls)
+        if controls.shape != (self.M, self.K):
+            raise ValueError("controls must have shape {}".format((self.M, self.K)))
+        nsl = self.N - 1
+        coef = np.zeros((nsl, self.q, self.KC))
+        jac = np.zeros((nsl, self.q, self.KC, self.KR)) if want_jacobian else None
+        dirs = [1.0] * self.K + ([1j] * self.K if self.complex_controls else [])
+        for j in range(nsl):
+            for i in range(self.q):
+                i0, i1, w0, w1 = self.pairs[j][i]
+                u = controls[i0] * w0 + controls[i1] * w1
+                t = float(self.times[j, i])
+                coef[j, i] = self._project(np.asarray(self.hamiltonian(u, t), dtype=np.complex128))
+                if not want_jacobian:
+                    continue
+                for r in range(self.KR):
+                    k = r % self.K
+                    h = 1e-3 * max(1.0, abs(u[k]))
+                    e = np.zeros(self.K, dtype=u.dtype)
+                    e[k] = dirs[r]
+
+                    def f(s_, e=e, h=h):
+                        return self._project(np.asarray(self.hamiltonian(u + s_ * h * e, t), dtype=np.complex128))
+                    jac[j, i, :, r] = (8.0 * (f(1.0) - f(-1.0)) - (f(2.0) - f(-2.0))) / (12.0 * h)
+        return coef, jac
+
+    def _upload(self, coef):
+        p = self.inner
+        off = np.ascontiguousarray(coef, dtype=np.float64)
+        _lib.check(p.lib.qocb_set_node_map(p.handle, _lib.ptr(off), None), p.handle)
+
+    _control_costs = SchroedingerPlan._control_costs
+
+    def cost(self, controls):
+        coef, _ = self._coefficients(controls, False)
+        self._upload(coef)
+        err, finals = self.inner.cost(None)
+        return err + self._control_costs(np.asarray(controls), False)[0], finals
+
+    def cost_and_grad(self, controls):
+        """(error, grads, final_states) as `SchroedingerPlan.cost_and_grad`."""
+        controls = np.asarray(controls)
+        coef, jac = self._coefficients(controls, True)
+        self._upload(coef)
+        err, _, finals = self.inner.cost_and_grad(None)
+        gc = self.inner.node_grad()                                          # dE / d coef [N-1][q][KC]
+        gx = np.zeros((self.M, self.KR))
+        for j in range(self.N - 1):
+            for i in range(self.q):
+                i0, i1, w0, w1 = self.pairs[j][i]
+                g = jac[j, i].T @ gc[j, i]
+                gx[i0] += w0 * g
+                gx[i1] += w1 * g
+        grads = gx[:, :self.K] + 1j * gx[:, self.K:] if self.complex_controls else gx
+        extra, extra_grad = self._control_costs(controls, True)
+        if extra_grad is not None:
+            grads = grads + extra_grad
+        return err + extra, grads, finals
+
+    cost_and_grad_autograd = SchroedingerPlan.cost_and_grad_autograd
+
+    def intermediate_states(self):
+        return self.inner.intermediate_states()
+
+    def launch_count(self, with_grad=True):
+        return self.inner.launch_count(with_grad)
+
+    def close(self):
+        self.inner.close()
+
+
+def make_schroedinger_plan(hamiltonian, *args, **kw):
+    """`SchroedingerPlan` when the callable is affine in the controls (time-dependent or not), `NonlinearSchroedingerPlan`
+    otherwise - what the public programs (`grape_schroedinger_discrete`, `evolve_schroedinger_discrete`) build."""
+    try:
+        return SchroedingerPlan(hamiltonian, *args, **kw)
+    except NonlinearHamiltonian:
+        return NonlinearSchroedingerPlan(hamiltonian, *args, **kw)
 
 
 # --- Lindblad --------------------------------------------------------------------------------------------

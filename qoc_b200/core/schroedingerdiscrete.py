@@ -9,7 +9,7 @@ through `SchroedingerPlan`.
 import numpy as np
 
 from qoc_b200.core.common import (initialize_controls, slap_controls, strip_controls, clip_control_norms)
-from qoc_b200.core.plan import SchroedingerPlan
+from qoc_b200.core.plan import make_schroedinger_plan
 from qoc_b200.models import (Dummy, EvolveSchroedingerDiscreteState, EvolveSchroedingerResult,
                              GrapeSchroedingerDiscreteState, GrapeSchroedingerResult, InterpolationPolicy,
                              MagnusPolicy, ProgramType)
@@ -20,7 +20,7 @@ from qoc_b200.standard.utils import autograd_available
 def _plan_for(pstate, control_count, complex_controls, device=0, store_tape=True):
     plan = getattr(pstate, "_b200_plan", None)
     if plan is None:
-        plan = SchroedingerPlan(pstate.hamiltonian, pstate.initial_states, pstate.costs, pstate.evolution_time,
+        plan = make_schroedinger_plan(pstate.hamiltonian, pstate.initial_states, pstate.costs, pstate.evolution_time,
                                 pstate.system_eval_count, control_eval_count=pstate.control_eval_count,
                                 control_count=control_count, complex_controls=complex_controls,
                                 magnus_policy=pstate.magnus_policy, cost_eval_step=pstate.cost_eval_step,

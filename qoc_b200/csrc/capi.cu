@@ -2058,6 +2058,15 @@ int qocb_get_final_states(qocb_plan *p, double *final_states) {
     return fetch_final_states(p, final_states);
 }
 
+int qocb_get_node_grad(qocb_plan *p, double *out) {
+    if (!p || !out) { set_error(p, "null argument"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    const size_t cnt = (size_t)p->pb.ensemble_count * (p->Nloc - 1) * p->q * p->KC;
+    if (cnt) CU_TRY(p, cudaMemcpy(out, p->node_grad.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int qocb_get_propagators(qocb_plan *p, double *props) {
     if (!p || !props) return -1;
     CU_TRY(p, cudaSetDevice(p->pb.device));
