@@ -83,6 +83,13 @@ int qocb_clear_costs(qocb_plan *plan);
 int qocb_cost(qocb_plan *plan, const double *controls, double *cost, double *final_states);
 /* grad: [M][KR] real */
 int qocb_cost_and_grad(qocb_plan *plan, const double *controls, double *cost, double *grad, double *final_states);
+/* The same evaluation in two calls, for cost terms the host must evaluate itself (user-defined Cost subclasses,
+   qoc/models/cost.py:5-51): qocb_forward runs the forward pass (keeping the reverse-pass tape) and returns the device costs'
+   value and the final states; the host adds its own terms c(psi_N) and hands their cotangent to qocb_backward as
+   final_seed[S][n] complex = d c / d Re psi - i d c / d Im psi (autograd's convention), or NULL; qocb_backward returns the
+   gradient of (device costs + host terms) with respect to the controls.  Unsharded single-member plans only. */
+int qocb_forward(qocb_plan *plan, const double *controls, double *cost, double *final_states);
+int qocb_backward(qocb_plan *plan, const double *final_seed, double *grad);
 /* all states of the last evaluation: [E][N][S][n] complex (the reference's save_intermediate_states payload,
    qoc/core/schroedingerdiscrete.py:395-402) */
 int qocb_get_states(qocb_plan *plan, double *states);

@@ -20,7 +20,7 @@ LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompil
 
 EXPORTS = [
     "qocb_plan_create", "qocb_plan_destroy", "qocb_last_error", "qocb_set_operators", "qocb_set_node_map", "qocb_set_states",
-    "qocb_add_cost", "qocb_clear_costs", "qocb_cost", "qocb_cost_and_grad", "qocb_get_states", "qocb_get_final_states", "qocb_get_node_grad",
+    "qocb_add_cost", "qocb_clear_costs", "qocb_cost", "qocb_cost_and_grad", "qocb_forward", "qocb_backward", "qocb_get_states", "qocb_get_final_states", "qocb_get_node_grad",
     "qocb_get_propagators", "qocb_upload_controls", "qocb_run_resident", "qocb_sync", "qocb_download_result",
     "qocb_time_resident", "qocb_launch_count", "qocb_stream", "qocb_expm_batched", "qocb_expm_vjp_batched",
     "qocb_expm_batched_time", "qocb_expm_batched_bench", "qocb_version", "qocb_flush_l2", "qocb_shard_matrix_doubles",
@@ -116,6 +116,8 @@ def load():
     lib.qocb_clear_costs.argtypes = [vp]
     lib.qocb_cost.argtypes = [vp, vp, vp, vp]
     lib.qocb_cost_and_grad.argtypes = [vp, vp, vp, vp, vp]
+    lib.qocb_forward.argtypes = [vp, vp, vp, vp]
+    lib.qocb_backward.argtypes = [vp, vp, vp]
     lib.qocb_get_states.argtypes = [vp, vp]
     lib.qocb_get_final_states.argtypes = [vp, vp]
     lib.qocb_get_node_grad.argtypes = [vp, vp]

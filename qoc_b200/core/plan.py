@@ -279,8 +279,20 @@ class SchroedingerPlan(object):
         psi0 = np.ascontiguousarray(initial_states.reshape(self.S, self.n), dtype=np.complex128)
         _lib.check(self.lib.qocb_set_states(handle, _lib.ptr(psi0)), handle)
         self.control_costs = []
+        self.user_costs = []
         from qoc_b200.models.cost import Cost
         for c in self.costs:
+            if (getattr(type(c), "device_terms", Cost.device_terms) is Cost.device_terms and
+                    getattr(type(c), "control_value_and_grad", Cost.control_value_and_grad) is Cost.control_value_and_grad):
+                # a user-defined Cost subclass (qoc/models/cost.py:5-51): only `cost(controls, states, step)` exists.  Its value and
+                # a numeric cotangent of the final states are computed on the host around qocb_forward / qocb_backward.
+                if getattr(c, "requires_step_evaluation", False):
+                    raise NotImplementedError("The user-defined cost {} requires step evaluation; only final-step user costs are "
+                                              "supported by the CUDA path (no CPU fallback).".format(c))
+                if ensemble_drifts is not None or slice_range is not None or state_slice is not None:
+                    raise NotImplementedError("user-defined costs cannot be combined with ensembles or sharded plans")
+                self.user_costs.append(c)
+                continue
             terms = c.device_terms(self.S_total, self.n)
             if state_slice is not None:                  # the vectors (and counts) of the local states only
                 terms = [(kind, step, weight, np.asarray(vecs)[self.state_first:self.state_first + self.S],
@@ -322,8 +334,77 @@ class SchroedingerPlan(object):
         fs = buf.reshape(self.E, self.S, self.n, 1)
         return fs[0] if self.E == 1 else fs
 
+    # -- user-defined costs: value and cotangents by 4-point central differences of `cost(controls, states, step)` ---------
+    def _user_value(self, controls, finals):
+        return float(sum(np.real(c.cost(controls, finals, self.N - 1)) for c in self.user_costs))
+
+    def _user_seed(self, controls, finals):
+        """d c / d Re psi - i d c / d Im psi of the summed user costs at the final states (autograd's cotangent convention)."""
+        seed = np.zeros((self.S, self.n), dtype=np.complex128)
+        psi = np.array(finals, dtype=np.complex128)
+        for s_ in range(self.S):
+            for a in range(self.n):
+                h = 1e-3 * max(1.0, abs(psi[s_, a, 0]))
+                d = []
+                for direction in (1.0, 1j):
+                    vals = []
+                    for k in (1.0, -1.0, 2.0, -2.0):
+                        q = psi.copy()
+                        q[s_, a, 0] += k * h * direction
+                        vals.append(self._user_value(controls, q))
+                    d.append((8.0 * (vals[0] - vals[1]) - (vals[2] - vals[3])) / (12.0 * h))
+                seed[s_, a] = d[0] - 1j * d[1]
+        return seed
+
+    def _user_control_grad(self, controls, finals):
+        """explicit dependence of the user costs on the controls (most have none: one probe decides)."""
+        controls = np.asarray(controls)
+        base = self._user_value(controls, finals)
+        rng = np.random.default_rng(0)
+        probe = controls + 1e-3 * (rng.standard_normal(controls.shape) + (1j * rng.standard_normal(controls.shape)
+                                                                            if np.iscomplexobj(controls) else 0))
+        if abs(self._user_value(probe, finals) - base) <= 1e-14 * max(1.0, abs(base)):
+            return None
+        g = np.zeros(controls.shape, dtype=controls.dtype)
+        for idx in np.ndindex(*controls.shape):
+            h = 1e-3 * max(1.0, abs(controls[idx]))
+            parts = []
+            for direction in ((1.0, 1j) if np.iscomplexobj(controls) else (1.0,)):
+                vals = []
+                for k in (1.0, -1.0, 2.0, -2.0):
+                    q = controls.copy()
+                    q[idx] += k * h * direction
+                    vals.append(self._user_value(q, finals))
+                parts.append((8.0 * (vals[0] - vals[1]) - (vals[2] - vals[3])) / (12.0 * h))
+            g[idx] = parts[0] + (1j * parts[1] if len(parts) > 1 else 0)
+        return g
+
+    def _eval_with_user_costs(self, controls, want_grad):
+        x = self._real_channels(controls)
+        out = np.zeros(1)
+        fs = np.empty((self.E, self.S, self.n), dtype=np.complex128)
+        _lib.check(self.lib.qocb_forward(self.handle, _lib.ptr(x), _lib.ptr(out), _lib.ptr(fs)), self.handle)
+        finals = self._final_states(fs)
+        err = float(out[0]) + self._user_value(controls, finals)
+        extra, extra_grad = self._control_costs(np.asarray(controls), want_grad)
+        if not want_grad:
+            return err + extra, None, finals
+        seed = np.ascontiguousarray(self._user_seed(controls, finals))
+        g = np.zeros((self.M, self.KR))
+        _lib.check(self.lib.qocb_backward(self.handle, _lib.ptr(seed), _lib.ptr(g)), self.handle)
+        grads = g[:, :self.K] + 1j * g[:, self.K:] if self.complex_controls else g
+        ug = self._user_control_grad(controls, finals)
+        if ug is not None:
+            grads = grads + ug
+        if extra_grad is not None:
+            grads = grads + extra_grad
+        return err + extra, grads, finals
+
     # -- the seam ---------------------------------------------------------------------------------------
     def cost(self, controls):
+        if self.user_costs:
+            err, _, finals = self._eval_with_user_costs(controls, False)
+            return err, finals
         x = self._real_channels(controls)
         out = np.zeros(1)
         fs = np.empty((self.E, self.S, self.n), dtype=np.complex128)
@@ -335,6 +416,8 @@ class SchroedingerPlan(object):
         """returns (error, grads, final_states); grads has controls' shape and dtype and is
         dE/dRe(u) + i dE/dIm(u) for complex controls (the value after the wrapper's conjugate,
         schroedingerdiscrete.py:323-324)."""
+        if self.user_costs:
+            return self._eval_with_user_costs(controls, True)
         x = self._real_channels(controls)
         out = np.zeros(1)
         g = np.zeros((self.M, self.KR))
@@ -484,6 +567,10 @@ class NonlinearSchroedingerPlan(object):
         channels = basis.matrices(self.g0.shape)
         offset = np.zeros((nsl, self.q, self.KC))
         gain = np.zeros((nsl, self.q, self.KC, 0))
+        for c in costs:
+            if (getattr(type(c), "device_terms", Cost.device_terms) is Cost.device_terms and
+                    getattr(type(c), "control_value_and_grad", Cost.control_value_and_grad) is Cost.control_value_and_grad):
+                raise NotImplementedError("user-defined costs together with a non-linear hamiltonian are not supported")
         self.state_costs = [c for c in costs if getattr(type(c), "control_value_and_grad", Cost.control_value_and_grad)
                             is Cost.control_value_and_grad]
         self.control_costs = [c for c in costs if c not in self.state_costs]

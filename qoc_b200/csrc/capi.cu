@@ -2034,6 +2034,56 @@ int qocb_cost_and_grad(qocb_plan *p, const double *controls, double *cost, doubl
     return host_eval(p, true, controls, cost, grad, final_states);
 }
 
+// ---- split evaluation: forward pass now, reverse pass later with an extra cotangent of the final states -------------------
+int qocb_forward(qocb_plan *p, const double *controls, double *cost, double *final_states) {
+    if (!p) return -1;
+    if (p->sharded || p->state_sharded || p->pb.ensemble_count != 1) { set_error(p, "qocb_forward / qocb_backward need an unsharded single-member plan"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    int rc = qocb_upload_controls(p, controls); if (rc) return rc;
+    rc = ready(p); if (rc) return rc;
+    if (p->large) {
+        rc = lg_expm_all(p); if (rc) return rc;
+        rc = lg_states_forward(p, p->psi0.p); if (rc) return rc;
+    } else {
+        rc = enqueue_expm_forward(p, true); if (rc) return rc;      // with the reverse-pass tape
+        rc = enqueue_state_forward(p, p->psi0.p, nullptr); if (rc) return rc;
+        rc = enqueue_finalize(p); if (rc) return rc;
+    }
+    rc = qocb_download_result(p, cost, nullptr); if (rc) return rc;
+    return fetch_final_states(p, final_states);
+}
+
+int qocb_backward(qocb_plan *p, const double *final_seed, double *grad) {
+    if (!p) return -1;
+    if (p->sharded || p->state_sharded || p->pb.ensemble_count != 1) { set_error(p, "qocb_forward / qocb_backward need an unsharded single-member plan"); return -1; }
+    CU_TRY(p, cudaSetDevice(p->pb.device));
+    const int n = p->pb.hilbert_size, NP = p->large ? n : p->NP, S = p->pb.state_count;
+    const double *lam_in = nullptr;
+    if (final_seed) {                                               // extra cotangent of the final states, autograd convention
+        const size_t VS = (size_t)S * 2 * NP;
+        if (p->lam_in.n < VS) CU_TRY(p, p->lam_in.alloc(VS));
+        std::vector<double> buf(VS, 0.0);
+        for (int s_ = 0; s_ < S; ++s_)
+            for (int a = 0; a < n; ++a) {
+                buf[(size_t)s_ * 2 * NP + a] = final_seed[2 * ((size_t)s_ * n + a)];
+                buf[(size_t)s_ * 2 * NP + NP + a] = final_seed[2 * ((size_t)s_ * n + a) + 1];
+            }
+        CU_TRY(p, cudaMemcpyAsync(p->lam_in.p, buf.data(), sizeof(double) * VS, cudaMemcpyHostToDevice, p->stream));
+        CU_TRY(p, cudaStreamSynchronize(p->stream));                // buf is pageable and dies with this scope
+        lam_in = p->lam_in.p;
+    }
+    int rc;
+    if (p->large) {
+        rc = lg_costates(p, lam_in, nullptr, true, true); if (rc) return rc;
+        rc = lg_backward_all(p); if (rc) return rc;
+    } else {
+        rc = enqueue_costate(p, lam_in, nullptr, true, true); if (rc) return rc;
+        rc = enqueue_expm_backward(p, nullptr); if (rc) return rc;
+    }
+    double dummy = 0.;
+    return qocb_download_result(p, &dummy, grad);
+}
+
 int qocb_get_states(qocb_plan *p, double *states) {
     if (!p || !states) return -1;
     CU_TRY(p, cudaSetDevice(p->pb.device));
