@@ -1455,7 +1455,7 @@ const char *qocb_version(void) { return "qocb200 0.1 (sm_100a, complex128)"; }
 #ifdef QOCB_PROFILE
 /* profiling build only: cumulative clock64 ticks per phase id of CTA 0 (then reset) */
 int qocb_debug_profile(long long *out32) {
-    long long zero[32] = {0};
+    long long zero[48] = {0};
     if (cudaMemcpyFromSymbol(out32, qocb::g_prof, sizeof(zero)) != cudaSuccess) return -2;
     if (cudaMemcpyToSymbol(qocb::g_prof, zero, sizeof(zero)) != cudaSuccess) return -2;
     return 0;

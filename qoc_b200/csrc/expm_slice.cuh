@@ -333,65 +333,156 @@ __device__ int pade_forward(const Smem<C> &sm, double *tape, int *piv_out, doubl
         stg2<C>(tA, row, col, a);
     });
     __syncthreads();
+    PROF_MARK(32);
     Acc<C> acc;
-    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X2);     // A2
-    for_owned<C>([&](int i, int j, int row, int col) {
-        const c2 v = accv<C>(acc, i, j);
-        sts2<C>(sm.X0, row, col, v);
-        if (keep) stg2<C>(tape + (size_t)T_A2 * C::GMAT, row, col, v);
-    });
-    __syncthreads();
-    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X0, sm.X0);     // A4
-    for_owned<C>([&](int i, int j, int row, int col) {
-        const c2 v = accv<C>(acc, i, j);
-        sts2<C>(sm.X1, row, col, v);
-        if (full) stg2<C>(tape + (size_t)T_A4 * C::GMAT, row, col, v);
-    });
-    __syncthreads();
-    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X0, sm.X1);     // A6 -> X2 (A is on the tape)
-    __syncthreads();                                                    // X0, X1 (operands) are overwritten below
-    for_owned<C>([&](int i, int j, int row, int col) {
-        const c2 a6 = accv<C>(acc, i, j);
-        const c2 a2 = lds2<C>(sm.X0, row, col), a4 = lds2<C>(sm.X1, row, col);
-        const c2 w1 = kB[13] * a6 + kB[11] * a4 + kB[9] * a2;
-        const c2 x1 = kB[12] * a6 + kB[10] * a4 + kB[8] * a2;
-        const c2 yu = add_diag(kB[7] * a6 + kB[5] * a4 + kB[3] * a2, row, col, kB[1]);
-        const c2 yv = add_diag(kB[6] * a6 + kB[4] * a4 + kB[2] * a2, row, col, kB[0]);
-        sts2<C>(sm.X2, row, col, a6);
-        sts2<C>(sm.X0, row, col, w1);          // over A2 (own elements only)
-        sts2<C>(sm.X1, row, col, x1);          // over A4
-        stg2<C>(tmpY, row, col, yu);
-        stg2<C>(keep ? tape + (size_t)T_LU * C::GMAT : tmpV + C::GMAT, row, col, yv);   // parked until Ve is formed
-        if (full) {
-            stg2<C>(tape + (size_t)T_A6 * C::GMAT, row, col, a6);
-            stg2<C>(tape + (size_t)T_W1 * C::GMAT, row, col, w1);
-            stg2<C>(tape + (size_t)T_X1 * C::GMAT, row, col, x1);
-        }
-    });
-    __syncthreads();
     double *gYV = keep ? tape + (size_t)T_LU * C::GMAT : tmpV + C::GMAT;
-    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X0);     // A6 W1
-    __syncthreads();
-    for_owned<C>([&](int i, int j, int row, int col) {
-        const c2 y = accv<C>(acc, i, j) + ldg2<C>(tmpY, row, col);
-        sts2<C>(sm.X0, row, col, y);                                    // Y over W1
-        if (full) stg2<C>(tape + (size_t)T_Y * C::GMAT, row, col, y);
-    });
-    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X1);     // A6 X1   (X0 not an operand)
-    __syncthreads();
-    for_owned<C>([&](int i, int j, int row, int col) {
-        sts2<C>(sm.X1, row, col, accv<C>(acc, i, j) + ldg2<C>(gYV, row, col));   // Ve over X1
-    });
-    g2s<C>(sm.X2, tA);                                                  // A back into X2 (A6 is dead)
-    __syncthreads();
-    acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X0);     // Uo = A Y
-    __syncthreads();
-    for_owned<C>([&](int i, int j, int row, int col) {
-        const c2 ve = lds2<C>(sm.X1, row, col), uo = accv<C>(acc, i, j);
-        sts2<C>(sm.X1, row, col, ve + uo);                              // P
-        sts2<C>(sm.X2, row, col, ve - uo);                              // Q
-    });
-    __syncthreads();
+    bool half = false;
+    if constexpr (C::NP == 64 && C::NWARP == 8) half = herm != 0;
+    if constexpr (C::NP == 64 && C::NWARP == 8) if (half) {
+        // anti-Hermitian A: every product below is Hermitian (the last one anti-Hermitian) - upper tiles only (tile.cuh)
+        HAcc h;
+        h.zero(); mma_herm<C>(h, sm.X2, sm.X2);                          // A2
+        PROF_MARK(33);
+        herm_store<C, false>(sm.X0, h);
+        __syncthreads();
+        if (keep) for_owned<C>([&](int, int, int row, int col) {
+            stg2<C>(tape + (size_t)T_A2 * C::GMAT, row, col, lds2<C>(sm.X0, row, col));
+        });
+        PROF_MARK(34);
+        h.zero(); mma_herm<C>(h, sm.X0, sm.X0);                          // A4
+        PROF_MARK(35);
+        herm_store<C, false>(sm.X1, h);
+        __syncthreads();
+        if (full) for_owned<C>([&](int, int, int row, int col) {
+            stg2<C>(tape + (size_t)T_A4 * C::GMAT, row, col, lds2<C>(sm.X1, row, col));
+        });
+        PROF_MARK(36);
+        h.zero(); mma_herm<C>(h, sm.X0, sm.X1);                          // A6
+        PROF_MARK(37);
+        __syncthreads();                                                 // X0, X1 (operands) are overwritten below
+        // the owner of an upper tile evaluates the four polynomials on it and writes the tile and its mirror image; the
+        // constant-term polynomials yu, yv stay in registers until the products they are added to are formed
+        c2 yu[5], yv[5];
+        for_herm_tiles([&](int q, int row, int col, bool diag) {
+            const c2 a6 = herm_val(h, q);
+            const c2 a2 = lds2<C>(sm.X0, row, col), a4 = lds2<C>(sm.X1, row, col);
+            const c2 w1 = kB[13] * a6 + kB[11] * a4 + kB[9] * a2;
+            const c2 x1 = kB[12] * a6 + kB[10] * a4 + kB[8] * a2;
+            yu[q] = add_diag(kB[7] * a6 + kB[5] * a4 + kB[3] * a2, row, col, kB[1]);
+            yv[q] = add_diag(kB[6] * a6 + kB[4] * a4 + kB[2] * a2, row, col, kB[0]);
+            sts2<C>(sm.X2, row, col, a6);                                // over A (on the tape; not an operand of A6)
+            sts2<C>(sm.X0, row, col, w1);
+            sts2<C>(sm.X1, row, col, x1);
+            if (!diag) {
+                sts2_mirror<C, false>(sm.X2, row, col, a6);
+                sts2_mirror<C, false>(sm.X0, row, col, w1);
+                sts2_mirror<C, false>(sm.X1, row, col, x1);
+            }
+        });
+        __syncthreads();
+        if (full) for_owned<C>([&](int, int, int row, int col) {
+            stg2<C>(tape + (size_t)T_A6 * C::GMAT, row, col, lds2<C>(sm.X2, row, col));
+            stg2<C>(tape + (size_t)T_W1 * C::GMAT, row, col, lds2<C>(sm.X0, row, col));
+            stg2<C>(tape + (size_t)T_X1 * C::GMAT, row, col, lds2<C>(sm.X1, row, col));
+        });
+        PROF_MARK(38);
+        h.zero(); mma_herm<C>(h, sm.X2, sm.X0);                          // A6 W1
+        for_herm_tiles([&](int q, int, int, bool) { yu[q] = yu[q] + herm_val(h, q); });       // Y
+        h.zero(); mma_herm<C>(h, sm.X2, sm.X1);                          // A6 X1
+        for_herm_tiles([&](int q, int, int, bool) { yv[q] = yv[q] + herm_val(h, q); });       // Ve
+        PROF_MARK(39);
+        __syncthreads();                                                 // operands are overwritten below
+        g2s_async<C>(sm.X2, tA);                                         // A back into X2 (A6 is dead), under the stores
+        for_herm_tiles([&](int q, int row, int col, bool diag) {
+            sts2<C>(sm.X0, row, col, yu[q]);                             // Y over W1
+            sts2<C>(sm.X1, row, col, yv[q]);                             // Ve over X1
+            if (!diag) { sts2_mirror<C, false>(sm.X0, row, col, yu[q]); sts2_mirror<C, false>(sm.X1, row, col, yv[q]); }
+        });
+        g2s_async_wait();
+        __syncthreads();
+        if (full) for_owned<C>([&](int, int, int row, int col) {
+            stg2<C>(tape + (size_t)T_Y * C::GMAT, row, col, lds2<C>(sm.X0, row, col));
+        });
+        PROF_MARK(40);
+        h.zero(); mma_herm<C>(h, sm.X2, sm.X0);                          // Uo = A Y, anti-Hermitian
+        PROF_MARK(41);
+        __syncthreads();                                                 // X2 (operand) is overwritten below
+        for_herm_tiles([&](int q, int row, int col, bool diag) {
+            const c2 ve = lds2<C>(sm.X1, row, col), uo = herm_val(h, q);
+            const c2 pp = ve + uo, qq = ve - uo;                         // P = Ve + Uo, Q = Ve - Uo = P^H
+            sts2<C>(sm.X1, row, col, pp);
+            sts2<C>(sm.X2, row, col, qq);
+            if (!diag) { sts2_mirror<C, false>(sm.X1, row, col, qq); sts2_mirror<C, false>(sm.X2, row, col, pp); }
+        });
+        __syncthreads();
+    }
+    if (!half) {
+        acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X2);     // A2
+        PROF_MARK(33);
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 v = accv<C>(acc, i, j);
+            sts2<C>(sm.X0, row, col, v);
+            if (keep) stg2<C>(tape + (size_t)T_A2 * C::GMAT, row, col, v);
+        });
+        __syncthreads();
+        acc.zero(); mma_smem<C, false, false, false>(acc, sm.X0, sm.X0);     // A4
+        PROF_MARK(35);
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 v = accv<C>(acc, i, j);
+            sts2<C>(sm.X1, row, col, v);
+            if (full) stg2<C>(tape + (size_t)T_A4 * C::GMAT, row, col, v);
+        });
+        __syncthreads();
+        acc.zero(); mma_smem<C, false, false, false>(acc, sm.X0, sm.X1);     // A6 -> X2 (A is on the tape)
+        PROF_MARK(37);
+        __syncthreads();                                                    // X0, X1 (operands) are overwritten below
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 a6 = accv<C>(acc, i, j);
+            const c2 a2 = lds2<C>(sm.X0, row, col), a4 = lds2<C>(sm.X1, row, col);
+            const c2 w1 = kB[13] * a6 + kB[11] * a4 + kB[9] * a2;
+            const c2 x1 = kB[12] * a6 + kB[10] * a4 + kB[8] * a2;
+            const c2 yu = add_diag(kB[7] * a6 + kB[5] * a4 + kB[3] * a2, row, col, kB[1]);
+            const c2 yv = add_diag(kB[6] * a6 + kB[4] * a4 + kB[2] * a2, row, col, kB[0]);
+            sts2<C>(sm.X2, row, col, a6);
+            sts2<C>(sm.X0, row, col, w1);          // over A2 (own elements only)
+            sts2<C>(sm.X1, row, col, x1);          // over A4
+            stg2<C>(tmpY, row, col, yu);
+            stg2<C>(gYV, row, col, yv);          // parked until Ve is formed
+            if (full) {
+                stg2<C>(tape + (size_t)T_A6 * C::GMAT, row, col, a6);
+                stg2<C>(tape + (size_t)T_W1 * C::GMAT, row, col, w1);
+                stg2<C>(tape + (size_t)T_X1 * C::GMAT, row, col, x1);
+            }
+        });
+        __syncthreads();
+        PROF_MARK(38);
+        acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X0);     // A6 W1
+        PROF_MARK(39);
+        __syncthreads();
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 y = accv<C>(acc, i, j) + ldg2<C>(tmpY, row, col);
+            sts2<C>(sm.X0, row, col, y);                                    // Y over W1
+            if (full) stg2<C>(tape + (size_t)T_Y * C::GMAT, row, col, y);
+        });
+        acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X1);     // A6 X1   (X0 not an operand)
+        PROF_MARK(42);
+        __syncthreads();
+        for_owned<C>([&](int i, int j, int row, int col) {
+            sts2<C>(sm.X1, row, col, accv<C>(acc, i, j) + ldg2<C>(gYV, row, col));   // Ve over X1
+        });
+        g2s<C>(sm.X2, tA);                                                  // A back into X2 (A6 is dead)
+        __syncthreads();
+        PROF_MARK(40);
+        acc.zero(); mma_smem<C, false, false, false>(acc, sm.X2, sm.X0);     // Uo = A Y
+        PROF_MARK(41);
+        __syncthreads();
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 ve = lds2<C>(sm.X1, row, col), uo = accv<C>(acc, i, j);
+            sts2<C>(sm.X1, row, col, ve + uo);                              // P
+            sts2<C>(sm.X2, row, col, ve - uo);                              // Q
+        });
+        __syncthreads();
+    }
     PROF_MARK(3);
     if (herm && s == 0 && norm < QOCB_NOPIV_NORM) lu_factor_blocked_nopiv<C>(sm.X2, sm.piv);
     else lu_factor_blocked<C>(sm.X2, sm.piv, sm.piv + C::NP);

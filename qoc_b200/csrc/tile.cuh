@@ -17,7 +17,7 @@ namespace qocb {
 
 // optional phase profiler (-DQOCB_PROFILE): thread 0 of CTA 0 accumulates clock64() deltas per phase id
 #ifdef QOCB_PROFILE
-__device__ long long g_prof[32];
+__device__ long long g_prof[48];
 #define PROF_DECL long long prof_t0__ = clock64();
 #define PROF_MARK(id) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t__ = clock64(); g_prof[id] += t__ - prof_t0__; prof_t0__ = t__; } else { prof_t0__ = 0; } } while (0)
 #else
@@ -144,6 +144,142 @@ __device__ __forceinline__ c2 operator+(const c2 &a, const c2 &b) { return {a.r0
 __device__ __forceinline__ c2 operator-(const c2 &a, const c2 &b) { return {a.r0 - b.r0, a.r1 - b.r1, a.i0 - b.i0, a.i1 - b.i1}; }
 __device__ __forceinline__ c2 operator*(double s, const c2 &a) { return {s * a.r0, s * a.r1, s * a.i0, s * a.i1}; }
 __device__ __forceinline__ c2 czero() { return {0., 0., 0., 0.}; }
+// ---- (anti-)Hermitian products at NP = 64, 8 warps -----------------------------------------------------------------------
+// Every product of the Pade polynomial of an ANTI-Hermitian argument A has a Hermitian result (A2 = A A and the polynomials in
+// it: A4, A6, A6 W1, A6 X1) or an anti-Hermitian one (A Y).  Only the 36 of the 64 8x8 tiles on and above the diagonal are
+// computed; herm_store writes each of them and its (+/-) conjugate transpose.  Tile assignment: rows p and 7 - p hold
+// 8 - p and p + 1 upper tiles, nine together; warp p takes the first five of row p, warp p + 4 the other 3 - p and the
+// p + 1 of row 7 - p.  Warps p and p + 4 share a scheduler, so every tensor pipe runs 9 tile-products per k-step instead of
+// the 16 of the full product.
+struct HAcc {
+    double v[5][6];              // per tile: P1 (col, col + 1), P2, P3 of the 3M scheme (Acc)
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int e = 0; e < 6; ++e) v[q][e] = 0.0;
+    }
+};
+// tile q of this warp -> (row tile, column tile); false for the fifth tile of a four-tile warp
+__device__ __forceinline__ bool herm_tile(int warp, int q, int &rt, int &ct) {
+    const int p = warp & 3;
+    if (warp < 4) { rt = p; ct = p + q; return true; }
+    const int n0 = 3 - p;
+    if (q < n0) { rt = p; ct = p + 5 + q; } else { rt = 7 - p; ct = 7 - p + (q - n0); }
+    if (q >= 4) { rt = 7 - p; ct = 7; return false; }
+    return true;
+}
+// NT tiles of one warp; ONE_ROW: all of them in the same row tile (one A fragment per k-step).  The fragments of k-step
+// kk + 1 are loaded while the DMMAs of kk-step kk issue (two warps per scheduler leave little else to hide the latency).
+template <class C, int NT, bool ONE_ROW>
+__device__ __forceinline__ void herm_loop(HAcc &acc, const double *__restrict__ A, const double *__restrict__ B,
+                                          const int (&ra)[5], const int (&cb)[5]) {
+    constexpr int NA = ONE_ROW ? 1 : NT;
+    double ar[NA], ai[NA], br[NT], bi[NT];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { ar[q] = A[ra[q]]; ai[q] = A[C::PLANE + ra[q]]; }
+#pragma unroll
+    for (int q = 0; q < NT; ++q) { br[q] = B[cb[q]]; bi[q] = B[C::PLANE + cb[q]]; }
+#pragma unroll 4
+    for (int kk = 0; kk < C::NP / 4; ++kk) {
+        const int kn = (kk + 1 < C::NP / 4) ? kk + 1 : kk;
+        double nar[NA], nai[NA], nbr[NT], nbi[NT], sa[NA], sb[NT];
+#pragma unroll
+        for (int q = 0; q < NA; ++q) { nar[q] = A[ra[q] + kn * 4]; nai[q] = A[C::PLANE + ra[q] + kn * 4]; sa[q] = ar[q] + ai[q]; }
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+            nbr[q] = B[cb[q] + kn * 4 * C::LD]; nbi[q] = B[C::PLANE + cb[q] + kn * 4 * C::LD]; sb[q] = br[q] + bi[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NT; ++q) dmma884(acc.v[q][0], acc.v[q][1], ar[ONE_ROW ? 0 : q], br[q]);
+#pragma unroll
+        for (int q = 0; q < NT; ++q) dmma884(acc.v[q][2], acc.v[q][3], ai[ONE_ROW ? 0 : q], bi[q]);
+#pragma unroll
+        for (int q = 0; q < NT; ++q) dmma884(acc.v[q][4], acc.v[q][5], sa[ONE_ROW ? 0 : q], sb[q]);
+#pragma unroll
+        for (int q = 0; q < NA; ++q) { ar[q] = nar[q]; ai[q] = nai[q]; }
+#pragma unroll
+        for (int q = 0; q < NT; ++q) { br[q] = nbr[q]; bi[q] = nbi[q]; }
+    }
+}
+template <class C>
+__device__ __forceinline__ void mma_herm(HAcc &acc, const double *__restrict__ A, const double *__restrict__ B) {
+    static_assert(C::NP == 64 && C::NWARP == 8, "tile assignment of the Hermitian product is for 64 x 64 and 8 warps");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int ra[5], cb[5];                                      // fragment offsets of k-step 0: A[row][t], B[t][col]
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        int rt, ct;
+        herm_tile(warp, q, rt, ct);
+        ra[q] = (rt * 8 + g) * C::LD + t;
+        cb[q] = t * C::LD + ct * 8 + g;
+    }
+    if (warp < 4) herm_loop<C, 5, true>(acc, A, B, ra, cb);
+    else herm_loop<C, 4, false>(acc, A, B, ra, cb);
+}
+// D = the product held in acc: upper tiles as computed, lower tiles as their conjugate transposes (ANTI: negated ones)
+template <class C, bool ANTI>
+__device__ __forceinline__ void herm_store(double *D, const HAcc &acc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        int rt, ct;
+        if (!herm_tile(warp, q, rt, ct)) continue;
+        const double *a = acc.v[q];
+        const c2 v = {a[0] - a[2], a[1] - a[3], a[4] - a[0] - a[2], a[5] - a[1] - a[3]};
+        const int row = rt * 8 + g, col = ct * 8 + 2 * t;
+        sts2<C>(D, row, col, v);
+        if (rt != ct) {
+            const double sr = ANTI ? -1.0 : 1.0, si = ANTI ? 1.0 : -1.0;
+            D[col * C::LD + row] = sr * v.r0;
+            D[(col + 1) * C::LD + row] = sr * v.r1;
+            D[C::PLANE + col * C::LD + row] = si * v.i0;
+            D[C::PLANE + (col + 1) * C::LD + row] = si * v.i1;
+        }
+    }
+}
+
+// the 3M recombination of tile q of a Hermitian product
+__device__ __forceinline__ c2 herm_val(const HAcc &acc, int q) {
+    const double *a = acc.v[q];
+    return {a[0] - a[2], a[1] - a[3], a[4] - a[0] - a[2], a[5] - a[1] - a[3]};
+}
+// D[col][row], D[col + 1][row] = conj(v) (ANTI: -conj(v)): the mirror image of the pair (row, col), (row, col + 1)
+template <class C, bool ANTI>
+__device__ __forceinline__ void sts2_mirror(double *D, int row, int col, const c2 &v) {
+    const double sr = ANTI ? -1.0 : 1.0, si = ANTI ? 1.0 : -1.0;
+    D[col * C::LD + row] = sr * v.r0;
+    D[(col + 1) * C::LD + row] = sr * v.r1;
+    D[C::PLANE + col * C::LD + row] = si * v.i0;
+    D[C::PLANE + (col + 1) * C::LD + row] = si * v.i1;
+}
+// visit the upper tiles of this warp: f(q, row, col, diagonal_tile) owns (row, col), (row, col + 1) of tile q
+template <class F>
+__device__ __forceinline__ void for_herm_tiles(F &&f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        int rt, ct;
+        if (!herm_tile(warp, q, rt, ct)) continue;
+        f(q, rt * 8 + (lane >> 2), ct * 8 + (lane & 3) * 2, rt == ct);
+    }
+}
+// asynchronous global -> shared copy of one planar matrix (16-byte cp.async); complete after g2s_async_wait + a barrier
+template <class C> __device__ __forceinline__ void g2s_async(double *__restrict__ s, const double *__restrict__ g) {
+    constexpr int CH = C::GMAT / 2, RCH = C::NP / 2;
+    for (int idx = threadIdx.x; idx < CH; idx += C::NT) {
+        const int plane = idx / (C::GPLANE / 2);
+        const int rem = idx - plane * (C::GPLANE / 2);
+        const int row = rem / RCH, cc = rem - row * RCH;
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(s + plane * C::PLANE + row * C::LD + cc * 2);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g + (size_t)idx * 2) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void g2s_async_wait() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 // real identity contribution on the diagonal of an owned pair
 __device__ __forceinline__ c2 add_diag(c2 v, int row, int col, double d) {
     if (row == col) v.r0 += d;

@@ -34,7 +34,7 @@ pol = {2: MagnusPolicy.M2, 4: MagnusPolicy.M4, 6: MagnusPolicy.M6}
 plan = SchroedingerPlan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M,
                         control_count=p.K, complex_controls=p.complex_controls, magnus_policy=pol[p.order])
 lib = _lib.load()
-buf = (ctypes.c_longlong * 32)()
+buf = (ctypes.c_longlong * 48)()
 for _ in range(3):
     plan.cost_and_grad(p.controls)
 lib.qocb_debug_profile(buf)
@@ -53,6 +53,10 @@ print("workload", name, "slices sampled by CTA 0:", int(slices))
 for k in sorted(names):
     print("  %-45s %8.2f us/slice" % (names[k], us[k]))
 
+for k, nm in ((32, "scale A + store"), (33, "A2 product"), (34, "A2 store"), (35, "A4 product"), (36, "A4 store"), (37, "A6 product"),
+              (38, "A6 store + epilogue"), (39, "A6 W1 product (half path: + A6 X1)"), (42, "epilogue + A6 X1 product (full path)"),
+              (40, "epilogues + A reload"), (41, "Uo product"), (3, "Uo store + P, Q")):
+    print("    poly: %-41s %8.2f us/slice" % (nm, us[k]))
 steps = max(v[24], 1.0)
 print("boundary forward pass (CTA 0,0), per chunk step over %d steps:" % int(steps))
 for k, nm in ((20, "issue prefetch of next propagator"), (21, "wait for current propagator + barrier"), (22, "mat-vec + barrier"), (23, "store boundary state")):
