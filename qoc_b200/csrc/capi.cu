@@ -483,6 +483,9 @@ struct qocb_plan {
     // sweep coarsening: the state / costate sweeps run on chunks merged pairwise `levels` times (propagator tree);
     // lvl_count[l] chunks at level l, their propagators at lvlP + lvl_off[l] matrices, boundaries at cb_lvl + cb_off[l]
     int levels = 0, lvl_count[16] = {}, lvl_off[16] = {}, cb_off[16] = {};
+    // three-level scheme: the sequential boundary passes run on level `coarse` >= levels, k_mid_* fill in the sweep-chunk
+    // boundaries (coarse == levels: two levels).  lv2 / lv3s, lv3c: the choices with / without step costs (pick_levels)
+    int coarse = 0, lv2 = 0, lv3s = 0, lv3c = 0;
     bool sharded = false, owns_final = true;
     bool ops_set = false, states_set = false, have_step_costs = false, comm_ok = false;
     cudaStream_t stream = nullptr;
@@ -655,6 +658,23 @@ SweepArgs make_sargs(qocb_plan *p) {
     return s;
 }
 
+// the arguments of the sequential boundary passes: those of the sweeps with the chunks of level `coarse`
+SweepArgs make_bargs(qocb_plan *p) {
+    SweepArgs s = make_sargs(p);
+    if (p->coarse > p->levels) {
+        s.chunkP = p->lvlP.p + (size_t)p->lvl_off[p->coarse] * 2 * p->NP * p->NP;
+        s.chunk_begin = p->cb_lvl.p + p->cb_off[p->coarse];
+        s.member_chunk0 = p->mc0_lvl.p + 2 * p->coarse;
+    }
+    return s;
+}
+// step costs couple the chunks of the costate pass through their particular parts, which the three-level scheme does not
+// carry: two levels then (called whenever the cost list changes)
+void pick_levels(qocb_plan *p) {
+    if (p->have_step_costs) { p->levels = p->lv2; p->coarse = p->lv2; }
+    else { p->levels = p->lv3s; p->coarse = p->lv3c; }
+}
+
 int upload_costs(qocb_plan *p) {
     if (p->terms.n == p->h_terms.size() && p->terms.n > 0) return 0;
     CU_TRY(p, p->terms.alloc(std::max<size_t>(1, p->h_terms.size())));
@@ -687,7 +707,7 @@ template <class C> int launch_reduce_radix(qocb_plan *p, const double *in, doubl
 int boundary_state_groups(const qocb_plan *p) {
     const int S = p->pb.state_count;
     if (p->pb.ensemble_count >= p->num_sms) return 1;
-    return std::min(S, 8);
+    return std::min((S + 3) / 4, 8);        // the mat-vec works on groups of four states (sweep.cuh)
 }
 
 int ready(qocb_plan *p) {
@@ -1332,7 +1352,7 @@ int enqueue_expm_forward(qocb_plan *p, bool with_grad, cudaEvent_t mid = nullptr
     // propagator tree up to the level the sweeps run on
     const size_t GM = 2 * (size_t)p->NP * p->NP;
     const double *in = p->chunkP.p;
-    for (int l = 1; l <= p->levels; ++l) {
+    for (int l = 1; l <= p->coarse; ++l) {
         double *out = p->lvlP.p + (size_t)p->lvl_off[l] * GM;
         rc = reduce_level(p, in, out, p->lvl_count[l - 1]);
         if (rc) return rc;
@@ -1368,9 +1388,15 @@ int enqueue_state_forward(qocb_plan *p, const double *psi_in_dev, cudaEvent_t mi
     sa.psi_in = psi_in_dev;
     const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
     const dim3 bgrid(sa.E, boundary_state_groups(p));
-    SWEEP_NP(p->NP, (k_boundary_fwd<NPc><<<bgrid, kSweepThreads, sw_smem, p->stream>>>(sa)));
+    SweepArgs ba = make_bargs(p);
+    ba.psi_in = psi_in_dev;
+    SWEEP_NP(p->NP, (k_boundary_fwd<NPc><<<bgrid, kSwThreads, sw_smem, p->stream>>>(ba)));
+    if (p->coarse > p->levels) {
+        const dim3 mgrid(p->lvl_count[p->coarse], boundary_state_groups(p));
+        SWEEP_NP(p->NP, (k_mid_fwd<NPc><<<mgrid, kSwThreads, sw_smem, p->stream>>>(sa, p->lvl_count[p->levels], 1 << (p->coarse - p->levels))));
+    }
     if (mid) cudaEventRecord(mid, p->stream);
-    SWEEP_NP(p->NP, (k_sweep_fwd<NPc><<<p->lvl_count[p->levels], kSweepThreads, sw_smem, p->stream>>>(sa)));
+    SWEEP_NP(p->NP, (k_sweep_fwd<NPc><<<p->lvl_count[p->levels], kSwThreads, sw_smem, p->stream>>>(sa)));
     CU_TRY(p, cudaGetLastError());
     return 0;
 }
@@ -1381,10 +1407,18 @@ int enqueue_costate(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, b
     SweepArgs sa = make_sargs(p);
     sa.lam_in = lam_in_dev; sa.b_out = b_out_dev;
     const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
-    if (do_particular && p->have_step_costs) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, true><<<p->lvl_count[p->levels], kSweepThreads, sw_smem, p->stream>>>(sa)));
+    if (do_particular && p->have_step_costs) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, true><<<p->lvl_count[p->levels], kSwThreads, sw_smem, p->stream>>>(sa)));
     const dim3 bgrid(sa.E, boundary_state_groups(p));
-    if (do_boundary) SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<bgrid, kSweepThreads, sw_smem, p->stream>>>(sa, p->have_step_costs ? 1 : 0)));
-    if (do_sweeps) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, false><<<p->lvl_count[p->levels], kSweepThreads, sw_smem, p->stream>>>(sa)));
+    if (do_boundary) {
+        SweepArgs ba = make_bargs(p);
+        ba.lam_in = lam_in_dev; ba.b_out = b_out_dev;
+        SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<bgrid, kSwThreads, sw_smem, p->stream>>>(ba, p->have_step_costs ? 1 : 0)));
+    }
+    if (do_sweeps && p->coarse > p->levels) {
+        const dim3 mgrid(p->lvl_count[p->coarse], boundary_state_groups(p));
+        SWEEP_NP(p->NP, (k_mid_bwd<NPc><<<mgrid, kSwThreads, sw_smem, p->stream>>>(sa, p->lvl_count[p->levels], 1 << (p->coarse - p->levels))));
+    }
+    if (do_sweeps) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, false><<<p->lvl_count[p->levels], kSwThreads, sw_smem, p->stream>>>(sa)));
     CU_TRY(p, cudaGetLastError());
     return 0;
 }
@@ -1561,7 +1595,22 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
             if (t < best_t) { best_t = t; best = l; }
         }
         if (pb->chunks_per_member > 0 || is_large) best = 0;   // explicit chunking: no coarsening
-        p->levels = best;
+        p->lv2 = p->lv3s = p->lv3c = best;
+        // three levels (one member, unsharded): boundary passes on level lc, the fill-in passes 2^(lc - ls) steps, sweeps
+        // on level ls - in as many waves as its chunks need (one CTA per SM)
+        if (E == 1 && !sliced && !st_sharded && !is_large && pb->chunks_per_member <= 0) {
+            double best3 = best_t;
+            for (int ls = 0; ls <= maxl; ++ls)
+                for (int lc = ls + 1; lc <= maxl; ++lc) {
+                    const double len = (double)Nm1 / p->lvl_count[ls];
+                    const int waves = (p->lvl_count[ls] + p->num_sms - 1) / p->num_sms;
+                    const double t = 2.0 * p->lvl_count[lc] * t_b + 2.0 * (double)(1 << (lc - ls)) * t_b + 2.5 * len * waves * t_s + lc * t_l;
+                    if (t < best3) { best3 = t; p->lv3s = ls; p->lv3c = lc; }
+                }
+            const char *n3 = getenv("QOCB_NO_THREE_LEVEL");
+            if (n3 && n3[0] == '1') { p->lv3s = p->lv3c = best; }
+        }
+        pick_levels(p);
         PTRY(p->lvlP.alloc((size_t)std::max(1, off) * GM));
         PTRY(p->cb_lvl.alloc(std::max<size_t>(1, cbl.size()))); PTRY(p->mc0_lvl.alloc(mcl.size()));
         if (!cbl.empty()) PTRY(cudaMemcpy(p->cb_lvl.p, cbl.data(), sizeof(int) * cbl.size(), cudaMemcpyHostToDevice));
@@ -1865,6 +1914,7 @@ int qocb_clear_costs(qocb_plan *p) {
     if (!p) return -1;
     drop_graphs(p);
     p->h_terms.clear(); p->h_vecs.clear(); p->h_counts.clear(); p->ip_total = 0; p->coh_total = 0; p->have_step_costs = false;
+    pick_levels(p);
     p->terms.release();
     return 0;
 }
@@ -1899,6 +1949,7 @@ int qocb_add_cost(qocb_plan *p, int32_t kind, int32_t step_cost, double weight, 
     }
     p->h_terms.push_back(t);
     if (t.step) p->have_step_costs = true;
+    pick_levels(p);
     p->terms.release();          // force re-upload
     drop_graphs(p);
     return 0;
@@ -2149,7 +2200,8 @@ static int launch_count_unmapped(qocb_plan *p, int32_t with_grad) {
     }
     const int pm = (p->premagnus_ok && (p->pb.magnus_order == 2 || (p->pb.magnus_order == 4 && p->comm_ok))) ? 1 : 0;   // k_magnus
     const int pa = (with_grad && pm && p->post_adj_ok && p->pb.control_count > 0) ? 2 : 0;                            // k_magnus_adj, k_magnus_adj_final
-    if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->levels + pm + pa;
+    const int mids = p->coarse > p->levels ? (with_grad ? 2 : 1) : 0;                                                 // k_mid_fwd, k_mid_bwd
+    if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->coarse + mids + pm + pa;
     int levels = p->levels + pm;                                          // pairwise levels for the sweeps, then radix 4 to the root
     for (int c = p->lvl_count[p->levels]; c > 1; c = (c + 3) / 4) ++levels;
     // forward: expm, tree, prefix, boundary, sweep; backward: [particular sweeps], boundary (twice only with step costs on a
@@ -2247,7 +2299,7 @@ int qocb_shard_backward_particular(qocb_plan *p, double *b_dev) {
         sa.lam_in = nullptr; sa.b_out = b_dev;
         const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
         const dim3 bgrid(1, boundary_state_groups(p));
-        SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<bgrid, kSweepThreads, sw_smem, p->stream>>>(sa, 0)));
+        SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<bgrid, kSwThreads, sw_smem, p->stream>>>(sa, 0)));
         CU_TRY(p, cudaGetLastError());
         return 0;                                                   // particular_fresh stays false: the finish phase runs the full pass
     }

@@ -62,6 +62,7 @@ struct SweepArgs {
 __device__ __forceinline__ int coh_slot(const CostTerm &tm, int k, int ces) { return tm.coh_off + (tm.step ? k / ces - 1 : 0); }
 
 constexpr int kSweepThreads = 512;
+constexpr int kSwThreads = 256;        // boundary / sweep kernels: a warp holds two 8-row A-fragment sets (128 registers)
 
 // ---- shared-memory staging of one propagator (16-byte cp.async), used only by the short prefix / suffix kernels of the
 // time-sharded path; the sweep and boundary kernels feed their mat-vecs from registers (see below) ------------------
@@ -92,85 +93,101 @@ __device__ __forceinline__ void prefetch_mat(double *sU, const double *gU) {
 
 // ---- mat-vec of the sweeps ---------------------------------------------------------------------------------------------
 // out[s][a] = sum_b U[a][b] in[s][b]   (TRANS: sum_b U[b][a] in[s][b]); vectors planar [s][2][NP] in shared memory.
-// Every element of a propagator is used exactly once per state, so the matrix is NOT staged through shared memory:
-// each thread loads the KPT elements it owns straight from global memory (L2) into registers - for the NEXT step while
-// the current one computes (`MatRegs` double buffer in the kernels) - and uses them for up to four states at a time.
-// Staging cost per 64 x 64 step measured before: 0.55 us of LDGSTS issue (or 1.0 us of per-row bulk copies) plus a
-// shared-memory-bandwidth-bound 0.95 us mat-vec; the sequential boundary passes are chains of exactly these steps.
-//   U v  : thread -> (row a = t / KS, k-part ks = t % KS), columns b = ks + KS i: KS consecutive lanes read KS
-//          consecutive doubles (full 32-byte sectors) and combine their partial sums by shuffles;
-//   U^T v: thread -> (column a = t % NP, k-part ks = t / NP), rows b = ks + KS i: a warp reads consecutive doubles of
-//          one row; the KS partial sums of a column live in different warps and are combined through `red`
-//          (shared scratch, kMvGroup * KS * 2 * NP doubles).
+// The step is a small real GEMM on the FP64 tensor pipe: four states form the eight columns (re, im interleaved) of
+//     D = Ur * B1 + Ui * B2,   B1[b][2s + p] = V[2s + p][b],   B2[b][2s + p] = -+ V[2s + (p ^ 1)][b]   (V = rows re_s, im_s)
+// so that one m8n8k4 accumulator fragment hands every lane the complex result (re, im) of one state and one row.
+// Every element of a propagator is used exactly once per state group, so the matrix is NOT staged through shared memory:
+// a warp owns one 8-row tile of the output and loads its A fragments straight from global memory (L2) into registers -
+// for the NEXT step while the current one computes (`MatRegs` double buffer in the kernels): 16-byte loads, 8 rows x 64
+// bytes per warp instruction (U v), or 4 rows x 64 bytes (U^T v).  The contraction index of the two DMMAs of an 8-wide
+// k block is permuted (slot t <-> columns 8 kk + 2 t and 8 kk + 2 t + 1) so that both the A and the B fragments of a block
+// are one 16-byte load per lane.  The vectors are copied (32 states at a time) into a scratch with row stride NP + 8, which
+// makes the B-fragment loads bank-conflict free; NP / 8 row tiles are spread over the 16 warps, the warps of one tile take
+// every GW-th group of four states.
 template <int NP> struct MvMap {
-    static constexpr int KS0 = kSweepThreads / NP;
-    static constexpr int KS = KS0 > 32 ? (NP < 32 ? NP : 32) : (KS0 > NP ? NP : KS0);
-    static constexpr int KPT = NP / KS, ACTIVE = NP * KS;
+    static constexpr int NW = kSwThreads / 32;
+    static constexpr int TILES = NP / 8;                 // 8-row tiles of the output
+    static constexpr int GW = NW / TILES;                // warps per row tile
+    static constexpr int KR = NP / 4;                    // A-fragment elements per lane and plane
+    static constexpr int LDV = NP + 8;                   // row stride of the padded vector scratch
+    static constexpr int BATCH = 32;                     // states per pass through the scratch
+    static_assert(NP % 8 == 0 && NW % TILES == 0, "row tiles must divide the warps");
 };
-constexpr int kMvGroup = 4;                      // states per pass over the registers
 
-template <int NP> struct MatRegs { double r[MvMap<NP>::KPT], i[MvMap<NP>::KPT]; };
+template <int NP> struct MatRegs { double r[MvMap<NP>::KR], i[MvMap<NP>::KR]; };
 
+// 16-byte / 8-byte read-only loads as volatile asm: they keep their place between the (volatile) DMMAs, which is how the
+// prefetch of the next matrix is interleaved with the products of the current one - a warp that issues all its loads at
+// once sits in the load/store queue for as long as the matrix takes to arrive (64 KB at ~64 B/clk)
+__device__ __forceinline__ void ldg_nc2(double &x, double &y, const double *p) {
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];\n" : "=d"(x), "=d"(y) : "l"(p));
+}
+__device__ __forceinline__ void ldg_nc1(double &x, const double *p) {
+    asm volatile("ld.global.nc.f64 %0, [%1];\n" : "=d"(x) : "l"(p));
+}
+// the A-fragment elements of k block kk (columns 8 kk + 2 t, 8 kk + 2 t + 1) of row a = tile * 8 + g
 template <int NP, bool TRANS>
-__device__ __forceinline__ void load_mat_regs(MatRegs<NP> &m, const double *__restrict__ g) {
-    constexpr int KS = MvMap<NP>::KS, KPT = MvMap<NP>::KPT;
-    const int t = threadIdx.x;
-    if (t >= MvMap<NP>::ACTIVE) return;
-    const int a = TRANS ? t % NP : t / KS, ks = TRANS ? t / NP : t % KS;
-#pragma unroll
-    for (int i = 0; i < KPT; ++i) {
-        const int b = ks + KS * i;
-        const int idx = TRANS ? b * NP + a : a * NP + b;
-        m.r[i] = __ldg(g + idx);
-        m.i[i] = __ldg(g + NP * NP + idx);
+__device__ __forceinline__ void load_mat_block(MatRegs<NP> &m, const double *__restrict__ g, int a, int t, int kk) {
+    if (TRANS) {
+        const int b = 8 * kk + 2 * t;
+        ldg_nc1(m.r[2 * kk], g + b * NP + a); ldg_nc1(m.r[2 * kk + 1], g + (b + 1) * NP + a);
+        ldg_nc1(m.i[2 * kk], g + NP * NP + b * NP + a); ldg_nc1(m.i[2 * kk + 1], g + NP * NP + (b + 1) * NP + a);
+    } else {
+        ldg_nc2(m.r[2 * kk], m.r[2 * kk + 1], g + a * NP + 8 * kk + 2 * t);
+        ldg_nc2(m.i[2 * kk], m.i[2 * kk + 1], g + NP * NP + a * NP + 8 * kk + 2 * t);
     }
 }
 
-// all threads call (TRANS contains a barrier); `in` must be complete and `out` free before the call
+// S: the states of the mat-vecs this matrix will be used for (warps without a state group load nothing)
 template <int NP, bool TRANS>
-__device__ __forceinline__ void matvec_regs(double *out, const double *in, const MatRegs<NP> &m, int S, double *red) {
-    constexpr int KS = MvMap<NP>::KS, KPT = MvMap<NP>::KPT;
-    const int t = threadIdx.x;
-    const bool active = t < MvMap<NP>::ACTIVE;
-    const int a = TRANS ? t % NP : t / KS, ks = TRANS ? t / NP : t % KS;
-    for (int s0 = 0; s0 < S; s0 += kMvGroup) {
-        const int sc = min(kMvGroup, S - s0);
-        if (active) {
+__device__ __forceinline__ void load_mat_regs(MatRegs<NP> &m, const double *__restrict__ g, int S) {
+    using M = MvMap<NP>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = warp % M::TILES, gsel = warp / M::TILES;
+    if (gsel * 4 >= S) return;
 #pragma unroll
-            for (int g = 0; g < kMvGroup; ++g) {
-                if (g < sc) {
-                    const double *vr = in + (s0 + g) * 2 * NP, *vi = vr + NP;
-                    double re = 0., im = 0.;
-#pragma unroll
-                    for (int i = 0; i < KPT; ++i) {
-                        const double br = vr[ks + KS * i], bi = vi[ks + KS * i];
-                        re = fma(m.r[i], br, re); re = fma(-m.i[i], bi, re);
-                        im = fma(m.r[i], bi, im); im = fma(m.i[i], br, im);
-                    }
-                    if (TRANS) {
-                        red[(g * KS + ks) * 2 * NP + a] = re;
-                        red[(g * KS + ks) * 2 * NP + NP + a] = im;
-                    } else {
-#pragma unroll
-                        for (int o = KS / 2; o > 0; o >>= 1) {
-                            re += __shfl_xor_sync(0xffffffffu, re, o);
-                            im += __shfl_xor_sync(0xffffffffu, im, o);
-                        }
-                        if (ks == 0) { out[(s0 + g) * 2 * NP + a] = re; out[(s0 + g) * 2 * NP + NP + a] = im; }
-                    }
-                }
-            }
+    for (int kk = 0; kk < NP / 8; ++kk) load_mat_block<NP, TRANS>(m, g, tile * 8 + (lane >> 2), lane & 3, kk);
+}
+
+// all threads call (contains barriers); `in` must be complete and `out` free before the call; `out` is complete after the
+// caller's next barrier.  vpad: 2 * BATCH * LDV doubles of scratch.  gnext != nullptr: the matrix at gnext is loaded into
+// `nxt` along the way (the loads of k block kk between the DMMAs of k block kk of the warp's first state group).
+template <int NP, bool TRANS>
+__device__ __forceinline__ void matvec_regs(double *out, const double *in, const MatRegs<NP> &m, int S, double *vpad,
+                                            MatRegs<NP> &nxt, const double *__restrict__ gnext) {
+    using M = MvMap<NP>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gi = lane >> 2, t = lane & 3;
+    const int tile = warp % M::TILES, gsel = warp / M::TILES;
+    for (int sb = 0; sb < S; sb += M::BATCH) {
+        const int sc = min(M::BATCH, S - sb);
+        if (sb > 0) __syncthreads();                                 // the fragment loads of the previous batch are done
+        for (int i = threadIdx.x; i < sc * 2 * NP; i += kSwThreads) {
+            const int row = i / NP, col = i - row * NP;
+            vpad[row * M::LDV + col] = in[(size_t)sb * 2 * NP + i];
         }
-        if (TRANS) {
-            __syncthreads();
-            for (int o = t; o < sc * 2 * NP; o += kSweepThreads) {
-                const int g = o / (2 * NP), x = o % (2 * NP);
-                double v = 0.;
+        __syncthreads();
+        for (int gq = gsel; gq * 4 < sc; gq += M::GW) {
+            const int row1 = min(8 * gq + gi, 2 * sc - 1), row2 = row1 ^ 1;      // columns past the last state: never stored
+            const double *p1 = vpad + row1 * M::LDV + 2 * t, *p2 = vpad + row2 * M::LDV + 2 * t;
+            const bool pf = gnext != nullptr && sb == 0 && gq == gsel;
+            double c0 = 0., c1 = 0., d0 = 0., d1 = 0.;
 #pragma unroll
-                for (int k = 0; k < KS; ++k) v += red[(g * KS + k) * 2 * NP + x];
-                out[(s0 + g) * 2 * NP + x] = v;
+            for (int kk = 0; kk < NP / 8; ++kk) {
+                if (pf) load_mat_block<NP, TRANS>(nxt, gnext, tile * 8 + gi, t, kk);
+                const double2 b1 = *reinterpret_cast<const double2 *>(p1 + 8 * kk);
+                const double2 b2 = *reinterpret_cast<const double2 *>(p2 + 8 * kk);
+                dmma884(c0, c1, m.r[2 * kk], b1.x);
+                dmma884(d0, d1, m.i[2 * kk], b2.x);
+                dmma884(c0, c1, m.r[2 * kk + 1], b1.y);
+                dmma884(d0, d1, m.i[2 * kk + 1], b2.y);
             }
-            if (s0 + kMvGroup < S) __syncthreads();             // `red` is reused by the next group
+            // column 2 t = re (B2 carries -Vi there), column 2 t + 1 = im (+Vr)
+            const int s = sb + 4 * gq + t;
+            if (s < S) {
+                out[(size_t)s * 2 * NP + tile * 8 + gi] = c0 - d0;
+                out[(size_t)s * 2 * NP + NP + tile * 8 + gi] = c1 + d1;
+            }
         }
     }
 }
@@ -210,7 +227,7 @@ __device__ __forceinline__ bool is_step_cost_state(int k, int ces) { return k !=
 
 // inner products <v_{t,s,f} | psi_s> for every active term -> ip[2*(ip_off + s*fmax + f)]; one warp per vector
 __device__ void cost_inner_products(const SweepArgs &a, const double *psi, double *ip, bool step_state, bool final_state) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kSweepThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int t = 0; t < a.nterms; ++t) {
         const CostTerm tm = a.terms[t];
         if (!((tm.step && step_state) || (!tm.step && final_state))) continue;
@@ -287,7 +304,7 @@ __device__ void cost_add_seed(const SweepArgs &a, const double *ip, double *lam,
             if (a.coh_in) { const int sl = coh_slot(tm, kglob, a.ces); tr = a.coh_in[2 * sl]; ti = a.coh_in[2 * sl + 1]; }
             else for (int s = 0; s < a.S; ++s) { tr += ip[2 * (tm.ip_off + s * tm.fmax)]; ti += ip[2 * (tm.ip_off + s * tm.fmax) + 1]; }
         }
-        for (int o = threadIdx.x; o < sc * a.NP; o += kSweepThreads) {
+        for (int o = threadIdx.x; o < sc * a.NP; o += blockDim.x) {
             const int sl = o / a.NP, s = sb + sl, b = o % a.NP;
             const int F = a.counts[tm.cnt_off + s];
             double sr = 0., si = 0.;
@@ -325,14 +342,10 @@ __global__ void k_coherent_value(const CostTerm *terms, int nterms, const double
     *cost += val / E;
 }
 
-// dynamic smem layout of the sweep kernels: red (U^T v partial sums) | v0 (S*2*NP) | v1 (S*2*NP) | ip (2*ip_total)
-__host__ __device__ inline size_t sweep_red_doubles(int NP) {
-    const int ks0 = kSweepThreads / NP;
-    const int ks = ks0 > 32 ? (NP < 32 ? NP : 32) : (ks0 > NP ? NP : ks0);       // MvMap<NP>::KS
-    return (size_t)kMvGroup * ks * 2 * NP;
-}
+// dynamic smem layout of the sweep kernels: vpad (padded vector scratch of the mat-vec) | v0 (S*2*NP) | v1 (S*2*NP) | ip (2*ip_total)
+__host__ __device__ inline size_t sweep_pad_doubles(int NP) { return (size_t)2 * 32 * (NP + 8); }   // 2 BATCH rows of LDV
 __host__ __device__ inline size_t sweep_smem_bytes(int NP, int S, int ip_total) {
-    return sizeof(double) * (sweep_red_doubles(NP) + (size_t)4 * S * NP + (size_t)2 * (ip_total > 0 ? ip_total : 1));
+    return sizeof(double) * (sweep_pad_doubles(NP) + (size_t)4 * S * NP + (size_t)2 * (ip_total > 0 ? ip_total : 1));
 }
 // prefix / suffix kernels of the time-sharded path: U (padded) | v0 | v1
 __host__ __device__ inline size_t prefix_smem_bytes(int NP, int S) {
@@ -340,11 +353,11 @@ __host__ __device__ inline size_t prefix_smem_bytes(int NP, int S) {
 }
 
 template <int NP> struct SweepSmem {
-    double *red, *v0, *v1, *ip;
+    double *vpad, *v0, *v1, *ip;
     // S: states held by this CTA
     __device__ __forceinline__ SweepSmem(double *sm, int S) {
-        red = sm;
-        v0 = sm + kMvGroup * MvMap<NP>::KS * 2 * NP; v1 = v0 + S * 2 * NP; ip = v1 + S * 2 * NP;
+        vpad = sm;
+        v0 = sm + 2 * MvMap<NP>::BATCH * MvMap<NP>::LDV; v1 = v0 + S * 2 * NP; ip = v1 + S * 2 * NP;
     }
     __device__ __forceinline__ void swap() { double *t = v0; v0 = v1; v1 = t; }
 };
@@ -361,7 +374,7 @@ template <int NP> struct SweepSmem {
 #endif
 
 template <int NP>
-__global__ void __launch_bounds__(kSweepThreads) k_boundary_fwd(SweepArgs a) {
+__global__ void __launch_bounds__(kSwThreads) k_boundary_fwd(SweepArgs a) {
     extern __shared__ __align__(16) double sm_raw[];
     const int spg = (a.S + gridDim.y - 1) / gridDim.y, sb = blockIdx.y * spg;
     const int S = min(spg, a.S - sb), VS = S * 2 * NP, VSA = a.S * 2 * NP, off = sb * 2 * NP;
@@ -370,21 +383,21 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_fwd(SweepArgs a) {
     const int e = blockIdx.x;
     const int c0 = a.member_chunk0[e], c1 = a.member_chunk0[e + 1];
     MatRegs<NP> cur = {}, nxt = {};
-    load_mat_regs<NP, false>(cur, a.chunkP + (size_t)c0 * 2 * NP * NP);
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = a.psi_in[off + i];
+    load_mat_regs<NP, false>(cur, a.chunkP + (size_t)c0 * 2 * NP * NP, S);
+    for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v0[i] = a.psi_in[off + i];
     double *psi_e = a.psi + (size_t)e * a.N * VSA + off;
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[i] = a.psi_in[off + i];
+    for (int i = threadIdx.x; i < VS; i += kSwThreads) psi_e[i] = a.psi_in[off + i];
     BPROF_DECL
     for (int c = c0; c < c1; ++c) {
-        if (c + 1 < c1) load_mat_regs<NP, false>(nxt, a.chunkP + (size_t)(c + 1) * 2 * NP * NP);
+        const double *gn = c + 1 < c1 ? a.chunkP + (size_t)(c + 1) * 2 * NP * NP : nullptr;   // prefetched inside the mat-vec
         const int kend = a.chunk_begin[c + 1] - e * (a.N - 1);      // state index at the end of chunk c
         BPROF(20);
         __syncthreads();                                            // v0 is complete
         BPROF(21);
-        matvec_regs<NP, false>(sm.v1, sm.v0, cur, S, sm.red);
+        matvec_regs<NP, false>(sm.v1, sm.v0, cur, S, sm.vpad, nxt, gn);
         __syncthreads();
         BPROF(22);
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[(size_t)kend * VSA + i] = sm.v1[i];
+        for (int i = threadIdx.x; i < VS; i += kSwThreads) psi_e[(size_t)kend * VSA + i] = sm.v1[i];
         sm.swap();
         cur = nxt;
         BPROF(23);
@@ -396,7 +409,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_fwd(SweepArgs a) {
 
 // (2) local forward sweeps + cost values; grid = nchunks
 template <int NP>
-__global__ void __launch_bounds__(kSweepThreads) k_sweep_fwd(SweepArgs a) {
+__global__ void __launch_bounds__(kSwThreads) k_sweep_fwd(SweepArgs a) {
     extern __shared__ __align__(16) double sm_raw[];
     const int S = a.S, VS = S * 2 * NP;
     SweepSmem<NP> sm(sm_raw, S);
@@ -406,19 +419,18 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_fwd(SweepArgs a) {
     const double *gU = a.U + (size_t)(e * (a.N - 1)) * 2 * NP * NP;
     double *psi_e = a.psi + (size_t)e * a.N * VS;
     MatRegs<NP> cur = {}, nxt = {};
-    load_mat_regs<NP, false>(cur, gU + (size_t)jb * 2 * NP * NP);
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = psi_e[(size_t)jb * VS + i];
+    load_mat_regs<NP, false>(cur, gU + (size_t)jb * 2 * NP * NP, S);
+    for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v0[i] = psi_e[(size_t)jb * VS + i];
     __syncthreads();
     double cost = 0.;
     for (int j = jb; j < je; ++j) {
         const int k = j + 1;                                          // state produced by slice j
         if (k < je) {
-            if (k + 1 < je) load_mat_regs<NP, false>(nxt, gU + (size_t)k * 2 * NP * NP);
-            matvec_regs<NP, false>(sm.v1, sm.v0, cur, S, sm.red);
+            matvec_regs<NP, false>(sm.v1, sm.v0, cur, S, sm.vpad, nxt, k + 1 < je ? gU + (size_t)k * 2 * NP * NP : nullptr);
             __syncthreads();
-            for (int i = threadIdx.x; i < VS; i += kSweepThreads) psi_e[(size_t)k * VS + i] = sm.v1[i];
+            for (int i = threadIdx.x; i < VS; i += kSwThreads) psi_e[(size_t)k * VS + i] = sm.v1[i];
         } else {
-            for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v1[i] = psi_e[(size_t)k * VS + i];   // boundary state
+            for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v1[i] = psi_e[(size_t)k * VS + i];   // boundary state
             __syncthreads();
         }
         const bool st = is_step_cost_state(k + a.j_off, a.ces), fin = (k + a.j_off == a.Nglob - 1);
@@ -436,7 +448,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_fwd(SweepArgs a) {
 // (3a/3c) local backward sweeps.  PARTICULAR: zero incoming costate, result -> part[c], nothing stored.
 // otherwise: incoming lam[je] read from the lam array (written by k_boundary_bwd), lam[j] stored for j in (jb, je).
 template <int NP, bool PARTICULAR>
-__global__ void __launch_bounds__(kSweepThreads) k_sweep_bwd(SweepArgs a) {
+__global__ void __launch_bounds__(kSwThreads) k_sweep_bwd(SweepArgs a) {
     extern __shared__ __align__(16) double sm_raw[];
     const int S = a.S, VS = S * 2 * NP;
     SweepSmem<NP> sm(sm_raw, S);
@@ -448,12 +460,12 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_bwd(SweepArgs a) {
     double *lam_e = a.lam + (size_t)e * a.N * VS;
     const int jstop = PARTICULAR ? jb : jb + 1;
     MatRegs<NP> cur = {}, nxt = {};
-    load_mat_regs<NP, true>(cur, gU + (size_t)(je - 1) * 2 * NP * NP);
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = PARTICULAR ? 0. : lam_e[(size_t)je * VS + i];
+    load_mat_regs<NP, true>(cur, gU + (size_t)(je - 1) * 2 * NP * NP, S);
+    for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v0[i] = PARTICULAR ? 0. : lam_e[(size_t)je * VS + i];
     __syncthreads();
     for (int j = je - 1; j >= jstop; --j) {
-        if (j - 1 >= jstop) load_mat_regs<NP, true>(nxt, gU + (size_t)(j - 1) * 2 * NP * NP);
-        matvec_regs<NP, true>(sm.v1, sm.v0, cur, S, sm.red);          // lam_j = U_j^T lam_{j+1}
+        matvec_regs<NP, true>(sm.v1, sm.v0, cur, S, sm.vpad, nxt,      // lam_j = U_j^T lam_{j+1}
+                              j - 1 >= jstop ? gU + (size_t)(j - 1) * 2 * NP * NP : nullptr);
         __syncthreads();
         const bool st = is_step_cost_state(j + a.j_off, a.ces);
         if (a.nterms > 0 && st) {                                     // + seed_j (state j < N-1: step costs only)
@@ -461,19 +473,19 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_bwd(SweepArgs a) {
             cost_add_seed(a, sm.ip, sm.v1, true, false, j + a.j_off);
         }
         if (!PARTICULAR)
-            for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)j * VS + i] = sm.v1[i];
+            for (int i = threadIdx.x; i < VS; i += kSwThreads) lam_e[(size_t)j * VS + i] = sm.v1[i];
         sm.swap();
         cur = nxt;
         __syncthreads();
     }
     if (PARTICULAR)
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.part[(size_t)c * VS + i] = sm.v0[i];
+        for (int i = threadIdx.x; i < VS; i += kSwThreads) a.part[(size_t)c * VS + i] = sm.v0[i];
 }
 
 // (3b) boundary costates, sequential over the chunks of one member (last to first); grid = (E, state groups).
 // lam[N-1] = lam_in + seed_{N-1};  lam[b_c] = P_c^T lam[b_{c+1}] + part_c
 template <int NP>
-__global__ void __launch_bounds__(kSweepThreads) k_boundary_bwd(SweepArgs a, int have_part) {
+__global__ void __launch_bounds__(kSwThreads) k_boundary_bwd(SweepArgs a, int have_part) {
     extern __shared__ __align__(16) double sm_raw[];
     const int spg = (a.S + gridDim.y - 1) / gridDim.y, sb = blockIdx.y * spg;
     const int S = min(spg, a.S - sb), VS = S * 2 * NP, VSA = a.S * 2 * NP, off = sb * 2 * NP;
@@ -484,32 +496,82 @@ __global__ void __launch_bounds__(kSweepThreads) k_boundary_bwd(SweepArgs a, int
     const double *psi_e = a.psi + (size_t)e * a.N * VSA;
     double *lam_e = a.lam + (size_t)e * a.N * VSA + off;
     MatRegs<NP> cur = {}, nxt = {};
-    load_mat_regs<NP, true>(cur, a.chunkP + (size_t)(c1 - 1) * 2 * NP * NP);
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v0[i] = a.lam_in ? a.lam_in[off + i] : 0.;
+    load_mat_regs<NP, true>(cur, a.chunkP + (size_t)(c1 - 1) * 2 * NP * NP, S);
+    for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v0[i] = a.lam_in ? a.lam_in[off + i] : 0.;
     __syncthreads();
     if (a.nterms > 0 && a.add_final_seed) {                         // inner products of ALL states (coherent sums)
         const bool st = is_step_cost_state(a.N - 1 + a.j_off, a.ces);
         cost_inner_products(a, psi_e + (size_t)(a.N - 1) * VSA, sm.ip, st, true);
         cost_add_seed(a, sm.ip, sm.v0, st, true, a.N - 1 + a.j_off, sb, S);
     }
-    for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)(a.N - 1) * VSA + i] = sm.v0[i];
+    for (int i = threadIdx.x; i < VS; i += kSwThreads) lam_e[(size_t)(a.N - 1) * VSA + i] = sm.v0[i];
     for (int c = c1 - 1; c >= c0; --c) {
-        if (c - 1 >= c0) load_mat_regs<NP, true>(nxt, a.chunkP + (size_t)(c - 1) * 2 * NP * NP);
         const int kbeg = a.chunk_begin[c] - e * (a.N - 1);
         __syncthreads();
-        matvec_regs<NP, true>(sm.v1, sm.v0, cur, S, sm.red);
+        matvec_regs<NP, true>(sm.v1, sm.v0, cur, S, sm.vpad, nxt, c - 1 >= c0 ? a.chunkP + (size_t)(c - 1) * 2 * NP * NP : nullptr);
         __syncthreads();
         if (have_part) {
-            for (int i = threadIdx.x; i < VS; i += kSweepThreads) sm.v1[i] += a.part[(size_t)c * VSA + off + i];
+            for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v1[i] += a.part[(size_t)c * VSA + off + i];
             __syncthreads();
         }
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) lam_e[(size_t)kbeg * VSA + i] = sm.v1[i];
+        for (int i = threadIdx.x; i < VS; i += kSwThreads) lam_e[(size_t)kbeg * VSA + i] = sm.v1[i];
         sm.swap();
         cur = nxt;
     }
     __syncthreads();
     if (a.b_out && e == 0)
-        for (int i = threadIdx.x; i < VS; i += kSweepThreads) a.b_out[off + i] = sm.v0[i];
+        for (int i = threadIdx.x; i < VS; i += kSwThreads) a.b_out[off + i] = sm.v0[i];
+}
+
+// ---- three-level scheme (single member, no step costs): the sequential boundary passes run on COARSE chunks (2^d sweep
+// chunks each); these kernels fill in the states / costates at the sweep-chunk boundaries inside every coarse chunk, all
+// coarse chunks at once.  grid = (coarse chunks, state groups); a.chunkP / a.chunk_begin: sweep level; span = 2^d.
+template <int NP>
+__global__ void __launch_bounds__(kSwThreads) k_mid_fwd(SweepArgs a, int nfine, int span) {
+    extern __shared__ __align__(16) double sm_raw[];
+    const int spg = (a.S + gridDim.y - 1) / gridDim.y, sb = blockIdx.y * spg;
+    const int S = min(spg, a.S - sb), VS = S * 2 * NP, VSA = a.S * 2 * NP, off = sb * 2 * NP;
+    const int c0 = blockIdx.x * span, c1 = min(c0 + span, nfine);
+    if (S <= 0 || c1 - c0 < 2) return;               // the end state of the last sweep chunk is the coarse pass's
+    SweepSmem<NP> sm(sm_raw, S);
+    MatRegs<NP> cur = {}, nxt = {};
+    load_mat_regs<NP, false>(cur, a.chunkP + (size_t)c0 * 2 * NP * NP, S);
+    double *psi_e = a.psi + off;
+    for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v0[i] = psi_e[(size_t)a.chunk_begin[c0] * VSA + i];
+    for (int c = c0; c < c1 - 1; ++c) {
+        const double *gn = c + 2 < c1 ? a.chunkP + (size_t)(c + 1) * 2 * NP * NP : nullptr;
+        const int kend = a.chunk_begin[c + 1];
+        __syncthreads();
+        matvec_regs<NP, false>(sm.v1, sm.v0, cur, S, sm.vpad, nxt, gn);
+        __syncthreads();
+        for (int i = threadIdx.x; i < VS; i += kSwThreads) psi_e[(size_t)kend * VSA + i] = sm.v1[i];
+        sm.swap();
+        cur = nxt;
+    }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kSwThreads) k_mid_bwd(SweepArgs a, int nfine, int span) {
+    extern __shared__ __align__(16) double sm_raw[];
+    const int spg = (a.S + gridDim.y - 1) / gridDim.y, sb = blockIdx.y * spg;
+    const int S = min(spg, a.S - sb), VS = S * 2 * NP, VSA = a.S * 2 * NP, off = sb * 2 * NP;
+    const int c0 = blockIdx.x * span, c1 = min(c0 + span, nfine);
+    if (S <= 0 || c1 - c0 < 2) return;
+    SweepSmem<NP> sm(sm_raw, S);
+    MatRegs<NP> cur = {}, nxt = {};
+    load_mat_regs<NP, true>(cur, a.chunkP + (size_t)(c1 - 1) * 2 * NP * NP, S);
+    double *lam_e = a.lam + off;
+    for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v0[i] = lam_e[(size_t)a.chunk_begin[c1] * VSA + i];
+    for (int c = c1 - 1; c > c0; --c) {                              // costate at the beginning of sweep chunk c
+        const double *gn = c - 1 > c0 ? a.chunkP + (size_t)(c - 1) * 2 * NP * NP : nullptr;
+        const int kbeg = a.chunk_begin[c];
+        __syncthreads();
+        matvec_regs<NP, true>(sm.v1, sm.v0, cur, S, sm.vpad, nxt, gn);
+        __syncthreads();
+        for (int i = threadIdx.x; i < VS; i += kSwThreads) lam_e[(size_t)kbeg * VSA + i] = sm.v1[i];
+        sm.swap();
+        cur = nxt;
+    }
 }
 
 template <int NP> struct PrefixSmem {
