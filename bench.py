@@ -362,6 +362,10 @@ def run_b200(args, name):
                         "peak_source": "FP64 DMMA pipe measured on this pool (profiles/r01_microbench_fp64.jsonl); "
                                        "MEASURED_PEAKS.json has HBM and bf16 only",
                         "algorithmic_flops_per_launch": dom_flops,
+                        "flop_model": "SURVEY 8(d): 4-real-multiplication complex products, c commutator products per slice, dense "
+                                      "reverse pass; the kernels execute fewer (3M products = 0.75, constant commutators tabulated, "
+                                      "Hermitian half products and the rank-S reverse pass at n = 64), so frac measures speed "
+                                      "against the algorithmic work and may exceed the pipe utilisation ncu reports",
                         "whole_eval_tflops": total_flops / (ms_per_step * 1e-3) / 1e12,
                         "whole_eval_frac": total_flops / (ms_per_step * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS / world},
            "stage_ms": stage_ms, "clocks": clocks, "cost": err}

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(C::NT) k_backward(KArgs a, const __grid_consta
                 const bool stored = tape != ctape;
                 tf.map = tmaps.tma ? (stored ? &tmaps.mapT : &tmaps.mapC) : nullptr;
                 tf.idx0 = stored ? (long long)w * a.tape_mats : (long long)c * (8 + kCtaTapeR);
-                pade_backward_krylov<C>(sm, tf, piv, psi, psi + VS, lam, a.S);
+                pade_backward_krylov<C>(sm, tf, piv, psi, psi + VS, lam, a.S, a.herm);
                 done = true;
             } else if (a.S <= 4 && s == 0 && a.lowrank == 1) {         // rank-S reverse pass, re-associated form (lowrank.cuh)
                 PROF_MARK(9);
@@ -1364,8 +1364,8 @@ int enqueue_expm_forward(qocb_plan *p, bool with_grad, cudaEvent_t mid = nullptr
 // product of all chunk propagators of this shard (member 0) -> out_dev[GMAT]
 int enqueue_shard_propagator(qocb_plan *p, double *out_dev) {
     const size_t GM = 2 * (size_t)p->NP * p->NP;
-    const double *in = p->levels > 0 ? p->lvlP.p + (size_t)p->lvl_off[p->levels] * GM : p->chunkP.p;   // continue the tree
-    int count = p->lvl_count[p->levels];
+    const double *in = p->coarse > 0 ? p->lvlP.p + (size_t)p->lvl_off[p->coarse] * GM : p->chunkP.p;   // continue the tree
+    int count = p->lvl_count[p->coarse];
     double *bufs[2] = {p->redA.p, p->redB.p};
     int which = 0;
     if (count == 1) {
@@ -1598,7 +1598,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
         p->lv2 = p->lv3s = p->lv3c = best;
         // three levels (one member, unsharded): boundary passes on level lc, the fill-in passes 2^(lc - ls) steps, sweeps
         // on level ls - in as many waves as its chunks need (one CTA per SM)
-        if (E == 1 && !sliced && !st_sharded && !is_large && pb->chunks_per_member <= 0) {
+        if (E == 1 && !st_sharded && !is_large && pb->chunks_per_member <= 0) {
             double best3 = best_t;
             for (int ls = 0; ls <= maxl; ++ls)
                 for (int lc = ls + 1; lc <= maxl; ++lc) {
@@ -2202,8 +2202,8 @@ static int launch_count_unmapped(qocb_plan *p, int32_t with_grad) {
     const int pa = (with_grad && pm && p->post_adj_ok && p->pb.control_count > 0) ? 2 : 0;                            // k_magnus_adj, k_magnus_adj_final
     const int mids = p->coarse > p->levels ? (with_grad ? 2 : 1) : 0;                                                 // k_mid_fwd, k_mid_bwd
     if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->coarse + mids + pm + pa;
-    int levels = p->levels + pm;                                          // pairwise levels for the sweeps, then radix 4 to the root
-    for (int c = p->lvl_count[p->levels]; c > 1; c = (c + 3) / 4) ++levels;
+    int levels = p->coarse + mids + pm;                                   // pairwise levels for the sweeps, then radix 4 to the root
+    for (int c = p->lvl_count[p->coarse]; c > 1; c = (c + 3) / 4) ++levels;
     // forward: expm, tree, prefix, boundary, sweep; backward: [particular sweeps], boundary (twice only with step costs on a
     // shard that is not the last), suffix, sweep, expm, gather, finalize, pack
     const int nb = (p->have_step_costs && !p->owns_final) ? 2 : 1;

@@ -854,7 +854,7 @@ __device__ __forceinline__ void tape_wait(const TapeFeed &tf, uint64_t *bar, uin
 
 template <class C>
 __device__ void pade_backward_krylov(const Smem<C> &sm, const TapeFeed &tf, const int *tperm, const double *psi, const double *psi1,
-                                     const double *lam1, int S) {
+                                     const double *lam1, int S, int herm = 0) {
     static_assert(C::NP == 64 && C::NWARP == 8, "the Krylov reverse pass is laid out for NP = 64 with 8 warps");
     PROF_DECL
     constexpr int NP = C::NP, LD = LR_LD, PL = LR_PL, TLD = LR_TLD, TPL = LR_TPL, ELD = 8, EPL = NP * ELD;
@@ -968,15 +968,33 @@ __device__ void pade_backward_krylov(const Smem<C> &sm, const TapeFeed &tf, cons
     __syncthreads();                                                // LEFT / RIGHT are dead
     for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(X1, row, col, accv<C>(acc, i, j)); });
     __syncthreads();
+    // anti-Hermitian A (Hermitian operators, real controls): every direction dM is anti-Hermitian, so only the
+    // anti-Hermitian part of mbar reaches the gradient, and with A^T = -conj(A)
+    //     mbar - mbar^H = Z - Z^H,   Z = l (Y p)^T + (a2bar + a2bar^H) A^T
+    // - one dense product instead of two.  sym(+1): X <- X + X^H, sym(-1): X <- (X - X^H) / 2, in place in two phases.
+    auto sym = [&](double *X, double sg, double scale) {
+        c2 hv[C::TM * C::TN];
+        for_owned<C>([&](int i, int j, int row, int col) {
+            const c2 v = lds2<C>(X, row, col);
+            const double tr0 = X[col * C::LD + row], tr1 = X[(col + 1) * C::LD + row];
+            const double ti0 = X[C::PLANE + col * C::LD + row], ti1 = X[C::PLANE + (col + 1) * C::LD + row];
+            hv[i * C::TN + j] = {scale * (v.r0 + sg * tr0), scale * (v.r1 + sg * tr1), scale * (v.i0 - sg * ti0), scale * (v.i1 - sg * ti1)};
+        });
+        __syncthreads();
+        for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(X, row, col, hv[i * C::TN + j]); });
+        __syncthreads();
+    };
+    if (herm) sym(X1, 1.0, 1.0);
     tape_wait(tf, tf.bar0, tf.ph0);
     // ---- stage 6: mbar = l (Y p)^T + a2bar A^T + A^T a2bar
     acc.zero();
     mma_lowrank<C, ELD, EPL, ELD, EPL>(acc, EL, 0, EL, 4, 4);
     mma_smem<C, false, true, false>(acc, X1, X0);
-    mma_smem<C, true, false, false>(acc, X0, X1);
+    if (!herm) mma_smem<C, true, false, false>(acc, X0, X1);
     __syncthreads();
     for_owned<C>([&](int i, int j, int row, int col) { sts2<C>(X0, row, col, accv<C>(acc, i, j)); });
     __syncthreads();
+    if (herm) sym(X0, -1.0, 0.5);
     PROF_MARK(12);
 }
 
