@@ -880,6 +880,7 @@ __device__ void pade_backward_krylov(const Smem<C> &sm, const TapeFeed &tf, cons
     for (int c = threadIdx.x; c < NP; c += C::NT) sm.piv[c] = tperm[c];
     __syncthreads();
     tape_wait(tf, tf.bar0, tf.ph0);
+    PROF_MARK(43);
     // ---- stage 1: l = Q^-T lam (thin solve on PP1[:, 0:8]); the LU factors are dead afterwards: A2 -> X0
     lu_solve_thin_T<C, TLD, TPL>(X0, PP1);
     tape_fetch<C>(tf, X0, T_A2, tf.bar0);
@@ -894,6 +895,7 @@ __device__ void pade_backward_krylov(const Smem<C> &sm, const TapeFeed &tf, cons
     }
     __syncthreads();
     tape_wait(tf, tf.bar1, tf.ph1);
+    PROF_MARK(44);
     // ---- stage 2: a = A^T l (A in X1) -> PP1[:, 0:4]
     {
         const c2 v = thin_tile<C, true, TLD, TPL>(X1, PP1, warp, 0);
@@ -921,6 +923,7 @@ __device__ void pade_backward_krylov(const Smem<C> &sm, const TapeFeed &tf, cons
     }
     __syncthreads();
     tape_wait(tf, tf.bar0, tf.ph0);
+    PROF_MARK(45);
     // ---- stage 4: the two Krylov chains with B = A2 in X0
     {
         double *cur = PP0, *nxt = PP1;
@@ -960,6 +963,7 @@ __device__ void pade_backward_krylov(const Smem<C> &sm, const TapeFeed &tf, cons
             double *tmp = cur; cur = nxt; nxt = tmp;
         }
     }
+    PROF_MARK(46);
     // ---- stage 5: A2 is dead: A -> X0 (asynchronous) while a2bar = [L_b A2^T L_b A2^T A2^T L_b] [X_a X_b X_c]^T is formed
     tape_fetch<C>(tf, X0, T_A, tf.bar0);
     Acc<C> acc;
@@ -986,6 +990,7 @@ __device__ void pade_backward_krylov(const Smem<C> &sm, const TapeFeed &tf, cons
     };
     if (herm) sym(X1, 1.0, 1.0);
     tape_wait(tf, tf.bar0, tf.ph0);
+    PROF_MARK(47);
     // ---- stage 6: mbar = l (Y p)^T + a2bar A^T + A^T a2bar
     acc.zero();
     mma_lowrank<C, ELD, EPL, ELD, EPL>(acc, EL, 0, EL, 4, 4);

@@ -288,16 +288,12 @@ __device__ __forceinline__ c2 add_diag(c2 v, int row, int col, double d) {
 }
 
 // cooperative copy global (dense planar) -> shared (padded planar); caller provides the barriers
+// global -> shared copy of one planar matrix.  cp.async keeps all of a thread's 16-byte chunks in flight at once (a loop of
+// load / store pairs whose trip count the compiler cannot see is one L2 round trip per chunk: 16 of them at NP = 64);
+// the data is visible to the other threads after the caller's next barrier, as with plain stores.
 template <class C> __device__ __forceinline__ void g2s(double *__restrict__ s, const double *__restrict__ g) {
-    constexpr int CH = C::GMAT / 2;            // 16-byte chunks
-    constexpr int RCH = C::NP / 2;
-    for (int idx = threadIdx.x; idx < CH; idx += C::NT) {
-        const int plane = idx / (C::GPLANE / 2);
-        const int rem = idx - plane * (C::GPLANE / 2);
-        const int row = rem / RCH, cc = rem - row * RCH;
-        const double2 v = reinterpret_cast<const double2 *>(g)[idx];
-        *reinterpret_cast<double2 *>(s + plane * C::PLANE + row * C::LD + cc * 2) = v;
-    }
+    g2s_async<C>(s, g);
+    g2s_async_wait();
 }
 template <class C> __device__ __forceinline__ void s2g(double *__restrict__ g, const double *__restrict__ s) {
     constexpr int CH = C::GMAT / 2;

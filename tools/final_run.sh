@@ -21,3 +21,5 @@ ncu -i /tmp/${TAG}_$k.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_${k}_raw.
 ncu -i /tmp/${TAG}_$k.ncu-rep --page source --print-source cuda,sass --csv > gpurun_out/${TAG}_ncu_${k}_source.csv 2>/dev/null
 ls -la gpurun_out/${TAG}_ncu_${k}_*.csv
 done
+# launch list of the default bench command (per-launch durations; cold cache, serialised)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launches.log 2>&1; tail -2 gpurun_out/${TAG}_launches.log | cut -c 1-200

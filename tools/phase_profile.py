@@ -57,6 +57,10 @@ for k, nm in ((32, "scale A + store"), (33, "A2 product"), (34, "A2 store"), (35
               (38, "A6 store + epilogue"), (39, "A6 W1 product (half path: + A6 X1)"), (42, "epilogue + A6 X1 product (full path)"),
               (40, "epilogues + A reload"), (41, "Uo product"), (3, "Uo store + P, Q")):
     print("    poly: %-41s %8.2f us/slice" % (nm, us[k]))
+for k, nm in ((43, "stage 0: thin blocks + wait for LU"), (44, "stage 1: thin transposed solve + unpermute (+ wait A)"),
+              (45, "stages 2-3: a = A^T l, chain start (+ wait A2)"), (46, "stage 4: two Krylov chains (6 steps)"),
+              (47, "stage 5: rank-48 product + H = a2bar + a2bar^H (+ wait A)"), (12, "stage 6: dense product + anti-Hermitian part")):
+    print("    krylov: %-50s %8.2f us/slice" % (nm, us[k]))
 steps = max(v[24], 1.0)
 print("boundary forward pass (CTA 0,0), per chunk step over %d steps:" % int(steps))
 for k, nm in ((20, "issue prefetch of next propagator"), (21, "wait for current propagator + barrier"), (22, "mat-vec + barrier"), (23, "store boundary state")):
