@@ -55,13 +55,23 @@ template <int LD, int PL> __device__ __forceinline__ void st_thin(double *M, int
     *reinterpret_cast<double2 *>(M + PL + row * LD + col) = make_double2(v.i0, v.i1);
 }
 
-// one 8 x 8 output tile (row tile rt) of op(M) * B[:, c0:c0+8], M = 64 x 64 in C layout
+// one 8 x 8 output tile (row tile rt) of op(M) * B[:, c0:c0+8], M = 64 x 64 in C layout.  The three 3M partial products
+// are accumulated over the whole contraction and recombined once (dependent DMMAs are three issues apart)
 template <class C, bool TA, int LDB, int PLB>
 __device__ __forceinline__ c2 thin_tile(const double *M, const double *B, int rt, int c0) {
-    c2 acc = czero();
-#pragma unroll 2
-    for (int kt = 0; kt < C::NP / 8; ++kt) tile_mma_thin<C, TA, MASK_NONE, false, LDB, PLB>(acc, M, rt * 8, kt * 8, B, kt * 8, c0);
-    return acc;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double p1a = 0., p1b = 0., p2a = 0., p2b = 0., p3a = 0., p3b = 0.;
+#pragma unroll 4
+    for (int ks = 0; ks < C::NP / 4; ++ks) {
+        double ar, ai;
+        ld_afrag<C, TA, MASK_NONE>(M, rt * 8, 4 * ks, g, t, ar, ai);
+        const int bidx = (4 * ks + t) * LDB + c0 + g;
+        const double br = B[bidx], bi = B[PLB + bidx];
+        dmma884(p1a, p1b, ar, br);
+        dmma884(p2a, p2b, ai, bi);
+        dmma884(p3a, p3b, ar + ai, br + bi);
+    }
+    return {p1a - p2a, p1b - p2b, p3a - p1a - p2a, p3b - p1b - p2b};
 }
 
 // acc += L[:, lc0:lc0+K] * R[:, rc0:rc0+K]^T  (L, R thin matrices; K a multiple of 4), warp tiling of Cfg
