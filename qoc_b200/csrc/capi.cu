@@ -486,6 +486,7 @@ struct qocb_plan {
     // three-level scheme: the sequential boundary passes run on level `coarse` >= levels, k_mid_* fill in the sweep-chunk
     // boundaries (coarse == levels: two levels).  lv2 / lv3s, lv3c: the choices with / without step costs (pick_levels)
     int coarse = 0, lv2 = 0, lv3s = 0, lv3c = 0;
+    DevBuf<double> part_coarse;         // [lvl_count[coarse]][S][2][NP] particular parts of the coarse chunks (step costs)
     bool sharded = false, owns_final = true;
     bool ops_set = false, states_set = false, have_step_costs = false, comm_ok = false;
     cudaStream_t stream = nullptr;
@@ -668,10 +669,11 @@ SweepArgs make_bargs(qocb_plan *p) {
     }
     return s;
 }
-// step costs couple the chunks of the costate pass through their particular parts, which the three-level scheme does not
-// carry: two levels then (called whenever the cost list changes)
+// called whenever the cost list changes.  With step costs the chunks of the costate pass are coupled through their particular
+// parts: k_mid_bwd<PARTICULAR> combines those of the sweep chunks into one per coarse chunk before the coarse pass
 void pick_levels(qocb_plan *p) {
-    if (p->have_step_costs) { p->levels = p->lv2; p->coarse = p->lv2; }
+    const char *n3 = getenv("QOCB_THREE_LEVEL_STEP");                // "0": step-cost plans stay on two levels (A/B)
+    if (p->have_step_costs && n3 && n3[0] == '0') { p->levels = p->lv2; p->coarse = p->lv2; }
     else { p->levels = p->lv3s; p->coarse = p->lv3c; }
 }
 
@@ -1409,15 +1411,19 @@ int enqueue_costate(qocb_plan *p, const double *lam_in_dev, double *b_out_dev, b
     const size_t sw_smem = sweep_smem_bytes(p->NP, sa.S, p->ip_total);
     if (do_particular && p->have_step_costs) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, true><<<p->lvl_count[p->levels], kSwThreads, sw_smem, p->stream>>>(sa)));
     const dim3 bgrid(sa.E, boundary_state_groups(p));
+    const bool three = p->coarse > p->levels;
+    const dim3 mgrid(p->lvl_count[p->coarse], boundary_state_groups(p));
+    const int nfine = p->lvl_count[p->levels], span = 1 << (p->coarse - p->levels), hp = p->have_step_costs ? 1 : 0;
+    if (three && do_particular && p->have_step_costs)
+        SWEEP_NP(p->NP, (k_mid_bwd<NPc, true><<<mgrid, kSwThreads, sw_smem, p->stream>>>(sa, nfine, span, 1, p->part_coarse.p)));
     if (do_boundary) {
         SweepArgs ba = make_bargs(p);
         ba.lam_in = lam_in_dev; ba.b_out = b_out_dev;
-        SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<bgrid, kSwThreads, sw_smem, p->stream>>>(ba, p->have_step_costs ? 1 : 0)));
+        if (three) ba.part = p->part_coarse.p;
+        SWEEP_NP(p->NP, (k_boundary_bwd<NPc><<<bgrid, kSwThreads, sw_smem, p->stream>>>(ba, hp)));
     }
-    if (do_sweeps && p->coarse > p->levels) {
-        const dim3 mgrid(p->lvl_count[p->coarse], boundary_state_groups(p));
-        SWEEP_NP(p->NP, (k_mid_bwd<NPc><<<mgrid, kSwThreads, sw_smem, p->stream>>>(sa, p->lvl_count[p->levels], 1 << (p->coarse - p->levels))));
-    }
+    if (do_sweeps && three)
+        SWEEP_NP(p->NP, (k_mid_bwd<NPc, false><<<mgrid, kSwThreads, sw_smem, p->stream>>>(sa, nfine, span, hp, nullptr)));
     if (do_sweeps) SWEEP_NP(p->NP, (k_sweep_bwd<NPc, false><<<p->lvl_count[p->levels], kSwThreads, sw_smem, p->stream>>>(sa)));
     CU_TRY(p, cudaGetLastError());
     return 0;
@@ -1672,7 +1678,7 @@ int qocb_plan_create(const qocb_problem *pb, qocb_plan **out) {
     PTRY(p->chunkP.alloc((size_t)p->nchunks * GM));
     const size_t VS = (size_t)S * 2 * NP;
     PTRY(p->psi.alloc((size_t)E * N * VS)); PTRY(p->lam.alloc((size_t)E * N * VS));
-    PTRY(p->part.alloc((size_t)p->nchunks * VS)); PTRY(p->cost_part.alloc(p->nchunks)); PTRY(p->psi0.alloc(VS));
+    PTRY(p->part.alloc((size_t)p->nchunks * VS)); PTRY(p->part_coarse.alloc((size_t)p->nchunks * VS)); PTRY(p->cost_part.alloc(p->nchunks)); PTRY(p->psi0.alloc(VS));
     if (sliced) {
         PTRY(p->redA.alloc((size_t)((p->nchunks + 1) / 2) * GM)); PTRY(p->redB.alloc((size_t)((p->nchunks + 3) / 4) * GM));
         PTRY(p->psi_in.alloc(VS)); PTRY(p->lam_in.alloc(VS));
@@ -2200,7 +2206,7 @@ static int launch_count_unmapped(qocb_plan *p, int32_t with_grad) {
     }
     const int pm = (p->premagnus_ok && (p->pb.magnus_order == 2 || (p->pb.magnus_order == 4 && p->comm_ok))) ? 1 : 0;   // k_magnus
     const int pa = (with_grad && pm && p->post_adj_ok && p->pb.control_count > 0) ? 2 : 0;                            // k_magnus_adj, k_magnus_adj_final
-    const int mids = p->coarse > p->levels ? (with_grad ? 2 : 1) : 0;                                                 // k_mid_fwd, k_mid_bwd
+    const int mids = p->coarse > p->levels ? (with_grad ? 2 + (p->have_step_costs ? 1 : 0) : 1) : 0;                  // k_mid_fwd, k_mid_bwd (+ particular)
     if (!p->sharded) return (with_grad ? (p->have_step_costs ? 9 : 8) : 4) + p->coarse + mids + pm + pa;
     int levels = p->coarse + mids + pm;                                   // pairwise levels for the sweeps, then radix 4 to the root
     for (int c = p->lvl_count[p->coarse]; c > 1; c = (c + 3) / 4) ++levels;

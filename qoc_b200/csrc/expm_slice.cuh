@@ -932,8 +932,13 @@ __device__ void pade_backward_krylov(const Smem<C> &sm, const TapeFeed &tf, cons
 #pragma unroll 1
         for (int k = 0; k < 6; ++k) {
             const int kk = k + 1;                                   // power produced in this step
-            const c2 v = thin_tile<C, false, TLD, TPL>(X0, cur, warp, 0);
+            const int off0 = (k % 3) * 16 + (k / 3) * 8, off1 = (kk % 3) * 16 + (kk / 3) * 8;   // KL[k], KL[kk] in LEFT
+            c2 v, w;
+            const bool pair = herm && k < 5;                        // Hermitian A2: both chains from one pass over X0
+            if (pair) thin_tile_pair<C, TLD, TPL, LD, PL>(X0, cur, 0, LEFT, off0, warp, v, w);
+            else v = thin_tile<C, false, TLD, TPL>(X0, cur, warp, 0);
             st_thin<TLD, TPL>(nxt, warp * 8, 0, v);
+            if (pair) st_thin<LD, PL>(LEFT, warp * 8, off1, w);      // KL[kk] = B^T KL[k] (other columns than off0)
             // contributions of B^kk p / B^kk m to X_a, X_b, X_c (sub-blocks 0 / 1 and 2 / 3) and to Y p
             double *Rr = RIGHT + frow * LD, *Ri = RIGHT + PL + frow * LD;
 #pragma unroll
@@ -955,10 +960,8 @@ __device__ void pade_backward_krylov(const Smem<C> &sm, const TapeFeed &tf, cons
                 double *Er = EL + frow * ELD + 4 + cc, *Ei = EL + EPL + frow * ELD + 4 + cc;
                 Er[0] += b * v.r0; Er[1] += b * v.r1; Ei[0] += b * v.i0; Ei[1] += b * v.i1;
             }
-            if (k < 5) {                                            // KL[kk] = B^T KL[k]
-                const int off0 = (k % 3) * 16 + (k / 3) * 8, off1 = (kk % 3) * 16 + (kk / 3) * 8;
+            if (k < 5 && !pair)                                     // KL[kk] = B^T KL[k]
                 st_thin<LD, PL>(LEFT, warp * 8, off1, thin_tile<C, true, LD, PL>(X0, LEFT, warp, off0));
-            }
             __syncthreads();
             double *tmp = cur; cur = nxt; nxt = tmp;
         }

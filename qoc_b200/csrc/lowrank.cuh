@@ -74,6 +74,33 @@ __device__ __forceinline__ c2 thin_tile(const double *M, const double *B, int rt
     return {p1a - p2a, p1b - p2b, p3a - p1a - p2a, p3b - p1b - p2b};
 }
 
+// Two thin products with ONE matrix in one pass (Hermitian M only): v1 = M * B1[:, c1:c1+8] and v2 = M^T * B2[:, c2:c2+8],
+// the second as conj(M * conj(B2)) since M^T = conj(M) - both read the same A fragments, and the six 3M chains interleave
+template <class C, int LDB1, int PLB1, int LDB2, int PLB2>
+__device__ __forceinline__ void thin_tile_pair(const double *M, const double *B1, int col1, const double *B2, int col2, int rt,
+                                               c2 &v1, c2 &v2) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double p1a = 0., p1b = 0., p2a = 0., p2b = 0., p3a = 0., p3b = 0.;
+    double q1a = 0., q1b = 0., q2a = 0., q2b = 0., q3a = 0., q3b = 0.;
+#pragma unroll 4
+    for (int ks = 0; ks < C::NP / 4; ++ks) {
+        double ar, ai;
+        ld_afrag<C, false, MASK_NONE>(M, rt * 8, 4 * ks, g, t, ar, ai);
+        const double as = ar + ai;
+        const int i1 = (4 * ks + t) * LDB1 + col1 + g, i2 = (4 * ks + t) * LDB2 + col2 + g;
+        const double br = B1[i1], bi = B1[PLB1 + i1];
+        const double cr = B2[i2], ci = -B2[PLB2 + i2];
+        dmma884(p1a, p1b, ar, br);
+        dmma884(q1a, q1b, ar, cr);
+        dmma884(p2a, p2b, ai, bi);
+        dmma884(q2a, q2b, ai, ci);
+        dmma884(p3a, p3b, as, br + bi);
+        dmma884(q3a, q3b, as, cr + ci);
+    }
+    v1 = {p1a - p2a, p1b - p2b, p3a - p1a - p2a, p3b - p1b - p2b};
+    v2 = {q1a - q2a, q1b - q2b, -(q3a - q1a - q2a), -(q3b - q1b - q2b)};
+}
+
 // acc += L[:, lc0:lc0+K] * R[:, rc0:rc0+K]^T  (L, R thin matrices; K a multiple of 4), warp tiling of Cfg
 template <class C, int LDL, int PLL, int LDR, int PLR>
 __device__ __forceinline__ void mma_lowrank(Acc<C> &acc, const double *L, int lc0, const double *R, int rc0, int K) {

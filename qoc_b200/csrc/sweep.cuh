@@ -550,28 +550,40 @@ __global__ void __launch_bounds__(kSwThreads) k_mid_fwd(SweepArgs a, int nfine, 
     }
 }
 
-template <int NP>
-__global__ void __launch_bounds__(kSwThreads) k_mid_bwd(SweepArgs a, int nfine, int span) {
+// PARTICULAR (step costs): zero incoming costate, the particular parts of the sweep chunks (a.part) combine into the
+// particular part of the coarse chunk -> part_out[coarse chunk]; nothing else stored.  Otherwise: incoming costate = the
+// coarse pass's value at the end of the coarse chunk, costates at the sweep-chunk beginnings stored (have_part: + part[c]).
+template <int NP, bool PARTICULAR>
+__global__ void __launch_bounds__(kSwThreads) k_mid_bwd(SweepArgs a, int nfine, int span, int have_part, double *part_out) {
     extern __shared__ __align__(16) double sm_raw[];
     const int spg = (a.S + gridDim.y - 1) / gridDim.y, sb = blockIdx.y * spg;
     const int S = min(spg, a.S - sb), VS = S * 2 * NP, VSA = a.S * 2 * NP, off = sb * 2 * NP;
     const int c0 = blockIdx.x * span, c1 = min(c0 + span, nfine);
-    if (S <= 0 || c1 - c0 < 2) return;
+    if (S <= 0 || c1 <= c0 || (!PARTICULAR && c1 - c0 < 2)) return;
     SweepSmem<NP> sm(sm_raw, S);
     MatRegs<NP> cur = {}, nxt = {};
     load_mat_regs<NP, true>(cur, a.chunkP + (size_t)(c1 - 1) * 2 * NP * NP, S);
     double *lam_e = a.lam + off;
-    for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v0[i] = lam_e[(size_t)a.chunk_begin[c1] * VSA + i];
-    for (int c = c1 - 1; c > c0; --c) {                              // costate at the beginning of sweep chunk c
-        const double *gn = c - 1 > c0 ? a.chunkP + (size_t)(c - 1) * 2 * NP * NP : nullptr;
+    for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v0[i] = PARTICULAR ? 0. : lam_e[(size_t)a.chunk_begin[c1] * VSA + i];
+    const int clast = PARTICULAR ? c0 : c0 + 1;
+    for (int c = c1 - 1; c >= clast; --c) {                          // costate at the beginning of sweep chunk c
+        const double *gn = c - 1 >= clast ? a.chunkP + (size_t)(c - 1) * 2 * NP * NP : nullptr;
         const int kbeg = a.chunk_begin[c];
         __syncthreads();
         matvec_regs<NP, true>(sm.v1, sm.v0, cur, S, sm.vpad, nxt, gn);
         __syncthreads();
-        for (int i = threadIdx.x; i < VS; i += kSwThreads) lam_e[(size_t)kbeg * VSA + i] = sm.v1[i];
+        if (have_part) {
+            for (int i = threadIdx.x; i < VS; i += kSwThreads) sm.v1[i] += a.part[(size_t)c * VSA + off + i];
+            __syncthreads();
+        }
+        if (!PARTICULAR)
+            for (int i = threadIdx.x; i < VS; i += kSwThreads) lam_e[(size_t)kbeg * VSA + i] = sm.v1[i];
         sm.swap();
         cur = nxt;
     }
+    __syncthreads();
+    if (PARTICULAR)
+        for (int i = threadIdx.x; i < VS; i += kSwThreads) part_out[(size_t)blockIdx.x * VSA + off + i] = sm.v0[i];
 }
 
 template <int NP> struct PrefixSmem {
