@@ -23,3 +23,4 @@ ls -la gpurun_out/${TAG}_ncu_${k}_*.csv
 done
 # launch list of the default bench command (per-launch durations; cold cache, serialised)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launches.log 2>&1; tail -2 gpurun_out/${TAG}_launches.log | cut -c 1-200
+timeout 300 python tools/phase_profile.py > gpurun_out/${TAG}_phases.txt 2>&1; tail -45 gpurun_out/${TAG}_phases.txt
