@@ -339,6 +339,35 @@ def test_lowrank_and_commutator_paths_match_dense(monkeypatch):
     assert abs(e1 - e2) < 1e-13 and rel(f1, f2) < 1e-12 and rel(g1, g2) < 1e-11
 
 
+VARIANTS = [{"QOCB_NO_NOPIV": "1"}, {"QOCB_NO_THREE_LEVEL": "1"}, {"QOCB_THREE_LEVEL_STEP": "0"}, {"QOCB_NO_TMA": "1"},
+            {"QOCB_NO_PREMAGNUS": "1"}, {"QOCB_LOWRANK": "1"}, {"QOCB_NO_LOWRANK": "1", "QOCB_NO_NOPIV": "1"}]
+
+
+@pytest.mark.parametrize("F,ces", [(0, 1), (2, 3)], ids=["final_cost", "step_costs"])
+def test_fast_paths_match_general_paths(monkeypatch, F, ces):
+    """Hermitian operators select the half products, the pivot-free LU, the one-product reverse stage and (with enough slices)
+    the three-level boundary scheme; every A/B switch must reproduce the default result, and the default the oracle."""
+    std, Plan, pol = product()
+    orc = oracle_mod()
+    p = Problem(64, 310, 3, 4, 4, complex_controls=False, F=F, seed=23, cost_eval_step=ces)
+    kw = dict(control_eval_count=p.M, control_count=3, magnus_policy=pol[4], cost_eval_step=ces)
+    plan = Plan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, **kw)
+    e0, g0, f0 = plan.cost_and_grad(p.controls)
+    plan.close()
+    o_err, o_grad, o_fin = orc.schroedinger_cost_and_grad(p.controls, orc.make_hamiltonian(p.h0, p.drives, False),
+                                                          p.initial_states, p.costs(orc), p.T, p.N, order=4, cost_eval_step=ces)
+    assert abs(e0 - o_err) <= RTOL * max(abs(o_err), 1e-3) and rel(g0, o_grad) < RTOL and rel(f0, o_fin) < RTOL
+    for env in VARIANTS:
+        with monkeypatch.context() as m:
+            for k, v in env.items():
+                m.setenv(k, v)
+            plan = Plan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, **kw)
+            e1, g1, f1 = plan.cost_and_grad(p.controls)
+            plan.close()
+        assert abs(e1 - e0) < 1e-12 * max(abs(e0), 1e-3), env
+        assert rel(f1, f0) < 1e-11 and rel(g1, g0) < 1e-10, (env, rel(g1, g0))
+
+
 def test_ensemble_with_lowrank_path():
     std, Plan, pol = product()
     orc = oracle_mod()
