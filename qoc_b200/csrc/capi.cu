@@ -589,6 +589,9 @@ template <int NP> cudaError_t set_sweep_attrs(int big) {
     if ((e = cudaFuncSetAttribute(k_sweep_bwd<NP, true>, A, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_sweep_bwd<NP, false>, A, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_boundary_bwd<NP>, A, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_mid_fwd<NP>, A, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_mid_bwd<NP, false>, A, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_mid_bwd<NP, true>, A, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_prefix_states<NP>, A, big)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_suffix_costates<NP>, A, big);
 }

@@ -122,6 +122,23 @@ def test_cfg5_shape_vs_oracle():
     assert finals.shape == (E, 64, 32, 1) and rel(finals, np.stack(o_fin)) < RTOL
 
 
+@pytest.mark.parametrize("step_target", [False, True], ids=["final_cost", "step_costs"])
+def test_single_member_many_states_three_levels(step_target):
+    """one member with S = 64 states at n = 32 and enough slices for the three-level boundary scheme: the boundary, fill-in and
+    sweep kernels run with eight state groups and more than 48 KB of dynamic shared memory (the parity line of the
+    member-sharded cfg5 bench has exactly this shape per rank)."""
+    std, Plan, pol = product()
+    p = Problem(32, 180, 2, 64, 2, complex_controls=False, F=0, seed=9, step_target=step_target, cost_eval_step=4)
+    plan = Plan(p.hamiltonian_numpy(), p.initial_states, p.costs(std), p.T, p.N, control_eval_count=p.M, control_count=2,
+                magnus_policy=pol[2], cost_eval_step=4)
+    err, grads, finals = plan.cost_and_grad(p.controls)
+    plan.close()
+    o_err, o_grad, o_fin = oracle(p)
+    assert abs(err - o_err) <= RTOL * abs(o_err)
+    assert rel(grads, o_grad) < RTOL, rel(grads, o_grad)
+    assert rel(finals, o_fin) < RTOL
+
+
 def _hadamard(n):
     h = np.array([[1.0]])
     while h.shape[0] < n:
