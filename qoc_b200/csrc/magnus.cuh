@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kMagThreads) k_magnus(GenArgs ga, int GMAT, in
 // k_backward leaves mbar_j in the (dead) A slot of the slice's tape, a CTA of k_magnus_adj keeps a 512-element slab of every
 // operator in shared memory and walks over tiles of 8 slices with DMMA (m = slices, n = operators, k = slab elements),
 // k_magnus_adj_final sums the slabs in a fixed order and applies the coefficient formulas.  HBM-bound: mbar is read once.
-constexpr int kAdjSlab = 512, kAdjLD = kAdjSlab + 4, kAdjMaxOps = 32, kAdjThreads = 256;
+constexpr int kAdjSlab = 512, kAdjLD = kAdjSlab + 8, kAdjMaxOps = 32, kAdjThreads = 256;
 
 __host__ __device__ inline int magnus_adj_op_count(int order, int KR) { return order == 4 ? 2 * KR + KR * (KR - 1) / 2 : KR; }
 __host__ inline size_t magnus_adj_smem_bytes(int order, int KR) {
@@ -127,31 +127,58 @@ __global__ void __launch_bounds__(kAdjThreads) k_magnus_adj(GenArgs ga, int GMAT
     double *ops = ad_sm;                                    // [NTn * 8][kAdjLD]
     double *red = ad_sm + (size_t)NTn * 8 * kAdjLD;         // [warps][NTn][64]
     const int e_base = blockIdx.x * kAdjSlab;
-    for (int idx = tid; idx < NTn * 8 * kAdjSlab; idx += kAdjThreads) {
-        const int c = idx / kAdjSlab, i = idx - c * kAdjSlab, e = e_base + i;
-        double v = 0.;
-        if (c < nops && e < GMAT) {
+    // operator slabs: kAdjSlab / kAdjThreads = 2 elements per thread and operator; the loads of eight operators are issued
+    // together (a plain strided loop is one L2 round trip per element)
+    for (int c0 = 0; c0 < NTn * 8; c0 += 8) {
+        double v[8][kAdjSlab / kAdjThreads];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            const int c = c0 + cc;
             const double *src = c < KR ? ga.G + (size_t)c * GMAT : (c < 2 * KR ? ga.C0 + (size_t)(c - KR) * GMAT : ga.Cs + (size_t)(c - 2 * KR) * GMAT);
-            v = e < GPLANE ? src[e] : -src[e];
+#pragma unroll
+            for (int h = 0; h < kAdjSlab / kAdjThreads; ++h) {
+                const int e = e_base + tid + h * kAdjThreads;
+                v[cc][h] = (c < nops && e < GMAT) ? (e < GPLANE ? __ldg(src + e) : -__ldg(src + e)) : 0.;
+            }
         }
-        ops[c * kAdjLD + i] = v;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+            for (int h = 0; h < kAdjSlab / kAdjThreads; ++h) ops[(c0 + cc) * kAdjLD + tid + h * kAdjThreads] = v[cc][h];
     }
     __syncthreads();
     const long long tiles = (W + 7) / 8;
     const long long tl0 = (long long)blockIdx.y * tiles_per_block, tl1 = min(tiles, tl0 + tiles_per_block);
-    for (long long tl = tl0; tl < tl1; ++tl) {
+    constexpr int KB = kAdjSlab / 32 / 8 * 4;                        // 8 blocks of 8 elements over this warp's 64
+    // the contraction index inside a block is permuted (slot t <-> elements 8 kk + 2 t and 8 kk + 2 t + 1 for the block's two
+    // DMMAs), so mbar and the operators are 16-byte loads: 64 contiguous bytes per slice row and instruction, all 8 in flight
+    // at once, and the fragments of the next tile are requested before the reduction of the current one
+    auto load_tile = [&](long long tl, double2 (&a)[KB]) {
         const long long j = tl * 8 + g;
         const double *row = mbar0 + (size_t)min(j, W - 1) * stride + e_base;
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+            const int k = warp * 64 + kk * 8 + 2 * t;
+            a[kk] = (j < W && e_base + k < GMAT) ? __ldg(reinterpret_cast<const double2 *>(row + k)) : make_double2(0., 0.);
+        }
+    };
+    double2 a[KB], an[KB];
+    if (tl0 < tl1) load_tile(tl0, a);
+    for (long long tl = tl0; tl < tl1; ++tl) {
+        if (tl + 1 < tl1) load_tile(tl + 1, an);
         double acc[4][2];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = 0.; acc[nt][1] = 0.; }
-#pragma unroll 4
-        for (int ks = 0; ks < kAdjSlab / 32 / 4 * 4; ++ks) {         // 16 k-steps of 4 over this warp's 64 elements
-            const int k = warp * 64 + ks * 4 + t;
-            const double a = (j < W && e_base + k < GMAT) ? row[k] : 0.;
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+            const int k = warp * 64 + kk * 8 + 2 * t;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
-                if (nt < NTn) dmma884(acc[nt][0], acc[nt][1], a, ops[(nt * 8 + g) * kAdjLD + k]);
+                if (nt < NTn) {
+                    const double2 b = *reinterpret_cast<const double2 *>(ops + (nt * 8 + g) * kAdjLD + k);
+                    dmma884(acc[nt][0], acc[nt][1], a[kk].x, b.x);
+                    dmma884(acc[nt][0], acc[nt][1], a[kk].y, b.y);
+                }
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
@@ -166,6 +193,8 @@ __global__ void __launch_bounds__(kAdjThreads) k_magnus_adj(GenArgs ga, int GMAT
             if (jj < W) partial[((size_t)blockIdx.x * W + jj) * kAdjMaxOps + nt * 8 + c] = v;
         }
         __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) a[kk] = an[kk];
     }
 }
 
